@@ -1,0 +1,180 @@
+/*
+ * same_b200.h — C-ABI of libsame_b200.so: the B200 (sm_100a) implementation of the
+ * data-parallel hot path of SAME (rohitsinghlab/SAME).
+ *
+ * The reference has no FFI: its boundary is a set of Python functions.  Every entry point
+ * below names the reference function (file:line, relative to the reference repository)
+ * whose array-level work it replaces; the Python package `same_b200` keeps the reference's
+ * own signatures on top of this header (see INTEGRATION.md for the ctypes binding a
+ * maintainer of the reference would add).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all functions return 0 on success, a negative
+ *     SAME_E_* code otherwise; same_last_error() gives the message (thread-local).
+ *   - "host or device": pointers marked HD may be host or device memory (the library
+ *     copies with cudaMemcpyDefault); everything else is host memory owned by the caller.
+ *   - a *section* is one pair of frames (aligned/moving + reference) resident in HBM;
+ *     a *batch* is a list of windows (rectangles, src/same.py:293-295) cut from a section
+ *     and processed together by every kernel.  run_same() on a single pair of frames is
+ *     a batch of one unbounded window.
+ *   - indices are int32 on the ABI (N < 2^31), offsets int64.  Within a batch every
+ *     per-window array is the concatenation over windows; same_batch_offsets() returns the
+ *     W+1 boundaries.  Indices stored inside the arrays are WINDOW-LOCAL, exactly the
+ *     numbers the reference would produce for that window.
+ *   - one CUDA stream per section/batch; calls on one batch must come from one thread at a
+ *     time (the reference's MIPSOL callback is serialised by Gurobi, src/same.py:1241).
+ */
+#ifndef SAME_B200_H
+#define SAME_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SAME_B200_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define SAME_API __attribute__((visibility("default")))
+#else
+#define SAME_API
+#endif
+
+enum {
+    SAME_OK = 0,
+    SAME_E_CUDA = -1,      /* a CUDA call failed; see same_last_error() */
+    SAME_E_ARG = -2,       /* invalid argument */
+    SAME_E_STATE = -3,     /* stage called out of order */
+    SAME_E_NOPAIRS = -4,   /* no valid pairs after KNN (reference raises ValueError, src/same.py:1002-1003) */
+    SAME_E_LIMIT = -5      /* size limit of this build exceeded (e.g. knn > SAME_MAX_KNN) */
+};
+
+#define SAME_MAX_KNN 256
+
+/* triangle classes written by same_batch_tri_classify (src/helpers.py:296-344) */
+enum { SAME_TRI_DROP_RADIUS = 0, SAME_TRI_DROP_ANGLE = 1, SAME_TRI_SAME_TYPE = 2, SAME_TRI_KEEP = 3 };
+
+/* arrays retrievable with same_batch_get(); element type in brackets */
+enum {
+    SAME_ARR_WIN_A = 1,        /* [i32]   section rows of the aligned cells of each window   (subset_data, src/same.py:293-295) */
+    SAME_ARR_WIN_R = 2,        /* [i32]   section rows of the reference cells of each window */
+    SAME_ARR_KEEP_A = 3,       /* [i32]   section rows kept after KNN compaction (+ unconstrained-node removal) (src/utils.py:734-737, src/same.py:1056-1085) */
+    SAME_ARR_KEEP_R = 4,       /* [i32]   same for the reference frame */
+    SAME_ARR_PAIRS = 5,        /* [i32x2] valid_pairs (src/utils.py:741, src/knn_utils.py:59-65) */
+    SAME_ARR_COST = 6,         /* [f64]   objective coefficient of each pair (src/same.py:1182-1189) */
+    SAME_ARR_REF_GROUP_NODE = 7,  /* [i32] ref index j of each ref_to_pairs group, first-appearance order (src/helpers.py:105-110) */
+    SAME_ARR_REF_GROUP_PTR = 8,   /* [i32] G_total+1 BATCH-GLOBAL offsets into REF_GROUP_IDX (subtract the window's pair offset) */
+    SAME_ARR_REF_GROUP_IDX = 9,   /* [i32] pair indices, ascending inside a group */
+    SAME_ARR_REF_GROUP_LIMIT = 10,/* [i32] right-hand side of max_matches_<j> (src/helpers.py:130-138) */
+    SAME_ARR_ROW_PTR = 11,     /* [i32]   nKeepA_total+1 BATCH-GLOBAL pair offsets: pairs of aligned row i are [ptr[i], ptr[i+1]) (aligned_to_pairs, src/helpers.py:107-110) */
+    SAME_ARR_TRI_IN = 12,      /* [i32x3] triangles before filtering, window-local vertices (src/same.py:1018-1031) */
+    SAME_ARR_TRI_IN_SRC = 13,  /* [i32]   index of each TRI_IN row in the global triangle list (remap path only) */
+    SAME_ARR_TRI_CLASS = 14,   /* [u8]    SAME_TRI_* per TRI_IN row */
+    SAME_ARR_TRI_BAND = 15,    /* [i32]   batch-global TRI_IN indices whose radius/angle decision lies within the guard band */
+    SAME_ARR_TRI = 16,         /* [i32x3] triangles after filtering + add-back + node renumbering (src/helpers.py:233-395, src/same.py:1072-1077) */
+    SAME_ARR_TRI_SRC = 17,     /* [i32]   window-local TRI_IN index of each TRI row */
+    SAME_ARR_TRI_WEIGHT = 18,  /* [f64]   triangle_weights (src/same.py:1128-1135) */
+    SAME_ARR_TRI_SIGN = 19,    /* [i8]    source_signs (src/same.py:1139-1146) */
+    SAME_ARR_TRI_BOUNDS = 20,  /* [f64x4] min_x,max_x,min_y,max_y (src/helpers.py:184-210) */
+    SAME_ARR_TRI_ARGV = 21,    /* [i32x4] max_x,min_x,max_y,min_y vertex (src/helpers.py:203-206) */
+    SAME_ARR_UNCONSTRAINED = 22,/* [i32]  window-local (pre-removal) indices of truly unconstrained nodes (src/helpers.py:355-358) */
+    SAME_ARR_MATCH_J = 23,     /* [i32]   per kept aligned row: matched ref index or -1 (src/same.py:634-639) */
+    SAME_ARR_MATCH_P = 24,     /* [i32]   per kept aligned row: pair index of the match or -1 */
+    SAME_ARR_TRI_MASK = 25,    /* [i32]   post-solve bits: 0-2 x-order violation of vertex pairs (0,1),(0,2),(1,2); 3-5 y-order; 8-10 vertex matched (src/violationhelper.py:54-121) */
+    SAME_ARR_AREA_BEFORE = 26, /* [f64]   calculate_signed_area on aligned XY (src/same.py:1362-1370) */
+    SAME_ARR_AREA_AFTER = 27,  /* [f64]   same on matched reference XY, NaN when a vertex is unmatched (src/same.py:1379-1395) */
+    SAME_ARR_FLIPPED = 28      /* [u8]    area_before*area_after < 0 (src/same.py:1398) */
+};
+
+typedef struct same_section same_section_t;
+typedef struct same_batch same_batch_t;
+
+SAME_API const char *same_last_error(void);
+SAME_API int same_abi_version(void);
+SAME_API int same_device_count(int *count);
+
+/* ---- section -------------------------------------------------------------------------- */
+/* Upload both frames.  XY are [N,2] row-major, prob blocks [N,K] row-major in commonCT order,
+ * type = integer code of `cell_type` (same code space for both frames), size = the `size`
+ * column (1 when absent, src/same.py:934-939).  `stream` = a cudaStream_t to run on, or NULL
+ * for a private stream.  All HD. */
+SAME_API int same_section_create(int device, void *stream, int64_t n_aligned, int64_t n_ref, int n_types,
+                        const double *a_xy, const double *r_xy, const double *a_prob, const double *r_prob,
+                        const int32_t *a_type, const int32_t *r_type, const double *a_size, const double *r_size,
+                        same_section_t **out);
+SAME_API int same_section_destroy(same_section_t *sec);
+/* bounding box of both frames: out[4] = x_min, x_max, y_min, y_max (src/same.py:481-482) */
+SAME_API int same_section_bbox(same_section_t *sec, double *out4);
+/* Cells of each frame inside M half-open rectangles (x_min,x_max,y_min,y_max), for the driver's
+ * small-window merge rule (src/same.py:523-542). rects HD. */
+SAME_API int same_section_count_rects(same_section_t *sec, int64_t m, const double *rects, int64_t *cnt_aligned, int64_t *cnt_ref);
+/* Precomputed triangulation in vertex-id space (src/same.py:262-290): a_vid[n_aligned] are the
+ * `__tri_vid` values (src/same.py:962-970), tri_vid[T,3] the triangles.  HD. */
+SAME_API int same_section_set_triangles(same_section_t *sec, const int64_t *a_vid, const int64_t *tri_vid, int64_t n_tri);
+
+/* ---- batch ---------------------------------------------------------------------------- */
+/* Cut W windows (subset_data, src/same.py:293-295).  rects == NULL with W == 1 means "the whole section". */
+SAME_API int same_batch_create(same_section_t *sec, int64_t n_windows, const double *rects, same_batch_t **out);
+SAME_API int same_batch_destroy(same_batch_t *b);
+SAME_API int64_t same_batch_num_windows(same_batch_t *b);
+
+/* a1 (+a2) + a3: find_knn_within_radius (src/utils.py:709-742), optional cell-type priority
+ * (src/knn_utils.py:31-65), pair costs (src/same.py:1182-1189).  Windows that end with zero pairs
+ * are reported through their sizes (the caller raises the reference's ValueError). */
+SAME_API int same_batch_candidates(same_batch_t *b, double radius, int knn, int priority, double dist_ct_coeff);
+
+/* a5: remap the section's precomputed triangles onto every window's post-KNN rows
+ * (src/same.py:1028-1031). */
+SAME_API int same_batch_triangles_remap(same_batch_t *b);
+/* ...or hand in per-window local triangulations (scipy Delaunay of the post-KNN aligned XY,
+ * src/same.py:1023): tri[T,3] window-local rows, tri_off[W+1].  HD. */
+SAME_API int same_batch_triangles_set(same_batch_t *b, const int32_t *tri, const int64_t *tri_off);
+
+/* a6 step 1: per-triangle radius / min-angle / same-type classification (src/helpers.py:296-344).
+ * use_angle = 0 reproduces min_angle_deg=None.  *n_band = number of guard-band triangles. */
+SAME_API int same_batch_tri_classify(same_batch_t *b, double radius, int use_angle, double min_angle_deg,
+                            int ignore_same_type, int64_t *n_band);
+/* optional: overwrite the class of n TRI_IN rows (batch-global indices) after a host re-decision */
+SAME_API int same_batch_tri_override(same_batch_t *b, int64_t n, const int32_t *tri_index, const uint8_t *cls);
+/* a6 step 2 + a7 + a8 + a9: keep / add back (src/helpers.py:346-389), optionally remove truly
+ * unconstrained nodes and renumber pairs + triangles + rows (src/same.py:1056-1085), then weights,
+ * source signs, bounds (src/same.py:1128-1146, src/helpers.py:184-210). */
+SAME_API int same_batch_tri_finalize(same_batch_t *b, int ignore_same_type, int ensure_min_triangle_per_node,
+                            int remove_unconstrained);
+
+/* a4: ref_to_pairs groups and limits (src/helpers.py:105-138).  multiplier < 0 = None
+ * (use the largest ref size of the window, src/helpers.py:123-126). */
+SAME_API int same_batch_groups(same_batch_t *b, int max_matches, int ref_metacell_match_multiplier);
+
+/* a10: lazy separation for windows [w_lo, w_hi) (src/same.py:621-703).  x HD = solution values of
+ * those windows' pairs, concatenated.  Per window: n_viol, n_checked, and the first
+ * min(n_viol, cap) cuts as (pair_a, pair_b, pair_c, triangle) in ascending triangle order into
+ * cuts[(w - w_lo) * cap * 4 ...].  The caps/threshold logic of src/same.py:671-703 is the caller's. */
+SAME_API int same_batch_separation(same_batch_t *b, int64_t w_lo, int64_t w_hi, const double *x, int64_t cap,
+                          int64_t *n_viol, int64_t *n_checked, int32_t *cuts);
+
+/* a11 + a12: post-solve analysis of windows [w_lo, w_hi) (src/violationhelper.py:1-134,
+ * src/same.py:1355-1408); results through same_batch_get(TRI_MASK / AREA_* / FLIPPED / MATCH_*). */
+SAME_API int same_batch_postsolve(same_batch_t *b, int64_t w_lo, int64_t w_hi, const double *x);
+
+/* ---- results -------------------------------------------------------------------------- */
+/* W+1 offsets (in elements) of array `what` */
+SAME_API int same_batch_offsets(same_batch_t *b, int what, int64_t *off);
+/* total number of elements of array `what` */
+SAME_API int same_batch_length(same_batch_t *b, int what, int64_t *n);
+/* copy elements [elem_lo, elem_hi) of array `what` to dst (host or device) */
+SAME_API int same_batch_get(same_batch_t *b, int what, int64_t elem_lo, int64_t elem_hi, void *dst);
+/* element size in bytes of array `what` */
+SAME_API int64_t same_elem_size(int what);
+/* block until everything queued on the batch's stream has finished */
+SAME_API int same_batch_sync(same_batch_t *b);
+/* stream the batch runs on (cudaStream_t), for event timing by the caller */
+SAME_API void *same_batch_stream(same_batch_t *b);
+/* number of kernel launches issued by this library in this process (bench.py "gpu_launches") */
+SAME_API int64_t same_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SAME_B200_H */

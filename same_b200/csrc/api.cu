@@ -1,0 +1,253 @@
+// api.cu — the extern "C" surface declared in include/same_b200.h.
+#include "common.cuh"
+
+using namespace same;
+
+namespace {
+
+template <typename F>
+int guarded(F &&f) {
+    try {
+        f();
+        return SAME_OK;
+    } catch (const same::Error &e) {
+        g_err = e.what();
+        return e.code;
+    } catch (const std::exception &e) {
+        g_err = e.what();
+        return SAME_E_CUDA;
+    }
+}
+
+struct ArrayView {
+    const void *p;
+    i64 n;         // elements
+    i64 esize;     // bytes per element
+    const std::vector<i64> *off;  // per-window offsets (may be null)
+};
+
+i64 elem_size(int what) {
+    switch (what) {
+        case SAME_ARR_PAIRS: return 8;
+        case SAME_ARR_COST: case SAME_ARR_TRI_WEIGHT: case SAME_ARR_AREA_BEFORE: case SAME_ARR_AREA_AFTER: return 8;
+        case SAME_ARR_TRI_IN: case SAME_ARR_TRI: return 12;
+        case SAME_ARR_TRI_CLASS: case SAME_ARR_TRI_SIGN: case SAME_ARR_FLIPPED: return 1;
+        case SAME_ARR_TRI_BOUNDS: return 32;
+        case SAME_ARR_TRI_ARGV: return 16;
+        case SAME_ARR_REF_GROUP_PTR: case SAME_ARR_ROW_PTR: return 4;
+        default: return 4;
+    }
+}
+
+ArrayView view(Batch *b, int what) {
+    auto need = [&](int st, const char *m) { REQUIRE(b->stage >= st, SAME_E_STATE, m); };
+    const i64 es = elem_size(what);
+    switch (what) {
+        case SAME_ARR_WIN_A: return {b->a_src.p, b->nAi, es, &b->a_off};
+        case SAME_ARR_WIN_R: return {b->r_src.p, b->nRi, es, &b->r_off};
+        case SAME_ARR_KEEP_A: need(1, "candidates not run"); return {b->keepA.p, b->nKA, es, &b->ka_off};
+        case SAME_ARR_KEEP_R: need(1, "candidates not run"); return {b->keepR.p, b->nKR, es, &b->kr_off};
+        case SAME_ARR_PAIRS: need(1, "candidates not run"); return {b->pairs.p, b->P, es, &b->p_off};
+        case SAME_ARR_COST: need(1, "candidates not run"); return {b->cost.p, b->P, es, &b->p_off};
+        case SAME_ARR_ROW_PTR: need(1, "candidates not run"); return {b->row_ptr.p, b->nKA + 1, es, nullptr};
+        case SAME_ARR_REF_GROUP_NODE: REQUIRE(b->have_groups, SAME_E_STATE, "groups not built"); return {b->g_node.p, b->G, es, &b->g_off};
+        case SAME_ARR_REF_GROUP_LIMIT: REQUIRE(b->have_groups, SAME_E_STATE, "groups not built"); return {b->g_limit.p, b->G, es, &b->g_off};
+        case SAME_ARR_REF_GROUP_PTR: REQUIRE(b->have_groups, SAME_E_STATE, "groups not built"); return {b->g_ptr.p, b->G + 1, es, nullptr};
+        case SAME_ARR_REF_GROUP_IDX: REQUIRE(b->have_groups, SAME_E_STATE, "groups not built"); return {b->g_idx.p, b->P, es, &b->p_off};
+        case SAME_ARR_TRI_IN: need(2, "no triangles"); return {b->tin.p, b->Tin, es, &b->tin_off};
+        case SAME_ARR_TRI_IN_SRC: need(2, "no triangles"); REQUIRE(b->tin_has_src, SAME_E_STATE, "triangles were not remapped"); return {b->tin_src.p, b->Tin, es, &b->tin_off};
+        case SAME_ARR_TRI_CLASS: need(3, "triangles not classified"); return {b->cls.p, b->Tin, es, &b->tin_off};
+        case SAME_ARR_TRI_BAND: need(3, "triangles not classified"); return {b->band_idx.p, b->n_band, es, nullptr};
+        case SAME_ARR_TRI: need(4, "triangles not finalized"); return {b->tri.p, b->T, es, &b->t_off};
+        case SAME_ARR_TRI_SRC: need(4, "triangles not finalized"); return {b->tri_src.p, b->T, es, &b->t_off};
+        case SAME_ARR_TRI_WEIGHT: need(4, "triangles not finalized"); return {b->t_weight.p, b->T, es, &b->t_off};
+        case SAME_ARR_TRI_SIGN: need(4, "triangles not finalized"); return {b->t_sign.p, b->T, es, &b->t_off};
+        case SAME_ARR_TRI_BOUNDS: need(4, "triangles not finalized"); return {b->t_bounds.p, b->T, es, &b->t_off};
+        case SAME_ARR_TRI_ARGV: need(4, "triangles not finalized"); return {b->t_argv.p, b->T, es, &b->t_off};
+        case SAME_ARR_UNCONSTRAINED: need(4, "triangles not finalized"); return {b->unc.p, b->nUnc, es, &b->unc_off};
+        case SAME_ARR_MATCH_J: need(4, "no matching yet"); return {b->match_j.p, b->match_j.p ? b->nKA : 0, es, &b->ka_off};
+        case SAME_ARR_MATCH_P: need(4, "no matching yet"); return {b->match_p.p, b->match_p.p ? b->nKA : 0, es, &b->ka_off};
+        case SAME_ARR_TRI_MASK: REQUIRE(b->have_post, SAME_E_STATE, "postsolve not run"); return {b->t_mask.p, b->T, es, &b->t_off};
+        case SAME_ARR_AREA_BEFORE: REQUIRE(b->have_post, SAME_E_STATE, "postsolve not run"); return {b->area_before.p, b->T, es, &b->t_off};
+        case SAME_ARR_AREA_AFTER: REQUIRE(b->have_post, SAME_E_STATE, "postsolve not run"); return {b->area_after.p, b->T, es, &b->t_off};
+        case SAME_ARR_FLIPPED: REQUIRE(b->have_post, SAME_E_STATE, "postsolve not run"); return {b->flipped.p, b->T, es, &b->t_off};
+        default: throw same::Error(SAME_E_ARG, "unknown array id");
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *same_last_error(void) { return g_err.c_str(); }
+int same_abi_version(void) { return SAME_B200_ABI_VERSION; }
+int same_device_count(int *count) {
+    return guarded([&] { CK(cudaGetDeviceCount(count)); });
+}
+int64_t same_launch_count(void) { return (int64_t)g_launches.load(); }
+int64_t same_elem_size(int what) { return elem_size(what); }
+
+int same_section_create(int device, void *stream, int64_t n_aligned, int64_t n_ref, int n_types, const double *a_xy, const double *r_xy,
+                        const double *a_prob, const double *r_prob, const int32_t *a_type, const int32_t *r_type, const double *a_size,
+                        const double *r_size, same_section_t **out) {
+    return guarded([&] {
+        REQUIRE(out, SAME_E_ARG, "out is NULL");
+        REQUIRE(n_aligned >= 0 && n_ref >= 0 && n_types >= 0, SAME_E_ARG, "negative size");
+        REQUIRE(n_aligned < (1ll << 31) && n_ref < (1ll << 31), SAME_E_LIMIT, "frames are limited to 2^31 rows");
+        REQUIRE((n_aligned == 0 || a_xy) && (n_ref == 0 || r_xy), SAME_E_ARG, "XY pointer is NULL");
+        REQUIRE(n_types == 0 || ((n_aligned == 0 || a_prob) && (n_ref == 0 || r_prob)), SAME_E_ARG, "probability pointer is NULL");
+        CK(cudaSetDevice(device));
+        Section *sec = new Section();
+        try {
+            sec->device = device;
+            if (stream) sec->stream = (cudaStream_t)stream;
+            else { CK(cudaStreamCreateWithFlags(&sec->stream, cudaStreamNonBlocking)); sec->own_stream = true; }
+            cudaMemPool_t pool;
+            CK(cudaDeviceGetDefaultMemPool(&pool, device));
+            unsigned long long thr = ~0ull;  // keep freed blocks cached: the pipeline reallocates the same sizes every window batch
+            CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+            sec->nA = n_aligned; sec->nR = n_ref; sec->K = n_types;
+            section_build(sec, a_xy, r_xy, a_prob, r_prob, a_type, r_type, a_size, r_size);
+        } catch (...) {
+            delete sec;
+            throw;
+        }
+        *out = (same_section_t *)sec;
+    });
+}
+
+int same_section_destroy(same_section_t *h) {
+    return guarded([&] {
+        Section *sec = (Section *)h;
+        if (!sec) return;
+        CK(cudaSetDevice(sec->device));
+        cudaStream_t s = sec->stream;
+        bool own = sec->own_stream;
+        delete sec;
+        CK(cudaStreamSynchronize(s));
+        if (own) CK(cudaStreamDestroy(s));
+    });
+}
+
+int same_section_bbox(same_section_t *h, double *out4) {
+    return guarded([&] {
+        REQUIRE(h && out4, SAME_E_ARG, "NULL argument");
+        memcpy(out4, ((Section *)h)->bbox, sizeof(double) * 4);
+    });
+}
+
+int same_section_count_rects(same_section_t *h, int64_t m, const double *rects, int64_t *cnt_aligned, int64_t *cnt_ref) {
+    return guarded([&] {
+        REQUIRE(h && (m == 0 || (rects && cnt_aligned && cnt_ref)), SAME_E_ARG, "NULL argument");
+        REQUIRE(m >= 0 && m < 65536, SAME_E_LIMIT, "at most 65535 rectangles per call");
+        if (m == 0) return;
+        CK(cudaSetDevice(((Section *)h)->device));
+        section_count_rects((Section *)h, m, rects, cnt_aligned, cnt_ref);
+    });
+}
+
+int same_section_set_triangles(same_section_t *h, const int64_t *a_vid, const int64_t *tri_vid, int64_t n_tri) {
+    return guarded([&] {
+        REQUIRE(h && (n_tri == 0 || tri_vid), SAME_E_ARG, "NULL argument");
+        REQUIRE(n_tri >= 0 && 3 * n_tri < (1ll << 31), SAME_E_LIMIT, "too many triangles");
+        CK(cudaSetDevice(((Section *)h)->device));
+        section_set_triangles((Section *)h, a_vid, tri_vid, n_tri);
+    });
+}
+
+int same_batch_create(same_section_t *h, int64_t n_windows, const double *rects, same_batch_t **out) {
+    return guarded([&] {
+        REQUIRE(h && out, SAME_E_ARG, "NULL argument");
+        REQUIRE(n_windows >= 1 && n_windows < 65536, SAME_E_LIMIT, "a batch holds 1..65535 windows");
+        REQUIRE(rects || n_windows == 1, SAME_E_ARG, "rects is NULL");
+        Section *sec = (Section *)h;
+        CK(cudaSetDevice(sec->device));
+        Batch *b = new Batch();
+        try {
+            b->sec = sec;
+            b->stream = sec->stream;
+            b->W = n_windows;
+            if (rects) b->rects.assign(rects, rects + 4 * n_windows);
+            else b->rects = {-INFINITY, INFINITY, -INFINITY, INFINITY};
+            batch_subset(b);
+        } catch (...) {
+            delete b;
+            throw;
+        }
+        *out = (same_batch_t *)b;
+    });
+}
+
+int same_batch_destroy(same_batch_t *h) {
+    return guarded([&] {
+        Batch *b = (Batch *)h;
+        if (!b) return;
+        CK(cudaSetDevice(b->sec->device));
+        cudaStream_t s = b->stream;
+        delete b;
+        CK(cudaStreamSynchronize(s));
+    });
+}
+
+int64_t same_batch_num_windows(same_batch_t *h) { return h ? ((Batch *)h)->W : 0; }
+void *same_batch_stream(same_batch_t *h) { return h ? (void *)((Batch *)h)->stream : nullptr; }
+
+#define BATCH_CALL(h, body)                              \
+    return guarded([&] {                                 \
+        REQUIRE(h, SAME_E_ARG, "batch is NULL");         \
+        Batch *b = (Batch *)h;                           \
+        CK(cudaSetDevice(b->sec->device));               \
+        body;                                            \
+    })
+
+int same_batch_candidates(same_batch_t *h, double radius, int knn, int priority, double dist_ct_coeff) {
+    BATCH_CALL(h, batch_candidates(b, radius, knn, priority, dist_ct_coeff));
+}
+int same_batch_triangles_remap(same_batch_t *h) { BATCH_CALL(h, batch_triangles_remap(b)); }
+int same_batch_triangles_set(same_batch_t *h, const int32_t *tri, const int64_t *tri_off) {
+    BATCH_CALL(h, { REQUIRE(tri_off, SAME_E_ARG, "tri_off is NULL"); batch_triangles_set(b, tri, tri_off); });
+}
+int same_batch_tri_classify(same_batch_t *h, double radius, int use_angle, double min_angle_deg, int ignore_same_type, int64_t *n_band) {
+    BATCH_CALL(h, { batch_tri_classify(b, radius, use_angle, min_angle_deg, ignore_same_type); if (n_band) *n_band = b->n_band; });
+}
+int same_batch_tri_override(same_batch_t *h, int64_t n, const int32_t *tri_index, const uint8_t *cls) {
+    BATCH_CALL(h, batch_tri_override(b, n, tri_index, cls));
+}
+int same_batch_tri_finalize(same_batch_t *h, int ignore_same_type, int ensure_min, int remove_unconstrained) {
+    BATCH_CALL(h, batch_tri_finalize(b, ignore_same_type, ensure_min, remove_unconstrained));
+}
+int same_batch_groups(same_batch_t *h, int max_matches, int multiplier) { BATCH_CALL(h, batch_groups(b, max_matches, multiplier)); }
+int same_batch_separation(same_batch_t *h, int64_t w_lo, int64_t w_hi, const double *x, int64_t cap, int64_t *n_viol, int64_t *n_checked,
+                          int32_t *cuts) {
+    BATCH_CALL(h, { REQUIRE(n_viol && n_checked, SAME_E_ARG, "NULL output"); batch_separation(b, w_lo, w_hi, x, cap, n_viol, n_checked, cuts); });
+}
+int same_batch_postsolve(same_batch_t *h, int64_t w_lo, int64_t w_hi, const double *x) { BATCH_CALL(h, batch_postsolve(b, w_lo, w_hi, x)); }
+
+int same_batch_offsets(same_batch_t *h, int what, int64_t *off) {
+    BATCH_CALL(h, {
+        REQUIRE(off, SAME_E_ARG, "off is NULL");
+        ArrayView v = view(b, what);
+        REQUIRE(v.off != nullptr, SAME_E_ARG, "array has no per-window offsets");
+        memcpy(off, v.off->data(), sizeof(i64) * (size_t)(b->W + 1));
+    });
+}
+
+int same_batch_length(same_batch_t *h, int what, int64_t *n) {
+    BATCH_CALL(h, { REQUIRE(n, SAME_E_ARG, "n is NULL"); *n = view(b, what).n; });
+}
+
+int same_batch_get(same_batch_t *h, int what, int64_t elem_lo, int64_t elem_hi, void *dst) {
+    BATCH_CALL(h, {
+        ArrayView v = view(b, what);
+        REQUIRE(elem_lo >= 0 && elem_lo <= elem_hi && elem_hi <= v.n, SAME_E_ARG, "element range out of bounds");
+        if (elem_hi > elem_lo) {
+            REQUIRE(dst, SAME_E_ARG, "dst is NULL");
+            CK(cudaMemcpyAsync(dst, (const char *)v.p + elem_lo * v.esize, (size_t)((elem_hi - elem_lo) * v.esize), cudaMemcpyDefault, b->stream));
+            CK(cudaStreamSynchronize(b->stream));
+        }
+    });
+}
+
+int same_batch_sync(same_batch_t *h) { BATCH_CALL(h, CK(cudaStreamSynchronize(b->stream))); }
+
+}  // extern "C"

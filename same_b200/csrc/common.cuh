@@ -1,0 +1,226 @@
+// common.cuh — shared host/device plumbing of libsame_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cub/cub.cuh>
+
+#include <atomic>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/same_b200.h"
+
+typedef int64_t i64;
+typedef int32_t i32;
+
+namespace same {
+
+extern thread_local std::string g_err;
+extern std::atomic<long long> g_launches;
+
+struct Error : std::runtime_error {
+    int code;
+    Error(int c, const std::string &m) : std::runtime_error(m), code(c) {}
+};
+
+#define CK(call)                                                                                            \
+    do {                                                                                                    \
+        cudaError_t e__ = (call);                                                                           \
+        if (e__ != cudaSuccess)                                                                             \
+            throw same::Error(SAME_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__) + " (" +    \
+                                               __FILE__ + ":" + std::to_string(__LINE__) + ")");          \
+    } while (0)
+
+#define REQUIRE(cond, code, msg)                                                                            \
+    do {                                                                                                    \
+        if (!(cond)) throw same::Error(code, std::string(msg));                                             \
+    } while (0)
+
+// every kernel launch goes through this macro so bench.py can report gpu_launches
+#define LAUNCH(kernel, grid, block, smem, stream, ...)                                                      \
+    do {                                                                                                    \
+        kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);                                         \
+        same::g_launches.fetch_add(1, std::memory_order_relaxed);                                           \
+        CK(cudaGetLastError());                                                                             \
+    } while (0)
+
+inline unsigned blocks_for(i64 n, int per_block) { return (unsigned)std::max<i64>(1, (n + per_block - 1) / per_block); }
+
+// stream-ordered device buffer
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    i64 n = 0;
+    cudaStream_t s = nullptr;
+    DevBuf() {}
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    ~DevBuf() { release(); }
+    void release() {
+        if (p) cudaFreeAsync(p, s);
+        p = nullptr;
+        n = 0;
+    }
+    // contents are NOT preserved
+    void alloc(i64 count, cudaStream_t stream) {
+        if (count <= n && p) { s = stream; return; }
+        release();
+        s = stream;
+        n = std::max<i64>(count, 1);
+        CK(cudaMallocAsync((void **)&p, sizeof(T) * (size_t)n, stream));
+    }
+    void zero(cudaStream_t stream) { CK(cudaMemsetAsync(p, 0, sizeof(T) * (size_t)n, stream)); }
+    void swap(DevBuf &o) { std::swap(p, o.p); std::swap(n, o.n); std::swap(s, o.s); }
+};
+
+struct Scratch {
+    DevBuf<unsigned char> buf;
+    void *get(size_t bytes, cudaStream_t s) {
+        buf.alloc((i64)bytes + 256, s);
+        return buf.p;
+    }
+};
+
+// exclusive prefix sum of n i32 -> out[n] (+ out[n] = total when with_total)
+void exclusive_scan_i32(const i32 *in, i32 *out, i64 n, Scratch &sc, cudaStream_t s);
+
+struct Section {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    i64 nA = 0, nR = 0;
+    int K = 0;
+    DevBuf<double2> a_xy, r_xy;
+    DevBuf<double> a_prob, r_prob, a_size, r_size;
+    DevBuf<i32> a_type, r_type;
+    double bbox[4] = {0, 0, 0, 0};  // x_min, x_max, y_min, y_max over both frames
+    // precomputed triangulation (vertex ids resolved to section rows; -1 = id not present)
+    i64 Tg = -1;
+    DevBuf<i32> tri_rows;  // [Tg*3]
+    Scratch scratch;
+};
+
+struct GridParams {  // uniform bin grid of one window (reference side)
+    double x0, y0, inv_w, w;
+    i32 nbx, nby, base, rings;
+};
+
+struct Batch {
+    Section *sec = nullptr;
+    cudaStream_t stream = nullptr;
+    i64 W = 0;
+    std::vector<double> rects;  // W*4
+    DevBuf<double> d_rects;
+    Scratch scratch;
+    int stage = 0;  // 0 created, 1 candidates, 2 triangles in, 3 classified, 4 finalized
+
+    // window instances (subset_data)
+    i64 nAi = 0, nRi = 0;
+    std::vector<i64> a_off, r_off;      // W+1
+    DevBuf<i32> d_a_off, d_r_off;       // W+1
+    DevBuf<i32> a_src, r_src;           // section row of each instance
+
+    // candidates
+    int knn = 0;
+    double radius = 0;
+    DevBuf<i32> cand, cnt, eff;         // [nAi*knn] ref instance, [nAi], [nAi] pairs emitted (priority)
+    DevBuf<i32> r_used;                 // [nRi]
+
+    // kept nodes (post-KNN frames), batch-global "kept index" = window offset + local index
+    i64 nKA = 0, nKR = 0, P = 0;
+    std::vector<i64> ka_off, kr_off, p_off;   // W+1 each
+    DevBuf<i32> d_ka_off, d_kr_off, d_p_off;  // W+1
+    DevBuf<i32> keepA, keepR;           // section rows
+    DevBuf<double2> ka_xy, kr_xy;
+    DevBuf<i32> ka_type;
+    DevBuf<double> ka_size, kr_size;
+    DevBuf<int2> pairs;                 // window-local (i, j)
+    DevBuf<double> cost;
+    DevBuf<i32> row_ptr;                // [nKA+1] batch-global pair offset of each aligned row
+
+    // groups (a4)
+    i64 G = 0;
+    std::vector<i64> g_off;
+    DevBuf<i32> g_node, g_ptr, g_idx, g_limit;
+    bool have_groups = false;
+
+    // triangles in
+    i64 Tin = 0;
+    std::vector<i64> tin_off;
+    DevBuf<i32> d_tin_off;
+    DevBuf<int3> tin;                   // window-local vertices
+    DevBuf<i32> tin_src;
+    bool tin_has_src = false;
+    DevBuf<unsigned char> cls;
+    DevBuf<double> score;
+    i64 n_band = 0;
+    DevBuf<i32> band_idx;
+    bool use_angle = false;
+
+    // triangles out
+    i64 T = 0;
+    std::vector<i64> t_off;
+    DevBuf<i32> d_t_off;
+    DevBuf<int3> tri;
+    DevBuf<i32> tri_src;
+    DevBuf<double> t_weight;
+    DevBuf<signed char> t_sign;
+    DevBuf<double> t_bounds;
+    DevBuf<i32> t_argv;
+    i64 nUnc = 0;
+    std::vector<i64> unc_off;
+    DevBuf<i32> unc;
+
+    // separation / postsolve
+    DevBuf<double> x_dev;
+    DevBuf<i32> match_j, match_p;       // [nKA]
+    DevBuf<i32> viol_flag, viol_pos, sep_counts, cuts;
+    DevBuf<i32> t_mask;
+    DevBuf<double> area_before, area_after;
+    DevBuf<unsigned char> flipped;
+    bool have_post = false;
+};
+
+// implemented across the .cu files
+void section_build(Section *sec, const double *a_xy, const double *r_xy, const double *a_prob, const double *r_prob,
+                   const i32 *a_type, const i32 *r_type, const double *a_size, const double *r_size);
+void section_count_rects(Section *sec, i64 m, const double *rects, i64 *cntA, i64 *cntR);
+void section_set_triangles(Section *sec, const i64 *a_vid, const i64 *tri_vid, i64 n_tri);
+void batch_subset(Batch *b);
+void batch_candidates(Batch *b, double radius, int knn, int priority, double dist_ct_coeff);
+void batch_groups(Batch *b, int max_matches, int multiplier);
+void batch_triangles_remap(Batch *b);
+void batch_triangles_set(Batch *b, const i32 *tri, const i64 *tri_off);
+void batch_tri_classify(Batch *b, double radius, int use_angle, double min_angle_deg, int ignore_same_type);
+void batch_tri_override(Batch *b, i64 n, const i32 *idx, const unsigned char *cls);
+void batch_tri_finalize(Batch *b, int ignore_same_type, int ensure_min, int remove_unconstrained);
+void batch_separation(Batch *b, i64 w_lo, i64 w_hi, const double *x, i64 cap, i64 *n_viol, i64 *n_checked, i32 *cuts);
+void batch_postsolve(Batch *b, i64 w_lo, i64 w_hi, const double *x);
+
+// upload a small host vector of i64 offsets as i32 device array
+void upload_offsets(const std::vector<i64> &h, DevBuf<i32> &d, cudaStream_t s);
+
+// ---- device helpers -----------------------------------------------------------------
+// window of element idx given W+1 ascending offsets (last offset = total)
+__device__ __forceinline__ int find_window(const i32 *__restrict__ off, int W, i32 idx) {
+    int lo = 0, hi = W;  // invariant: off[lo] <= idx < off[hi]
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (off[mid] <= idx) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+// (bx-ax)*(cy-ay) - (by-ay)*(cx-ax), one IEEE operation at a time (src/same.py:658,1146)
+__device__ __forceinline__ double orient_naive(double ax, double ay, double bx, double by, double cx, double cy) {
+    const double t1 = __dmul_rn(__dsub_rn(bx, ax), __dsub_rn(cy, ay));
+    const double t2 = __dmul_rn(__dsub_rn(by, ay), __dsub_rn(cx, ax));
+    return __dsub_rn(t1, t2);
+}
+__device__ __forceinline__ int sign_of(double v) { return (v > 0.0) - (v < 0.0); }
+
+}  // namespace same

@@ -1,0 +1,491 @@
+// triangles.cu — a5 _remap_triangles_by_vertex_ids (src/same.py:262-290), a6 filter_triangles_by_radius
+// (src/helpers.py:233-395), a7 unconstrained-node removal (src/same.py:1056-1085), a8 triangle info
+// (src/helpers.py:184-210), a9 weights + source signs (src/same.py:1128-1146), batched over windows.
+#include "common.cuh"
+
+namespace same {
+
+constexpr int TR_THREADS = 256;
+constexpr int TR_ITEMS = 4;
+constexpr int TR_CHUNK = TR_THREADS * TR_ITEMS;
+
+// local (window) index of section row `row` among the window's kept aligned rows, or -1
+__device__ __forceinline__ i32 kept_lookup(const i32 *__restrict__ keepA, i32 lo, i32 hi, i32 row) {
+    const i32 base = lo, end = hi;
+    while (lo < hi) {
+        const i32 mid = (lo + hi) >> 1;
+        if (keepA[mid] < row) lo = mid + 1; else hi = mid;
+    }
+    return (lo < end && keepA[lo] == row) ? lo - base : -1;
+}
+
+__device__ __forceinline__ bool tri_in_window(const i32 *__restrict__ tri_rows, i64 t, const i32 *__restrict__ keepA, i32 lo, i32 hi, int3 &out) {
+    const i32 ra = tri_rows[3 * t], rb = tri_rows[3 * t + 1], rc = tri_rows[3 * t + 2];
+    if (ra < 0 || rb < 0 || rc < 0) return false;
+    out.x = kept_lookup(keepA, lo, hi, ra);
+    if (out.x < 0) return false;
+    out.y = kept_lookup(keepA, lo, hi, rb);
+    if (out.y < 0) return false;
+    out.z = kept_lookup(keepA, lo, hi, rc);
+    return out.z >= 0;
+}
+
+__global__ void __launch_bounds__(TR_THREADS) k_remap_count(const i32 *__restrict__ tri_rows, i64 Tg, const i32 *__restrict__ keepA,
+                                                            const i32 *__restrict__ ka_off, i32 *__restrict__ block_counts) {
+    const int w = blockIdx.y;
+    const i32 lo = ka_off[w], hi = ka_off[w + 1];
+    const i64 base = (i64)blockIdx.x * TR_CHUNK;
+    int c = 0;
+    int3 tmp3;
+#pragma unroll
+    for (int it = 0; it < TR_ITEMS; ++it) {
+        const i64 t = base + it * TR_THREADS + threadIdx.x;
+        c += (t < Tg) && tri_in_window(tri_rows, t, keepA, lo, hi, tmp3);
+    }
+    typedef cub::BlockReduce<int, TR_THREADS> BR;
+    __shared__ typename BR::TempStorage tmp;
+    const int tot = BR(tmp).Sum(c);
+    if (threadIdx.x == 0) block_counts[(i64)w * gridDim.x + blockIdx.x] = tot;
+}
+
+__global__ void __launch_bounds__(TR_THREADS) k_remap_fill(const i32 *__restrict__ tri_rows, i64 Tg, const i32 *__restrict__ keepA,
+                                                           const i32 *__restrict__ ka_off, const i32 *__restrict__ block_base,
+                                                           int3 *__restrict__ tin, i32 *__restrict__ tin_src) {
+    const int w = blockIdx.y;
+    const i32 lo = ka_off[w], hi = ka_off[w + 1];
+    const i64 base = (i64)blockIdx.x * TR_CHUNK;
+    typedef cub::BlockScan<int, TR_THREADS> BS;
+    __shared__ typename BS::TempStorage tmp;
+    int run = block_base[(i64)w * gridDim.x + blockIdx.x];
+#pragma unroll 1
+    for (int it = 0; it < TR_ITEMS; ++it) {
+        const i64 t = base + it * TR_THREADS + threadIdx.x;
+        int3 v = make_int3(0, 0, 0);
+        const int f = (t < Tg) && tri_in_window(tri_rows, t, keepA, lo, hi, v);
+        int rank, tot;
+        BS(tmp).ExclusiveSum(f, rank, tot);
+        if (f) { tin[run + rank] = v; tin_src[run + rank] = (i32)t; }
+        run += tot;
+        __syncthreads();
+    }
+}
+
+__global__ void k_pick_strided(const i32 *__restrict__ scanned, i64 stride, i64 W, i32 *__restrict__ off) {
+    i64 w = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w <= W) off[w] = scanned[w * stride];
+}
+
+static void reset_triangles(Batch *b) {
+    b->Tin = 0; b->T = 0; b->n_band = 0; b->tin_has_src = false; b->have_post = false;
+}
+
+void batch_triangles_remap(Batch *b) {
+    Section *sec = b->sec;
+    cudaStream_t s = b->stream;
+    REQUIRE(b->stage >= 1, SAME_E_STATE, "same_batch_triangles_remap before same_batch_candidates");
+    REQUIRE(sec->Tg >= 0, SAME_E_STATE, "same_section_set_triangles was not called");
+    reset_triangles(b);
+    const i64 W = b->W, Tg = sec->Tg;
+    const i64 chunks = blocks_for(Tg, TR_CHUNK);
+    DevBuf<i32> counts, scanned;
+    counts.alloc(W * chunks + 1, s); scanned.alloc(W * chunks + 1, s);
+    CK(cudaMemsetAsync(counts.p, 0, sizeof(i32) * (W * chunks + 1), s));
+    if (Tg > 0) LAUNCH(k_remap_count, dim3((unsigned)chunks, (unsigned)W), TR_THREADS, 0, s, sec->tri_rows.p, Tg, b->keepA.p, b->d_ka_off.p, counts.p);
+    exclusive_scan_i32(counts.p, scanned.p, W * chunks + 1, b->scratch, s);
+    b->d_tin_off.alloc(W + 1, s);
+    LAUNCH(k_pick_strided, blocks_for(W + 1, 128), 128, 0, s, scanned.p, chunks, W, b->d_tin_off.p);
+    std::vector<i32> h(W + 1);
+    CK(cudaMemcpyAsync(h.data(), b->d_tin_off.p, sizeof(i32) * (W + 1), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    b->tin_off.assign(h.begin(), h.end());
+    b->Tin = b->tin_off[W];
+    b->tin.alloc(b->Tin, s); b->tin_src.alloc(b->Tin, s);
+    if (Tg > 0 && b->Tin > 0)
+        LAUNCH(k_remap_fill, dim3((unsigned)chunks, (unsigned)W), TR_THREADS, 0, s, sec->tri_rows.p, Tg, b->keepA.p, b->d_ka_off.p, scanned.p,
+               b->tin.p, b->tin_src.p);
+    CK(cudaStreamSynchronize(s));
+    b->tin_has_src = true;
+    b->stage = 2;
+}
+
+void batch_triangles_set(Batch *b, const i32 *tri, const i64 *tri_off) {
+    cudaStream_t s = b->stream;
+    REQUIRE(b->stage >= 1, SAME_E_STATE, "same_batch_triangles_set before same_batch_candidates");
+    reset_triangles(b);
+    const i64 W = b->W;
+    b->tin_off.assign(tri_off, tri_off + W + 1);
+    REQUIRE(b->tin_off[0] == 0, SAME_E_ARG, "tri_off[0] must be 0");
+    for (i64 w = 0; w < W; ++w) REQUIRE(b->tin_off[w + 1] >= b->tin_off[w], SAME_E_ARG, "tri_off must be non-decreasing");
+    b->Tin = b->tin_off[W];
+    b->tin.alloc(b->Tin, s);
+    if (b->Tin > 0) CK(cudaMemcpyAsync(b->tin.p, tri, sizeof(int3) * (size_t)b->Tin, cudaMemcpyDefault, s));
+    upload_offsets(b->tin_off, b->d_tin_off, s);
+    b->stage = 2;
+}
+
+// ---- a6 step 1: classification ---------------------------------------------------------------
+// 1-D np.linalg.norm / np.dot go through BLAS ddot == fma(y1,y2,x1*x2)
+__device__ __forceinline__ double norm2_blas(double x, double y) { return __dsqrt_rn(__fma_rn(y, y, __dmul_rn(x, x))); }
+// compute_angle(p1, p2, p3): angle at p2 in degrees (src/helpers.py:278-288)
+__device__ __forceinline__ double angle_at(double2 p1, double2 p2, double2 p3) {
+    const double v1x = __dsub_rn(p1.x, p2.x), v1y = __dsub_rn(p1.y, p2.y);
+    const double v2x = __dsub_rn(p3.x, p2.x), v2y = __dsub_rn(p3.y, p2.y);
+    const double n1 = norm2_blas(v1x, v1y), n2 = norm2_blas(v2x, v2y);
+    if (n1 == 0.0 || n2 == 0.0) return 0.0;
+    double c = __ddiv_rn(__fma_rn(v1y, v2y, __dmul_rn(v1x, v2x)), __dmul_rn(n1, n2));
+    c = fmin(fmax(c, -1.0), 1.0);
+    return __dmul_rn(acos(c), 57.29577951308232);  // np.degrees: x * (180/pi)
+}
+
+__global__ void k_tri_classify(const int3 *__restrict__ tin, i64 Tin, const i32 *__restrict__ tin_off, const i32 *__restrict__ ka_off, int W,
+                               const double2 *__restrict__ ka_xy, const i32 *__restrict__ ka_type, double radius, int use_angle,
+                               double min_angle, int ignore_same_type, unsigned char *__restrict__ cls, double *__restrict__ score,
+                               i32 *__restrict__ band_idx, i32 *__restrict__ band_count) {
+    const i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= Tin) return;
+    const int w = find_window(tin_off, W, (i32)t);
+    const i32 nb = ka_off[w];
+    const int3 v = tin[t];
+    const double2 p1 = ka_xy[nb + v.x], p2 = ka_xy[nb + v.y], p3 = ka_xy[nb + v.z];
+    const double s1 = norm2_blas(__dsub_rn(p2.x, p1.x), __dsub_rn(p2.y, p1.y));
+    const double s2 = norm2_blas(__dsub_rn(p3.x, p2.x), __dsub_rn(p3.y, p2.y));
+    const double s3 = norm2_blas(__dsub_rn(p1.x, p3.x), __dsub_rn(p1.y, p3.y));
+    const double mx = fmax(s1, fmax(s2, s3));
+    bool band = fabs(mx - radius) <= 1e-12 * fabs(radius);
+    score[t] = __dadd_rn(__dadd_rn(s1, s2), s3);  // helpers.py:333
+    unsigned char k;
+    if (mx >= radius) k = SAME_TRI_DROP_RADIUS;  // helpers.py:310
+    else {
+        k = SAME_TRI_KEEP;
+        if (use_angle) {  // helpers.py:315-321
+            const double a1 = angle_at(p2, p1, p3), a2 = angle_at(p1, p2, p3), a3 = angle_at(p1, p3, p2);
+            const double mn = fmin(a1, fmin(a2, a3));
+            if (fabs(mn - min_angle) <= 1e-9) band = true;
+            if (mn < min_angle) k = SAME_TRI_DROP_ANGLE;
+        }
+        if (k == SAME_TRI_KEEP && ignore_same_type) {  // helpers.py:328-330
+            const i32 ta = ka_type[nb + v.x], tb = ka_type[nb + v.y], tc = ka_type[nb + v.z];
+            if (ta == tb && tb == tc) k = SAME_TRI_SAME_TYPE;
+        }
+    }
+    cls[t] = k;
+    if (band) band_idx[atomicAdd(band_count, 1)] = (i32)t;
+}
+
+void batch_tri_classify(Batch *b, double radius, int use_angle, double min_angle_deg, int ignore_same_type) {
+    cudaStream_t s = b->stream;
+    REQUIRE(b->stage >= 2, SAME_E_STATE, "same_batch_tri_classify before triangles were provided");
+    const i64 Tin = b->Tin;
+    b->cls.alloc(Tin, s); b->score.alloc(Tin, s); b->band_idx.alloc(Tin + 1, s);
+    DevBuf<i32> bc;
+    bc.alloc(1, s);
+    bc.zero(s);
+    if (Tin > 0)
+        LAUNCH(k_tri_classify, blocks_for(Tin, 256), 256, 0, s, b->tin.p, Tin, b->d_tin_off.p, b->d_ka_off.p, (int)b->W, b->ka_xy.p, b->ka_type.p,
+               radius, use_angle, min_angle_deg, ignore_same_type, b->cls.p, b->score.p, b->band_idx.p, bc.p);
+    i32 h = 0;
+    CK(cudaMemcpyAsync(&h, bc.p, sizeof(i32), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    b->n_band = h;
+    b->stage = 3;
+}
+
+__global__ void k_tri_override(i64 n, const i32 *__restrict__ idx, const unsigned char *__restrict__ v, i64 Tin, unsigned char *__restrict__ cls) {
+    i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && idx[i] >= 0 && idx[i] < Tin) cls[idx[i]] = v[i];
+}
+
+void batch_tri_override(Batch *b, i64 n, const i32 *idx, const unsigned char *cls) {
+    cudaStream_t s = b->stream;
+    REQUIRE(b->stage >= 3, SAME_E_STATE, "same_batch_tri_override before same_batch_tri_classify");
+    if (n == 0) return;
+    DevBuf<i32> d_i;
+    DevBuf<unsigned char> d_c;
+    d_i.alloc(n, s); d_c.alloc(n, s);
+    CK(cudaMemcpyAsync(d_i.p, idx, sizeof(i32) * n, cudaMemcpyDefault, s));
+    CK(cudaMemcpyAsync(d_c.p, cls, n, cudaMemcpyDefault, s));
+    LAUNCH(k_tri_override, blocks_for(n, 256), 256, 0, s, n, d_i.p, d_c.p, b->Tin, b->cls.p);
+    CK(cudaStreamSynchronize(s));
+}
+
+// ---- a6 step 2 -----------------------------------------------------------------------------------
+__global__ void k_tri_nodes(const int3 *__restrict__ tin, i64 Tin, const i32 *__restrict__ tin_off, const i32 *__restrict__ ka_off, int W,
+                            const unsigned char *__restrict__ cls, const double *__restrict__ score, int track_best,
+                            i32 *__restrict__ node_valid, i32 *__restrict__ has_tri, unsigned long long *__restrict__ best_score,
+                            i32 *__restrict__ kept_flag) {
+    const i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t == Tin) kept_flag[t] = 0;
+    if (t >= Tin) return;
+    const unsigned char c = cls[t];
+    kept_flag[t] = (c == SAME_TRI_KEEP);
+    if (c < SAME_TRI_SAME_TYPE) return;
+    const i32 nb = ka_off[find_window(tin_off, W, (i32)t)];
+    const int3 v = tin[t];
+    node_valid[nb + v.x] = 1; node_valid[nb + v.y] = 1; node_valid[nb + v.z] = 1;  // helpers.py:324-325
+    if (c == SAME_TRI_KEEP) { has_tri[nb + v.x] = 1; has_tri[nb + v.y] = 1; has_tri[nb + v.z] = 1; }
+    else if (track_best) {
+        const unsigned long long k = (unsigned long long)__double_as_longlong(score[t]);  // score >= 0: bit order == value order
+        atomicMin(best_score + nb + v.x, k); atomicMin(best_score + nb + v.y, k); atomicMin(best_score + nb + v.z, k);
+    }
+}
+// strict '<' + first wins (helpers.py:335-339) == smallest triangle index among the minimal scores
+__global__ void k_tri_best(const int3 *__restrict__ tin, i64 Tin, const i32 *__restrict__ tin_off, const i32 *__restrict__ ka_off, int W,
+                           const unsigned char *__restrict__ cls, const double *__restrict__ score,
+                           const unsigned long long *__restrict__ best_score, i32 *__restrict__ best_tri) {
+    const i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= Tin || cls[t] != SAME_TRI_SAME_TYPE) return;
+    const i32 nb = ka_off[find_window(tin_off, W, (i32)t)];
+    const int3 v = tin[t];
+    const unsigned long long k = (unsigned long long)__double_as_longlong(score[t]);
+    if (best_score[nb + v.x] == k) atomicMin(best_tri + nb + v.x, (i32)t);
+    if (best_score[nb + v.y] == k) atomicMin(best_tri + nb + v.y, (i32)t);
+    if (best_score[nb + v.z] == k) atomicMin(best_tri + nb + v.z, (i32)t);
+}
+// node v re-adds its best same-type triangle unless a smaller uncovered node already did (helpers.py:365-383)
+__global__ void k_addback(i64 nKA, const i32 *__restrict__ ka_off, int W, const i32 *__restrict__ node_valid, const i32 *__restrict__ has_tri,
+                          const i32 *__restrict__ best_tri, const int3 *__restrict__ tin, int enabled, i32 *__restrict__ ab_flag,
+                          i32 *__restrict__ unc_flag) {
+    const i64 v = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v == nKA) { ab_flag[v] = 0; unc_flag[v] = 0; }
+    if (v >= nKA) return;
+    unc_flag[v] = node_valid[v] == 0;
+    int f = 0;
+    if (enabled && !has_tri[v] && node_valid[v] && best_tri[v] != 0x7fffffff) {
+        const i32 t = best_tri[v];
+        const i32 nb = ka_off[find_window(ka_off, W, (i32)v)];
+        const int3 tv = tin[t];
+        f = 1;
+        const i32 u3[3] = {nb + tv.x, nb + tv.y, nb + tv.z};
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const i32 u = u3[c];
+            if (u < (i32)v && !has_tri[u] && best_tri[u] == t) f = 0;
+        }
+    }
+    ab_flag[v] = f;
+}
+
+// single block: per-window output offsets
+__global__ void k_tri_window_offsets(const i32 *__restrict__ kpos, const i32 *__restrict__ abpos, const i32 *__restrict__ uncpos,
+                                     const i32 *__restrict__ validpos, const i32 *__restrict__ tin_off, const i32 *__restrict__ ka_off, int W,
+                                     i32 *__restrict__ out /* 4*(W+1): t_off, nkept(per window), unc_off, new ka_off */) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    i32 acc = 0;
+    for (int w = 0; w < W; ++w) {
+        const i32 nk = kpos[tin_off[w + 1]] - kpos[tin_off[w]];
+        const i32 na = abpos[ka_off[w + 1]] - abpos[ka_off[w]];
+        out[w] = acc;
+        out[(W + 1) + w] = nk;
+        acc += nk + na;
+    }
+    out[W] = acc;
+    out[(W + 1) + W] = 0;
+    for (int w = 0; w <= W; ++w) {
+        out[2 * (W + 1) + w] = uncpos[ka_off[w]];
+        out[3 * (W + 1) + w] = validpos[ka_off[w]];
+    }
+}
+
+__global__ void k_tri_emit_kept(const int3 *__restrict__ tin, i64 Tin, const i32 *__restrict__ tin_off, const i32 *__restrict__ ka_off, int W,
+                                const i32 *__restrict__ kept_flag, const i32 *__restrict__ kpos, const i32 *__restrict__ t_off,
+                                const i32 *__restrict__ validpos, int renumber, int3 *__restrict__ tri, i32 *__restrict__ tri_src) {
+    const i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= Tin || !kept_flag[t]) return;
+    const int w = find_window(tin_off, W, (i32)t);
+    const i32 pos = t_off[w] + (kpos[t] - kpos[tin_off[w]]);
+    int3 v = tin[t];
+    if (renumber) {
+        const i32 nb = ka_off[w], vb = validpos[nb];
+        v.x = validpos[nb + v.x] - vb; v.y = validpos[nb + v.y] - vb; v.z = validpos[nb + v.z] - vb;
+    }
+    tri[pos] = v;
+    tri_src[pos] = (i32)t - tin_off[w];
+}
+__global__ void k_tri_emit_addback(i64 nKA, const i32 *__restrict__ ka_off, int W, const i32 *__restrict__ ab_flag, const i32 *__restrict__ abpos,
+                                   const i32 *__restrict__ best_tri, const int3 *__restrict__ tin, const i32 *__restrict__ tin_off,
+                                   const i32 *__restrict__ t_off, const i32 *__restrict__ nkept, const i32 *__restrict__ validpos, int renumber,
+                                   int3 *__restrict__ tri, i32 *__restrict__ tri_src) {
+    const i64 n = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= nKA || !ab_flag[n]) return;
+    const int w = find_window(ka_off, W, (i32)n);
+    const i32 nb = ka_off[w];
+    const i32 pos = t_off[w] + nkept[w] + (abpos[n] - abpos[nb]);
+    const i32 t = best_tri[n];
+    int3 v = tin[t];
+    if (renumber) {
+        const i32 vb = validpos[nb];
+        v.x = validpos[nb + v.x] - vb; v.y = validpos[nb + v.y] - vb; v.z = validpos[nb + v.z] - vb;
+    }
+    tri[pos] = v;
+    tri_src[pos] = t - tin_off[w];
+}
+__global__ void k_emit_unconstrained(i64 nKA, const i32 *__restrict__ ka_off, int W, const i32 *__restrict__ unc_flag,
+                                     const i32 *__restrict__ uncpos, i32 *__restrict__ unc) {
+    const i64 n = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= nKA || !unc_flag[n]) return;
+    unc[uncpos[n]] = (i32)n - ka_off[find_window(ka_off, W, (i32)n)];
+}
+
+// ---- a7: drop unconstrained nodes, renumber rows and pairs (src/same.py:1056-1085) ---------------------
+__global__ void k_compact_nodes(i64 nKA, const i32 *__restrict__ node_valid, const i32 *__restrict__ validpos, const i32 *__restrict__ keepA,
+                                const double2 *__restrict__ xy, const i32 *__restrict__ type, const double *__restrict__ size,
+                                i32 *__restrict__ keepA2, double2 *__restrict__ xy2, i32 *__restrict__ type2, double *__restrict__ size2) {
+    const i64 n = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= nKA || !node_valid[n]) return;
+    const i32 k = validpos[n];
+    keepA2[k] = keepA[n]; xy2[k] = xy[n]; type2[k] = type[n]; size2[k] = size[n];
+}
+__global__ void k_pair_flags(const int2 *__restrict__ pairs, i64 P, const i32 *__restrict__ p_off, const i32 *__restrict__ ka_off, int W,
+                             const i32 *__restrict__ node_valid, i32 *__restrict__ pf) {
+    const i64 p = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p == P) pf[p] = 0;
+    if (p >= P) return;
+    const int w = find_window(p_off, W, (i32)p);
+    pf[p] = node_valid[ka_off[w] + pairs[p].x];
+}
+__global__ void k_compact_pairs(const int2 *__restrict__ pairs, const double *__restrict__ cost, i64 P, const i32 *__restrict__ p_off,
+                                const i32 *__restrict__ ka_off, int W, const i32 *__restrict__ pf, const i32 *__restrict__ ppos,
+                                const i32 *__restrict__ validpos, int2 *__restrict__ pairs2, double *__restrict__ cost2) {
+    const i64 p = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P || !pf[p]) return;
+    const int w = find_window(p_off, W, (i32)p);
+    const i32 nb = ka_off[w];
+    const int2 q = pairs[p];
+    pairs2[ppos[p]] = make_int2(validpos[nb + q.x] - validpos[nb], q.y);
+    cost2[ppos[p]] = cost[p];
+}
+__global__ void k_compact_rowptr(i64 nKA, const i32 *__restrict__ node_valid, const i32 *__restrict__ validpos, const i32 *__restrict__ row_ptr,
+                                 const i32 *__restrict__ ppos, i32 *__restrict__ row_ptr2, i64 nKA2, i32 P2) {
+    const i64 n = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n == 0) row_ptr2[nKA2] = P2;
+    if (n >= nKA || !node_valid[n]) return;
+    row_ptr2[validpos[n]] = ppos[row_ptr[n]];
+}
+__global__ void k_fill_i32_tri(i32 *p, i64 n, i32 v) {
+    i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+__global__ void k_pick2(const i32 *__restrict__ scanned, const i32 *__restrict__ at, int n, i32 *__restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = scanned[at[i]];
+}
+
+// ---- a8 + a9 ------------------------------------------------------------------------------------------
+__global__ void k_tri_tables(const int3 *__restrict__ tri, i64 T, const i32 *__restrict__ t_off, const i32 *__restrict__ ka_off, int W,
+                             const double2 *__restrict__ ka_xy, const double *__restrict__ ka_size, double *__restrict__ weight,
+                             signed char *__restrict__ sign, double *__restrict__ bounds, i32 *__restrict__ argv) {
+    const i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    const i32 nb = ka_off[find_window(t_off, W, (i32)t)];
+    const int3 v = tri[t];
+    const i32 vv[3] = {v.x, v.y, v.z};
+    const double2 p[3] = {ka_xy[nb + v.x], ka_xy[nb + v.y], ka_xy[nb + v.z]};
+    weight[t] = __dadd_rn(__dadd_rn(ka_size[nb + v.x], ka_size[nb + v.y]), ka_size[nb + v.z]);  // same.py:1131-1134
+    sign[t] = (signed char)sign_of(orient_naive(p[0].x, p[0].y, p[1].x, p[1].y, p[2].x, p[2].y));  // same.py:1146
+    const double mnx = fmin(p[0].x, fmin(p[1].x, p[2].x)), mxx = fmax(p[0].x, fmax(p[1].x, p[2].x));
+    const double mny = fmin(p[0].y, fmin(p[1].y, p[2].y)), mxy = fmax(p[0].y, fmax(p[1].y, p[2].y));
+    reinterpret_cast<double4 *>(bounds)[t] = make_double4(mnx, mxx, mny, mxy);
+    int amx = 0, amn = 0, amy = 0, any_ = 0;  // first vertex attaining the bound (helpers.py:203-206)
+#pragma unroll
+    for (int c = 2; c >= 0; --c) {
+        if (p[c].x == mxx) amx = c;
+        if (p[c].x == mnx) amn = c;
+        if (p[c].y == mxy) amy = c;
+        if (p[c].y == mny) any_ = c;
+    }
+    reinterpret_cast<int4 *>(argv)[t] = make_int4(vv[amx], vv[amn], vv[amy], vv[any_]);
+}
+
+void batch_tri_finalize(Batch *b, int ignore_same_type, int ensure_min, int remove_unconstrained) {
+    cudaStream_t s = b->stream;
+    REQUIRE(b->stage >= 3, SAME_E_STATE, "same_batch_tri_finalize before same_batch_tri_classify");
+    const i64 W = b->W, Tin = b->Tin, nKA = b->nKA, P = b->P;
+    const int addback = ignore_same_type && ensure_min;
+    DevBuf<i32> node_valid, has_tri, best_tri, kept_flag, kpos, ab_flag, abpos, unc_flag, uncpos, validpos, woff;
+    DevBuf<unsigned long long> best_score;
+    node_valid.alloc(nKA + 1, s); has_tri.alloc(nKA + 1, s); best_tri.alloc(nKA + 1, s); best_score.alloc(nKA + 1, s);
+    kept_flag.alloc(Tin + 1, s); kpos.alloc(Tin + 1, s);
+    ab_flag.alloc(nKA + 1, s); abpos.alloc(nKA + 1, s); unc_flag.alloc(nKA + 1, s); uncpos.alloc(nKA + 1, s); validpos.alloc(nKA + 1, s);
+    woff.alloc(4 * (W + 1), s);
+    node_valid.zero(s); has_tri.zero(s);
+    CK(cudaMemsetAsync(best_score.p, 0xff, sizeof(unsigned long long) * (nKA + 1), s));
+    LAUNCH(k_fill_i32_tri, blocks_for(nKA + 1, 256), 256, 0, s, best_tri.p, nKA + 1, 0x7fffffff);
+    LAUNCH(k_tri_nodes, blocks_for(Tin + 1, 256), 256, 0, s, b->tin.p, Tin, b->d_tin_off.p, b->d_ka_off.p, (int)W, b->cls.p, b->score.p, addback,
+           node_valid.p, has_tri.p, best_score.p, kept_flag.p);
+    if (addback && Tin > 0)
+        LAUNCH(k_tri_best, blocks_for(Tin, 256), 256, 0, s, b->tin.p, Tin, b->d_tin_off.p, b->d_ka_off.p, (int)W, b->cls.p, b->score.p, best_score.p,
+               best_tri.p);
+    LAUNCH(k_addback, blocks_for(nKA + 1, 256), 256, 0, s, nKA, b->d_ka_off.p, (int)W, node_valid.p, has_tri.p, best_tri.p, b->tin.p, addback, ab_flag.p,
+           unc_flag.p);
+    exclusive_scan_i32(kept_flag.p, kpos.p, Tin + 1, b->scratch, s);
+    exclusive_scan_i32(ab_flag.p, abpos.p, nKA + 1, b->scratch, s);
+    exclusive_scan_i32(unc_flag.p, uncpos.p, nKA + 1, b->scratch, s);
+    exclusive_scan_i32(node_valid.p, validpos.p, nKA + 1, b->scratch, s);  // node_valid[nKA] == 0 from the memset
+    LAUNCH(k_tri_window_offsets, 1, 32, 0, s, kpos.p, abpos.p, uncpos.p, validpos.p, b->d_tin_off.p, b->d_ka_off.p, (int)W, woff.p);
+    std::vector<i32> h(4 * (W + 1));
+    CK(cudaMemcpyAsync(h.data(), woff.p, sizeof(i32) * h.size(), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    b->t_off.assign(h.begin(), h.begin() + W + 1);
+    b->unc_off.assign(h.begin() + 2 * (W + 1), h.begin() + 3 * (W + 1));
+    std::vector<i64> new_ka(h.begin() + 3 * (W + 1), h.end());
+    b->T = b->t_off[W];
+    b->nUnc = b->unc_off[W];
+    const int renumber = remove_unconstrained && b->nUnc > 0;
+
+    b->d_t_off.alloc(W + 1, s);
+    CK(cudaMemcpyAsync(b->d_t_off.p, woff.p, sizeof(i32) * (W + 1), cudaMemcpyDeviceToDevice, s));
+    b->tri.alloc(b->T, s); b->tri_src.alloc(b->T, s);
+    b->unc.alloc(b->nUnc, s);
+    if (Tin > 0)
+        LAUNCH(k_tri_emit_kept, blocks_for(Tin, 256), 256, 0, s, b->tin.p, Tin, b->d_tin_off.p, b->d_ka_off.p, (int)W, kept_flag.p, kpos.p, b->d_t_off.p,
+               validpos.p, renumber, b->tri.p, b->tri_src.p);
+    if (addback && nKA > 0)
+        LAUNCH(k_tri_emit_addback, blocks_for(nKA, 256), 256, 0, s, nKA, b->d_ka_off.p, (int)W, ab_flag.p, abpos.p, best_tri.p, b->tin.p, b->d_tin_off.p,
+               b->d_t_off.p, woff.p + (W + 1), validpos.p, renumber, b->tri.p, b->tri_src.p);
+    if (b->nUnc > 0)
+        LAUNCH(k_emit_unconstrained, blocks_for(nKA, 256), 256, 0, s, nKA, b->d_ka_off.p, (int)W, unc_flag.p, uncpos.p, b->unc.p);
+
+    if (renumber) {
+        const i64 nKA2 = new_ka[W];
+        DevBuf<i32> keepA2, type2, pf, ppos, row_ptr2, poff2;
+        DevBuf<double2> xy2;
+        DevBuf<double> size2, cost2;
+        DevBuf<int2> pairs2;
+        keepA2.alloc(nKA2, s); type2.alloc(nKA2, s); xy2.alloc(nKA2, s); size2.alloc(nKA2, s);
+        pf.alloc(P + 1, s); ppos.alloc(P + 1, s); poff2.alloc(W + 1, s);
+        LAUNCH(k_compact_nodes, blocks_for(nKA, 256), 256, 0, s, nKA, node_valid.p, validpos.p, b->keepA.p, b->ka_xy.p, b->ka_type.p, b->ka_size.p,
+               keepA2.p, xy2.p, type2.p, size2.p);
+        LAUNCH(k_pair_flags, blocks_for(P + 1, 256), 256, 0, s, b->pairs.p, P, b->d_p_off.p, b->d_ka_off.p, (int)W, node_valid.p, pf.p);
+        exclusive_scan_i32(pf.p, ppos.p, P + 1, b->scratch, s);
+        LAUNCH(k_pick2, blocks_for(W + 1, 128), 128, 0, s, ppos.p, b->d_p_off.p, (int)(W + 1), poff2.p);
+        std::vector<i32> hp(W + 1);
+        CK(cudaMemcpyAsync(hp.data(), poff2.p, sizeof(i32) * (W + 1), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        const i64 P2 = hp[W];
+        pairs2.alloc(P2, s); cost2.alloc(P2, s); row_ptr2.alloc(nKA2 + 1, s);
+        if (P > 0)
+            LAUNCH(k_compact_pairs, blocks_for(P, 256), 256, 0, s, b->pairs.p, b->cost.p, P, b->d_p_off.p, b->d_ka_off.p, (int)W, pf.p, ppos.p, validpos.p,
+                   pairs2.p, cost2.p);
+        LAUNCH(k_compact_rowptr, blocks_for(std::max<i64>(nKA, 1), 256), 256, 0, s, nKA, node_valid.p, validpos.p, b->row_ptr.p, ppos.p, row_ptr2.p, nKA2,
+               (i32)P2);
+        CK(cudaStreamSynchronize(s));
+        b->keepA.swap(keepA2); b->ka_xy.swap(xy2); b->ka_type.swap(type2); b->ka_size.swap(size2);
+        b->pairs.swap(pairs2); b->cost.swap(cost2); b->row_ptr.swap(row_ptr2);
+        b->nKA = nKA2; b->P = P2;
+        b->ka_off = new_ka;
+        b->p_off.assign(hp.begin(), hp.end());
+        upload_offsets(b->ka_off, b->d_ka_off, s);
+        upload_offsets(b->p_off, b->d_p_off, s);
+        b->have_groups = false;
+    }
+
+    b->t_weight.alloc(b->T, s); b->t_sign.alloc(b->T, s); b->t_bounds.alloc(4 * b->T, s); b->t_argv.alloc(4 * b->T, s);
+    if (b->T > 0)
+        LAUNCH(k_tri_tables, blocks_for(b->T, 256), 256, 0, s, b->tri.p, b->T, b->d_t_off.p, b->d_ka_off.p, (int)W, b->ka_xy.p, b->ka_size.p, b->t_weight.p,
+               b->t_sign.p, b->t_bounds.p, b->t_argv.p);
+    CK(cudaStreamSynchronize(s));
+    b->stage = 4;
+    b->have_post = false;
+}
+
+}  // namespace same

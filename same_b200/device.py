@@ -1,0 +1,225 @@
+"""Thin object wrappers over the C-ABI: `Section` (frames resident in HBM) and `WindowBatch`
+(a list of windows processed together).  Arrays come back as numpy; per-window slices are
+views into the concatenated result.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+
+
+def _f64(a, shape=None):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    return a if shape is None else a.reshape(shape)
+
+
+class Section:
+    """Both frames of one tissue section pair on the GPU (same_section_create)."""
+
+    def __init__(self, a_xy, r_xy, a_prob, r_prob, a_type=None, r_type=None, a_size=None, r_size=None,
+                 device: int = 0, stream=None):
+        lib = L.load()
+        self._keep = []
+        a_xy, r_xy = _f64(a_xy, (-1, 2)), _f64(r_xy, (-1, 2))
+        self.n_aligned, self.n_ref = len(a_xy), len(r_xy)
+        a_prob = _f64(a_prob).reshape(self.n_aligned, -1) if self.n_aligned else np.zeros((0, np.asarray(r_prob).reshape(self.n_ref, -1).shape[1]))
+        r_prob = _f64(r_prob).reshape(self.n_ref, -1) if self.n_ref else np.zeros((0, a_prob.shape[1]))
+        if a_prob.shape[1] != r_prob.shape[1]:
+            raise ValueError("probability blocks of the two frames have different widths")
+        self.n_types = a_prob.shape[1]
+        conv = lambda v, dt, n: None if v is None else np.ascontiguousarray(v, dtype=dt).reshape(n)
+        a_type, r_type = conv(a_type, np.int32, self.n_aligned), conv(r_type, np.int32, self.n_ref)
+        a_size, r_size = conv(a_size, np.float64, self.n_aligned), conv(r_size, np.float64, self.n_ref)
+        h = C.c_void_p()
+        L.check(lib.same_section_create(device, C.c_void_p(stream) if stream else None, self.n_aligned, self.n_ref, self.n_types,
+                                        L.ptr(a_xy), L.ptr(r_xy), L.ptr(np.ascontiguousarray(a_prob)), L.ptr(np.ascontiguousarray(r_prob)),
+                                        L.ptr(a_type), L.ptr(r_type), L.ptr(a_size), L.ptr(r_size), C.byref(h)))
+        self._h = h
+        self.device = device
+        self.h2d_bytes = a_xy.nbytes + r_xy.nbytes + a_prob.nbytes + r_prob.nbytes + sum(
+            v.nbytes for v in (a_type, r_type, a_size, r_size) if v is not None)
+
+    @property
+    def bbox(self):
+        out = np.zeros(4)
+        L.check(L.load().same_section_bbox(self._h, L.ptr(out)))
+        return out
+
+    def count_rects(self, rects):
+        rects = _f64(rects, (-1, 4))
+        m = len(rects)
+        ca, cr = np.zeros(m, np.int64), np.zeros(m, np.int64)
+        L.check(L.load().same_section_count_rects(self._h, m, L.ptr(rects), L.ptr(ca), L.ptr(cr)))
+        return ca, cr
+
+    def set_triangles(self, tri_vid, a_vid=None):
+        """Precomputed triangulation in vertex-id space (same.py:262-290)."""
+        tri = np.ascontiguousarray(tri_vid, dtype=np.int64).reshape(-1, 3)
+        vid = None if a_vid is None else np.ascontiguousarray(a_vid, dtype=np.int64).reshape(self.n_aligned)
+        L.check(L.load().same_section_set_triangles(self._h, L.ptr(vid), L.ptr(tri), len(tri)))
+        self.n_global_triangles = len(tri)
+
+    def batch(self, rects=None):
+        return WindowBatch(self, rects)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            L.check(L.load().same_section_destroy(self._h))
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+
+class WindowBatch:
+    """A list of windows of one section (same_batch_create).  `rects=None` = the whole section."""
+
+    def __init__(self, section: Section, rects=None):
+        lib = L.load()
+        self.section = section
+        if rects is None:
+            self.W, r = 1, None
+        else:
+            r = _f64(rects, (-1, 4))
+            self.W = len(r)
+        h = C.c_void_p()
+        L.check(lib.same_batch_create(section._h, self.W, L.ptr(r), C.byref(h)))
+        self._h = h
+        self._off_cache = {}
+
+    # ---- stages ----
+    def candidates(self, radius, knn, priority=False, dist_ct_coeff=1.0):
+        self._off_cache.clear()
+        L.check(L.load().same_batch_candidates(self._h, float(radius), int(knn), int(bool(priority)), float(dist_ct_coeff)))
+
+    def triangles_remap(self):
+        self._off_cache.clear()
+        L.check(L.load().same_batch_triangles_remap(self._h))
+
+    def triangles_set(self, tri, tri_off):
+        self._off_cache.clear()
+        tri = np.ascontiguousarray(tri, dtype=np.int32).reshape(-1, 3)
+        off = np.ascontiguousarray(tri_off, dtype=np.int64)
+        L.check(L.load().same_batch_triangles_set(self._h, L.ptr(tri), L.ptr(off)))
+
+    def tri_classify(self, radius, min_angle_deg, ignore_same_type):
+        nb = C.c_int64(0)
+        L.check(L.load().same_batch_tri_classify(self._h, float(radius), int(min_angle_deg is not None),
+                                                 0.0 if min_angle_deg is None else float(min_angle_deg),
+                                                 int(bool(ignore_same_type)), C.byref(nb)))
+        return nb.value
+
+    def tri_override(self, idx, cls):
+        idx = np.ascontiguousarray(idx, dtype=np.int32)
+        cls = np.ascontiguousarray(cls, dtype=np.uint8)
+        L.check(L.load().same_batch_tri_override(self._h, len(idx), L.ptr(idx), L.ptr(cls)))
+
+    def tri_finalize(self, ignore_same_type, ensure_min=True, remove_unconstrained=False):
+        self._off_cache.clear()
+        L.check(L.load().same_batch_tri_finalize(self._h, int(bool(ignore_same_type)), int(bool(ensure_min)),
+                                                 int(bool(remove_unconstrained))))
+
+    def groups(self, max_matches, multiplier=None):
+        self._off_cache.clear()
+        L.check(L.load().same_batch_groups(self._h, int(max_matches), -1 if multiplier is None else int(multiplier)))
+
+    def separation(self, x, w_lo=0, w_hi=None, cap=1000):
+        """-> (n_viol[nw], n_checked[nw], cuts[nw, cap, 4]); x may be a numpy array or a device address."""
+        w_hi = self.W if w_hi is None else w_hi
+        nw = w_hi - w_lo
+        nv, nc = np.zeros(nw, np.int64), np.zeros(nw, np.int64)
+        cuts = np.full((nw, max(cap, 1), 4), -1, np.int32)
+        if not isinstance(x, int):
+            x = np.ascontiguousarray(x, dtype=np.float64)
+        L.check(L.load().same_batch_separation(self._h, w_lo, w_hi, L.ptr(x), cap, L.ptr(nv), L.ptr(nc), L.ptr(cuts)))
+        return nv, nc, cuts
+
+    def postsolve(self, x, w_lo=0, w_hi=None):
+        w_hi = self.W if w_hi is None else w_hi
+        if not isinstance(x, int):
+            x = np.ascontiguousarray(x, dtype=np.float64)
+        L.check(L.load().same_batch_postsolve(self._h, w_lo, w_hi, L.ptr(x)))
+
+    # ---- results ----
+    def offsets(self, what):
+        if what not in self._off_cache:
+            off = np.zeros(self.W + 1, np.int64)
+            L.check(L.load().same_batch_offsets(self._h, what, L.ptr(off)))
+            self._off_cache[what] = off
+        return self._off_cache[what]
+
+    def length(self, what):
+        n = C.c_int64(0)
+        L.check(L.load().same_batch_length(self._h, what, C.byref(n)))
+        return n.value
+
+    def get(self, what, lo=0, hi=None):
+        dt, tail = L.ARRAY_SPEC[what]
+        hi = self.length(what) if hi is None else hi
+        out = np.empty((hi - lo,) + tail, dtype=dt)
+        L.check(L.load().same_batch_get(self._h, what, lo, hi, L.ptr(out)))
+        return out
+
+    def get_window(self, what, w):
+        off = self.offsets(what)
+        return self.get(what, int(off[w]), int(off[w + 1]))
+
+    def sync(self):
+        L.check(L.load().same_batch_sync(self._h))
+
+    @property
+    def stream(self):
+        return L.load().same_batch_stream(self._h)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            L.check(L.load().same_batch_destroy(self._h))
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # ---- convenience: one window's model arrays in the reference's index spaces ----
+    def window_model(self, w):
+        """dict of numpy arrays for window w (everything run_same needs to build its model)."""
+        p0 = int(self.offsets(L.PAIRS)[w])
+        out = dict(keepA=self.get_window(L.KEEP_A, w), keepR=self.get_window(L.KEEP_R, w),
+                   pairs=self.get_window(L.PAIRS, w), cost=self.get_window(L.COST, w))
+        try:
+            out.update(tri=self.get_window(L.TRI, w), tri_src=self.get_window(L.TRI_SRC, w), weight=self.get_window(L.TRI_WEIGHT, w),
+                       sign=self.get_window(L.TRI_SIGN, w), bounds=self.get_window(L.TRI_BOUNDS, w), argv=self.get_window(L.TRI_ARGV, w),
+                       unconstrained=self.get_window(L.UNCONSTRAINED, w))
+        except L.SameError:
+            pass
+        try:
+            goff = self.offsets(L.REF_GROUP_NODE)
+            g0, g1 = int(goff[w]), int(goff[w + 1])
+            out.update(ref_group_node=self.get(L.REF_GROUP_NODE, g0, g1), ref_group_limit=self.get(L.REF_GROUP_LIMIT, g0, g1),
+                       ref_group_ptr=self.get(L.REF_GROUP_PTR, g0, g1 + 1).astype(np.int64) - p0,
+                       ref_group_idx=self.get_window(L.REF_GROUP_IDX, w))
+        except L.SameError:
+            pass
+        ka = self.offsets(L.KEEP_A)
+        out["row_ptr"] = self.get(L.ROW_PTR, int(ka[w]), int(ka[w + 1]) + 1).astype(np.int64) - p0
+        return out

@@ -1,0 +1,51 @@
+"""CPU-side checks of the boundary: the library builds, loads and exports every symbol the header declares."""
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_header_symbols_exported():
+    from same_b200 import _lib as L
+    from same_b200 import build
+    build.build()
+    lib = L.load()
+    header = open(os.path.join(ROOT, "include", "same_b200.h")).read()
+    declared = sorted(set(re.findall(r"^SAME_API [^;(]*?\b(same_[a-z_]+)\(", header, flags=re.M)))
+    assert declared, "no declarations found in the header"
+    for name in declared:
+        assert hasattr(lib, name), f"{name} is declared in include/same_b200.h but not exported"
+    assert sorted(L.SYMBOLS) == declared
+
+
+def test_array_spec_matches_elem_size():
+    import numpy as np
+    from same_b200 import _lib as L
+    lib = L.load()
+    for what, (dt, tail) in L.ARRAY_SPEC.items():
+        n = int(np.prod(tail)) if tail else 1
+        assert lib.same_elem_size(what) == np.dtype(dt).itemsize * n, what
+
+
+def test_no_cpu_fallback_without_gpu():
+    """On a box without a CUDA device the product must fail loudly, not compute on the CPU."""
+    import numpy as np
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from same_b200 import _lib as L
+    from same_b200.device import Section
+    with pytest.raises(L.SameError):
+        Section(np.zeros((4, 2)), np.zeros((4, 2)), np.zeros((4, 1)), np.zeros((4, 1)))
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "same_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+                assert "same_oracle" not in src, f
