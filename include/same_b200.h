@@ -165,6 +165,12 @@ SAME_API int same_batch_offsets(same_batch_t *b, int what, int64_t *off);
 SAME_API int same_batch_length(same_batch_t *b, int what, int64_t *n);
 /* copy elements [elem_lo, elem_hi) of array `what` to dst (host or device) */
 SAME_API int same_batch_get(same_batch_t *b, int what, int64_t elem_lo, int64_t elem_hi, void *dst);
+/* n copies issued back to back on the batch's stream with ONE synchronisation at the end:
+ * array what[k], elements [lo[k], hi[k]) -> dst[k] (host, ideally pinned, or device) */
+SAME_API int same_batch_get_many(same_batch_t *b, int64_t n, const int32_t *what, const int64_t *lo, const int64_t *hi, void *const *dst);
+/* page-locked host memory for inputs/outputs (cudaHostAlloc / cudaFreeHost) */
+SAME_API int same_pinned_alloc(int64_t bytes, void **out);
+SAME_API int same_pinned_free(void *p);
 /* element size in bytes of array `what` */
 SAME_API int64_t same_elem_size(int what);
 /* block until everything queued on the batch's stream has finished */
@@ -173,6 +179,11 @@ SAME_API int same_batch_sync(same_batch_t *b);
 SAME_API void *same_batch_stream(same_batch_t *b);
 /* number of kernel launches issued by this library in this process (bench.py "gpu_launches") */
 SAME_API int64_t same_launch_count(void);
+/* Per-kernel device timing for bench.py's roofline block: while enabled every launch is bracketed by CUDA
+ * events on its stream.  same_profile_report() synchronises, writes "name<TAB>launches<TAB>total_ms" lines into
+ * buf (NUL-terminated, truncated to cap) and clears the records; returns the untruncated length or < 0. */
+SAME_API int same_profile_enable(int on);
+SAME_API int64_t same_profile_report(char *buf, int64_t cap);
 
 #ifdef __cplusplus
 }

@@ -46,6 +46,7 @@ SYMBOLS = [
     "same_batch_triangles_set", "same_batch_tri_classify", "same_batch_tri_override", "same_batch_tri_finalize",
     "same_batch_groups", "same_batch_separation", "same_batch_postsolve", "same_batch_offsets", "same_batch_length",
     "same_batch_get", "same_elem_size", "same_batch_sync", "same_batch_stream", "same_launch_count",
+    "same_profile_enable", "same_profile_report", "same_batch_get_many", "same_pinned_alloc", "same_pinned_free",
 ]
 
 
@@ -99,6 +100,12 @@ def load():
     lib.same_batch_stream.argtypes = [vp]
     lib.same_batch_stream.restype = vp
     lib.same_launch_count.restype = i64
+    lib.same_batch_get_many.argtypes = [vp, i64, vp, vp, vp, vp]
+    lib.same_pinned_alloc.argtypes = [i64, C.POINTER(vp)]
+    lib.same_pinned_free.argtypes = [vp]
+    lib.same_profile_enable.argtypes = [i32]
+    lib.same_profile_report.argtypes = [C.c_char_p, i64]
+    lib.same_profile_report.restype = i64
     assert lib.same_abi_version() == 1
     _lib = lib
     return lib
@@ -120,3 +127,20 @@ def ptr(a):
 
 def launch_count() -> int:
     return int(load().same_launch_count())
+
+
+def profile_enable(on: bool):
+    check(load().same_profile_enable(int(bool(on))))
+
+
+def profile_report():
+    """-> {kernel name: (launches, total_ms)} since profiling was enabled / last reported."""
+    buf = C.create_string_buffer(1 << 16)
+    n = load().same_profile_report(buf, len(buf))
+    if n < 0:
+        check(int(n))
+    out = {}
+    for line in buf.value.decode().splitlines():
+        name, cnt, ms = line.split("\t")
+        out[name] = (int(cnt), float(ms))
+    return out

@@ -85,6 +85,38 @@ int same_device_count(int *count) {
     return guarded([&] { CK(cudaGetDeviceCount(count)); });
 }
 int64_t same_launch_count(void) { return (int64_t)g_launches.load(); }
+
+int same_profile_enable(int on) {
+    return guarded([&] {
+        for (auto &r : g_prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+        g_prof_recs.clear();
+        g_prof = on != 0;
+    });
+}
+
+int64_t same_profile_report(char *buf, int64_t cap) {
+    int64_t written = -1;
+    int rc = guarded([&] {
+        CK(cudaDeviceSynchronize());
+        struct Acc { std::string name; long long n; double ms; };
+        std::vector<Acc> acc;
+        for (auto &r : g_prof_recs) {
+            float ms = 0.f;
+            CK(cudaEventElapsedTime(&ms, r.a, r.b));
+            cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+            bool hit = false;
+            for (auto &a : acc) if (a.name == r.name) { a.n++; a.ms += ms; hit = true; break; }
+            if (!hit) acc.push_back({r.name, 1, (double)ms});
+        }
+        g_prof_recs.clear();
+        std::string out;
+        char line[512];
+        for (auto &a : acc) { snprintf(line, sizeof(line), "%s\t%lld\t%.6f\n", a.name.c_str(), a.n, a.ms); out += line; }
+        written = (int64_t)out.size();
+        if (buf && cap > 0) { size_t k = std::min<size_t>(out.size(), (size_t)cap - 1); memcpy(buf, out.data(), k); buf[k] = 0; }
+    });
+    return rc == SAME_OK ? written : rc;
+}
 int64_t same_elem_size(int what) { return elem_size(what); }
 
 int same_section_create(int device, void *stream, int64_t n_aligned, int64_t n_ref, int n_types, const double *a_xy, const double *r_xy,
@@ -246,6 +278,31 @@ int same_batch_get(same_batch_t *h, int what, int64_t elem_lo, int64_t elem_hi, 
             CK(cudaStreamSynchronize(b->stream));
         }
     });
+}
+
+int same_batch_get_many(same_batch_t *h, int64_t n, const int32_t *what, const int64_t *lo, const int64_t *hi, void *const *dst) {
+    BATCH_CALL(h, {
+        REQUIRE(n >= 0 && (n == 0 || (what && lo && hi && dst)), SAME_E_ARG, "NULL argument");
+        for (int64_t k = 0; k < n; ++k) {
+            ArrayView v = view(b, what[k]);
+            REQUIRE(lo[k] >= 0 && lo[k] <= hi[k] && hi[k] <= v.n, SAME_E_ARG, "element range out of bounds");
+            if (hi[k] > lo[k]) {
+                REQUIRE(dst[k], SAME_E_ARG, "dst is NULL");
+                CK(cudaMemcpyAsync(dst[k], (const char *)v.p + lo[k] * v.esize, (size_t)((hi[k] - lo[k]) * v.esize), cudaMemcpyDefault, b->stream));
+            }
+        }
+        CK(cudaStreamSynchronize(b->stream));
+    });
+}
+
+int same_pinned_alloc(int64_t bytes, void **out) {
+    return guarded([&] {
+        REQUIRE(out && bytes >= 0, SAME_E_ARG, "bad argument");
+        CK(cudaHostAlloc(out, (size_t)std::max<int64_t>(bytes, 1), cudaHostAllocDefault));
+    });
+}
+int same_pinned_free(void *p) {
+    return guarded([&] { if (p) CK(cudaFreeHost(p)); });
 }
 
 int same_batch_sync(same_batch_t *h) { BATCH_CALL(h, CK(cudaStreamSynchronize(b->stream))); }

@@ -361,7 +361,10 @@ void batch_candidates(Batch *b, double radius, int knn, int priority, double dis
         size_t bytes = 0;
         CK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, keys_in.p, keys_out.p, vals_in.p, out_inst.p, (int)n, 0, kb, s));
         void *tmp = b->scratch.get(bytes, s);
-        CK(cub::DeviceRadixSort::SortPairs(tmp, bytes, keys_in.p, keys_out.p, vals_in.p, out_inst.p, (int)n, 0, kb, s));
+        {
+            ProfScope prof("cub::DeviceRadixSort::SortPairs(bins)", s);
+            CK(cub::DeviceRadixSort::SortPairs(tmp, bytes, keys_in.p, keys_out.p, vals_in.p, out_inst.p, (int)n, 0, kb, s));
+        }
         g_launches.fetch_add(1, std::memory_order_relaxed);
         LAUNCH(k_gather_xy, blocks_for(n, 256), 256, 0, s, out_inst.p, src.p, xy.p, n, out_xy.p);
     };
@@ -525,7 +528,10 @@ void batch_groups(Batch *b, int max_matches, int multiplier) {
     const int kb = bits_for(P + 1);
     CK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, keys.p, keys_out.p, vals.p, sorted_p.p, (int)P, 0, kb, s));
     void *tmp = b->scratch.get(bytes, s);
-    CK(cub::DeviceRadixSort::SortPairs(tmp, bytes, keys.p, keys_out.p, vals.p, sorted_p.p, (int)P, 0, kb, s));
+    {
+        ProfScope prof("cub::DeviceRadixSort::SortPairs(groups)", s);
+        CK(cub::DeviceRadixSort::SortPairs(tmp, bytes, keys.p, keys_out.p, vals.p, sorted_p.p, (int)P, 0, kb, s));
+    }
     g_launches.fetch_add(1, std::memory_order_relaxed);
     LAUNCH(k_group_heads, blocks_for(P + 1, 256), 256, 0, s, keys_out.p, P, head.p);
     exclusive_scan_i32(head.p, gid.p, P + 1, b->scratch, s);

@@ -40,9 +40,31 @@ struct Error : std::runtime_error {
         if (!(cond)) throw same::Error(code, std::string(msg));                                             \
     } while (0)
 
+// Optional per-kernel timing (bench.py's roofline section): when enabled, every launch is bracketed by
+// CUDA events on the launching stream; same_profile_report() sums elapsed time per kernel name.
+struct ProfRec { const char *name; cudaEvent_t a, b; };
+extern bool g_prof;
+extern std::vector<ProfRec> g_prof_recs;
+struct ProfScope {
+    ProfRec r{nullptr, nullptr, nullptr};
+    cudaStream_t s;
+    ProfScope(const char *name, cudaStream_t stream) : s(stream) {
+        if (!g_prof) return;
+        r.name = name;
+        cudaEventCreate(&r.a); cudaEventCreate(&r.b);
+        cudaEventRecord(r.a, s);
+    }
+    ~ProfScope() {
+        if (!r.name) return;
+        cudaEventRecord(r.b, s);
+        g_prof_recs.push_back(r);
+    }
+};
+
 // every kernel launch goes through this macro so bench.py can report gpu_launches
 #define LAUNCH(kernel, grid, block, smem, stream, ...)                                                      \
     do {                                                                                                    \
+        same::ProfScope prof__(#kernel, (stream));                                                          \
         kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);                                         \
         same::g_launches.fetch_add(1, std::memory_order_relaxed);                                           \
         CK(cudaGetLastError());                                                                             \

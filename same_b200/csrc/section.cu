@@ -6,13 +6,16 @@ namespace same {
 
 thread_local std::string g_err;
 std::atomic<long long> g_launches{0};
+bool g_prof = false;
+std::vector<ProfRec> g_prof_recs;
 
 void exclusive_scan_i32(const i32 *in, i32 *out, i64 n, Scratch &sc, cudaStream_t s) {
     size_t bytes = 0;
     CK(cub::DeviceScan::ExclusiveSum(nullptr, bytes, in, out, (int)n, s));
     void *tmp = sc.get(bytes, s);
+    ProfScope prof("cub::DeviceScan::ExclusiveSum", s);
     CK(cub::DeviceScan::ExclusiveSum(tmp, bytes, in, out, (int)n, s));
-    g_launches.fetch_add(1, std::memory_order_relaxed);
+    g_launches.fetch_add(2, std::memory_order_relaxed);  // init + scan kernels
 }
 
 void upload_offsets(const std::vector<i64> &h, DevBuf<i32> &d, cudaStream_t s) {
@@ -242,7 +245,10 @@ void section_set_triangles(Section *sec, const i64 *a_vid, const i64 *tri_vid, i
         size_t bytes = 0;
         CK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, vid_in.p, vid_out.p, row_in.p, row_out.p, (int)n, 0, 64, s));
         void *tmp = sec->scratch.get(bytes, s);
-        CK(cub::DeviceRadixSort::SortPairs(tmp, bytes, vid_in.p, vid_out.p, row_in.p, row_out.p, (int)n, 0, 64, s));
+        {
+            ProfScope prof("cub::DeviceRadixSort::SortPairs(vid)", s);
+            CK(cub::DeviceRadixSort::SortPairs(tmp, bytes, vid_in.p, vid_out.p, row_in.p, row_out.p, (int)n, 0, 64, s));
+        }
         g_launches.fetch_add(1, std::memory_order_relaxed);
         LAUNCH(k_resolve_vids, blocks_for(m, 256), 256, 0, s, vid_out.p, row_out.p, n, d_tri.p, m, sec->tri_rows.p);
     }

@@ -79,20 +79,27 @@ __global__ void k_sep_counts(const i32 *__restrict__ vpos, const i32 *__restrict
     out[2 * (w - w_lo) + 1] = checked[w];
 }
 
-static void upload_x(Batch *b, i64 w_lo, i64 w_hi, const double *x) {
+// x may be host or device memory; a device-resident solution vector is used in place
+static const double *resolve_x(Batch *b, i64 w_lo, i64 w_hi, const double *x) {
     cudaStream_t s = b->stream;
     const i64 n = b->p_off[w_hi] - b->p_off[w_lo];
+    if (n == 0) return x;
+    REQUIRE(x != nullptr, SAME_E_ARG, "x is NULL");
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, x) == cudaSuccess && attr.type == cudaMemoryTypeDevice && attr.device == b->sec->device) return x;
+    cudaGetLastError();  // clear "invalid value" for plain host pointers on older drivers
     b->x_dev.alloc(n, s);
-    if (n > 0) CK(cudaMemcpyAsync(b->x_dev.p, x, sizeof(double) * (size_t)n, cudaMemcpyDefault, s));
+    CK(cudaMemcpyAsync(b->x_dev.p, x, sizeof(double) * (size_t)n, cudaMemcpyDefault, s));
+    return b->x_dev.p;
 }
 
-static void run_matching(Batch *b, i64 w_lo, i64 w_hi) {
+static void run_matching(Batch *b, i64 w_lo, i64 w_hi, const double *xd) {
     cudaStream_t s = b->stream;
     b->match_j.alloc(b->nKA, s);
     b->match_p.alloc(b->nKA, s);
     const i32 k_lo = (i32)b->ka_off[w_lo], k_hi = (i32)b->ka_off[w_hi];
     if (k_hi > k_lo)
-        LAUNCH(k_match_rows, blocks_for(k_hi - k_lo, 256), 256, 0, s, b->x_dev.p, (i32)b->p_off[w_lo], b->pairs.p, b->row_ptr.p, b->d_ka_off.p,
+        LAUNCH(k_match_rows, blocks_for(k_hi - k_lo, 256), 256, 0, s, xd, (i32)b->p_off[w_lo], b->pairs.p, b->row_ptr.p, b->d_ka_off.p,
                b->d_p_off.p, (int)b->W, k_lo, k_hi, b->match_j.p, b->match_p.p);
 }
 
@@ -102,8 +109,7 @@ void batch_separation(Batch *b, i64 w_lo, i64 w_hi, const double *x, i64 cap, i6
     REQUIRE(w_lo >= 0 && w_hi <= b->W && w_lo < w_hi, SAME_E_ARG, "bad window range");
     REQUIRE(cap >= 0, SAME_E_ARG, "cap must be >= 0");
     const i64 nw = w_hi - w_lo;
-    upload_x(b, w_lo, w_hi, x);
-    run_matching(b, w_lo, w_hi);
+    run_matching(b, w_lo, w_hi, resolve_x(b, w_lo, w_hi, x));
     const i32 t_lo = (i32)b->t_off[w_lo], t_hi = (i32)b->t_off[w_hi];
     const i64 nt = t_hi - t_lo;
     b->viol_flag.alloc(nt + 1, s); b->viol_pos.alloc(nt + 1, s);
@@ -190,8 +196,7 @@ void batch_postsolve(Batch *b, i64 w_lo, i64 w_hi, const double *x) {
     cudaStream_t s = b->stream;
     REQUIRE(b->stage >= 4, SAME_E_STATE, "same_batch_postsolve before same_batch_tri_finalize");
     REQUIRE(w_lo >= 0 && w_hi <= b->W && w_lo < w_hi, SAME_E_ARG, "bad window range");
-    upload_x(b, w_lo, w_hi, x);
-    run_matching(b, w_lo, w_hi);
+    run_matching(b, w_lo, w_hi, resolve_x(b, w_lo, w_hi, x));
     if (!b->have_post) {
         b->t_mask.alloc(b->T, s); b->area_before.alloc(b->T, s); b->area_after.alloc(b->T, s); b->flipped.alloc(b->T, s);
         b->have_post = true;

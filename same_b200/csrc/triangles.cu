@@ -5,9 +5,6 @@
 
 namespace same {
 
-constexpr int TR_THREADS = 256;
-constexpr int TR_ITEMS = 4;
-constexpr int TR_CHUNK = TR_THREADS * TR_ITEMS;
 
 // local (window) index of section row `row` among the window's kept aligned rows, or -1
 __device__ __forceinline__ i32 kept_lookup(const i32 *__restrict__ keepA, i32 lo, i32 hi, i32 row) {
@@ -19,60 +16,81 @@ __device__ __forceinline__ i32 kept_lookup(const i32 *__restrict__ keepA, i32 lo
     return (lo < end && keepA[lo] == row) ? lo - base : -1;
 }
 
-__device__ __forceinline__ bool tri_in_window(const i32 *__restrict__ tri_rows, i64 t, const i32 *__restrict__ keepA, i32 lo, i32 hi, int3 &out) {
-    const i32 ra = tri_rows[3 * t], rb = tri_rows[3 * t + 1], rc = tri_rows[3 * t + 2];
-    if (ra < 0 || rb < 0 || rc < 0) return false;
-    out.x = kept_lookup(keepA, lo, hi, ra);
-    if (out.x < 0) return false;
-    out.y = kept_lookup(keepA, lo, hi, rb);
-    if (out.y < 0) return false;
-    out.z = kept_lookup(keepA, lo, hi, rc);
-    return out.z >= 0;
-}
+// Remap = for every global triangle, every window whose rectangle holds all three vertices AND whose post-KNN
+// frame kept all three rows.  One thread per triangle walks the rectangle list staged in shared memory (no
+// per-window pass over the triangle list), a first launch counts, a second appends (window, triangle) records,
+// and one radix sort on (window << 32 | triangle) restores the reference's order: window-major, input order inside.
+constexpr int RECT_TILE = 512;
 
-__global__ void __launch_bounds__(TR_THREADS) k_remap_count(const i32 *__restrict__ tri_rows, i64 Tg, const i32 *__restrict__ keepA,
-                                                            const i32 *__restrict__ ka_off, i32 *__restrict__ block_counts) {
-    const int w = blockIdx.y;
-    const i32 lo = ka_off[w], hi = ka_off[w + 1];
-    const i64 base = (i64)blockIdx.x * TR_CHUNK;
-    int c = 0;
-    int3 tmp3;
-#pragma unroll
-    for (int it = 0; it < TR_ITEMS; ++it) {
-        const i64 t = base + it * TR_THREADS + threadIdx.x;
-        c += (t < Tg) && tri_in_window(tri_rows, t, keepA, lo, hi, tmp3);
+template <bool FILL>
+__global__ void __launch_bounds__(256) k_remap_scan(const i32 *__restrict__ tri_rows, i64 Tg, const double2 *__restrict__ sec_xy,
+                                                    const double *__restrict__ rects, int W, const i32 *__restrict__ keepA,
+                                                    const i32 *__restrict__ ka_off, i32 *__restrict__ win_count,
+                                                    unsigned long long *__restrict__ keys, int3 *__restrict__ recs, i32 *__restrict__ cursor, int tbits) {
+    __shared__ double4 srect[RECT_TILE];
+    const i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    i32 ra = -1, rb = -1, rc = -1;
+    double mnx = 0, mxx = 0, mny = 0, mxy = 0;
+    bool live = false;
+    if (t < Tg) {
+        ra = tri_rows[3 * t]; rb = tri_rows[3 * t + 1]; rc = tri_rows[3 * t + 2];
+        live = ra >= 0 && rb >= 0 && rc >= 0;
+        if (live) {
+            const double2 A = sec_xy[ra], B = sec_xy[rb], C = sec_xy[rc];
+            mnx = fmin(A.x, fmin(B.x, C.x)); mxx = fmax(A.x, fmax(B.x, C.x));
+            mny = fmin(A.y, fmin(B.y, C.y)); mxy = fmax(A.y, fmax(B.y, C.y));
+        }
     }
-    typedef cub::BlockReduce<int, TR_THREADS> BR;
-    __shared__ typename BR::TempStorage tmp;
-    const int tot = BR(tmp).Sum(c);
-    if (threadIdx.x == 0) block_counts[(i64)w * gridDim.x + blockIdx.x] = tot;
-}
-
-__global__ void __launch_bounds__(TR_THREADS) k_remap_fill(const i32 *__restrict__ tri_rows, i64 Tg, const i32 *__restrict__ keepA,
-                                                           const i32 *__restrict__ ka_off, const i32 *__restrict__ block_base,
-                                                           int3 *__restrict__ tin, i32 *__restrict__ tin_src) {
-    const int w = blockIdx.y;
-    const i32 lo = ka_off[w], hi = ka_off[w + 1];
-    const i64 base = (i64)blockIdx.x * TR_CHUNK;
-    typedef cub::BlockScan<int, TR_THREADS> BS;
-    __shared__ typename BS::TempStorage tmp;
-    int run = block_base[(i64)w * gridDim.x + blockIdx.x];
-#pragma unroll 1
-    for (int it = 0; it < TR_ITEMS; ++it) {
-        const i64 t = base + it * TR_THREADS + threadIdx.x;
-        int3 v = make_int3(0, 0, 0);
-        const int f = (t < Tg) && tri_in_window(tri_rows, t, keepA, lo, hi, v);
-        int rank, tot;
-        BS(tmp).ExclusiveSum(f, rank, tot);
-        if (f) { tin[run + rank] = v; tin_src[run + rank] = (i32)t; }
-        run += tot;
+    const unsigned lane = threadIdx.x & 31u;
+    for (int w0 = 0; w0 < W; w0 += RECT_TILE) {
+        const int nw = min(RECT_TILE, W - w0);
         __syncthreads();
+        for (int k = threadIdx.x; k < nw; k += blockDim.x) srect[k] = reinterpret_cast<const double4 *>(rects)[w0 + k];
+        __syncthreads();
+        // every lane walks the rectangle list in lockstep so that hits on the same window can be counted /
+        // placed with ONE atomic per warp (2 M single-address atomics cost 1.1 ms otherwise)
+        for (int k = 0; k < nw; ++k) {
+            const double4 r = srect[k];  // x_min, x_max, y_min, y_max ; half-open (same.py:293-295)
+            const int w = w0 + k;
+            bool hit = live && mnx >= r.x && mxx < r.y && mny >= r.z && mxy < r.w;
+            int3 v = make_int3(-1, -1, -1);
+            if (hit) {
+                const i32 lo = ka_off[w], hi = ka_off[w + 1];
+                v.x = kept_lookup(keepA, lo, hi, ra);
+                if (v.x >= 0) v.y = kept_lookup(keepA, lo, hi, rb);
+                if (v.y >= 0) v.z = kept_lookup(keepA, lo, hi, rc);
+                hit = v.z >= 0;
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, hit);
+            if (m == 0u) continue;
+            const int leader = __ffs(m) - 1;
+            if (!FILL) {
+                if ((int)lane == leader) atomicAdd(win_count + w, __popc(m));
+            } else {
+                i32 base = 0;
+                if ((int)lane == leader) base = atomicAdd(cursor, __popc(m));
+                base = __shfl_sync(0xffffffffu, base, leader);
+                if (hit) {
+                    const i32 pos = base + __popc(m & ((1u << lane) - 1u));
+                    keys[pos] = ((unsigned long long)w << tbits) | (unsigned long long)t;
+                    recs[pos] = v;
+                }
+            }
+        }
     }
 }
 
-__global__ void k_pick_strided(const i32 *__restrict__ scanned, i64 stride, i64 W, i32 *__restrict__ off) {
-    i64 w = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (w <= W) off[w] = scanned[w * stride];
+__global__ void k_remap_gather(const unsigned long long *__restrict__ sorted_keys, const i32 *__restrict__ sorted_idx,
+                               const int3 *__restrict__ recs, i64 n, int tbits, int3 *__restrict__ tin, i32 *__restrict__ tin_src) {
+    const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    tin[i] = recs[sorted_idx[i]];
+    tin_src[i] = (i32)(sorted_keys[i] & ((1ull << tbits) - 1ull));
+}
+
+__global__ void k_iota_tri(i32 *p, i64 n) {
+    i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = (i32)i;
 }
 
 static void reset_triangles(Batch *b) {
@@ -86,24 +104,44 @@ void batch_triangles_remap(Batch *b) {
     REQUIRE(sec->Tg >= 0, SAME_E_STATE, "same_section_set_triangles was not called");
     reset_triangles(b);
     const i64 W = b->W, Tg = sec->Tg;
-    const i64 chunks = blocks_for(Tg, TR_CHUNK);
-    DevBuf<i32> counts, scanned;
-    counts.alloc(W * chunks + 1, s); scanned.alloc(W * chunks + 1, s);
-    CK(cudaMemsetAsync(counts.p, 0, sizeof(i32) * (W * chunks + 1), s));
-    if (Tg > 0) LAUNCH(k_remap_count, dim3((unsigned)chunks, (unsigned)W), TR_THREADS, 0, s, sec->tri_rows.p, Tg, b->keepA.p, b->d_ka_off.p, counts.p);
-    exclusive_scan_i32(counts.p, scanned.p, W * chunks + 1, b->scratch, s);
-    b->d_tin_off.alloc(W + 1, s);
-    LAUNCH(k_pick_strided, blocks_for(W + 1, 128), 128, 0, s, scanned.p, chunks, W, b->d_tin_off.p);
-    std::vector<i32> h(W + 1);
-    CK(cudaMemcpyAsync(h.data(), b->d_tin_off.p, sizeof(i32) * (W + 1), cudaMemcpyDeviceToHost, s));
+    int tbits = 1;
+    while ((1ll << tbits) < Tg) ++tbits;
+    DevBuf<i32> win_count, cursor;
+    win_count.alloc(W, s); cursor.alloc(1, s);
+    win_count.zero(s); cursor.zero(s);
+    if (Tg > 0)
+        LAUNCH(k_remap_scan<false>, blocks_for(Tg, 256), 256, 0, s, sec->tri_rows.p, Tg, sec->a_xy.p, b->d_rects.p, (int)W, b->keepA.p, b->d_ka_off.p,
+               win_count.p, (unsigned long long *)nullptr, (int3 *)nullptr, (i32 *)nullptr, tbits);
+    std::vector<i32> h(W);
+    CK(cudaMemcpyAsync(h.data(), win_count.p, sizeof(i32) * W, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
-    b->tin_off.assign(h.begin(), h.end());
+    b->tin_off.assign(W + 1, 0);
+    for (i64 w = 0; w < W; ++w) b->tin_off[w + 1] = b->tin_off[w] + h[w];
     b->Tin = b->tin_off[W];
+    REQUIRE(b->Tin < (1ll << 31), SAME_E_LIMIT, "too many window triangles");
+    upload_offsets(b->tin_off, b->d_tin_off, s);
     b->tin.alloc(b->Tin, s); b->tin_src.alloc(b->Tin, s);
-    if (Tg > 0 && b->Tin > 0)
-        LAUNCH(k_remap_fill, dim3((unsigned)chunks, (unsigned)W), TR_THREADS, 0, s, sec->tri_rows.p, Tg, b->keepA.p, b->d_ka_off.p, scanned.p,
-               b->tin.p, b->tin_src.p);
-    CK(cudaStreamSynchronize(s));
+    if (b->Tin > 0) {
+        DevBuf<unsigned long long> keys, keys_out;
+        DevBuf<int3> recs;
+        DevBuf<i32> idx, idx_out;
+        keys.alloc(b->Tin, s); keys_out.alloc(b->Tin, s); recs.alloc(b->Tin, s); idx.alloc(b->Tin, s); idx_out.alloc(b->Tin, s);
+        LAUNCH(k_remap_scan<true>, blocks_for(Tg, 256), 256, 0, s, sec->tri_rows.p, Tg, sec->a_xy.p, b->d_rects.p, (int)W, b->keepA.p, b->d_ka_off.p,
+               (i32 *)nullptr, keys.p, recs.p, cursor.p, tbits);
+        LAUNCH(k_iota_tri, blocks_for(b->Tin, 256), 256, 0, s, idx.p, b->Tin);
+        int wbits = 1;
+        while ((1ll << wbits) < W) ++wbits;
+        size_t bytes = 0;
+        CK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, keys.p, keys_out.p, idx.p, idx_out.p, (int)b->Tin, 0, tbits + wbits, s));
+        void *tmp = b->scratch.get(bytes, s);
+        {
+            ProfScope prof("cub::DeviceRadixSort::SortPairs(remap)", s);
+            CK(cub::DeviceRadixSort::SortPairs(tmp, bytes, keys.p, keys_out.p, idx.p, idx_out.p, (int)b->Tin, 0, tbits + wbits, s));
+        }
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        LAUNCH(k_remap_gather, blocks_for(b->Tin, 256), 256, 0, s, keys_out.p, idx_out.p, recs.p, b->Tin, tbits, b->tin.p, b->tin_src.p);
+        CK(cudaStreamSynchronize(s));
+    }
     b->tin_has_src = true;
     b->stage = 2;
 }

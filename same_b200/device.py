@@ -16,6 +16,45 @@ def _f64(a, shape=None):
     return a if shape is None else a.reshape(shape)
 
 
+_PINNED_POOL: dict = {}    # size class -> [host pointers ready for reuse]
+
+
+class _PinnedLease:
+    """Holds one cudaHostAlloc block; when the last numpy view dies the block goes back to the pool."""
+
+    def __init__(self, nbytes):
+        pool = _PINNED_POOL.setdefault(nbytes, [])
+        if pool:
+            self.ptr = pool.pop()
+        else:
+            p = C.c_void_p()
+            L.check(L.load().same_pinned_alloc(nbytes, C.byref(p)))
+            self.ptr = p.value
+        self.nbytes = nbytes
+
+    def __del__(self):
+        try:
+            pool = _PINNED_POOL.setdefault(self.nbytes, [])
+            if len(pool) < 8:
+                pool.append(self.ptr)
+            else:
+                L.load().same_pinned_free(C.c_void_p(self.ptr))
+        except Exception:
+            pass
+
+
+def pinned_empty(shape, dtype):
+    """numpy array backed by page-locked host memory (1 MiB size classes, recycled through a small pool)."""
+    dtype = np.dtype(dtype)
+    shape = tuple(int(v) for v in (shape if isinstance(shape, (tuple, list)) else (shape,)))
+    count = int(np.prod(shape)) if shape else 1
+    cls = max(1 << 20, -(-(count * dtype.itemsize) // (1 << 20)) * (1 << 20))
+    lease = _PinnedLease(cls)
+    raw = (C.c_ubyte * cls).from_address(lease.ptr)
+    raw._lease = lease        # the ctypes array is the base of every view: keeps the lease alive
+    return np.frombuffer(raw, dtype=dtype, count=count).reshape(shape)
+
+
 class Section:
     """Both frames of one tissue section pair on the GPU (same_section_create)."""
 
@@ -140,7 +179,7 @@ class WindowBatch:
         w_hi = self.W if w_hi is None else w_hi
         nw = w_hi - w_lo
         nv, nc = np.zeros(nw, np.int64), np.zeros(nw, np.int64)
-        cuts = np.full((nw, max(cap, 1), 4), -1, np.int32)
+        cuts = pinned_empty((nw, max(cap, 1), 4), np.int32)   # rows beyond min(n_viol, cap) are unspecified
         if not isinstance(x, int):
             x = np.ascontiguousarray(x, dtype=np.float64)
         L.check(L.load().same_batch_separation(self._h, w_lo, w_hi, L.ptr(x), cap, L.ptr(nv), L.ptr(nc), L.ptr(cuts)))
@@ -171,6 +210,20 @@ class WindowBatch:
         out = np.empty((hi - lo,) + tail, dtype=dt)
         L.check(L.load().same_batch_get(self._h, what, lo, hi, L.ptr(out)))
         return out
+
+    def get_many(self, whats, pinned=True):
+        """Fetch several whole arrays with one stream synchronisation -> {what: ndarray}."""
+        whats = list(whats)
+        n = len(whats)
+        outs, lo, hi = [], np.zeros(n, np.int64), np.zeros(n, np.int64)
+        for k, what in enumerate(whats):
+            dt, tail = L.ARRAY_SPEC[what]
+            hi[k] = self.length(what)
+            outs.append(pinned_empty((int(hi[k]),) + tail, dt) if pinned else np.empty((int(hi[k]),) + tail, dt))
+        dst = (C.c_void_p * n)(*[o.ctypes.data for o in outs])
+        w = np.asarray(whats, dtype=np.int32)
+        L.check(L.load().same_batch_get_many(self._h, n, L.ptr(w), L.ptr(lo), L.ptr(hi), dst))
+        return dict(zip(whats, outs))
 
     def get_window(self, what, w):
         off = self.offsets(what)
