@@ -158,6 +158,13 @@ SAME_API int same_batch_separation(same_batch_t *b, int64_t w_lo, int64_t w_hi, 
  * src/same.py:1355-1408); results through same_batch_get(TRI_MASK / AREA_* / FLIPPED / MATCH_*). */
 SAME_API int same_batch_postsolve(same_batch_t *b, int64_t w_lo, int64_t w_hi, const double *x);
 
+/* Stateless form of a11 + a12 for callers that hold plain arrays (verify_spatial_preservation called on its
+ * own, src/violationhelper.py:1-134): tri[T,3] rows of a_xy, match_j[n_aligned] = matched row of r_xy or -1.
+ * Outputs (host): mask[T] i32 (bit layout of SAME_ARR_TRI_MASK), area_before[T], area_after[T], flipped[T] u8. */
+SAME_API int same_postsolve_arrays(int device, int64_t n_tri, const int32_t *tri, int64_t n_aligned, const double *a_xy, int64_t n_ref,
+                                   const double *r_xy, const int32_t *match_j, int32_t *mask, double *area_before, double *area_after,
+                                   uint8_t *flipped);
+
 /* ---- results -------------------------------------------------------------------------- */
 /* W+1 offsets (in elements) of array `what` */
 SAME_API int same_batch_offsets(same_batch_t *b, int what, int64_t *off);

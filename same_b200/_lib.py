@@ -47,6 +47,7 @@ SYMBOLS = [
     "same_batch_groups", "same_batch_separation", "same_batch_postsolve", "same_batch_offsets", "same_batch_length",
     "same_batch_get", "same_elem_size", "same_batch_sync", "same_batch_stream", "same_launch_count",
     "same_profile_enable", "same_profile_report", "same_batch_get_many", "same_pinned_alloc", "same_pinned_free",
+    "same_postsolve_arrays",
 ]
 
 
@@ -103,6 +104,7 @@ def load():
     lib.same_batch_get_many.argtypes = [vp, i64, vp, vp, vp, vp]
     lib.same_pinned_alloc.argtypes = [i64, C.POINTER(vp)]
     lib.same_pinned_free.argtypes = [vp]
+    lib.same_postsolve_arrays.argtypes = [i32, i64, vp, i64, vp, i64, vp, vp, vp, vp, vp, vp]
     lib.same_profile_enable.argtypes = [i32]
     lib.same_profile_report.argtypes = [C.c_char_p, i64]
     lib.same_profile_report.restype = i64

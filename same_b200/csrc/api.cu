@@ -255,6 +255,15 @@ int same_batch_separation(same_batch_t *h, int64_t w_lo, int64_t w_hi, const dou
 }
 int same_batch_postsolve(same_batch_t *h, int64_t w_lo, int64_t w_hi, const double *x) { BATCH_CALL(h, batch_postsolve(b, w_lo, w_hi, x)); }
 
+int same_postsolve_arrays(int device, int64_t n_tri, const int32_t *tri, int64_t n_aligned, const double *a_xy, int64_t n_ref, const double *r_xy,
+                          const int32_t *match_j, int32_t *mask, double *area_before, double *area_after, uint8_t *flipped) {
+    return guarded([&] {
+        REQUIRE(n_tri >= 0 && n_aligned >= 0 && n_ref >= 0, SAME_E_ARG, "negative size");
+        REQUIRE(n_tri == 0 || (tri && mask && area_before && area_after && flipped), SAME_E_ARG, "NULL argument");
+        postsolve_arrays(device, n_tri, tri, n_aligned, a_xy, n_ref, r_xy, match_j, mask, area_before, area_after, flipped);
+    });
+}
+
 int same_batch_offsets(same_batch_t *h, int what, int64_t *off) {
     BATCH_CALL(h, {
         REQUIRE(off, SAME_E_ARG, "off is NULL");

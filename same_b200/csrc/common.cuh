@@ -222,6 +222,8 @@ void batch_tri_override(Batch *b, i64 n, const i32 *idx, const unsigned char *cl
 void batch_tri_finalize(Batch *b, int ignore_same_type, int ensure_min, int remove_unconstrained);
 void batch_separation(Batch *b, i64 w_lo, i64 w_hi, const double *x, i64 cap, i64 *n_viol, i64 *n_checked, i32 *cuts);
 void batch_postsolve(Batch *b, i64 w_lo, i64 w_hi, const double *x);
+void postsolve_arrays(int device, i64 T, const i32 *tri, i64 nA, const double *a_xy, i64 nR, const double *r_xy, const i32 *match_j, i32 *mask,
+                      double *area_before, double *area_after, unsigned char *flipped);
 
 // upload a small host vector of i64 offsets as i32 device array
 void upload_offsets(const std::vector<i64> &h, DevBuf<i32> &d, cudaStream_t s);

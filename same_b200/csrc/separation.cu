@@ -208,4 +208,38 @@ void batch_postsolve(Batch *b, i64 w_lo, i64 w_hi, const double *x) {
     CK(cudaStreamSynchronize(s));
 }
 
+void postsolve_arrays(int device, i64 T, const i32 *tri, i64 nA, const double *a_xy, i64 nR, const double *r_xy, const i32 *match_j, i32 *mask,
+                      double *area_before, double *area_after, unsigned char *flipped) {
+    CK(cudaSetDevice(device));
+    cudaStream_t s;
+    CK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    try {
+        DevBuf<int3> d_tri; DevBuf<double2> d_a, d_r; DevBuf<i32> d_m, d_off, d_mask; DevBuf<double> d_ab, d_aa; DevBuf<unsigned char> d_fl;
+        d_tri.alloc(T, s); d_a.alloc(nA, s); d_r.alloc(nR, s); d_m.alloc(nA, s); d_off.alloc(6, s);
+        d_mask.alloc(T, s); d_ab.alloc(T, s); d_aa.alloc(T, s); d_fl.alloc(T, s);
+        if (T) CK(cudaMemcpyAsync(d_tri.p, tri, sizeof(int3) * T, cudaMemcpyDefault, s));
+        if (nA) CK(cudaMemcpyAsync(d_a.p, a_xy, sizeof(double2) * nA, cudaMemcpyDefault, s));
+        if (nR) CK(cudaMemcpyAsync(d_r.p, r_xy, sizeof(double2) * nR, cudaMemcpyDefault, s));
+        if (nA) CK(cudaMemcpyAsync(d_m.p, match_j, sizeof(i32) * nA, cudaMemcpyDefault, s));
+        const i32 off[6] = {0, (i32)T, 0, (i32)nA, 0, (i32)nR};
+        CK(cudaMemcpyAsync(d_off.p, off, sizeof(off), cudaMemcpyHostToDevice, s));
+        if (T > 0)
+            LAUNCH(k_postsolve, blocks_for(T, 256), 256, 0, s, d_tri.p, 0, (i32)T, d_off.p, d_off.p + 2, d_off.p + 4, 1, d_m.p, d_a.p, d_r.p, d_mask.p,
+                   d_ab.p, d_aa.p, d_fl.p);
+        if (T) {
+            CK(cudaMemcpyAsync(mask, d_mask.p, sizeof(i32) * T, cudaMemcpyDefault, s));
+            CK(cudaMemcpyAsync(area_before, d_ab.p, sizeof(double) * T, cudaMemcpyDefault, s));
+            CK(cudaMemcpyAsync(area_after, d_aa.p, sizeof(double) * T, cudaMemcpyDefault, s));
+            CK(cudaMemcpyAsync(flipped, d_fl.p, T, cudaMemcpyDefault, s));
+        }
+        CK(cudaStreamSynchronize(s));
+    } catch (...) {
+        cudaStreamSynchronize(s);
+        cudaStreamDestroy(s);
+        throw;
+    }
+    CK(cudaStreamSynchronize(s));
+    CK(cudaStreamDestroy(s));
+}
+
 }  // namespace same

@@ -64,8 +64,16 @@ class Section:
         self._keep = []
         a_xy, r_xy = _f64(a_xy, (-1, 2)), _f64(r_xy, (-1, 2))
         self.n_aligned, self.n_ref = len(a_xy), len(r_xy)
-        a_prob = _f64(a_prob).reshape(self.n_aligned, -1) if self.n_aligned else np.zeros((0, np.asarray(r_prob).reshape(self.n_ref, -1).shape[1]))
-        r_prob = _f64(r_prob).reshape(self.n_ref, -1) if self.n_ref else np.zeros((0, a_prob.shape[1]))
+        def _block(p, n):
+            p = _f64(p)
+            if p.ndim == 2 and p.shape[0] == n:
+                return p
+            return p.reshape(n, p.size // n if n else 0)
+        a_prob, r_prob = _block(a_prob, self.n_aligned), _block(r_prob, self.n_ref)
+        if self.n_aligned == 0:
+            a_prob = np.zeros((0, r_prob.shape[1]))
+        if self.n_ref == 0:
+            r_prob = np.zeros((0, a_prob.shape[1]))
         if a_prob.shape[1] != r_prob.shape[1]:
             raise ValueError("probability blocks of the two frames have different widths")
         self.n_types = a_prob.shape[1]

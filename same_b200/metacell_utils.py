@@ -1,0 +1,257 @@
+"""Metacell pre/post-processing with the reference's API (src/metacell_utils.py): `MetaCell`,
+`greedy_triangle_collapse`, `unpack_metacell_matches`.
+
+These sit OUTSIDE the per-window GPU hot path (Qhull runs once per collapse iteration on
+the host either way).  They are host code, written from the reference's documented behaviour with numpy-vectorised
+triangle scoring; the collapse loop keeps the reference's greedy order (perimeter ascending, non-overlapping batch).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Any, Dict, List, Optional
+
+import numpy as np
+import pandas as pd
+from scipy.spatial import Delaunay
+
+
+@dataclass
+class MetaCell:
+    """Collapse result + metadata; same fields and helpers as the reference dataclass (src/metacell_utils.py:25-157)."""
+    original_df: pd.DataFrame
+    params: Dict[str, Any]
+    x_col: str
+    y_col: str
+    cell_type_col: str
+    original_idx_col: str
+    metacell_idx_col: str
+    original_delaunay: np.ndarray      # (n, 3) in original-ID space
+    metacell_df: pd.DataFrame
+    metacell_delaunay: np.ndarray      # (n, 3) rows of metacell_df
+
+    def metacell_members(self, metacell_idx: int) -> List[Any]:
+        return list(self.metacell_df.iloc[int(metacell_idx)]["members"])
+
+    def original_delaunay_to_row_indices(self, triangles: Optional[np.ndarray] = None, *, on_missing: str = "drop") -> np.ndarray:
+        tri = self.original_delaunay if triangles is None else np.asarray(triangles)
+        if tri.size == 0:
+            return np.array([], dtype=int).reshape(0, 3)
+        if tri.ndim != 2 or tri.shape[1] != 3:
+            raise ValueError(f"triangles must have shape (n, 3); got {tri.shape}")
+        ids = self.original_df[self.original_idx_col].to_numpy()
+        lut = pd.Series(np.arange(len(ids)), index=ids)
+        lut = lut[~lut.index.duplicated(keep="last")]
+        pos = lut.reindex(tri.reshape(-1)).to_numpy()
+        missing = np.isnan(pos)
+        if missing.any() and on_missing == "error":
+            bad = list(dict.fromkeys(tri.reshape(-1)[missing].tolist()))[:10]
+            raise KeyError(f"Found triangle vertices not in original_df[{self.original_idx_col}]: {bad}")
+        pos = np.where(missing, -1, pos).astype(int).reshape(tri.shape)
+        return pos[(pos >= 0).all(axis=1)]
+
+    def original_delaunay_to_pos(self, triangles: Optional[np.ndarray] = None, *, on_missing: str = "drop") -> np.ndarray:
+        return self.original_delaunay_to_row_indices(triangles=triangles, on_missing=on_missing)
+
+    def original_delaunay_to_xy(self, triangles: Optional[np.ndarray] = None, *, on_missing: str = "drop") -> np.ndarray:
+        pos = self.original_delaunay_to_row_indices(triangles=triangles, on_missing=on_missing)
+        if pos.size == 0:
+            return np.array([], dtype=float).reshape(0, 3, 2)
+        return self.original_df[[self.x_col, self.y_col]].to_numpy(dtype=float)[pos]
+
+    def metacell_delaunay_to_xy(self) -> np.ndarray:
+        tri = np.asarray(self.metacell_delaunay)
+        if tri.size == 0:
+            return np.array([], dtype=float).reshape(0, 3, 2)
+        return self.metacell_df[[self.x_col, self.y_col]].to_numpy(dtype=float)[tri.astype(int)]
+
+    def to_summary_dict(self) -> Dict[str, Any]:
+        return {"n_original": int(len(self.original_df)), "n_metacells": int(len(self.metacell_df)), "params": dict(self.params),
+                "x_col": self.x_col, "y_col": self.y_col, "cell_type_col": self.cell_type_col,
+                "original_idx_col": self.original_idx_col, "metacell_idx_col": self.metacell_idx_col,
+                "n_original_triangles": int(getattr(self.original_delaunay, "shape", [0])[0]),
+                "n_metacell_triangles": int(getattr(self.metacell_delaunay, "shape", [0])[0])}
+
+
+def _valid_triangles(coords, tri, r_max, min_angle_deg):
+    """Edge length <= r_max (note: '>' drops, src/metacell_utils.py:251) and min angle >= min_angle_deg (:257-261)."""
+    if len(tri) == 0:
+        return np.zeros(0, bool)
+    p = coords[tri]                                    # (T, 3, 2)
+    ok = np.ones(len(tri), bool)
+    e = [np.linalg.norm(p[:, (k + 1) % 3] - p[:, k], axis=1) for k in range(3)]
+    if r_max is not None:
+        ok &= ~(np.maximum(np.maximum(e[0], e[1]), e[2]) > r_max)
+    if min_angle_deg is not None:
+        angs = []
+        for k in range(3):
+            v1, v2 = p[:, (k + 1) % 3] - p[:, k], p[:, (k + 2) % 3] - p[:, k]
+            with np.errstate(invalid="ignore", divide="ignore"):
+                c = np.einsum("ij,ij->i", v1, v2) / (np.linalg.norm(v1, axis=1) * np.linalg.norm(v2, axis=1))
+            angs.append(np.degrees(np.arccos(np.clip(c, -1, 1))))
+        mn = np.minimum(np.minimum(angs[0], angs[1]), angs[2])
+        ok &= ~(mn < min_angle_deg)                    # NaN (degenerate) compares False -> kept, as in the reference
+    return ok
+
+
+def _filter_triangles(coords, tri, r_max, min_angle_deg, use_alpha_shape, alpha):
+    ok = _valid_triangles(coords, tri, r_max, min_angle_deg)
+    if use_alpha_shape:
+        try:
+            from alphashape import alphashape
+            from shapely.geometry import Polygon
+            shape = alphashape([tuple(c) for c in coords], alpha)
+            ok &= np.array([shape.contains(Polygon(coords[t])) for t in tri], dtype=bool)
+        except ImportError:
+            print("Warning: alphashape not available, skipping alpha shape filtering")
+    out = tri[ok]
+    return out if len(out) else np.array([]).reshape(0, 3)
+
+
+def greedy_triangle_collapse(aligned_df, max_metacell_size=3, max_iterations=1000, r_max=None, min_angle_deg=10, use_alpha_shape=False,
+                             alpha=0.05, *, original_idx_col: str = "Cell_Num_Old", metacell_idx_col: str = "metacell_id",
+                             x_col: str = "X", y_col: str = "Y", cell_type_col: str = "cell_type", return_object: bool = False):
+    """Iteratively collapse same-type Delaunay triangles into metacells (src/metacell_utils.py:160-561).
+
+    Returns `(metacell_df, metacell_delaunay)` or a `MetaCell` (`return_object=True`).  With `max_metacell_size=1`
+    nothing collapses and the call only produces the filtered triangulation `run_same` reuses."""
+    required = [x_col, y_col, cell_type_col, original_idx_col]
+    missing = [c for c in required if c not in aligned_df.columns]
+    if missing:
+        raise ValueError(f"Input dataframe missing required columns: {missing}")
+    aligned_df = aligned_df.copy()
+    if aligned_df[original_idx_col].duplicated().any():
+        dups = aligned_df.loc[aligned_df[original_idx_col].duplicated(), original_idx_col].head(5).tolist()
+        raise ValueError(f"'{original_idx_col}' must be unique per original cell. Found duplicates (examples): {dups}")
+    indexed = aligned_df.set_index(original_idx_col, drop=False)
+
+    coords0 = aligned_df[[x_col, y_col]].to_numpy()
+    if len(coords0) >= 4:
+        pos = _filter_triangles(coords0, Delaunay(coords0).simplices, r_max, min_angle_deg, use_alpha_shape, alpha)
+    else:
+        pos = np.array([], dtype=int).reshape(0, 3)
+    ids = aligned_df[original_idx_col].to_numpy()
+    original_delaunay = np.array([], dtype=ids.dtype).reshape(0, 3) if pos.size == 0 else ids[pos.astype(int)]
+
+    id_columns = ["Cell_Num", "Cell_Num_Old", "cell_id", "Cell_ID", "ID", "id"]
+    id_cols_present = [c for c in aligned_df.columns if c in id_columns]
+    if original_idx_col not in id_cols_present:
+        id_cols_present.append(original_idx_col)
+    if metacell_idx_col in aligned_df.columns and metacell_idx_col not in id_cols_present:
+        id_cols_present.append(metacell_idx_col)
+    extra = [c for c in aligned_df.columns if c not in [x_col, y_col, cell_type_col] + id_cols_present]
+    mdf = pd.DataFrame({x_col: aligned_df[x_col].to_numpy(), y_col: aligned_df[y_col].to_numpy(),
+                        cell_type_col: aligned_df[cell_type_col].to_numpy(), "size": 1})
+    mdf["members"] = [[v] for v in aligned_df[original_idx_col].tolist()]
+    for c in extra:
+        mdf[c] = aligned_df[c].to_numpy()
+    mdf[metacell_idx_col] = range(len(mdf))
+
+    for _ in range(max_iterations):
+        coords = mdf[[x_col, y_col]].values
+        if len(coords) < 4:
+            break
+        tri = _filter_triangles(coords, Delaunay(coords).simplices, r_max, min_angle_deg, use_alpha_shape, alpha)
+        if len(tri) == 0:
+            break
+        tri = tri.astype(int)
+        types = mdf[cell_type_col].to_numpy()
+        sizes = mdf["size"].to_numpy()
+        same = (types[tri[:, 0]] == types[tri[:, 1]]) & (types[tri[:, 1]] == types[tri[:, 2]])
+        tot = sizes[tri[:, 0]] + sizes[tri[:, 1]] + sizes[tri[:, 2]]
+        cand = np.flatnonzero(same & ~(tot > max_metacell_size))
+        if len(cand) == 0:
+            break
+        a, b, c = coords[tri[cand, 0]], coords[tri[cand, 1]], coords[tri[cand, 2]]
+        perim = np.linalg.norm(a - b, axis=1) + np.linalg.norm(b - c, axis=1) + np.linalg.norm(c - a, axis=1)
+        used = np.zeros(len(mdf), bool)
+        batch = []
+        for k in np.argsort(perim, kind="stable"):                     # list.sort is stable (src/metacell_utils.py:424)
+            v = tri[cand[k]]
+            if not used[v].any():
+                batch.append(cand[k])
+                used[v] = True
+        merged, remove = [], []
+        for t in batch:
+            va, vb, vc = tri[t]
+            remove.extend([va, vb, vc])
+            members = mdf.iloc[va]["members"] + mdf.iloc[vb]["members"] + mdf.iloc[vc]["members"]
+            rows = indexed.loc[members]
+            m = {x_col: rows[x_col].mean(), y_col: rows[y_col].mean(), cell_type_col: mdf.iloc[va][cell_type_col],
+                 "size": tot[t], "members": members}
+            for col in mdf.columns:
+                if col in [x_col, y_col, cell_type_col, "size", "members", metacell_idx_col] + id_cols_present:
+                    continue
+                if pd.api.types.is_numeric_dtype(mdf[col]):
+                    if col in aligned_df.columns:
+                        m[col] = rows[col].mean()
+                    else:
+                        m[col] = np.average([mdf.iloc[i][col] for i in (va, vb, vc)], weights=[mdf.iloc[i]["size"] for i in (va, vb, vc)])
+                else:
+                    m[col] = mdf.iloc[va][col]
+            merged.append(m)
+        mdf = mdf.drop(remove).reset_index(drop=True)
+        if merged:
+            mdf = pd.concat([mdf, pd.DataFrame(merged)], ignore_index=True)
+        mdf[metacell_idx_col] = range(len(mdf))
+
+    final_coords = mdf[[x_col, y_col]].values
+    if len(final_coords) >= 4:
+        final = _filter_triangles(final_coords, Delaunay(final_coords).simplices, r_max, min_angle_deg, use_alpha_shape, alpha)
+    else:
+        final = np.array([]).reshape(0, 3)
+    if return_object:
+        params = {"max_metacell_size": max_metacell_size, "max_iterations": max_iterations, "r_max": r_max,
+                  "min_angle_deg": min_angle_deg, "use_alpha_shape": use_alpha_shape, "alpha": alpha}
+        return MetaCell(original_df=aligned_df, params=params, x_col=x_col, y_col=y_col, cell_type_col=cell_type_col,
+                        original_idx_col=original_idx_col, metacell_idx_col=metacell_idx_col, original_delaunay=original_delaunay,
+                        metacell_df=mdf, metacell_delaunay=final)
+    return mdf, final
+
+
+def unpack_metacell_matches(metacell_matches, metacell_aligned_df, metacell_ref_df, aligned_df=None, ref_df=None,
+                            strategy="distribute", aligned_original_idx_col: Optional[str] = None,
+                            ref_original_idx_col: Optional[str] = None, x_col: str = "X", y_col: str = "Y"):
+    """Metacell-level matches -> individual cells (src/metacell_utils.py:564-766): columns `Aligned_cell_id`, `Ref_cell_id`.
+    Reads `Aligned_metacell_id` / `Ref_metacell_id`; 'distribute' = round-robin over ref members, 'nearest' = Hungarian on
+    member coordinates (ref members tiled when there are more aligned than ref members)."""
+    from scipy.optimize import linear_sum_assignment
+    from scipy.spatial.distance import cdist
+    a_idx = r_idx = None
+    if aligned_df is not None and aligned_original_idx_col is not None:
+        if aligned_original_idx_col not in aligned_df.columns:
+            raise ValueError(f"aligned_df missing aligned_original_idx_col='{aligned_original_idx_col}'")
+        a_idx = aligned_df.set_index(aligned_original_idx_col, drop=False)
+    if ref_df is not None and ref_original_idx_col is not None:
+        if ref_original_idx_col not in ref_df.columns:
+            raise ValueError(f"ref_df missing ref_original_idx_col='{ref_original_idx_col}'")
+        r_idx = ref_df.set_index(ref_original_idx_col, drop=False)
+    ref_has_mc = "members" in metacell_ref_df.columns and metacell_ref_df["members"].apply(lambda v: isinstance(v, list)).any()
+    if ref_has_mc and strategy == "nearest" and (aligned_df is None or ref_df is None):
+        raise ValueError("When ref has metacells and strategy='nearest', must provide both aligned_df and ref_df "
+                         "for nearest neighbor unpacking.")
+    if strategy == "nearest" and aligned_df is None:
+        raise ValueError("strategy='nearest' requires aligned_df parameter")
+    if strategy not in ("distribute", "nearest"):
+        if ref_has_mc and len(metacell_matches):
+            raise ValueError(f"Unknown strategy: {strategy}")
+    out = []
+    a_members = metacell_aligned_df["members"].tolist()
+    r_members = metacell_ref_df["members"].tolist() if ref_has_mc else None
+    for ma, mr in zip(metacell_matches["Aligned_metacell_id"].tolist(), metacell_matches["Ref_metacell_id"].tolist()):
+        am = a_members[int(ma)]
+        if not ref_has_mc:
+            if strategy in ("distribute", "nearest"):
+                out.extend({"Aligned_cell_id": m, "Ref_cell_id": mr} for m in am)
+            continue
+        rm = r_members[int(mr)]
+        if strategy == "distribute":
+            out.extend({"Aligned_cell_id": m, "Ref_cell_id": rm[i % len(rm)]} for i, m in enumerate(am))
+        else:
+            ac = (a_idx if a_idx is not None else aligned_df).loc[am, [x_col, y_col]].values
+            rc = (r_idx if r_idx is not None else ref_df).loc[rm, [x_col, y_col]].values
+            d = cdist(ac, rc)
+            if len(am) > len(rm):
+                d = np.tile(d, (1, int(np.ceil(len(am) / len(rm)))))
+            rows, cols = linear_sum_assignment(d)
+            out.extend({"Aligned_cell_id": am[i], "Ref_cell_id": rm[j % len(rm)]} for i, j in zip(rows, cols))
+    return pd.DataFrame(out)

@@ -1,0 +1,428 @@
+"""`run_same` and `sliding_window_matching` with the reference's signatures and DataFrame contract
+(src/same.py:297-595, 706-1489).  Host orchestration stays Python; every array loop of the reference —
+candidate search, pair costs, constraint grouping, triangle remap/filter/tables, lazy separation, post-solve
+analysis, window subsetting — runs in libsame_b200 on the GPU.  Gurobi stays the host solver.
+
+There is no CPU fallback: without the CUDA library / a CUDA device these functions raise.
+"""
+from __future__ import annotations
+
+import os
+from typing import Any, Dict, List, Optional
+
+import numpy as np
+import pandas as pd
+from scipy.spatial import Delaunay
+
+from . import _lib as L
+from . import helpers as H
+from . import windows as WN
+from .frames import build_section
+from .params import init_gurobi_params, init_optim_params
+from .solver import ModelSpec, get_backend
+from .violationhelper import violations_from_mask
+
+
+# --------------------------------------------------------------------------------------------------------
+def _as_triangle_array(delaunay_like):
+    """Normalise a triangulation-like object to an int ndarray (n, 3) (src/same.py:245-259)."""
+    if delaunay_like is None:
+        return None
+    if isinstance(delaunay_like, np.ndarray):
+        tri = delaunay_like
+    elif isinstance(delaunay_like, pd.DataFrame):
+        tri = delaunay_like.iloc[:, :3].to_numpy()
+    else:
+        tri = np.asarray(delaunay_like)
+    if tri.size == 0:
+        return np.array([], dtype=int).reshape(0, 3)
+    if tri.ndim != 2 or tri.shape[1] != 3:
+        raise ValueError(f"aligned_delaunay must have shape (n, 3); got {tri.shape}")
+    return tri.astype(int, copy=False)
+
+
+def _remap_triangles_by_vertex_ids(triangles, vertex_ids):
+    """Triangles in vertex-id space -> 0..n-1 row indices, dropping triangles with a missing vertex
+    (src/same.py:262-290).  GPU: id resolution (radix sort + binary search) and the remap kernel."""
+    tri = _as_triangle_array(triangles)
+    if tri is None:
+        return None
+    if tri.size == 0:
+        return tri
+    from .device import Section
+    vid = np.ascontiguousarray(vertex_ids, dtype=np.int64)
+    n = len(vid)
+    z = np.zeros((n, 2))
+    z[:, 0] = np.arange(n)      # distinct points so that every row keeps itself as its only candidate
+    with Section(z, z, np.zeros((n, 0)), np.zeros((n, 0))) as sec, sec.batch() as b:
+        b.candidates(0.0, 1)
+        sec.set_triangles(tri.astype(np.int64), vid)
+        b.triangles_remap()
+        return b.get(L.TRI_IN).astype(int)
+
+
+def subset_data(df, x_min, x_max, y_min, y_max):
+    """Half-open window (src/same.py:293-295) — host convenience; the driver subsets on the GPU."""
+    return df[(df["X"] >= x_min) & (df["X"] < x_max) & (df["Y"] >= y_min) & (df["Y"] < y_max)]
+
+
+def load_gurobi_config():
+    """WLS credentials from `.gurobienv` next to this file (src/same.py:598-618)."""
+    config = {}
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), ".gurobienv")
+    try:
+        with open(path) as f:
+            for line in f:
+                line = line.strip()
+                if line and not line.startswith("#") and "=" in line:
+                    k, v = line.split("=", 1)
+                    config[k.strip()] = v.strip()
+    except FileNotFoundError:
+        pass
+    return config
+
+
+def _env_options():
+    cfg = load_gurobi_config()
+    return {"WLSACCESSID": os.environ.get("GUROBI_WLSACCESSID", "") or cfg.get("WLSACCESSID", ""),
+            "WLSSECRET": os.environ.get("GUROBI_WLSSECRET", "") or cfg.get("WLSSECRET", ""),
+            "LICENSEID": int(os.environ.get("GUROBI_LICENSEID", 0)) or int(cfg.get("LICENSEID", 0))}
+
+
+# --------------------------------------------------------------------------------------------------------
+class _Run:
+    """A section + one batch of windows on the GPU, driven stage by stage; shared by run_same (one unbounded
+    window) and sliding_window_matching (all runnable windows at once)."""
+
+    def __init__(self, aligned_df, ref_df, commonCT, optim, rects=None, aligned_delaunay=None, vertex_ids=None,
+                 ignore_precomputed=False, section=None):
+        self.aligned_df, self.ref_df, self.commonCT, self.optim = aligned_df, ref_df, list(commonCT), optim
+        self.section = section if section is not None else build_section(aligned_df, ref_df, self.commonCT)
+        self.batch = self.section.batch(rects)
+        self.W = self.batch.W
+        o = optim
+        self.batch.candidates(o["radius"], o["knn"], bool(o["ignore_knn_if_matched"]), o["dist_ct_coeff"])
+        p_off = self.batch.offsets(L.PAIRS)
+        self.n_pairs = np.diff(p_off)
+        self.using_precomputed = aligned_delaunay is not None and not ignore_precomputed
+        self._a_xy = aligned_df[["X", "Y"]].to_numpy(dtype=np.float64)
+        self._a_type = None
+        if "cell_type" in aligned_df.columns and "cell_type" in ref_df.columns:
+            from .frames import joint_type_codes
+            self._a_type, _ = joint_type_codes(aligned_df["cell_type"].to_numpy(), ref_df["cell_type"].to_numpy())
+        if self.using_precomputed:
+            tri = _as_triangle_array(aligned_delaunay)
+            self.section.set_triangles(tri.astype(np.int64), vertex_ids)
+            self.batch.triangles_remap()                                              # same.py:1028-1031
+        else:
+            ka_off, keepA = self.batch.offsets(L.KEEP_A), self.batch.get(L.KEEP_A)
+            tris, off = [], [0]
+            for w in range(self.W):
+                rows = keepA[ka_off[w]:ka_off[w + 1]]
+                if self.n_pairs[w] == 0:
+                    t = np.zeros((0, 3), np.int32)
+                else:
+                    t = Delaunay(self._a_xy[rows]).simplices.astype(np.int32)         # same.py:1023 (Qhull stays on the host)
+                tris.append(t)
+                off.append(off[-1] + len(t))
+            self.batch.triangles_set(np.concatenate(tris) if tris else np.zeros((0, 3), np.int32), off)
+        same = bool(o["ignore_same_type_triangles"])
+        mad = o.get("min_angle_deg", 15)
+        if self.batch.tri_classify(o["radius"], mad, same) > 0:
+            H.redecide_band(self.batch, self._a_xy, self._a_type, o["radius"], mad, same)
+        self.batch.tri_finalize(same, True, remove_unconstrained=self.using_precomputed)   # same.py:1034-1085
+        self.batch.groups(o["max_matches"], o["ref_metacell_match_multiplier"])            # helpers.py:105-138
+
+    def close(self):
+        self.batch.close()
+        self.section.close()
+
+
+def _solve_window(run: _Run, w: int, aligned_src: pd.DataFrame, ref_src: pd.DataFrame, optim, gurobi, outprefix, backend):
+    """Model build + solve + post-analysis of window `w` (src/same.py:1112-1481).  `aligned_src` / `ref_src` are the
+    frames whose `.iloc[section rows]` give the window's post-KNN frames."""
+    b = run.batch
+    m = b.window_model(w)
+    if len(m["pairs"]) == 0:
+        raise ValueError("No valid_pairs after KNN filtering. Increase radius and/or knn.")       # same.py:1002-1003
+    commonCT = run.commonCT
+    cell_id_col = optim["cell_id_col"]
+    aligned_df = aligned_src.iloc[m["keepA"]].reset_index(drop=True)
+    ref_df = ref_src.iloc[m["keepR"]].reset_index(drop=True)
+    pairs, tri = m["pairs"], m["tri"]
+    n_aligned, n_ref, P, T = len(aligned_df), len(ref_df), len(pairs), len(tri)
+    lazy = bool(optim["lazy_constraints"])
+    if not lazy:
+        raise NotImplementedError("lazy_constraints=False (the O(n*k^3) eager builder, src/helpers.py:444-573) is outside the "
+                                  "GPU hot path; use lazy_constraints=True (the reference's default)")
+    if gurobi.get("init_method") is not None:
+        raise NotImplementedError("init_method (MIP start, src/init_helpers.py) is not part of the GPU hot path yet")
+
+    spec = ModelSpec(n_pairs=P, n_ref=n_ref, n_aligned=n_aligned, n_tri=T, cost=m["cost"], row_ptr=m["row_ptr"],
+                     ref_group_node=m["ref_group_node"], ref_group_ptr=m["ref_group_ptr"], ref_group_idx=m["ref_group_idx"],
+                     ref_group_limit=m["ref_group_limit"], aligned_size=aligned_df["size"].to_numpy(dtype=np.float64),
+                     tri_weight=m["weight"], penalty_coeff=optim["penalty_coeff"], no_match_penalty=optim["no_match_penalty"],
+                     delaunay_penalty=optim["delaunay_penalty"])
+    allowed = gurobi["lazy_allowed_flip_fraction"]
+    per_inc = gurobi["lazy_max_cuts_per_incumbent"]
+    lazy_max = gurobi["lazy_max_cuts"]
+
+    def separate(x_vals, cuts_so_far):
+        """same.py:631-703 with the triangle loop on the GPU; returns the cuts to add, in order."""
+        cap = T if per_inc is None else min(int(per_inc), T)
+        if lazy_max is not None:
+            cap = min(cap, max(0, int(lazy_max) - cuts_so_far))
+        nv, nc, cuts = b.separation(x_vals, w, w + 1, cap=max(cap, 0))
+        viol, checked = int(nv[0]), int(nc[0])
+        if checked == 0 or viol == 0:
+            return np.zeros((0, 4), np.int32)
+        if allowed is not None and viol / float(checked) <= allowed:
+            return np.zeros((0, 4), np.int32)
+        return cuts[0, :min(viol, cap)].copy()
+
+    res = backend.solve(spec, separate, gurobi, outprefix=outprefix, env_options=_env_options())
+    time_limit_reached = res.status == "time_limit"
+    if res.status not in ("optimal", "time_limit"):
+        out_df, var_out = pd.DataFrame(), {}
+        if outprefix:
+            os.makedirs(outprefix, exist_ok=True)
+            out_df.to_csv(os.path.join(outprefix, "matches_df.csv"), index=False)
+        return out_df, var_out
+
+    x = np.asarray(res.x, dtype=np.float64)
+    sel = np.flatnonzero(x > 0.5)
+    out_df = pd.DataFrame({"aligned_idx": pairs[sel, 0].astype(np.int64), "ref_idx": pairs[sel, 1].astype(np.int64)})
+    ai, rj = out_df["aligned_idx"].to_numpy(), out_df["ref_idx"].to_numpy()
+    for ct in list(commonCT) + ["X", "Y"]:
+        out_df[ct] = aligned_df[ct].to_numpy()[ai]
+    for ct in ["X", "Y"]:
+        out_df[f"ref_{ct}"] = ref_df[ct].to_numpy()[rj]
+    out_df["size"] = aligned_df["size"].to_numpy()[ai]
+    out_df["ref_size"] = ref_df["size"].to_numpy()[rj]
+    out_df[f"Ref_{cell_id_col}"] = ref_df[cell_id_col].to_numpy()[rj]
+    out_df[f"Aligned_{cell_id_col}"] = aligned_df[cell_id_col].to_numpy()[ai]
+    out_df["time_limit_reached"] = time_limit_reached
+
+    # ---- post-solve analysis on the GPU (violationhelper.py:1-134, same.py:1355-1408) ----
+    b.postsolve(x, w, w + 1)
+    mask = b.get_window(L.TRI_MASK, w)
+    area_before, area_after = b.get_window(L.AREA_BEFORE, w), b.get_window(L.AREA_AFTER, w)
+    flipped = np.flatnonzero(b.get_window(L.FLIPPED, w))
+    match_j = b.get_window(L.MATCH_J, w)
+    aligned_simplex_map = {i: set() for i in range(n_aligned)}                                     # same.py:1096-1099
+    for idx in range(T):
+        for v in tri[idx]:
+            aligned_simplex_map[int(v)].add(idx)
+    aligned_delaunay = tri.astype(int)
+    triangle_info = H.precompute_triangle_info(aligned_df, aligned_delaunay, aligned_simplex_map, bounds=m["bounds"], argv=m["argv"])
+    a_xy = aligned_df[["X", "Y"]].to_numpy(dtype=np.float64)
+    r_xy = ref_df[["X", "Y"]].to_numpy(dtype=np.float64)
+    violations = violations_from_mask(mask, tri, match_j, a_xy, r_xy, list(triangle_info.keys()), len(triangle_info))
+    violation_points = set(violations["points_with_violations"])
+    penalty_points = set()
+    for t in np.flatnonzero(np.asarray(res.q) > 1e-6):                                             # same.py:1325-1346
+        penalty_points.update(int(v) for v in tri[t])
+    points_both = violation_points & penalty_points
+    matched_bits = (mask >> 8) & 7
+    var_out = {
+        "x": x.tolist(), "no_match_vars": np.asarray(res.no_match).tolist(), "penalty_vars": np.asarray(res.penalty).tolist(),
+        "area_penalty_vars": np.asarray(res.q).tolist(), "violations": violations,
+        "violation_penalty_comparison": {"points_both": list(points_both), "points_only_violations": list(violation_points - penalty_points),
+                                         "points_only_penalties": list(penalty_points - violation_points)},
+        "triangle_data": {
+            "triangles": aligned_delaunay, "triangle_info": triangle_info, "aligned_simplex_map": aligned_simplex_map,
+            "areas_before": {t: area_before[t] for t in range(T)},
+            "areas_after": {t: (None if np.isnan(area_after[t]) else area_after[t]) for t in range(T)},
+            "flipped_triangles": [int(t) for t in flipped],
+            "matched_vertices": {t: [bool(matched_bits[t] & 1), bool(matched_bits[t] & 2), bool(matched_bits[t] & 4)] for t in range(T)}},
+        "lazy_constraints": lazy, "lazy_cuts_added": res.cuts_added if lazy else 0,
+    }
+    if outprefix:                                                                                  # same.py:1455-1463
+        os.makedirs(outprefix, exist_ok=True)
+        np.save(os.path.join(outprefix, "var_out.npy"), var_out, allow_pickle=True)
+        aligned_df.to_csv(os.path.join(outprefix, "aligned_df.csv"), index=False)
+        ref_df.to_csv(os.path.join(outprefix, "ref_df.csv"), index=False)
+    flipped_nodes = set(int(v) for t in flipped for v in tri[t])                                   # same.py:1466-1472
+    out_df["triangle_violation"] = out_df["aligned_idx"].isin(flipped_nodes)
+    out_df["filtered_violation"] = out_df["aligned_idx"].isin(points_both)
+    out_df["run_time"] = res.runtime
+    if outprefix:
+        out_df.to_csv(os.path.join(outprefix, "matches_df.csv"), index=False)
+    return out_df, var_out
+
+
+def _prepare_frames(ref_df, aligned_df, aligned_delaunay_vertex_col):
+    """`size`, `__orig_idx`, `__tri_vid` helper columns on copies (src/same.py:934-970)."""
+    if "size" not in aligned_df.columns:
+        aligned_df = aligned_df.copy()
+        aligned_df["size"] = 1
+    if "size" not in ref_df.columns:
+        ref_df = ref_df.copy()
+        ref_df["size"] = 1
+    aligned_df, ref_df = aligned_df.copy(), ref_df.copy()
+    if "__orig_idx" not in aligned_df.columns:
+        aligned_df["__orig_idx"] = aligned_df.index.to_numpy()
+    if "__orig_idx" not in ref_df.columns:
+        ref_df["__orig_idx"] = ref_df.index.to_numpy()
+    if aligned_delaunay_vertex_col is None:
+        aligned_df["__tri_vid"] = aligned_df.index.to_numpy()
+    else:
+        if aligned_delaunay_vertex_col not in aligned_df.columns:
+            raise ValueError(f"aligned_delaunay_vertex_col='{aligned_delaunay_vertex_col}' not in aligned_df")
+        aligned_df["__tri_vid"] = aligned_df[aligned_delaunay_vertex_col].to_numpy()
+    return ref_df, aligned_df
+
+
+def run_same(ref_df, aligned_df, commonCT, outprefix=None, aligned_delaunay=None, aligned_delaunay_vertex_col=None,
+             optim_params: Optional[Dict[str, Any]] = None, gurobi_params: Optional[Dict[str, Any]] = None,
+             ignore_precomputed_triangulation: bool = False, solver=None):
+    """Optimal spatial matches between aligned and reference cells (reference `run_same`, src/same.py:706-1489).
+
+    Same arguments, DataFrame contract, return value `(matches_df, var_out)` and error behaviour as the reference;
+    `solver` (extra, optional) selects the host MIP back-end (`'gurobi'` default, `'highs'`, or an object)."""
+    if gurobi_params is None:
+        gurobi_params = {}
+    if optim_params is None:
+        optim_params = {}
+    if hasattr(aligned_df, "metacell_df") and hasattr(aligned_df, "metacell_delaunay"):          # same.py:891-900
+        mc = aligned_df
+        aligned_df = mc.metacell_df
+        if aligned_delaunay is None and not ignore_precomputed_triangulation:
+            aligned_delaunay = mc.metacell_delaunay
+        if aligned_delaunay_vertex_col is None and hasattr(mc, "metacell_idx_col"):
+            aligned_delaunay_vertex_col = mc.metacell_idx_col
+        if (optim_params.get("cell_id_col") is None) and hasattr(mc, "metacell_idx_col"):
+            optim_params["cell_id_col"] = mc.metacell_idx_col
+    if hasattr(ref_df, "metacell_df"):
+        ref_df = ref_df.metacell_df
+    optim = init_optim_params(**(optim_params or {}))
+    gurobi = init_gurobi_params(**gurobi_params)
+    ref_df, aligned_df = _prepare_frames(ref_df, aligned_df, aligned_delaunay_vertex_col)
+    vid = aligned_df["__tri_vid"].to_numpy()
+    run = _Run(aligned_df, ref_df, commonCT, optim, rects=None, aligned_delaunay=aligned_delaunay,
+               vertex_ids=None if aligned_delaunay is None else vid.astype(np.int64),
+               ignore_precomputed=ignore_precomputed_triangulation)
+    try:
+        return _solve_window(run, 0, aligned_df, ref_df, optim, gurobi, outprefix, get_backend(solver))
+    finally:
+        run.close()
+
+
+def sliding_window_matching(ref, moving, commonCT=None, outprefix=None, moving_delaunay=None, moving_delaunay_vertex_col=None,
+                            optim_params: Optional[Dict[str, Any]] = None, gurobi_params: Optional[Dict[str, Any]] = None,
+                            ignore_precomputed_triangulation: bool = False, solver=None, window_shard=None):
+    """Sliding-window matching (reference `sliding_window_matching`, src/same.py:297-595): same window grid, merge
+    rule, central-region ownership, `window_id` and CSV checkpoint/resume.  All runnable windows are cut, searched
+    and tabulated on the GPU as ONE batch; the per-window MIPs then run on the host in the reference's order.
+
+    `window_shard=(rank, world_size)` (extra, optional) restricts this process to its contiguous block of the
+    window list (one process per GPU; results are concatenated by the caller)."""
+    ref_cell_type_col = moving_cell_type_col = "cell_type"
+    if optim_params is None:
+        optim_params = {}
+    if gurobi_params is None:
+        gurobi_params = {}
+    if hasattr(ref, "metacell_df"):                                                                # same.py:415-421
+        mc_ref = ref
+        ref = mc_ref.metacell_df
+        if hasattr(mc_ref, "cell_type_col"):
+            ref_cell_type_col = mc_ref.cell_type_col
+        if (optim_params.get("cell_id_col") is None) and hasattr(mc_ref, "metacell_idx_col"):
+            optim_params["cell_id_col"] = mc_ref.metacell_idx_col
+    if hasattr(moving, "metacell_df") and hasattr(moving, "metacell_delaunay"):                    # same.py:422-432
+        mc = moving
+        moving = mc.metacell_df
+        if moving_delaunay is None and not ignore_precomputed_triangulation:
+            moving_delaunay = mc.metacell_delaunay
+        if moving_delaunay_vertex_col is None and hasattr(mc, "metacell_idx_col"):
+            moving_delaunay_vertex_col = mc.metacell_idx_col
+        if hasattr(mc, "cell_type_col"):
+            moving_cell_type_col = mc.cell_type_col
+        if (optim_params.get("cell_id_col") is None) and hasattr(mc, "metacell_idx_col"):
+            optim_params["cell_id_col"] = mc.metacell_idx_col
+    optim = init_optim_params(**(optim_params or {}))
+    gurobi = init_gurobi_params(**(gurobi_params or {}))
+    window_size, overlap = optim["window_size"], optim["overlap"]
+    min_cells, cell_id_col = optim["min_cells_per_window"], optim["cell_id_col"]
+
+    ref_types = mov_types = None                                                                   # same.py:445-458
+    if ref_cell_type_col in ref.columns and moving_cell_type_col in moving.columns:
+        ref_types = set(pd.Series(ref[ref_cell_type_col]).dropna().unique().tolist())
+        mov_types = set(pd.Series(moving[moving_cell_type_col]).dropna().unique().tolist())
+        if ref_types != mov_types:
+            raise ValueError(
+                f"Cell type categories differ between ref and moving.\n"
+                f"ref ({ref_cell_type_col}) has {len(ref_types)} types, moving ({moving_cell_type_col}) has {len(mov_types)} types.\n"
+                f"Only-in-ref: {sorted(ref_types - mov_types)[:20]}\n"
+                f"Only-in-moving: {sorted(mov_types - ref_types)[:20]}")
+    if commonCT is None:                                                                           # same.py:462-478
+        if ref_types is None:
+            raise ValueError("commonCT is None, but cell_type columns were not found to infer it. Pass commonCT explicitly "
+                             f"(list of probability/one-hot columns), or ensure both dataframes have "
+                             f"'{ref_cell_type_col}'/'{moving_cell_type_col}'.")
+        commonCT = sorted(ref_types)
+        missing_ref = [c for c in commonCT if c not in ref.columns]
+        missing_mov = [c for c in commonCT if c not in moving.columns]
+        if missing_ref or missing_mov:
+            raise ValueError("commonCT is None so it was inferred as the unique values of the cell_type column, but those names are "
+                             f"not present as probability/one-hot columns.\nMissing in ref columns (first 20): {missing_ref[:20]}\n"
+                             f"Missing in moving columns (first 20): {missing_mov[:20]}\nEither rename your probability columns to "
+                             "match cell type names, or pass commonCT explicitly.")
+
+    x_min, x_max = min(ref["X"].min(), moving["X"].min()), max(ref["X"].max(), moving["X"].max())  # same.py:481-488
+    y_min, y_max = min(ref["Y"].min(), moving["Y"].min()), max(ref["Y"].max(), moving["Y"].max())
+    x_windows, y_windows = WN.window_grid(x_min, x_max, y_min, y_max, window_size, overlap)
+    all_matches: List[pd.DataFrame] = []
+    output_file = None
+    if outprefix:
+        os.makedirs(outprefix, exist_ok=True)
+        output_file = os.path.join(outprefix, "matchedDF.csv")
+
+    ref_p, mov_p = _prepare_frames(ref, moving, moving_delaunay_vertex_col)
+    # cell counts of every rectangle the merge rule may ask for: one GPU launch (same.py:523-542)
+    section = build_section(mov_p, ref_p, commonCT)
+    rects, keys = WN.candidate_rects(x_windows, y_windows, window_size)
+    cnt_mov, cnt_ref = np.zeros(len(rects), np.int64), np.zeros(len(rects), np.int64)
+    for lo in range(0, len(rects), 60000):
+        a, r = section.count_rects(rects[lo:lo + 60000])
+        cnt_mov[lo:lo + 60000], cnt_ref[lo:lo + 60000] = a, r
+    counter = WN.table_counter(keys, cnt_ref, cnt_mov)
+    windows_to_process = None
+    if outprefix:                                                                                  # same.py:497-501
+        base_counts = {(i, j): int(cnt_mov[keys[(x, x + window_size, y, y + window_size)]])
+                       for i, x in enumerate(x_windows) for j, y in enumerate(y_windows)}
+        windows_to_process, existing = H.get_unprocessed_windows(moving, output_file, x_windows, y_windows, window_size, overlap,
+                                                                 cell_id_col=cell_id_col, counts=base_counts)
+        if existing is not None:
+            all_matches.append(existing)
+    wins = WN.enumerate_windows(x_windows, y_windows, window_size, overlap, min_cells, counter,
+                                (int(x_min), int(x_max), int(y_min), int(y_max)), windows_to_process)
+    runnable = [wd for wd in wins if wd.run]
+    if window_shard is not None:
+        lo, hi = WN.shard_windows(len(runnable), window_shard[1], window_shard[0])
+        runnable = runnable[lo:hi]
+    if not runnable:
+        section.close()
+        return pd.concat(all_matches, ignore_index=True) if all_matches else pd.DataFrame()
+
+    vid = mov_p["__tri_vid"].to_numpy()
+    run = _Run(mov_p, ref_p, commonCT, optim, rects=np.asarray([wd.rect for wd in runnable], dtype=np.float64),
+               aligned_delaunay=moving_delaunay, vertex_ids=None if moving_delaunay is None else vid.astype(np.int64),
+               ignore_precomputed=ignore_precomputed_triangulation, section=section)
+    backend = get_backend(solver)
+    try:
+        for w, wd in enumerate(runnable):
+            window_outprefix = os.path.join(outprefix, f"window_{wd.window_id}") if outprefix else None
+            window_matches, _ = _solve_window(run, w, mov_p, ref_p, optim, gurobi, window_outprefix, backend)
+            if window_matches.shape[0] > 0:                                                        # same.py:564-590
+                cx0, cx1, cy0, cy1 = wd.central
+                central = window_matches[(window_matches["X"] >= cx0) & (window_matches["X"] < cx1) &
+                                         (window_matches["Y"] >= cy0) & (window_matches["Y"] < cy1)].copy()
+                central["window_id"] = wd.window_id
+                if len(central) > 0:
+                    all_matches.append(central)
+                    if outprefix:
+                        pd.concat(all_matches, ignore_index=True).to_csv(output_file, index=False)
+    finally:
+        run.close()
+    return pd.concat(all_matches, ignore_index=True) if all_matches else pd.DataFrame()

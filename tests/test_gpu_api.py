@@ -1,0 +1,238 @@
+"""Drop-in parity of the public API on the GPU: `run_same` / `sliding_window_matching` of same_b200 against the golden
+records of the UNMODIFIED reference (tests/golden/gen_golden.py).  Both sides talk to the same recording fake
+`gurobipy` (oracle/ref_loader.py): every variable, objective coefficient, constraint (names, order, members) and lazy
+cut is compared, then the returned matches frame column by column."""
+import os
+import sys
+
+import numpy as np
+import pandas as pd
+import pytest
+
+from tests.util import GOLDEN_CASES, golden_frame, golden_params, incumbent_rule, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture()
+def fake_gurobi():
+    from oracle import ref_loader
+    saved = sys.modules.get("gurobipy")
+    ref_loader.install_stubs()
+    Model = ref_loader.Model
+    if not hasattr(Model, "_orig_optimize"):
+        Model._orig_optimize = Model.optimize
+
+    def optimize(self, callback=None):   # same rule as gen_golden.patched_optimize
+        Model._orig_optimize(self, callback)
+        for terms, sense, rhs in self.lazy:
+            for k, v in terms.items():
+                if v < 0:
+                    self.vars[k].x = 1.0
+    Model.optimize = optimize
+    ref_loader.MODELS.clear()
+    yield ref_loader
+    Model.optimize = Model._orig_optimize
+    ref_loader.INCUMBENT_FN = None
+    if saved is not None:
+        sys.modules["gurobipy"] = saved
+    else:
+        sys.modules.pop("gurobipy", None)
+
+
+def _incumbent_fn(seed):
+    def fn(model):
+        rp = np.asarray(model._row_ptr)
+        rows = np.repeat(np.arange(len(rp) - 1), np.diff(rp))
+        return incumbent_rule(np.column_stack([rows, rows]), seed)
+    return fn
+
+
+def _record(model):
+    xs = [v.index for v in model.vars if v.VarName.startswith("x[")]
+    qs = [v.index for v in model.vars if v.VarName.startswith("q_tri[")]
+    pen = [v.index for v in model.vars if v.VarName.startswith("penalty[")]
+    nom = [v.index for v in model.vars if v.VarName.startswith("no_match[")]
+    obj = model.objective[0].terms
+    out = dict(cost=np.array([obj.get(i, 0.0) for i in xs]), obj_q=np.array([obj.get(i, 0.0) for i in qs]),
+               obj_penalty=np.array([obj.get(i, 0.0) for i in pen]), obj_no_match=np.array([obj.get(i, 0.0) for i in nom]),
+               n_vars=len(model.vars))
+    cname, csense, crhs, cptr, cidx, cval = [], [], [], [0], [], []
+    for nm, sense, terms, rhs in model.constrs:
+        cname.append(nm); csense.append(sense); crhs.append(rhs)
+        cidx.extend(terms.keys()); cval.extend(terms.values()); cptr.append(len(cidx))
+    out.update(con_name=np.asarray(cname), con_sense=np.asarray(csense), con_rhs=np.asarray(crhs, dtype=float), con_ptr=np.asarray(cptr),
+               con_idx=np.asarray(cidx), con_val=np.asarray(cval, dtype=float))
+    cuts = []
+    for terms, sense, rhs in model.lazy:
+        p = [k for k, v in terms.items() if v > 0]
+        q = [k for k, v in terms.items() if v < 0]
+        cuts.append([xs.index(p[0]), xs.index(p[1]), xs.index(p[2]), qs.index(q[0])])
+    out["cuts"] = np.asarray(cuts, dtype=np.int64).reshape(-1, 4)
+    return out
+
+
+def _compare_models(ref_loader, g):
+    assert len(ref_loader.MODELS) == int(g["n_models"])
+    for w, model in enumerate(ref_loader.MODELS):
+        rec = _record(model)
+        for k, v in rec.items():
+            want = g[f"w{w}_{k}"]
+            if k == "n_vars":
+                assert v == int(want), (w, k)
+            else:
+                assert np.array_equal(v, want), (w, k)
+
+
+def _compare_matches(got: pd.DataFrame, g):
+    cols = [str(c) for c in g["matches_columns"]]
+    assert list(got.columns) == cols
+    for c in cols:
+        want = g[f"matches__{c}"]
+        have = got[c].to_numpy()
+        if c == "run_time":
+            continue
+        if have.dtype == object:
+            have = have.astype("U")
+        assert np.array_equal(have, want), c
+
+
+def _mc_params(g):
+    return dict(max_metacell_size=1, r_max=5, min_angle_deg=5, use_alpha_shape=False, alpha=None)
+
+
+@pytest.mark.parametrize("case", GOLDEN_CASES)
+def test_public_api_vs_reference(case, fake_gurobi, tmp_path):
+    import same_b200
+    g = load_golden(case)
+    ref_df, al_df = golden_frame(g, "ref"), golden_frame(g, "aligned")
+    ct = [str(c) for c in g["commonCT"]]
+    optim, gurobi = golden_params(g, "optim"), golden_params(g, "gurobi")
+    id_col = str(g["id_col"])
+    fake_gurobi.INCUMBENT_FN = _incumbent_fn(int(g["seed"]))
+    sliding = case in ("fig2_script", "tiles4_sliding", "sparse_merge")
+    cwd = os.getcwd()
+    os.chdir(tmp_path)
+    try:
+        if case == "fig2_script":
+            mc_al = same_b200.greedy_triangle_collapse(al_df, cell_type_col="cell_type", original_idx_col=id_col, return_object=True, **_mc_params(g))
+            mc_rf = same_b200.greedy_triangle_collapse(ref_df, cell_type_col="cell_type", original_idx_col=id_col, return_object=True, **_mc_params(g))
+            assert np.array_equal(np.asarray(mc_al.metacell_delaunay, dtype=np.int64), g["mc_aligned_delaunay"])
+            got = same_b200.sliding_window_matching(mc_rf, mc_al, commonCT=ct, outprefix=str(tmp_path / "out"), optim_params=dict(optim),
+                                                    gurobi_params=dict(gurobi))
+        elif sliding:
+            got = same_b200.sliding_window_matching(ref_df, al_df, commonCT=ct, outprefix=str(tmp_path / "out"), optim_params=dict(optim),
+                                                    gurobi_params=dict(gurobi))
+        else:
+            got, var_out = same_b200.run_same(ref_df, al_df, ct, outprefix=None, optim_params=dict(optim), gurobi_params=dict(gurobi))
+    finally:
+        os.chdir(cwd)
+    _compare_models(fake_gurobi, g)
+    _compare_matches(got, g)
+    if not sliding:
+        td = var_out["triangle_data"]
+        T = len(td["triangles"])
+        assert np.array_equal(np.array([td["areas_before"][t] for t in range(T)]), g["vo_areas_before"])
+        assert np.array_equal(np.asarray(td["flipped_triangles"], dtype=np.int64), g["vo_flipped"])
+        assert np.array_equal(np.asarray(list(td["triangle_info"].keys()), dtype=np.int64), g["vo_tri_info_order"])
+        vio = var_out["violations"]
+        s = vio["violation_summary"]
+        assert [s["total_triangles"], s["violated_triangles"], s["total_comparisons"], s["total_violations"]] == g["vo_summary"].tolist()
+        assert np.allclose([s["percent_triangles_violated"], s["percent_violations"]], g["vo_percent"], rtol=0, atol=0)
+        xv = np.asarray([[d["triangle_idx"], d["point1"]["aligned_idx"], d["point2"]["aligned_idx"]] for d in vio["x_order_violations"]],
+                        dtype=np.int64).reshape(-1, 3)
+        yv = np.asarray([[d["triangle_idx"], d["point1"]["aligned_idx"], d["point2"]["aligned_idx"]] for d in vio["y_order_violations"]],
+                        dtype=np.int64).reshape(-1, 3)
+        assert np.array_equal(xv, g["vo_xviol"]) and np.array_equal(yv, g["vo_yviol"])
+        assert sorted(vio["triangles_with_violations"]) == g["vo_tri_with_viol"].tolist()
+        assert sorted(int(p) for p in vio["points_with_violations"]) == g["vo_pts_with_viol"].tolist()
+        assert var_out["lazy_cuts_added"] == int(g["vo_lazy_cuts_added"])
+        assert sorted(var_out["violation_penalty_comparison"]["points_both"]) == g["vo_points_both"].tolist()
+
+
+def test_sliding_resume_from_checkpoint(fake_gurobi, tmp_path):
+    """CSV checkpoint/resume (same.py:497-515, helpers.py:21-70): a second call skips windows already in matchedDF.csv."""
+    import same_b200
+    g = load_golden("tiles4_sliding")
+    ref_df, al_df = golden_frame(g, "ref"), golden_frame(g, "aligned")
+    ct = [str(c) for c in g["commonCT"]]
+    optim, gurobi = golden_params(g, "optim"), golden_params(g, "gurobi")
+    fake_gurobi.INCUMBENT_FN = _incumbent_fn(int(g["seed"]))
+    out = str(tmp_path / "out")
+    cwd = os.getcwd()
+    os.chdir(tmp_path)
+    try:
+        full = same_b200.sliding_window_matching(ref_df, al_df, commonCT=ct, outprefix=out, optim_params=dict(optim), gurobi_params=dict(gurobi))
+        n_models = len(fake_gurobi.MODELS)
+        saved = pd.read_csv(os.path.join(out, "matchedDF.csv"))
+        keep_ids = sorted(saved["window_id"].unique())[:4]
+        saved[saved["window_id"].isin(keep_ids)].to_csv(os.path.join(out, "matchedDF.csv"), index=False)
+        fake_gurobi.MODELS.clear()
+        again = same_b200.sliding_window_matching(ref_df, al_df, commonCT=ct, outprefix=out, optim_params=dict(optim), gurobi_params=dict(gurobi))
+    finally:
+        os.chdir(cwd)
+    assert len(fake_gurobi.MODELS) == n_models - len(keep_ids)
+    assert len(again) == len(full)
+    key = ["window_id", "aligned_idx", "ref_idx"]
+    a = full.sort_values(key).reset_index(drop=True)[key]
+    b = again.sort_values(key).reset_index(drop=True)[key]
+    assert a.equals(b.astype(a.dtypes.to_dict()))
+
+
+def test_window_shard_union_equals_full(fake_gurobi, tmp_path):
+    """Multi-GPU contract: the union of the rank shards equals the single-process result."""
+    import same_b200
+    g = load_golden("tiles4_sliding")
+    ref_df, al_df = golden_frame(g, "ref"), golden_frame(g, "aligned")
+    ct = [str(c) for c in g["commonCT"]]
+    optim, gurobi = golden_params(g, "optim"), golden_params(g, "gurobi")
+    fake_gurobi.INCUMBENT_FN = _incumbent_fn(int(g["seed"]))
+    cwd = os.getcwd()
+    os.chdir(tmp_path)
+    try:
+        full = same_b200.sliding_window_matching(ref_df, al_df, commonCT=ct, optim_params=dict(optim), gurobi_params=dict(gurobi))
+        parts = [same_b200.sliding_window_matching(ref_df, al_df, commonCT=ct, optim_params=dict(optim), gurobi_params=dict(gurobi),
+                                                   window_shard=(r, 3)) for r in range(3)]
+    finally:
+        os.chdir(cwd)
+    merged = pd.concat(parts, ignore_index=True)
+    assert merged.drop(columns=["run_time"]).equals(full.drop(columns=["run_time"]))
+
+
+def test_mirror_functions(fake_gurobi):
+    """The helper functions keep the reference's signatures and results."""
+    from same_b200.helpers import filter_triangles_by_radius
+    from same_b200.knn_utils import find_knn_with_cell_type_priority
+    from same_b200.same import _remap_triangles_by_vertex_ids
+    from same_b200.utils import find_knn_within_radius
+    g = load_golden("fig2_direct")
+    o = golden_params(g, "optim")
+    ref_df, al_df = golden_frame(g, "ref"), golden_frame(g, "aligned")
+    a1, r1, pairs = find_knn_within_radius(al_df, ref_df, radius=o["radius"], knn=int(o["knn"]))
+    assert np.array_equal(pairs, g["knn_pairs"]) and len(a1) == len(g["knn_keepA"]) and list(a1.index) == list(range(len(a1)))
+    a2, r2, pp = find_knn_with_cell_type_priority(al_df, ref_df, o["radius"], knn=int(o["knn"]))
+    assert np.array_equal(np.asarray(pp), g["prio_pairs"])
+    pts = a1[["X", "Y"]].values
+    kept, unc = filter_triangles_by_radius(pts, g["delaunay"], float(g["filt_tight_radius"]), aligned_df=a1, ignore_same_type_triangles=True,
+                                           remove_unconstrained_nodes=True, min_angle_deg=o["min_angle_deg"])
+    assert np.array_equal(np.asarray(kept).reshape(-1, 3), g["filt_tight"]) and sorted(unc) == g["filt_tight_unc"].tolist()
+    out = _remap_triangles_by_vertex_ids(g["remap_tri_global"], g["remap_vid_all"][g["remap_rows"]])
+    assert np.array_equal(out, g["remap_out"])
+
+
+def test_errors(fake_gurobi):
+    import same_b200
+    g = load_golden("fig2_direct")
+    ref_df, al_df = golden_frame(g, "ref"), golden_frame(g, "aligned")
+    ct = [str(c) for c in g["commonCT"]]
+    with pytest.raises(ValueError, match="No valid_pairs"):
+        same_b200.run_same(ref_df, al_df, ct, optim_params=dict(radius=1e-9, knn=3, cell_id_col="cell_idx"))
+    bad = ref_df.copy()
+    bad["cell_type"] = "zzz"
+    with pytest.raises(ValueError, match="Cell type categories differ"):
+        same_b200.sliding_window_matching(bad, al_df, commonCT=ct, optim_params=dict(cell_id_col="cell_idx"))
+    with pytest.raises(ValueError, match="not in aligned_df"):
+        same_b200.run_same(ref_df, al_df, ct, aligned_delaunay=np.zeros((1, 3), int), aligned_delaunay_vertex_col="nope",
+                           optim_params=dict(cell_id_col="cell_idx"))
+    with pytest.raises(ValueError, match="shape"):
+        same_b200.run_same(ref_df, al_df, ct, aligned_delaunay=np.zeros((4, 2), int), optim_params=dict(cell_id_col="cell_idx", radius=1.2))

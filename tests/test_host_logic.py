@@ -1,0 +1,184 @@
+"""CPU tests of the host-side logic: parameter dictionaries, the sliding-window walk, metacell triangulation,
+sharding + the two small collectives (gloo, world_size 2)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pandas as pd
+import pytest
+
+from tests.util import golden_frame, golden_params, load_golden
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_param_defaults_are_the_reference_contract():
+    from same_b200 import init_gurobi_params, init_optim_params
+    assert init_optim_params() == {
+        "window_size": 1000, "overlap": 250, "min_cells_per_window": 10, "max_matches": 1, "ref_metacell_match_multiplier": None,
+        "radius": 250, "penalty_coeff": 100, "no_match_penalty": 100, "delaunay_penalty": 5, "dist_ct_coeff": 1, "knn": 8,
+        "cell_id_col": "Cell_Num_Old", "hard_spatial_constraints": False, "ignore_same_type_triangles": True,
+        "ignore_knn_if_matched": False, "lazy_constraints": True, "min_angle_deg": 15}
+    assert init_gurobi_params() == {
+        "time_limit": 7200, "mip_gap": 0.05, "mip_focus": 2, "cuts": 2, "heuristics": 0.1, "init_method": None, "init_big_m": 1e9,
+        "init_hungarian_max_n": 5000, "lazy_max_cuts": None, "lazy_allowed_flip_fraction": 0.05, "lazy_max_cuts_per_incumbent": 1000}
+    assert init_optim_params(radius=5, knn=3)["radius"] == 5 and init_gurobi_params(time_limit=1)["time_limit"] == 1
+
+
+def test_public_names():
+    import same_b200
+    for n in ["init_gurobi_params", "init_optim_params", "sliding_window_matching", "run_same", "merge_window_matches_unique_ref",
+              "MetaCell", "greedy_triangle_collapse", "unpack_metacell_matches"]:
+        assert n in same_b200.__all__ and callable(getattr(same_b200, n))
+
+
+@pytest.mark.parametrize("case", ["tiles4_sliding", "sparse_merge", "fig2_script"])
+def test_window_walk_matches_reference(case):
+    """enumerate_windows reproduces the reference's grid walk incl. the small-window merge rule: the windows it runs are
+    exactly the models the reference built, and every window_id in the reference's output is one of ours."""
+    from same_b200 import windows as WN
+    g = load_golden(case)
+    o = golden_params(g, "optim")
+    rxy, axy = g["ref_xy"], g["aligned_xy"]
+    x_min, x_max = min(rxy[:, 0].min(), axy[:, 0].min()), max(rxy[:, 0].max(), axy[:, 0].max())
+    y_min, y_max = min(rxy[:, 1].min(), axy[:, 1].min()), max(rxy[:, 1].max(), axy[:, 1].max())
+    xw, yw = WN.window_grid(x_min, x_max, y_min, y_max, int(o["window_size"]), int(o["overlap"]))
+    count = WN.numpy_counter(rxy, axy)
+    wins = WN.enumerate_windows(xw, yw, int(o["window_size"]), int(o["overlap"]), int(o["min_cells_per_window"]), count,
+                                (int(x_min), int(x_max), int(y_min), int(y_max)))
+    runnable = [w for w in wins if w.run]
+    assert len(runnable) == int(g["n_models"])
+    ids = [w.window_id for w in runnable]
+    assert set(np.unique(g["matches__window_id"]).tolist()) <= set(ids)
+    # the batched GPU counter sees the same rectangles
+    rects, keys = WN.candidate_rects(xw, yw, int(o["window_size"]))
+    cr = np.array([count(tuple(r))[0] for r in rects])
+    ca = np.array([count(tuple(r))[1] for r in rects])
+    wins2 = WN.enumerate_windows(xw, yw, int(o["window_size"]), int(o["overlap"]), int(o["min_cells_per_window"]),
+                                 WN.table_counter(keys, cr, ca), (int(x_min), int(x_max), int(y_min), int(y_max)))
+    assert [(w.i, w.j, w.rect, w.window_id, w.central, w.run) for w in wins] == [(w.i, w.j, w.rect, w.window_id, w.central, w.run) for w in wins2]
+    # per-window pair counts of the reference = number of x variables of each model; sizes sanity
+    for k, w in enumerate(runnable):
+        assert w.n_ref >= int(o["min_cells_per_window"]) and w.n_moving >= int(o["min_cells_per_window"])
+
+
+def test_sparse_merge_case_really_merges():
+    from same_b200 import windows as WN
+    g = load_golden("sparse_merge")
+    o = golden_params(g, "optim")
+    rxy, axy = g["ref_xy"], g["aligned_xy"]
+    x_min, x_max = min(rxy[:, 0].min(), axy[:, 0].min()), max(rxy[:, 0].max(), axy[:, 0].max())
+    y_min, y_max = min(rxy[:, 1].min(), axy[:, 1].min()), max(rxy[:, 1].max(), axy[:, 1].max())
+    xw, yw = WN.window_grid(x_min, x_max, y_min, y_max, int(o["window_size"]), int(o["overlap"]))
+    wins = WN.enumerate_windows(xw, yw, int(o["window_size"]), int(o["overlap"]), int(o["min_cells_per_window"]), WN.numpy_counter(rxy, axy),
+                                (int(x_min), int(x_max), int(y_min), int(y_max)))
+    ws = int(o["window_size"])
+    assert any((w.rect[1] - w.rect[0] > ws) or (w.rect[3] - w.rect[2] > ws) for w in wins), "fixture should trigger the merge rule"
+
+
+def test_metacell_size1_triangulation_matches_reference():
+    """greedy_triangle_collapse(max_metacell_size=1) only filters the Delaunay triangulation (examples/synthetic/run_same.sh:85-95)."""
+    import same_b200
+    g = load_golden("fig2_script")
+    al = golden_frame(g, "aligned")
+    mc = same_b200.greedy_triangle_collapse(al, cell_type_col="cell_type", original_idx_col=str(g["id_col"]), return_object=True,
+                                            max_metacell_size=1, r_max=5, min_angle_deg=5, use_alpha_shape=False, alpha=None)
+    assert np.array_equal(np.asarray(mc.metacell_delaunay, dtype=np.int64), g["mc_aligned_delaunay"])
+    assert np.array_equal(mc.metacell_df["metacell_id"].to_numpy(), g["mc_aligned_metacell_id"])
+    assert list(mc.metacell_df["size"].unique()) == [1] and mc.metacell_idx_col == "metacell_id"
+    assert mc.metacell_members(3) == [al[str(g["id_col"])].iloc[3]]
+
+
+def test_metacell_collapse_and_unpack_roundtrip():
+    import same_b200
+    from same_b200 import datagen
+    ref, qry, ct = datagen.make_section_pair(n_tiles=1, seed=3)
+    mdf, tri = same_b200.greedy_triangle_collapse(qry, max_metacell_size=3, r_max=1.5, min_angle_deg=10)
+    assert mdf["size"].sum() == len(qry) and mdf["size"].max() <= 3 and len(mdf) < len(qry)
+    members = sorted(m for ms in mdf["members"] for m in ms)
+    assert members == sorted(qry["Cell_Num_Old"].tolist())
+    big = mdf[mdf["size"] == 3].iloc[0]
+    sub = qry.set_index("Cell_Num_Old").loc[big["members"]]
+    assert np.isclose(big["X"], sub["X"].mean()) and np.isclose(big["c1"], sub["c1"].mean()) and len(set(sub["cell_type"])) == 1
+    matches = pd.DataFrame({"Aligned_metacell_id": [0, int(big["metacell_id"])], "Ref_metacell_id": [5, 7]})
+    ind = same_b200.unpack_metacell_matches(matches, mdf, ref)
+    assert len(ind) == len(mdf.iloc[0]["members"]) + 3 and set(ind["Ref_cell_id"]) == {5, 7}
+
+
+def test_merge_window_matches_unique_ref():
+    import same_b200
+    a = pd.DataFrame({"window_id": [0, 0], "Aligned_Cell_Num_Old": [1, 2], "Ref_Cell_Num_Old": [10, 10], "X": 0.0, "Y": 0.0,
+                      "filtered_violation": [False, False]})
+    b = pd.DataFrame({"window_id": [1, 1], "Aligned_Cell_Num_Old": [2, 3], "Ref_Cell_Num_Old": [11, 11], "X": 0.0, "Y": 0.0,
+                      "filtered_violation": [True, False]})
+    out = same_b200.merge_window_matches_unique_ref([a, b])
+    assert out["Aligned_Cell_Num_Old"].is_unique and out["Ref_Cell_Num_Old"].is_unique and len(out) == 2
+    assert same_b200.merge_window_matches_unique_ref([]).empty
+
+
+def test_shard_windows_partitions():
+    from same_b200.windows import shard_windows
+    for n in (0, 1, 7, 49, 392):
+        for world in (1, 2, 3, 8):
+            blocks = [shard_windows(n, world, r) for r in range(world)]
+            assert blocks[0][0] == 0 and blocks[-1][1] == n
+            assert all(blocks[r][1] == blocks[r + 1][0] for r in range(world - 1))
+            sizes = [b - a for a, b in blocks]
+            assert max(sizes) - min(sizes) <= 1
+
+
+# ---- gloo, world_size 2 ---------------------------------------------------------------------------------
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        sys.path.insert(0, ROOT)
+        from same_b200 import sharding as S
+        from same_b200.windows import shard_windows
+        # each rank owns a strip of 100 units; rows below strip_lo + 30 are the border band its predecessor needs
+        rng = np.random.default_rng(rank)
+        n = 50 + 10 * rank
+        xy = np.column_stack([rng.uniform(0, 100, n), rng.uniform(100 * rank, 100 * (rank + 1), n)])
+        val = np.arange(n, dtype=np.float64)[:, None] + 1000 * rank
+        halo, info = S.exchange_halo({"xy": xy, "val": val, "y": xy[:, 1:2]}, "y", 100 * rank + 30.0)
+        lo, hi = shard_windows(7, world, rank)
+        local = pd.DataFrame({"window_id": list(range(lo, hi)), "rank": rank})
+        merged = S.gather_matches(local)
+        q.put((rank, halo["xy"], halo["val"], info, merged, xy, val))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gloo_halo_exchange_and_gather():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = {}
+    for _ in range(2):
+        r = q.get(timeout=120)
+        res[r[0]] = r
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    # rank 0 received exactly rank 1's border band; the last rank receives nothing
+    xy1, val1 = res[1][5], res[1][6]
+    band = xy1[:, 1] < 130.0
+    assert np.array_equal(res[0][1], xy1[band]) and np.array_equal(res[0][2], val1[band])
+    assert len(res[1][1]) == 0 and res[0][3]["rows"] == int(band.sum())
+    for r in (0, 1):
+        assert res[r][4]["window_id"].tolist() == list(range(7))
+        assert res[r][4]["rank"].tolist() == [0, 0, 0, 0, 1, 1, 1]
