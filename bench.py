@@ -356,6 +356,10 @@ def main():
         n_e2e = max(2, min(args.steps, 5))
         x_pin = pinned(x_dev["t"].cpu().numpy())                 # the incumbent comes from the host solver in real use
         saved = x_dev["t"]
+        s2 = make_section()                                      # one untimed pass: first-touch of the pinned result pool
+        x_dev["t"] = x_pin[0].to(device, non_blocking=True)
+        one_pass(s2, fetch=True)
+        s2.close()
         barrier()
         t0 = time.perf_counter()
         for _ in range(n_e2e):

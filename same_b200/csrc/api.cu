@@ -12,9 +12,11 @@ int guarded(F &&f) {
         return SAME_OK;
     } catch (const same::Error &e) {
         g_err = e.what();
+        cudaGetLastError();  // do not leave a non-sticky error pending for the next call
         return e.code;
     } catch (const std::exception &e) {
         g_err = e.what();
+        cudaGetLastError();
         return SAME_E_CUDA;
     }
 }

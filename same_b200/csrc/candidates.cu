@@ -514,7 +514,12 @@ void batch_groups(Batch *b, int max_matches, int multiplier) {
     b->g_off.assign(W + 1, 0);
     b->G = 0;
     b->have_groups = true;
-    if (P == 0) return;
+    if (P == 0) {  // keep REF_GROUP_PTR (G + 1 = 1 element) readable
+        b->g_ptr.alloc(1, s);
+        b->g_ptr.zero(s);
+        CK(cudaStreamSynchronize(s));
+        return;
+    }
     DevBuf<i32> first, vals, sorted_p, head, gid, goff;
     DevBuf<unsigned> keys, keys_out;
     DevBuf<unsigned long long> wmax;

@@ -44,6 +44,7 @@ struct Error : std::runtime_error {
 // CUDA events on the launching stream; same_profile_report() sums elapsed time per kernel name.
 struct ProfRec { const char *name; cudaEvent_t a, b; };
 extern bool g_prof;
+extern bool g_debug;  // SAME_B200_DEBUG=1: synchronise + check after every launch
 extern std::vector<ProfRec> g_prof_recs;
 struct ProfScope {
     ProfRec r{nullptr, nullptr, nullptr};
@@ -64,10 +65,17 @@ struct ProfScope {
 // every kernel launch goes through this macro so bench.py can report gpu_launches
 #define LAUNCH(kernel, grid, block, smem, stream, ...)                                                      \
     do {                                                                                                    \
+        if (same::g_debug) {                                                                                \
+            cudaError_t pre__ = cudaGetLastError();                                                         \
+            if (pre__ != cudaSuccess)                                                                       \
+                throw same::Error(SAME_E_CUDA, std::string("stale CUDA error before " #kernel ": ") + cudaGetErrorString(pre__) + \
+                                                   " (" + __FILE__ + ":" + std::to_string(__LINE__) + ")"); \
+        }                                                                                                   \
         same::ProfScope prof__(#kernel, (stream));                                                          \
         kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);                                         \
         same::g_launches.fetch_add(1, std::memory_order_relaxed);                                           \
         CK(cudaGetLastError());                                                                             \
+        if (same::g_debug) CK(cudaStreamSynchronize(stream));                                               \
     } while (0)
 
 inline unsigned blocks_for(i64 n, int per_block) { return (unsigned)std::max<i64>(1, (n + per_block - 1) / per_block); }

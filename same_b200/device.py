@@ -267,20 +267,23 @@ class WindowBatch:
         p0 = int(self.offsets(L.PAIRS)[w])
         out = dict(keepA=self.get_window(L.KEEP_A, w), keepR=self.get_window(L.KEEP_R, w),
                    pairs=self.get_window(L.PAIRS, w), cost=self.get_window(L.COST, w))
+        def stage_missing(e):
+            if e.code != L.E_STATE:      # only "stage not run yet" is an expected condition here
+                raise e
         try:
             out.update(tri=self.get_window(L.TRI, w), tri_src=self.get_window(L.TRI_SRC, w), weight=self.get_window(L.TRI_WEIGHT, w),
                        sign=self.get_window(L.TRI_SIGN, w), bounds=self.get_window(L.TRI_BOUNDS, w), argv=self.get_window(L.TRI_ARGV, w),
                        unconstrained=self.get_window(L.UNCONSTRAINED, w))
-        except L.SameError:
-            pass
+        except L.SameError as e:
+            stage_missing(e)
         try:
             goff = self.offsets(L.REF_GROUP_NODE)
             g0, g1 = int(goff[w]), int(goff[w + 1])
             out.update(ref_group_node=self.get(L.REF_GROUP_NODE, g0, g1), ref_group_limit=self.get(L.REF_GROUP_LIMIT, g0, g1),
                        ref_group_ptr=self.get(L.REF_GROUP_PTR, g0, g1 + 1).astype(np.int64) - p0,
                        ref_group_idx=self.get_window(L.REF_GROUP_IDX, w))
-        except L.SameError:
-            pass
+        except L.SameError as e:
+            stage_missing(e)
         ka = self.offsets(L.KEEP_A)
         out["row_ptr"] = self.get(L.ROW_PTR, int(ka[w]), int(ka[w + 1]) + 1).astype(np.int64) - p0
         return out
