@@ -69,39 +69,22 @@ def make_workload(tiles, rank, world):
 
 
 def exchange_halo(W, rank, world, device):
-    """The one collective of the path: cells of the NEXT strip within `WINDOW` of the strip border are
-    all-gathered so that windows starting in this strip see every cell of their rectangle."""
+    """The one collective of the path (same_b200.sharding.exchange_halo, NCCL all_gather): cells of the NEXT strip
+    within `WINDOW` of the strip border, so that windows starting in this strip see every cell of their rectangle."""
     import torch
-    import torch.distributed as dist
+    from same_b200 import sharding as S
     t0 = time.perf_counter()
-    lo = W["strip_lo"]
-    packs = []
-    for xy, prob, ty in ((W["a_xy"], W["a_prob"], W["a_type"]), (W["r_xy"], W["r_prob"], W["r_type"])):
-        m = xy[:, 1] < lo + WINDOW
-        packs.append(np.concatenate([xy[m], prob[m], ty[m, None].astype(np.float64)], axis=1))
-    counts = torch.tensor([len(packs[0]), len(packs[1])], dtype=torch.int64, device=device)
-    all_counts = [torch.zeros_like(counts) for _ in range(world)]
-    dist.all_gather(all_counts, counts)
-    all_counts = torch.stack(all_counts).cpu().numpy()
-    width = packs[0].shape[1]
-    nbytes = 0
-    halos = []
-    for f in range(2):
-        mx = int(all_counts[:, f].max())
-        buf = torch.zeros((mx, width), dtype=torch.float64, device=device)
-        buf[: len(packs[f])] = torch.from_numpy(packs[f]).to(device)
-        out = [torch.empty_like(buf) for _ in range(world)]
-        dist.all_gather(out, buf)
-        nbytes += buf.numel() * 8 * world
-        nxt = rank + 1
-        halos.append(out[nxt][: int(all_counts[nxt, f])].cpu().numpy() if nxt < world else np.zeros((0, width)))
+    nbytes = rows = 0
+    for name in ("a", "r"):
+        xy, prob, ty = W[f"{name}_xy"], W[f"{name}_prob"], W[f"{name}_type"]
+        halo, info = S.exchange_halo({"xy": xy, "prob": prob, "type": ty[:, None].astype(np.float64), "y": xy[:, 1:2]}, "y",
+                                     W["strip_lo"] + WINDOW, device=device)
+        W[f"{name}_xy"] = np.ascontiguousarray(np.concatenate([xy, halo["xy"]]))
+        W[f"{name}_prob"] = np.ascontiguousarray(np.concatenate([prob, halo["prob"]]))
+        W[f"{name}_type"] = np.concatenate([ty, halo["type"][:, 0].astype(np.int32)])
+        nbytes += info["bytes"]; rows += info["rows"]
     torch.cuda.synchronize()
-    K = W["a_prob"].shape[1]
-    for name, h in (("a", halos[0]), ("r", halos[1])):
-        W[f"{name}_xy"] = np.ascontiguousarray(np.concatenate([W[f"{name}_xy"], h[:, :2]]))
-        W[f"{name}_prob"] = np.ascontiguousarray(np.concatenate([W[f"{name}_prob"], h[:, 2:2 + K]]))
-        W[f"{name}_type"] = np.concatenate([W[f"{name}_type"], h[:, 2 + K].astype(np.int32)])
-    return dict(ms=(time.perf_counter() - t0) * 1e3, bytes=int(nbytes), halo_cells=int(len(halos[0]) + len(halos[1])))
+    return dict(ms=(time.perf_counter() - t0) * 1e3, bytes=int(nbytes), halo_cells=int(rows))
 
 
 def window_rects(W, rank, world):
@@ -260,6 +243,7 @@ def main():
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # keep stdout = the one JSON line
         dist.init_process_group("nccl", device_id=device)
 
     # ---- workload (untimed setup) ----
@@ -361,15 +345,25 @@ def main():
         one_pass(s2, fetch=True)
         s2.close()
         barrier()
+        import gc
+        gc.collect()
+        gc.disable()                                             # a gen-2 collection inside the timed loop costs 10+ ms
         t0 = time.perf_counter()
+        iters = []
         for _ in range(n_e2e):
+            t1 = time.perf_counter()
             s2 = make_section()                                  # H2D of both frames + triangulation from pinned memory
             x_dev["t"] = x_pin[0].to(device, non_blocking=True)  # H2D of the solution vector
+            t2 = time.perf_counter()
             st, d2h = one_pass(s2, fetch=True)
+            t3 = time.perf_counter()
             s2.close()
+            iters.append([round((t2 - t1) * 1e3, 3), round((t3 - t2) * 1e3, 3), round((time.perf_counter() - t3) * 1e3, 3)])
         x_dev["t"] = saved
         barrier()
         e2e_ms = (time.perf_counter() - t0) * 1e3 / n_e2e
+        gc.enable()
+        sys.stderr.write(f"[bench] e2e iterations (upload, pass+fetch, close) ms: {iters}\n")
         h2d = sum(p[1].nbytes for p in pins.values()) + tri_pin[1].nbytes + x_pin[1].nbytes
         e2e = dict(ms=e2e_ms, h2d=h2d, d2h=d2h, P=st["P"])
         sec = make_section()

@@ -55,7 +55,9 @@ __global__ void k_gather_xy(const i32 *__restrict__ inst, const i32 *__restrict_
 }
 
 // ---- top-k search ----------------------------------------------------------------------
-__device__ __forceinline__ bool cand_less(double d, i32 j, double bd, i32 bj) { return d < bd || (d == bd && j < bj); }
+// (d, j) < (bd, bj) lexicographically; bitwise ops so that the compiler emits predicate logic, not branches (the
+// short-circuit form compiled to divergent branches inside the insertion: 180 SASS instructions at ~3 active lanes)
+__device__ __forceinline__ bool cand_less(double d, i32 j, double bd, i32 bj) { return (d < bd) | ((d == bd) & (j < bj)); }
 
 template <int KCAP>
 __global__ void __launch_bounds__(128) k_knn(const double2 *__restrict__ sa_xy, const i32 *__restrict__ sa_inst, i64 nAi,
@@ -111,20 +113,21 @@ __global__ void __launch_bounds__(128) k_knn(const double2 *__restrict__ sa_xy, 
                     const double2 p = sr_xy[s];
                     const double ddx = __dsub_rn(p.x, q.x), ddy = __dsub_rn(p.y, q.y);
                     const double d2 = __dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy));
-                    if (d2 <= r2 && d2 <= tau_d) {
+                    if ((d2 <= r2) & (d2 <= tau_d)) {
                         const i32 j = sr_inst[s];
                         if (cand_less(d2, j, tau_d, tau_j)) {
-                            // sorted insertion, entries shift towards the tail
+                            // branch-free sorted insertion: lt[u] = candidate sorts before slot u (computed on the old
+                            // values); slot u takes slot u-1 if lt[u-1], the candidate if lt[u] only, else keeps its value
+                            bool lt[KCAP];
+#pragma unroll
+                            for (int u = 0; u < KCAP; ++u) lt[u] = cand_less(d2, j, bd[u], bj[u]);
 #pragma unroll
                             for (int u = KCAP - 1; u > 0; --u) {
-                                const bool before_prev = cand_less(d2, j, bd[u - 1], bj[u - 1]);
-                                const bool before_this = cand_less(d2, j, bd[u], bj[u]);
-                                const double nd = before_prev ? bd[u - 1] : (before_this ? d2 : bd[u]);
-                                const i32 nj = before_prev ? bj[u - 1] : (before_this ? j : bj[u]);
-                                bd[u] = nd;
-                                bj[u] = nj;
+                                bd[u] = lt[u - 1] ? bd[u - 1] : (lt[u] ? d2 : bd[u]);
+                                bj[u] = lt[u - 1] ? bj[u - 1] : (lt[u] ? j : bj[u]);
                             }
-                            if (cand_less(d2, j, bd[0], bj[0])) { bd[0] = d2; bj[0] = j; }
+                            bd[0] = lt[0] ? d2 : bd[0];
+                            bj[0] = lt[0] ? j : bj[0];
                             found = min(found + 1, knn);
                         }
                     }
@@ -449,25 +452,24 @@ void batch_candidates(Batch *b, double radius, int knn, int priority, double dis
 }
 
 // ---- a4: ref_to_pairs groups ----------------------------------------------------------------
-__global__ void k_first_pair(const int2 *__restrict__ pairs, i64 P, const i32 *__restrict__ p_off, const i32 *__restrict__ kr_off, int W,
-                             i32 *__restrict__ first) {
+// Groups must come out in FIRST-APPEARANCE order of j with pair indices ascending inside (dict insertion order,
+// helpers.py:105-110).  first[j] = smallest pair index of ref j (atomicMin); a pair p is a group head iff first[j_p] == p, so
+// an exclusive scan of the head flags numbers the groups in first-appearance order (window-major for free, pairs are
+// window-major); group sizes come from a per-ref counter; members are scattered with a per-group cursor and every
+// (small, ~knn entries) group is then sorted by its own thread.  No 8M-element radix sort.
+__global__ void k_group_count(const int2 *__restrict__ pairs, i64 P, const i32 *__restrict__ p_off, const i32 *__restrict__ kr_off, int W,
+                              i32 *__restrict__ first, i32 *__restrict__ cnt) {
     i64 p = (i64)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= P) return;
-    const int w = find_window(p_off, W, (i32)p);
-    atomicMin(first + kr_off[w] + pairs[p].y, (i32)p);
+    const i32 r = kr_off[find_window(p_off, W, (i32)p)] + pairs[p].y;
+    atomicMin(first + r, (i32)p);
+    atomicAdd(cnt + r, 1);
 }
-__global__ void k_group_keys(const int2 *__restrict__ pairs, i64 P, const i32 *__restrict__ p_off, const i32 *__restrict__ kr_off, int W,
-                             const i32 *__restrict__ first, unsigned *__restrict__ keys, i32 *__restrict__ vals) {
+__global__ void k_group_heads(const int2 *__restrict__ pairs, i64 P, const i32 *__restrict__ p_off, const i32 *__restrict__ kr_off, int W,
+                              const i32 *__restrict__ first, i32 *__restrict__ head) {
     i64 p = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= P) return;
-    const int w = find_window(p_off, W, (i32)p);
-    keys[p] = (unsigned)first[kr_off[w] + pairs[p].y];
-    vals[p] = (i32)p;
-}
-__global__ void k_group_heads(const unsigned *__restrict__ keys, i64 P, i32 *__restrict__ head) {
-    i64 s = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s < P) head[s] = (s == 0) || keys[s] != keys[s - 1];
-    if (s == P) head[s] = 0;
+    if (p < P) head[p] = first[kr_off[find_window(p_off, W, (i32)p)] + pairs[p].y] == (i32)p;
+    if (p == P) head[p] = 0;
 }
 __device__ __forceinline__ unsigned long long enc_pos_f64(double d) { return (unsigned long long)__double_as_longlong(d); }  // d >= 0
 __global__ void k_window_max_size(const double *__restrict__ kr_size, i64 nKR, const i32 *__restrict__ kr_off, int W,
@@ -477,29 +479,62 @@ __global__ void k_window_max_size(const double *__restrict__ kr_size, i64 nKR, c
     const double v = kr_size[i];
     if (v > 1.0) atomicMax(wmax + find_window(kr_off, W, (i32)i), enc_pos_f64(v));
 }
-__global__ void k_group_emit(const unsigned *__restrict__ keys, const i32 *__restrict__ sorted_p, const i32 *__restrict__ head,
-                             const i32 *__restrict__ gid, i64 P, const int2 *__restrict__ pairs, const i32 *__restrict__ p_off,
-                             const i32 *__restrict__ kr_off, int W, const double *__restrict__ kr_size,
-                             const unsigned long long *__restrict__ wmax, int max_matches, int multiplier, i32 *__restrict__ g_node,
-                             i32 *__restrict__ g_ptr, i32 *__restrict__ g_idx, i32 *__restrict__ g_limit, i64 G) {
-    i64 s = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s == 0) g_ptr[G] = (i32)P;
-    if (s >= P) return;
-    const i32 p = sorted_p[s];
-    const int w = find_window(p_off, W, p);
-    g_idx[s] = p - p_off[w];
-    if (head[s]) {
-        const i32 g = gid[s];
-        const i32 j = pairs[p].y;
-        g_node[g] = j;
-        g_ptr[g] = (i32)s;
-        const unsigned long long m = wmax[w];  // 0 = no ref with size > 1 in this window (helpers.py:121)
-        int lim = max_matches;
-        if (m != 0ull && kr_size[kr_off[w] + j] > 1.0) {
-            const int mult = multiplier >= 0 ? multiplier : (int)__longlong_as_double((long long)m);  // int(ref_df['size'].max())
-            lim = mult * max_matches;
+// one thread per kept ref: its group id, node, size and limit
+__global__ void k_group_setup(i64 nKR, const i32 *__restrict__ kr_off, int W, const i32 *__restrict__ first, const i32 *__restrict__ cnt,
+                              const i32 *__restrict__ gid_at, const double *__restrict__ kr_size, const unsigned long long *__restrict__ wmax,
+                              int max_matches, int multiplier, i32 *__restrict__ ref_gid, i32 *__restrict__ g_node, i32 *__restrict__ g_cnt,
+                              i32 *__restrict__ g_limit, i64 G) {
+    i64 r = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r == 0) g_cnt[G] = 0;
+    if (r >= nKR) return;
+    if (first[r] == 0x7fffffff) { ref_gid[r] = -1; return; }
+    const int w = find_window(kr_off, W, (i32)r);
+    const i32 g = gid_at[first[r]];
+    ref_gid[r] = g;
+    g_node[g] = (i32)r - kr_off[w];
+    g_cnt[g] = cnt[r];
+    const unsigned long long m = wmax[w];  // 0 = no ref with size > 1 in this window (helpers.py:121)
+    int lim = max_matches;
+    if (m != 0ull && kr_size[r] > 1.0) {
+        const int mult = multiplier >= 0 ? multiplier : (int)__longlong_as_double((long long)m);  // int(ref_df['size'].max())
+        lim = mult * max_matches;
+    }
+    g_limit[g] = lim;
+}
+__global__ void k_group_fill(const int2 *__restrict__ pairs, i64 P, const i32 *__restrict__ p_off, const i32 *__restrict__ kr_off, int W,
+                             const i32 *__restrict__ ref_gid, const i32 *__restrict__ g_ptr, i32 *__restrict__ cursor, i32 *__restrict__ g_idx) {
+    i64 p = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    const int w = find_window(p_off, W, (i32)p);
+    const i32 g = ref_gid[kr_off[w] + pairs[p].y];
+    g_idx[g_ptr[g] + atomicAdd(cursor + g, 1)] = (i32)p - p_off[w];
+}
+// ascending pair index inside every group (insertion sort; groups hold ~knn entries)
+__global__ void k_group_sort(const i32 *__restrict__ g_ptr, i64 G, i32 *__restrict__ g_idx) {
+    i64 g = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= G) return;
+    const i32 lo = g_ptr[g], n = g_ptr[g + 1] - lo;
+    i32 *a = g_idx + lo;
+    if (n <= 32) {
+        i32 v[32];
+#pragma unroll
+        for (int k = 0; k < 32; ++k) v[k] = k < n ? a[k] : 0x7fffffff;
+        // odd-even transposition network would touch all 32 slots; groups are ~8 long, so a bounded insertion sort over the
+        // live prefix is cheaper.  Indexing is dynamic -> local memory, but it stays in L1.
+        for (int i = 1; i < n; ++i) {
+            const i32 x = v[i];
+            int j = i - 1;
+            while (j >= 0 && v[j] > x) { v[j + 1] = v[j]; --j; }
+            v[j + 1] = x;
         }
-        g_limit[g] = lim;
+        for (int k = 0; k < n; ++k) a[k] = v[k];
+    } else {
+        for (int i = 1; i < n; ++i) {
+            const i32 x = a[i];
+            int j = i - 1;
+            while (j >= 0 && a[j] > x) { a[j + 1] = a[j]; --j; }
+            a[j + 1] = x;
+        }
     }
 }
 __global__ void k_pick(const i32 *__restrict__ scanned, const i32 *__restrict__ at, int n, i32 *__restrict__ out) {
@@ -509,7 +544,7 @@ __global__ void k_pick(const i32 *__restrict__ scanned, const i32 *__restrict__ 
 
 void batch_groups(Batch *b, int max_matches, int multiplier) {
     cudaStream_t s = b->stream;
-    const i64 W = b->W, P = b->P;
+    const i64 W = b->W, P = b->P, nKR = b->nKR;
     REQUIRE(b->stage >= 1, SAME_E_STATE, "same_batch_groups before same_batch_candidates");
     b->g_off.assign(W + 1, 0);
     b->G = 0;
@@ -520,36 +555,31 @@ void batch_groups(Batch *b, int max_matches, int multiplier) {
         CK(cudaStreamSynchronize(s));
         return;
     }
-    DevBuf<i32> first, vals, sorted_p, head, gid, goff;
-    DevBuf<unsigned> keys, keys_out;
+    DevBuf<i32> first, cnt, head, gid_at, goff, ref_gid, g_cnt, cursor;
     DevBuf<unsigned long long> wmax;
-    first.alloc(b->nKR, s); vals.alloc(P, s); sorted_p.alloc(P, s); head.alloc(P + 1, s); gid.alloc(P + 1, s);
-    keys.alloc(P, s); keys_out.alloc(P, s); wmax.alloc(W, s); goff.alloc(W + 1, s);
+    first.alloc(nKR, s); cnt.alloc(nKR, s); head.alloc(P + 1, s); gid_at.alloc(P + 1, s); goff.alloc(W + 1, s); ref_gid.alloc(nKR, s);
+    wmax.alloc(W, s);
     wmax.zero(s);
-    LAUNCH(k_fill_i32, blocks_for(b->nKR, 256), 256, 0, s, first.p, b->nKR, 0x7fffffff);
-    LAUNCH(k_first_pair, blocks_for(P, 256), 256, 0, s, b->pairs.p, P, b->d_p_off.p, b->d_kr_off.p, (int)W, first.p);
-    LAUNCH(k_group_keys, blocks_for(P, 256), 256, 0, s, b->pairs.p, P, b->d_p_off.p, b->d_kr_off.p, (int)W, first.p, keys.p, vals.p);
-    size_t bytes = 0;
-    const int kb = bits_for(P + 1);
-    CK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, keys.p, keys_out.p, vals.p, sorted_p.p, (int)P, 0, kb, s));
-    void *tmp = b->scratch.get(bytes, s);
-    {
-        ProfScope prof("cub::DeviceRadixSort::SortPairs(groups)", s);
-        CK(cub::DeviceRadixSort::SortPairs(tmp, bytes, keys.p, keys_out.p, vals.p, sorted_p.p, (int)P, 0, kb, s));
-    }
-    g_launches.fetch_add(1, std::memory_order_relaxed);
-    LAUNCH(k_group_heads, blocks_for(P + 1, 256), 256, 0, s, keys_out.p, P, head.p);
-    exclusive_scan_i32(head.p, gid.p, P + 1, b->scratch, s);
-    LAUNCH(k_pick, blocks_for(W + 1, 128), 128, 0, s, gid.p, b->d_p_off.p, (int)(W + 1), goff.p);
+    cnt.zero(s);
+    LAUNCH(k_fill_i32, blocks_for(nKR, 256), 256, 0, s, first.p, nKR, 0x7fffffff);
+    LAUNCH(k_group_count, blocks_for(P, 256), 256, 0, s, b->pairs.p, P, b->d_p_off.p, b->d_kr_off.p, (int)W, first.p, cnt.p);
+    LAUNCH(k_group_heads, blocks_for(P + 1, 256), 256, 0, s, b->pairs.p, P, b->d_p_off.p, b->d_kr_off.p, (int)W, first.p, head.p);
+    exclusive_scan_i32(head.p, gid_at.p, P + 1, b->scratch, s);
+    LAUNCH(k_pick, blocks_for(W + 1, 128), 128, 0, s, gid_at.p, b->d_p_off.p, (int)(W + 1), goff.p);
+    LAUNCH(k_window_max_size, blocks_for(nKR, 256), 256, 0, s, b->kr_size.p, nKR, b->d_kr_off.p, (int)W, wmax.p);
     std::vector<i32> h(W + 1);
     CK(cudaMemcpyAsync(h.data(), goff.p, sizeof(i32) * (W + 1), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     b->g_off.assign(h.begin(), h.end());
-    b->G = b->g_off[W];
-    b->g_node.alloc(b->G, s); b->g_ptr.alloc(b->G + 1, s); b->g_idx.alloc(P, s); b->g_limit.alloc(b->G, s);
-    LAUNCH(k_window_max_size, blocks_for(b->nKR, 256), 256, 0, s, b->kr_size.p, b->nKR, b->d_kr_off.p, (int)W, wmax.p);
-    LAUNCH(k_group_emit, blocks_for(P, 256), 256, 0, s, keys_out.p, sorted_p.p, head.p, gid.p, P, b->pairs.p, b->d_p_off.p, b->d_kr_off.p,
-           (int)W, b->kr_size.p, wmax.p, max_matches, multiplier, b->g_node.p, b->g_ptr.p, b->g_idx.p, b->g_limit.p, b->G);
+    const i64 G = b->G = b->g_off[W];
+    b->g_node.alloc(G, s); b->g_ptr.alloc(G + 1, s); b->g_idx.alloc(P, s); b->g_limit.alloc(G, s);
+    g_cnt.alloc(G + 1, s); cursor.alloc(G, s);
+    cursor.zero(s);
+    LAUNCH(k_group_setup, blocks_for(nKR, 256), 256, 0, s, nKR, b->d_kr_off.p, (int)W, first.p, cnt.p, gid_at.p, b->kr_size.p, wmax.p, max_matches,
+           multiplier, ref_gid.p, b->g_node.p, g_cnt.p, b->g_limit.p, G);
+    exclusive_scan_i32(g_cnt.p, b->g_ptr.p, G + 1, b->scratch, s);
+    LAUNCH(k_group_fill, blocks_for(P, 256), 256, 0, s, b->pairs.p, P, b->d_p_off.p, b->d_kr_off.p, (int)W, ref_gid.p, b->g_ptr.p, cursor.p, b->g_idx.p);
+    LAUNCH(k_group_sort, blocks_for(G, 128), 128, 0, s, b->g_ptr.p, G, b->g_idx.p);
     CK(cudaStreamSynchronize(s));
 }
 

@@ -139,12 +139,29 @@ struct GridParams {  // uniform bin grid of one window (reference side)
     i32 nbx, nby, base, rings;
 };
 
+// Coarse uniform grid over the section bbox listing, per grid cell, the window rectangles that overlap it: a point /
+// triangle only tests the handful of rectangles of its own cell instead of all W (built on the host, batch_subset).
+struct RectIndexDev {
+    double x0, y0, inv_cs;
+    i32 nx, ny, max_len;
+    const i32 *cell_ptr;    // [nx*ny + 1]
+    const i32 *cell_rects;  // rectangle ids, ascending inside a cell
+};
+__device__ __forceinline__ int rect_cell(const RectIndexDev &ri, double x, double y) {
+    int cx = (int)floor((x - ri.x0) * ri.inv_cs), cy = (int)floor((y - ri.y0) * ri.inv_cs);
+    cx = min(max(cx, 0), ri.nx - 1);
+    cy = min(max(cy, 0), ri.ny - 1);
+    return cy * ri.nx + cx;
+}
+
 struct Batch {
     Section *sec = nullptr;
     cudaStream_t stream = nullptr;
     i64 W = 0;
     std::vector<double> rects;  // W*4
     DevBuf<double> d_rects;
+    DevBuf<i32> ri_ptr, ri_rects;
+    RectIndexDev rindex{};
     Scratch scratch;
     int stage = 0;  // 0 created, 1 candidates, 2 triangles in, 3 classified, 4 finalized
 

@@ -168,25 +168,149 @@ void section_count_rects(Section *sec, i64 m, const double *rects, i64 *cntA, i6
     for (i64 i = 0; i < m; ++i) { cntA[i] = (i64)h[i]; cntR[i] = (i64)h[m + i]; }
 }
 
-static void subset_frame(Batch *b, const DevBuf<double2> &xy, i64 n, std::vector<i64> &off, DevBuf<i32> &d_off, DevBuf<i32> &src, i64 &total) {
+// ---- window subsetting: subset_data (src/same.py:293-295) for all windows at once ---------------------------
+// One thread per cell looks up the rectangles overlapping its index-grid cell, tests them exactly (half-open) and
+// appends (window << rowbits | row); a key-only radix sort then yields, per window, the rows in ascending order —
+// exactly `df[mask]` of the reference.  Lanes walk their candidate lists in lockstep so a warp needs one atomic per slot.
+// pass 1: number of windows holding each cell; pass 2 (after an exclusive scan): keys written at scan[i].. in ascending
+// window order.  The key stream is then ordered by (row, window), so ONE stable radix pass over the window bits
+// yields (window, row) order — no atomics, no multi-pass sort.
+template <bool FILL, typename KeyT>
+__global__ void __launch_bounds__(256) k_subset_scan(const double2 *__restrict__ xy, i64 n, const double *__restrict__ rects, RectIndexDev ri,
+                                                     int rowbits, i32 *__restrict__ count, const i32 *__restrict__ pos, KeyT *__restrict__ keys) {
+    const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n) return;
+    if (i == n) { if (!FILL) count[i] = 0; return; }
+    const double2 p = xy[i];
+    const int c = rect_cell(ri, p.x, p.y);
+    const i32 lo = ri.cell_ptr[c], hi = ri.cell_ptr[c + 1];
+    i32 out = FILL ? pos[i] : 0;
+    for (i32 k = lo; k < hi; ++k) {
+        const int w = ri.cell_rects[k];
+        if (in_rect(p, rects + 4 * (i64)w)) {
+            if (FILL) keys[out] = (KeyT)(((unsigned long long)w << rowbits) | (unsigned long long)i);
+            ++out;
+        }
+    }
+    if (!FILL) count[i] = out;
+}
+
+template <typename KeyT>
+__global__ void k_subset_finish(const KeyT *__restrict__ sorted, i64 total, int rowbits, i64 W, i32 *__restrict__ src, i32 *__restrict__ off) {
+    const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < total) src[i] = (i32)((unsigned long long)sorted[i] & ((1ull << rowbits) - 1ull));
+    if (i <= W) {  // offset of window i = lower bound of key (i << rowbits)
+        const unsigned long long key = (unsigned long long)i << rowbits;
+        i64 lo = 0, hi = total;
+        while (lo < hi) {
+            const i64 mid = (lo + hi) >> 1;
+            if ((unsigned long long)sorted[mid] < key) lo = mid + 1; else hi = mid;
+        }
+        off[i] = (i32)lo;
+    }
+}
+
+static int bits_needed(i64 n) {
+    int b = 1;
+    while ((1ll << b) < n) ++b;
+    return b;
+}
+
+template <typename KeyT>
+static void subset_frame_t(Batch *b, const DevBuf<double2> &xy, i64 n, std::vector<i64> &off, DevBuf<i32> &d_off, DevBuf<i32> &src, i64 &total,
+                           int rowbits, int wbits) {
     cudaStream_t s = b->stream;
     const i64 W = b->W;
-    const i64 chunks = blocks_for(n, SUB_CHUNK);
-    DevBuf<i32> counts, scanned;
-    counts.alloc(W * chunks + 1, s);
-    scanned.alloc(W * chunks + 1, s);
-    CK(cudaMemsetAsync(counts.p, 0, sizeof(i32) * (W * chunks + 1), s));
-    if (n > 0) LAUNCH(k_rect_count, dim3((unsigned)chunks, (unsigned)W), SUB_THREADS, 0, s, xy.p, n, b->d_rects.p, counts.p, (unsigned long long *)nullptr);
-    exclusive_scan_i32(counts.p, scanned.p, W * chunks + 1, b->scratch, s);
-    d_off.alloc(W + 1, s);
-    LAUNCH(k_pick_offsets, blocks_for(W + 1, 256), 256, 0, s, scanned.p, chunks, W, d_off.p);
-    std::vector<i32> h(W + 1);
-    CK(cudaMemcpyAsync(h.data(), d_off.p, sizeof(i32) * (W + 1), cudaMemcpyDeviceToHost, s));
+    DevBuf<i32> count, pos;
+    DevBuf<KeyT> keys, keys_out;
+    count.alloc(n + 1, s); pos.alloc(n + 1, s);
+    LAUNCH((k_subset_scan<false, KeyT>), blocks_for(n + 1, 256), 256, 0, s, xy.p, n, b->d_rects.p, b->rindex, rowbits, count.p, (const i32 *)nullptr,
+           (KeyT *)nullptr);
+    exclusive_scan_i32(count.p, pos.p, n + 1, b->scratch, s);
+    i32 h = 0;
+    CK(cudaMemcpyAsync(&h, pos.p + n, sizeof(h), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
-    off.assign(h.begin(), h.end());
-    total = off[W];
+    total = (i64)h;
+    REQUIRE(total >= 0, SAME_E_LIMIT, "batch exceeds 2^31 window instances");
     src.alloc(total, s);
-    if (n > 0 && total > 0) LAUNCH(k_rect_fill, dim3((unsigned)chunks, (unsigned)W), SUB_THREADS, 0, s, xy.p, n, b->d_rects.p, scanned.p, src.p);
+    d_off.alloc(W + 1, s);
+    keys.alloc(total, s); keys_out.alloc(total, s);
+    if (total > 0) {
+        LAUNCH((k_subset_scan<true, KeyT>), blocks_for(n + 1, 256), 256, 0, s, xy.p, n, b->d_rects.p, b->rindex, rowbits, (i32 *)nullptr, pos.p, keys.p);
+        size_t bytes = 0;
+        CK(cub::DeviceRadixSort::SortKeys(nullptr, bytes, keys.p, keys_out.p, (int)total, rowbits, rowbits + wbits, s));
+        void *tmp = b->scratch.get(bytes, s);
+        {
+            ProfScope prof("cub::DeviceRadixSort::SortKeys(subset)", s);
+            CK(cub::DeviceRadixSort::SortKeys(tmp, bytes, keys.p, keys_out.p, (int)total, rowbits, rowbits + wbits, s));
+        }
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+    }
+    LAUNCH((k_subset_finish<KeyT>), blocks_for(std::max<i64>(total, W + 1), 256), 256, 0, s, keys_out.p, total, rowbits, W, src.p, d_off.p);
+    std::vector<i32> ho(W + 1);
+    CK(cudaMemcpyAsync(ho.data(), d_off.p, sizeof(i32) * (W + 1), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    off.assign(ho.begin(), ho.end());
+}
+
+static void subset_frame(Batch *b, const DevBuf<double2> &xy, i64 n, std::vector<i64> &off, DevBuf<i32> &d_off, DevBuf<i32> &src, i64 &total) {
+    const int rowbits = bits_needed(std::max<i64>(n, 2)), wbits = bits_needed(b->W + 1);
+    if (rowbits + wbits <= 32) subset_frame_t<unsigned>(b, xy, n, off, d_off, src, total, rowbits, wbits);
+    else subset_frame_t<unsigned long long>(b, xy, n, off, d_off, src, total, rowbits, wbits);
+}
+
+// host: uniform index grid over the section bbox, each rectangle registered in every grid cell it overlaps (+1 cell of slack)
+static void build_rect_index(Batch *b) {
+    Section *sec = b->sec;
+    cudaStream_t s = b->stream;
+    const i64 W = b->W;
+    const double bx0 = sec->bbox[0], bx1 = sec->bbox[1], by0 = sec->bbox[2], by1 = sec->bbox[3];
+    const double ext = std::max(std::max(bx1 - bx0, by1 - by0), 1e-300);
+    int G = (int)std::min<i64>(256, std::max<i64>(1, (i64)std::ceil(std::sqrt((double)W)) * 4));
+    std::vector<i32> ptr, lst;
+    double cs = 1.0, inv = 1.0;
+    int nx = 1, ny = 1, max_len = 0;
+    for (;; G = std::max(1, G / 2)) {
+        cs = ext / G;
+        if (!(cs > 0.0) || !std::isfinite(cs)) cs = 1.0;
+        inv = 1.0 / cs;
+        nx = (int)std::floor((bx1 - bx0) * inv) + 1;
+        ny = (int)std::floor((by1 - by0) * inv) + 1;
+        auto cell = [&](double v, double o, int nmax) {
+            double t = std::floor((v - o) * inv);
+            if (!(t > -1e9)) t = -1e9;   // -inf / NaN
+            if (t > 1e9) t = 1e9;
+            return (int)std::min<double>(std::max<double>(t, 0.0), (double)(nmax - 1));
+        };
+        std::vector<i32> cnt((size_t)nx * ny + 1, 0);
+        i64 total = 0;
+        std::vector<int> cx0(W), cx1(W), cy0(W), cy1(W);
+        for (i64 w = 0; w < W; ++w) {
+            const double *r = &b->rects[4 * w];
+            cx0[w] = std::max(0, cell(r[0], bx0, nx) - 1); cx1[w] = std::min(nx - 1, cell(r[1], bx0, nx) + 1);
+            cy0[w] = std::max(0, cell(r[2], by0, ny) - 1); cy1[w] = std::min(ny - 1, cell(r[3], by0, ny) + 1);
+            if (r[1] < bx0 || r[0] > bx1 || r[3] < by0 || r[2] > by1) { cx1[w] = cx0[w] - 1; continue; }  // misses the section
+            total += (i64)(cx1[w] - cx0[w] + 1) * (cy1[w] - cy0[w] + 1);
+        }
+        if (total > (1ll << 24) && G > 1) continue;  // too fine for this many rectangles: coarsen
+        for (i64 w = 0; w < W; ++w)
+            for (int cy = cy0[w]; cy <= cy1[w] && cx1[w] >= cx0[w]; ++cy)
+                for (int cx = cx0[w]; cx <= cx1[w]; ++cx) cnt[(size_t)cy * nx + cx + 1]++;
+        for (size_t c = 0; c < (size_t)nx * ny; ++c) { max_len = std::max(max_len, cnt[c + 1]); cnt[c + 1] += cnt[c]; }
+        ptr = cnt;
+        lst.assign((size_t)std::max<i64>(total, 1), 0);
+        std::vector<i32> fill(ptr.begin(), ptr.end() - 1);
+        for (i64 w = 0; w < W; ++w)   // ascending w inside every cell
+            for (int cy = cy0[w]; cy <= cy1[w] && cx1[w] >= cx0[w]; ++cy)
+                for (int cx = cx0[w]; cx <= cx1[w]; ++cx) lst[fill[(size_t)cy * nx + cx]++] = (i32)w;
+        break;
+    }
+    b->ri_ptr.alloc((i64)ptr.size(), s);
+    b->ri_rects.alloc((i64)lst.size(), s);
+    CK(cudaMemcpyAsync(b->ri_ptr.p, ptr.data(), sizeof(i32) * ptr.size(), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(b->ri_rects.p, lst.data(), sizeof(i32) * lst.size(), cudaMemcpyHostToDevice, s));
+    CK(cudaStreamSynchronize(s));
+    b->rindex = RectIndexDev{bx0, by0, inv, nx, ny, max_len, b->ri_ptr.p, b->ri_rects.p};
 }
 
 void batch_subset(Batch *b) {
@@ -194,10 +318,9 @@ void batch_subset(Batch *b) {
     cudaStream_t s = b->stream;
     b->d_rects.alloc(4 * b->W, s);
     CK(cudaMemcpyAsync(b->d_rects.p, b->rects.data(), sizeof(double) * 4 * b->W, cudaMemcpyHostToDevice, s));
-    REQUIRE((double)b->W * (double)std::max(sec->nA, sec->nR) < 2.0e12, SAME_E_LIMIT, "too many windows x cells for one batch");
+    build_rect_index(b);
     subset_frame(b, sec->a_xy, sec->nA, b->a_off, b->d_a_off, b->a_src, b->nAi);
     subset_frame(b, sec->r_xy, sec->nR, b->r_off, b->d_r_off, b->r_src, b->nRi);
-    REQUIRE(b->nAi < (1ll << 31) && b->nRi < (1ll << 31), SAME_E_LIMIT, "batch exceeds 2^31 window instances");
 }
 
 // ---- vertex ids -> section rows ------------------------------------------------------

@@ -17,75 +17,67 @@ __device__ __forceinline__ i32 kept_lookup(const i32 *__restrict__ keepA, i32 lo
 }
 
 // Remap = for every global triangle, every window whose rectangle holds all three vertices AND whose post-KNN
-// frame kept all three rows.  One thread per triangle walks the rectangle list staged in shared memory (no
-// per-window pass over the triangle list), a first launch counts, a second appends (window, triangle) records,
-// and one radix sort on (window << 32 | triangle) restores the reference's order: window-major, input order inside.
-constexpr int RECT_TILE = 512;
-
-template <bool FILL>
+// frame kept all three rows.  One thread per triangle looks up the rectangles of the index-grid cell of its
+// bounding-box corner (a handful instead of all W), binary-searches the window's kept-row list, and appends
+// (window << tbits | triangle) records; lanes walk their candidate lists in lockstep so a warp needs one atomic per
+// slot.  A first launch only counts (to size the buffers); one radix sort restores the reference's order
+// (window-major, input order inside) and the window offsets are lower bounds in the sorted keys.
+template <bool FILL, typename KeyT>
 __global__ void __launch_bounds__(256) k_remap_scan(const i32 *__restrict__ tri_rows, i64 Tg, const double2 *__restrict__ sec_xy,
-                                                    const double *__restrict__ rects, int W, const i32 *__restrict__ keepA,
-                                                    const i32 *__restrict__ ka_off, i32 *__restrict__ win_count,
-                                                    unsigned long long *__restrict__ keys, int3 *__restrict__ recs, i32 *__restrict__ cursor, int tbits) {
-    __shared__ double4 srect[RECT_TILE];
+                                                    const double *__restrict__ rects, RectIndexDev ri, const i32 *__restrict__ keepA,
+                                                    const i32 *__restrict__ ka_off, i32 *__restrict__ count, const i32 *__restrict__ pos,
+                                                    KeyT *__restrict__ keys, int3 *__restrict__ recs, int tbits) {
     const i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-    i32 ra = -1, rb = -1, rc = -1;
-    double mnx = 0, mxx = 0, mny = 0, mxy = 0;
-    bool live = false;
-    if (t < Tg) {
-        ra = tri_rows[3 * t]; rb = tri_rows[3 * t + 1]; rc = tri_rows[3 * t + 2];
-        live = ra >= 0 && rb >= 0 && rc >= 0;
-        if (live) {
-            const double2 A = sec_xy[ra], B = sec_xy[rb], C = sec_xy[rc];
-            mnx = fmin(A.x, fmin(B.x, C.x)); mxx = fmax(A.x, fmax(B.x, C.x));
-            mny = fmin(A.y, fmin(B.y, C.y)); mxy = fmax(A.y, fmax(B.y, C.y));
+    if (t > Tg) return;
+    if (t == Tg) { if (!FILL) count[t] = 0; return; }
+    i32 out = FILL ? pos[t] : 0;
+    const i32 ra = tri_rows[3 * t], rb = tri_rows[3 * t + 1], rc = tri_rows[3 * t + 2];
+    if (ra >= 0 && rb >= 0 && rc >= 0) {
+        const double2 A = sec_xy[ra], B = sec_xy[rb], C = sec_xy[rc];
+        const double mnx = fmin(A.x, fmin(B.x, C.x)), mxx = fmax(A.x, fmax(B.x, C.x));
+        const double mny = fmin(A.y, fmin(B.y, C.y)), mxy = fmax(A.y, fmax(B.y, C.y));
+        const int c = rect_cell(ri, mnx, mny);   // a rectangle holding the whole bbox holds this corner
+        const i32 hi = ri.cell_ptr[c + 1];
+        for (i32 k = ri.cell_ptr[c]; k < hi; ++k) {
+            const int w = ri.cell_rects[k];
+            const double *r = rects + 4 * (i64)w;   // x_min, x_max, y_min, y_max ; half-open (same.py:293-295)
+            if (!(mnx >= r[0] && mxx < r[1] && mny >= r[2] && mxy < r[3])) continue;
+            const i32 klo = ka_off[w], khi = ka_off[w + 1];
+            int3 v;
+            v.x = kept_lookup(keepA, klo, khi, ra);
+            if (v.x < 0) continue;
+            v.y = kept_lookup(keepA, klo, khi, rb);
+            if (v.y < 0) continue;
+            v.z = kept_lookup(keepA, klo, khi, rc);
+            if (v.z < 0) continue;
+            if (FILL) {
+                keys[out] = (KeyT)(((unsigned long long)w << tbits) | (unsigned long long)t);
+                recs[out] = v;
+            }
+            ++out;
         }
     }
-    const unsigned lane = threadIdx.x & 31u;
-    for (int w0 = 0; w0 < W; w0 += RECT_TILE) {
-        const int nw = min(RECT_TILE, W - w0);
-        __syncthreads();
-        for (int k = threadIdx.x; k < nw; k += blockDim.x) srect[k] = reinterpret_cast<const double4 *>(rects)[w0 + k];
-        __syncthreads();
-        // every lane walks the rectangle list in lockstep so that hits on the same window can be counted /
-        // placed with ONE atomic per warp (2 M single-address atomics cost 1.1 ms otherwise)
-        for (int k = 0; k < nw; ++k) {
-            const double4 r = srect[k];  // x_min, x_max, y_min, y_max ; half-open (same.py:293-295)
-            const int w = w0 + k;
-            bool hit = live && mnx >= r.x && mxx < r.y && mny >= r.z && mxy < r.w;
-            int3 v = make_int3(-1, -1, -1);
-            if (hit) {
-                const i32 lo = ka_off[w], hi = ka_off[w + 1];
-                v.x = kept_lookup(keepA, lo, hi, ra);
-                if (v.x >= 0) v.y = kept_lookup(keepA, lo, hi, rb);
-                if (v.y >= 0) v.z = kept_lookup(keepA, lo, hi, rc);
-                hit = v.z >= 0;
-            }
-            const unsigned m = __ballot_sync(0xffffffffu, hit);
-            if (m == 0u) continue;
-            const int leader = __ffs(m) - 1;
-            if (!FILL) {
-                if ((int)lane == leader) atomicAdd(win_count + w, __popc(m));
-            } else {
-                i32 base = 0;
-                if ((int)lane == leader) base = atomicAdd(cursor, __popc(m));
-                base = __shfl_sync(0xffffffffu, base, leader);
-                if (hit) {
-                    const i32 pos = base + __popc(m & ((1u << lane) - 1u));
-                    keys[pos] = ((unsigned long long)w << tbits) | (unsigned long long)t;
-                    recs[pos] = v;
-                }
-            }
-        }
-    }
+    if (!FILL) count[t] = out;
 }
 
-__global__ void k_remap_gather(const unsigned long long *__restrict__ sorted_keys, const i32 *__restrict__ sorted_idx,
-                               const int3 *__restrict__ recs, i64 n, int tbits, int3 *__restrict__ tin, i32 *__restrict__ tin_src) {
+template <typename KeyT>
+__global__ void k_remap_gather(const KeyT *__restrict__ sorted_keys, const i32 *__restrict__ sorted_idx,
+                               const int3 *__restrict__ recs, i64 n, int tbits, i64 W, int3 *__restrict__ tin, i32 *__restrict__ tin_src,
+                               i32 *__restrict__ tin_off) {
     const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    tin[i] = recs[sorted_idx[i]];
-    tin_src[i] = (i32)(sorted_keys[i] & ((1ull << tbits) - 1ull));
+    if (i < n) {
+        tin[i] = recs[sorted_idx[i]];
+        tin_src[i] = (i32)((unsigned long long)sorted_keys[i] & ((1ull << tbits) - 1ull));
+    }
+    if (i <= W) {
+        const unsigned long long key = (unsigned long long)i << tbits;
+        i64 lo = 0, hi = n;
+        while (lo < hi) {
+            const i64 mid = (lo + hi) >> 1;
+            if ((unsigned long long)sorted_keys[mid] < key) lo = mid + 1; else hi = mid;
+        }
+        tin_off[i] = (i32)lo;
+    }
 }
 
 __global__ void k_iota_tri(i32 *p, i64 n) {
@@ -97,51 +89,59 @@ static void reset_triangles(Batch *b) {
     b->Tin = 0; b->T = 0; b->n_band = 0; b->tin_has_src = false; b->have_post = false;
 }
 
-void batch_triangles_remap(Batch *b) {
+template <typename KeyT>
+static void remap_t(Batch *b, int tbits, int wbits) {
     Section *sec = b->sec;
     cudaStream_t s = b->stream;
-    REQUIRE(b->stage >= 1, SAME_E_STATE, "same_batch_triangles_remap before same_batch_candidates");
-    REQUIRE(sec->Tg >= 0, SAME_E_STATE, "same_section_set_triangles was not called");
-    reset_triangles(b);
     const i64 W = b->W, Tg = sec->Tg;
-    int tbits = 1;
-    while ((1ll << tbits) < Tg) ++tbits;
-    DevBuf<i32> win_count, cursor;
-    win_count.alloc(W, s); cursor.alloc(1, s);
-    win_count.zero(s); cursor.zero(s);
-    if (Tg > 0)
-        LAUNCH(k_remap_scan<false>, blocks_for(Tg, 256), 256, 0, s, sec->tri_rows.p, Tg, sec->a_xy.p, b->d_rects.p, (int)W, b->keepA.p, b->d_ka_off.p,
-               win_count.p, (unsigned long long *)nullptr, (int3 *)nullptr, (i32 *)nullptr, tbits);
-    std::vector<i32> h(W);
-    CK(cudaMemcpyAsync(h.data(), win_count.p, sizeof(i32) * W, cudaMemcpyDeviceToHost, s));
+    // count -> exclusive scan -> fill in (triangle, window) order -> ONE stable radix pass over the window bits
+    DevBuf<i32> count, pos;
+    count.alloc(Tg + 1, s); pos.alloc(Tg + 1, s);
+    LAUNCH((k_remap_scan<false, KeyT>), blocks_for(Tg + 1, 256), 256, 0, s, sec->tri_rows.p, Tg, sec->a_xy.p, b->d_rects.p, b->rindex, b->keepA.p,
+           b->d_ka_off.p, count.p, (const i32 *)nullptr, (KeyT *)nullptr, (int3 *)nullptr, tbits);
+    exclusive_scan_i32(count.p, pos.p, Tg + 1, b->scratch, s);
+    i32 h = 0;
+    CK(cudaMemcpyAsync(&h, pos.p + Tg, sizeof(h), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
-    b->tin_off.assign(W + 1, 0);
-    for (i64 w = 0; w < W; ++w) b->tin_off[w + 1] = b->tin_off[w] + h[w];
-    b->Tin = b->tin_off[W];
-    REQUIRE(b->Tin < (1ll << 31), SAME_E_LIMIT, "too many window triangles");
-    upload_offsets(b->tin_off, b->d_tin_off, s);
+    b->Tin = (i64)h;
+    REQUIRE(b->Tin >= 0, SAME_E_LIMIT, "too many window triangles");
+    DevBuf<KeyT> keys, keys_out;
+    DevBuf<int3> recs;
+    DevBuf<i32> idx, idx_out;
     b->tin.alloc(b->Tin, s); b->tin_src.alloc(b->Tin, s);
+    b->d_tin_off.alloc(W + 1, s);
+    keys.alloc(b->Tin, s); recs.alloc(b->Tin, s); keys_out.alloc(b->Tin, s); idx.alloc(b->Tin, s); idx_out.alloc(b->Tin, s);
     if (b->Tin > 0) {
-        DevBuf<unsigned long long> keys, keys_out;
-        DevBuf<int3> recs;
-        DevBuf<i32> idx, idx_out;
-        keys.alloc(b->Tin, s); keys_out.alloc(b->Tin, s); recs.alloc(b->Tin, s); idx.alloc(b->Tin, s); idx_out.alloc(b->Tin, s);
-        LAUNCH(k_remap_scan<true>, blocks_for(Tg, 256), 256, 0, s, sec->tri_rows.p, Tg, sec->a_xy.p, b->d_rects.p, (int)W, b->keepA.p, b->d_ka_off.p,
-               (i32 *)nullptr, keys.p, recs.p, cursor.p, tbits);
+        LAUNCH((k_remap_scan<true, KeyT>), blocks_for(Tg + 1, 256), 256, 0, s, sec->tri_rows.p, Tg, sec->a_xy.p, b->d_rects.p, b->rindex, b->keepA.p,
+               b->d_ka_off.p, (i32 *)nullptr, pos.p, keys.p, recs.p, tbits);
         LAUNCH(k_iota_tri, blocks_for(b->Tin, 256), 256, 0, s, idx.p, b->Tin);
-        int wbits = 1;
-        while ((1ll << wbits) < W) ++wbits;
         size_t bytes = 0;
-        CK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, keys.p, keys_out.p, idx.p, idx_out.p, (int)b->Tin, 0, tbits + wbits, s));
+        CK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, keys.p, keys_out.p, idx.p, idx_out.p, (int)b->Tin, tbits, tbits + wbits, s));
         void *tmp = b->scratch.get(bytes, s);
         {
             ProfScope prof("cub::DeviceRadixSort::SortPairs(remap)", s);
-            CK(cub::DeviceRadixSort::SortPairs(tmp, bytes, keys.p, keys_out.p, idx.p, idx_out.p, (int)b->Tin, 0, tbits + wbits, s));
+            CK(cub::DeviceRadixSort::SortPairs(tmp, bytes, keys.p, keys_out.p, idx.p, idx_out.p, (int)b->Tin, tbits, tbits + wbits, s));
         }
         g_launches.fetch_add(1, std::memory_order_relaxed);
-        LAUNCH(k_remap_gather, blocks_for(b->Tin, 256), 256, 0, s, keys_out.p, idx_out.p, recs.p, b->Tin, tbits, b->tin.p, b->tin_src.p);
-        CK(cudaStreamSynchronize(s));
     }
+    LAUNCH((k_remap_gather<KeyT>), blocks_for(std::max<i64>(b->Tin, W + 1), 256), 256, 0, s, keys_out.p, idx_out.p, recs.p, b->Tin, tbits, W, b->tin.p,
+           b->tin_src.p, b->d_tin_off.p);
+    std::vector<i32> ho(W + 1);
+    CK(cudaMemcpyAsync(ho.data(), b->d_tin_off.p, sizeof(i32) * (W + 1), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    b->tin_off.assign(ho.begin(), ho.end());
+}
+
+void batch_triangles_remap(Batch *b) {
+    Section *sec = b->sec;
+    REQUIRE(b->stage >= 1, SAME_E_STATE, "same_batch_triangles_remap before same_batch_candidates");
+    REQUIRE(sec->Tg >= 0, SAME_E_STATE, "same_section_set_triangles was not called");
+    reset_triangles(b);
+    int tbits = 1, wbits = 1;
+    while ((1ll << tbits) < sec->Tg) ++tbits;
+    while ((1ll << wbits) < b->W + 1) ++wbits;
+    if (tbits + wbits <= 32) remap_t<unsigned>(b, tbits, wbits);
+    else remap_t<unsigned long long>(b, tbits, wbits);
     b->tin_has_src = true;
     b->stage = 2;
 }
