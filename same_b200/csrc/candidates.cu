@@ -14,7 +14,14 @@
 namespace same {
 
 constexpr int MAX_RINGS = 4;
-constexpr double TARGET_PER_BIN = 12.0;
+static double target_per_bin() {   // reference cells per bin; SAME_B200_BIN_TARGET overrides (tuning only)
+    static const double v = [] {
+        const char *e = getenv("SAME_B200_BIN_TARGET");
+        const double x = e ? atof(e) : 0.0;
+        return x >= 1.0 ? x : 12.0;
+    }();
+    return v;
+}
 constexpr int MAX_BINS_AXIS = 2048;
 
 // ---- binning -------------------------------------------------------------------------
@@ -59,82 +66,147 @@ __global__ void k_gather_xy(const i32 *__restrict__ inst, const i32 *__restrict_
 // short-circuit form compiled to divergent branches inside the insertion: 180 SASS instructions at ~3 active lanes)
 __device__ __forceinline__ bool cand_less(double d, i32 j, double bd, i32 bj) { return (d < bd) | ((d == bd) & (j < bj)); }
 
+// Sorted top-k of one query in registers, right-aligned: slots [KCAP-knn, KCAP) hold the list (ascending), the
+// slots before it are -inf sentinels that never move, so the k-th best is always the LAST slot (a static register
+// index; a runtime index would push the arrays into local memory).  Branch-free: lt[u] = candidate sorts before
+// slot u (on the old values); slot u takes slot u-1 if lt[u-1], the candidate if only lt[u], else keeps its value.
+// A candidate that does not beat the last slot — e.g. the (inf, INT_MAX) filler of an idle lane — is a no-op.
+template <int KCAP>
+__device__ __forceinline__ void topk_insert(double (&bd)[KCAP], i32 (&bj)[KCAP], double d2, i32 j) {
+    bool lt[KCAP];
+#pragma unroll
+    for (int u = 0; u < KCAP; ++u) lt[u] = cand_less(d2, j, bd[u], bj[u]);
+#pragma unroll
+    for (int u = KCAP - 1; u > 0; --u) {
+        bd[u] = lt[u - 1] ? bd[u - 1] : (lt[u] ? d2 : bd[u]);
+        bj[u] = lt[u - 1] ? bj[u - 1] : (lt[u] ? j : bj[u]);
+    }
+    bd[0] = lt[0] ? d2 : bd[0];
+    bj[0] = lt[0] ? j : bj[0];
+}
+
+// Search kernel.  Thread = query, but the WARP walks one shared candidate stream: the 32 queries of a warp are
+// neighbours in bin order, so the warp takes the strip of bins that holds them ("home" strip, <= KNN_SPAN bins of one
+// bin row of one window), then the frames of bins around it ring by ring; every reference cell of a visited bin is
+// loaded once (warp-uniform address) and scored by all lanes.  A lane does not insert right away — the sorted
+// insertion is ~80 instructions and only a few lanes need it for any given candidate (ncu: 3 of 32 lanes active in
+// the thread-per-query version) — it appends the candidate to its own small queue in shared memory, and the warp
+// drains all queues together when one is nearly full, so the insertion network runs with most lanes busy.
+// Bins / rings that no lane can still use (per-lane gap^2 > min(r^2, k-th best), any-vote) are skipped.  The inclusion
+// predicate and the ranking stay exact fp64 (d2 = dx*dx + dy*dy, no FMA; d2 <= r*r; order (d2, ref index)).
+constexpr int KNN_Q = 8;      // queue slots per lane
+constexpr int KNN_CH = 4;     // candidates scored between two queue checks (a lane can add KNN_CH entries)
+constexpr int KNN_SPAN = 6;   // widest home strip (bins) of one warp pass; lanes beyond it take another pass
+
+// drain every lane's queue: as many insertion rounds as the fullest queue of the warp holds
+template <int KCAP>
+__device__ __forceinline__ void knn_flush(double (&bd)[KCAP], i32 (&bj)[KCAP], int &qn, const double (*q_d)[128], const i32 (*q_j)[128], int tid) {
+    const int rounds = __reduce_max_sync(0xffffffffu, qn);
+    for (int r = 0; r < rounds; ++r) {
+        const bool have = r < qn;
+        const double d2 = have ? q_d[r][tid] : INFINITY;
+        const i32 j = have ? q_j[r][tid] : 0x7fffffff;
+        topk_insert<KCAP>(bd, bj, d2, j);
+    }
+    qn = 0;
+}
+
 template <int KCAP>
 __global__ void __launch_bounds__(128) k_knn(const double2 *__restrict__ sa_xy, const i32 *__restrict__ sa_inst, i64 nAi,
                                              const i32 *__restrict__ a_off, int W, const GridParams *__restrict__ grids,
                                              const i32 *__restrict__ bin_start, const double2 *__restrict__ sr_xy,
                                              const i32 *__restrict__ sr_inst, double r2, int knn, i32 *__restrict__ cand,
                                              i32 *__restrict__ cnt, i32 *__restrict__ r_used) {
-    const i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= nAi) return;
-    const i32 inst = sa_inst[t];
-    const double2 q = sa_xy[t];
-    const GridParams g = grids[find_window(a_off, W, inst)];
-    int cbx, cby;
-    bin_of(g, q, cbx, cby);
-    const double px = q.x - g.x0, py = q.y - g.y0;
-    const double eps = 1e-7 * g.w;
-
-    // Sorted top-k in registers, right-aligned: slots [KCAP-knn, KCAP) hold the list (ascending), the slots
-    // before it are -inf sentinels that never move, so the k-th best is always the LAST slot (a static
-    // register index; a runtime index would push the arrays into local memory).
+    __shared__ double q_d[KNN_Q][128];
+    __shared__ i32 q_j[KNN_Q][128];
+    constexpr unsigned FULL = 0xffffffffu;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const i64 t = (i64)blockIdx.x * blockDim.x + tid;
+    const bool live = t < nAi;
+    i32 inst = 0;
+    double2 q = make_double2(0.0, 0.0);
+    int w = -1;
+    if (live) {
+        inst = sa_inst[t];
+        q = sa_xy[t];
+        w = find_window(a_off, W, inst);
+    }
     double bd[KCAP];
     i32 bj[KCAP];
     const int head = KCAP - knn;
 #pragma unroll
     for (int s = 0; s < KCAP; ++s) { bd[s] = (s < head) ? -INFINITY : INFINITY; bj[s] = 0x7fffffff; }
-#define tau_d bd[KCAP - 1]
-#define tau_j bj[KCAP - 1]
-    int found = 0;
+    int qn = 0;
 
-    for (int ring = 0; ring <= g.rings; ++ring) {
-        const double lim = fmin(tau_d, r2);
-        if (ring > 0) {
-            // nearest possible point of this ring (Chebyshev distance `ring` bins from the centre bin)
-            const double fx = px - cbx * g.w, fy = py - cby * g.w;
-            const double gap = (ring - 1) * g.w + fmin(fmin(fx, g.w - fx), fmin(fy, g.w - fy)) - eps;
-            if (gap > 0.0 && gap * gap > lim) break;
+    unsigned todo = __ballot_sync(FULL, live);
+    while (todo) {
+        // one pass = the lanes of the leader's window and bin row whose bin lies within KNN_SPAN of the leader's
+        const int leader = __ffs(todo) - 1;
+        const int w0 = __shfl_sync(FULL, w, leader);
+        // field-by-field: a struct copy of GridParams goes through local memory
+        const GridParams *gp = grids + w0;
+        struct { double x0, y0, inv_w, w; i32 nbx, nby, base, rings; } g = {gp->x0, gp->y0, gp->inv_w, gp->w, gp->nbx, gp->nby, gp->base, gp->rings};
+        int cbx = 0, cby = 0;
+        if (live) {
+            cbx = min(max((int)floor((q.x - g.x0) * g.inv_w), 0), g.nbx - 1);
+            cby = min(max((int)floor((q.y - g.y0) * g.inv_w), 0), g.nby - 1);
         }
-        for (int dy = -ring; dy <= ring; ++dy) {
-            const int by = cby + dy;
-            if (by < 0 || by >= g.nby) continue;
-            const int step = (dy == -ring || dy == ring || ring == 0) ? 1 : 2 * ring;
-            const double ylo = by * g.w, yhi = ylo + g.w;
-            const double gy = fmax(0.0, fmax(ylo - py, py - yhi) - eps);
-            for (int dx = -ring; dx <= ring; dx += step) {
-                const int bx = cbx + dx;
-                if (bx < 0 || bx >= g.nbx) continue;
-                const double xlo = bx * g.w, xhi = xlo + g.w;
-                const double gx = fmax(0.0, fmax(xlo - px, px - xhi) - eps);
-                if (gx * gx + gy * gy > fmin(tau_d, r2)) continue;
-                const i32 b = g.base + by * g.nbx + bx;
-                const i32 s1 = bin_start[b + 1];
-                for (i32 s = bin_start[b]; s < s1; ++s) {
-                    const double2 p = sr_xy[s];
-                    const double ddx = __dsub_rn(p.x, q.x), ddy = __dsub_rn(p.y, q.y);
-                    const double d2 = __dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy));
-                    if ((d2 <= r2) & (d2 <= tau_d)) {
-                        const i32 j = sr_inst[s];
-                        if (cand_less(d2, j, tau_d, tau_j)) {
-                            // branch-free sorted insertion: lt[u] = candidate sorts before slot u (computed on the old
-                            // values); slot u takes slot u-1 if lt[u-1], the candidate if lt[u] only, else keeps its value
-                            bool lt[KCAP];
+        const int bx0 = __shfl_sync(FULL, cbx, leader), by0 = __shfl_sync(FULL, cby, leader);
+        const bool mine = ((todo >> lane) & 1u) && w == w0 && cby == by0 && cbx >= bx0 && cbx < bx0 + KNN_SPAN;
+        todo &= ~__ballot_sync(FULL, mine);
+        const int bx1 = __reduce_max_sync(FULL, mine ? cbx : bx0);
+        const double px = q.x - g.x0, py = q.y - g.y0;
+        const double eps = 1e-7 * g.w;
+        for (int ring = 0; ring <= g.rings; ++ring) {
+            if (ring > 0) {
+                // every cell of this ring lies outside the home strip grown by ring-1 bins: its distance to the query is at
+                // least the query's distance to the nearest side of that rectangle
+                const double gl = px - (bx0 - ring + 1) * g.w, gr = (bx1 + ring) * g.w - px;
+                const double gb = py - (by0 - ring + 1) * g.w, gt = (by0 + ring) * g.w - py;
+                const double gap = fmin(fmin(gl, gr), fmin(gb, gt)) - eps;
+                const bool need = mine && !(gap > 0.0 && gap * gap > fmin(bd[KCAP - 1], r2));
+                if (!__any_sync(FULL, need)) break;
+            }
+            const int xa = bx0 - ring, xb = bx1 + ring;
+            for (int by = by0 - ring; by <= by0 + ring; ++by) {
+                if (by < 0 || by >= g.nby) continue;
+                const bool edge_row = (by == by0 - ring) || (by == by0 + ring);
+                const double gy = fmax(0.0, fmax(by * g.w - py, py - (by + 1) * g.w) - eps);
+                const double gy2 = gy * gy;
+                const int step = edge_row ? 1 : max(xb - xa, 1);   // inner rows of a ring: only its two end columns
+                for (int bx = xa; bx <= xb; bx += step) {
+                    if (bx < 0 || bx >= g.nbx) continue;
+                    const double gx = fmax(0.0, fmax(bx * g.w - px, px - (bx + 1) * g.w) - eps);
+                    const bool want = mine && gx * gx + gy2 <= fmin(bd[KCAP - 1], r2);
+                    if (!__any_sync(FULL, want)) continue;
+                    const i32 b = g.base + by * g.nbx + bx;
+                    const i32 s1 = bin_start[b + 1];
+                    for (i32 s = bin_start[b]; s < s1; s += KNN_CH) {
+                        if (__any_sync(FULL, qn > KNN_Q - KNN_CH)) knn_flush<KCAP>(bd, bj, qn, q_d, q_j, tid);
+                        const double lim = mine ? fmin(bd[KCAP - 1], r2) : -1.0;
 #pragma unroll
-                            for (int u = 0; u < KCAP; ++u) lt[u] = cand_less(d2, j, bd[u], bj[u]);
-#pragma unroll
-                            for (int u = KCAP - 1; u > 0; --u) {
-                                bd[u] = lt[u - 1] ? bd[u - 1] : (lt[u] ? d2 : bd[u]);
-                                bj[u] = lt[u - 1] ? bj[u - 1] : (lt[u] ? j : bj[u]);
+                        for (int c = 0; c < KNN_CH; ++c) {
+                            if (s + c < s1) {
+                                const double2 p = sr_xy[s + c];
+                                const double ddx = __dsub_rn(p.x, q.x), ddy = __dsub_rn(p.y, q.y);
+                                const double d2 = __dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy));
+                                if (d2 <= lim) {
+                                    q_d[qn][tid] = d2;
+                                    q_j[qn][tid] = sr_inst[s + c];
+                                    ++qn;
+                                }
                             }
-                            bd[0] = lt[0] ? d2 : bd[0];
-                            bj[0] = lt[0] ? j : bj[0];
-                            found = min(found + 1, knn);
                         }
                     }
                 }
             }
         }
     }
+    knn_flush<KCAP>(bd, bj, qn, q_d, q_j, tid);
+    if (!live) return;
+    int found = 0;
+#pragma unroll
+    for (int u = 0; u < KCAP; ++u) found += (u >= head) && (bd[u] < INFINITY);
     cnt[inst] = found;
     i32 *out = cand + (i64)inst * knn;
 #pragma unroll
@@ -144,8 +216,6 @@ __global__ void __launch_bounds__(128) k_knn(const double2 *__restrict__ sa_xy, 
             out[u - head] = ok ? bj[u] : -1;
             if (ok) r_used[bj[u]] = 1;
         }
-#undef tau_d
-#undef tau_j
 }
 
 // generic path for knn > 32: top-k lives in global scratch ([slot][query] so threads coalesce)
@@ -329,7 +399,7 @@ void batch_candidates(Batch *b, double radius, int knn, int priority, double dis
         if (!(y1 > y0)) y1 = y0;
         const double ex = x1 - x0, ey = y1 - y0;
         const i64 nref = b->r_off[w + 1] - b->r_off[w];
-        double bw = std::sqrt(TARGET_PER_BIN * std::max(ex, 1e-300) * std::max(ey, 1e-300) / (double)std::max<i64>(nref, 1));
+        double bw = std::sqrt(target_per_bin() * std::max(ex, 1e-300) * std::max(ey, 1e-300) / (double)std::max<i64>(nref, 1));
         bw = std::max(bw, radius * (1.0 + 1e-9) / MAX_RINGS);
         bw = std::max(bw, std::max(ex, ey) / MAX_BINS_AXIS);
         if (!(bw > 0.0) || !std::isfinite(bw)) bw = 1.0;
