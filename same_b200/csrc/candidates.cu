@@ -85,18 +85,17 @@ __device__ __forceinline__ void topk_insert(double (&bd)[KCAP], i32 (&bj)[KCAP],
     bj[0] = lt[0] ? j : bj[0];
 }
 
-// Search kernel.  Thread = query, but the WARP walks one shared candidate stream: the 32 queries of a warp are
-// neighbours in bin order, so the warp takes the strip of bins that holds them ("home" strip, <= KNN_SPAN bins of one
-// bin row of one window), then the frames of bins around it ring by ring; every reference cell of a visited bin is
-// loaded once (warp-uniform address) and scored by all lanes.  A lane does not insert right away — the sorted
-// insertion is ~80 instructions and only a few lanes need it for any given candidate (ncu: 3 of 32 lanes active in
-// the thread-per-query version) — it appends the candidate to its own small queue in shared memory, and the warp
-// drains all queues together when one is nearly full, so the insertion network runs with most lanes busy.
-// Bins / rings that no lane can still use (per-lane gap^2 > min(r^2, k-th best), any-vote) are skipped.  The inclusion
-// predicate and the ranking stay exact fp64 (d2 = dx*dx + dy*dy, no FMA; d2 <= r*r; order (d2, ref index)).
+// Search kernel.  Thread = query; every lane walks the bins around ITS OWN bin, nearest ring first, and skips bins and
+// rings that cannot beat min(r^2, current k-th best) (conservative bounds; the exact fp64 predicate decides each
+// candidate).  What is shared by the warp is the CONTROL FLOW: all lanes step through the same (ring, dy, dx)
+// offsets and the same candidate slots of "their" bin, a lane whose bin is pruned or shorter is just predicated off.
+// That keeps the warp converged, which lets a lane postpone its insertions: the sorted insertion is ~80
+// instructions and only ~1 candidate in 6 needs it (ncu on the divergent version: 47 % of all warp instructions ran
+// with 3 of 32 lanes active), so a lane appends a passing candidate to a small queue in shared memory and the warp
+// drains all queues together when one is nearly full — the insertion network then runs with most lanes busy.
+// A warp-wide shared candidate stream was tried and rejected: 30/32 lanes active, but 3-4x the distance evaluations
+// and insertions in stream order (profiles/r1j_knn_warp_stream_experiment.md).
 constexpr int KNN_Q = 8;      // queue slots per lane
-constexpr int KNN_CH = 4;     // candidates scored between two queue checks (a lane can add KNN_CH entries)
-constexpr int KNN_SPAN = 6;   // widest home strip (bins) of one warp pass; lanes beyond it take another pass
 
 // drain every lane's queue: as many insertion rounds as the fullest queue of the warp holds
 template <int KCAP>
@@ -120,82 +119,71 @@ __global__ void __launch_bounds__(128) k_knn(const double2 *__restrict__ sa_xy, 
     __shared__ double q_d[KNN_Q][128];
     __shared__ i32 q_j[KNN_Q][128];
     constexpr unsigned FULL = 0xffffffffu;
-    const int tid = threadIdx.x, lane = tid & 31;
+    const int tid = threadIdx.x;
     const i64 t = (i64)blockIdx.x * blockDim.x + tid;
     const bool live = t < nAi;
     i32 inst = 0;
     double2 q = make_double2(0.0, 0.0);
-    int w = -1;
+    double gw = 1.0, px = 0.0, py = 0.0;
+    int nbx = 0, nby = 0, base = 0, rings = -1, cbx = 0, cby = 0;
     if (live) {
         inst = sa_inst[t];
         q = sa_xy[t];
-        w = find_window(a_off, W, inst);
+        const GridParams *gp = grids + find_window(a_off, W, inst);
+        gw = gp->w; nbx = gp->nbx; nby = gp->nby; base = gp->base; rings = gp->rings;
+        px = q.x - gp->x0; py = q.y - gp->y0;
+        cbx = min(max((int)floor(px * gp->inv_w), 0), nbx - 1);
+        cby = min(max((int)floor(py * gp->inv_w), 0), nby - 1);
     }
+    const double eps = 1e-7 * gw;
+    const double fx = px - cbx * gw, fy = py - cby * gw;
+    const double edge = fmin(fmin(fx, gw - fx), fmin(fy, gw - fy)) - eps;   // distance to the nearest side of the own bin
     double bd[KCAP];
     i32 bj[KCAP];
     const int head = KCAP - knn;
 #pragma unroll
     for (int s = 0; s < KCAP; ++s) { bd[s] = (s < head) ? -INFINITY : INFINITY; bj[s] = 0x7fffffff; }
     int qn = 0;
-
-    unsigned todo = __ballot_sync(FULL, live);
-    while (todo) {
-        // one pass = the lanes of the leader's window and bin row whose bin lies within KNN_SPAN of the leader's
-        const int leader = __ffs(todo) - 1;
-        const int w0 = __shfl_sync(FULL, w, leader);
-        // field-by-field: a struct copy of GridParams goes through local memory
-        const GridParams *gp = grids + w0;
-        struct { double x0, y0, inv_w, w; i32 nbx, nby, base, rings; } g = {gp->x0, gp->y0, gp->inv_w, gp->w, gp->nbx, gp->nby, gp->base, gp->rings};
-        int cbx = 0, cby = 0;
-        if (live) {
-            cbx = min(max((int)floor((q.x - g.x0) * g.inv_w), 0), g.nbx - 1);
-            cby = min(max((int)floor((q.y - g.y0) * g.inv_w), 0), g.nby - 1);
+    bool open = live;   // this lane still has rings to visit
+    const int max_rings = __reduce_max_sync(FULL, rings);
+    for (int ring = 0; ring <= max_rings; ++ring) {
+        if (ring > 0) {
+            // nearest possible point of this ring (Chebyshev distance `ring` bins from the own bin)
+            if (__any_sync(FULL, qn > 0)) knn_flush<KCAP>(bd, bj, qn, q_d, q_j, tid);   // the ring test wants the true k-th best
+            const double gap = (ring - 1) * gw + edge;
+            open = open && ring <= rings && !(gap > 0.0 && gap * gap > fmin(bd[KCAP - 1], r2));
+            if (!__any_sync(FULL, open)) break;
         }
-        const int bx0 = __shfl_sync(FULL, cbx, leader), by0 = __shfl_sync(FULL, cby, leader);
-        const bool mine = ((todo >> lane) & 1u) && w == w0 && cby == by0 && cbx >= bx0 && cbx < bx0 + KNN_SPAN;
-        todo &= ~__ballot_sync(FULL, mine);
-        const int bx1 = __reduce_max_sync(FULL, mine ? cbx : bx0);
-        const double px = q.x - g.x0, py = q.y - g.y0;
-        const double eps = 1e-7 * g.w;
-        for (int ring = 0; ring <= g.rings; ++ring) {
-            if (ring > 0) {
-                // every cell of this ring lies outside the home strip grown by ring-1 bins: its distance to the query is at
-                // least the query's distance to the nearest side of that rectangle
-                const double gl = px - (bx0 - ring + 1) * g.w, gr = (bx1 + ring) * g.w - px;
-                const double gb = py - (by0 - ring + 1) * g.w, gt = (by0 + ring) * g.w - py;
-                const double gap = fmin(fmin(gl, gr), fmin(gb, gt)) - eps;
-                const bool need = mine && !(gap > 0.0 && gap * gap > fmin(bd[KCAP - 1], r2));
-                if (!__any_sync(FULL, need)) break;
-            }
-            const int xa = bx0 - ring, xb = bx1 + ring;
-            for (int by = by0 - ring; by <= by0 + ring; ++by) {
-                if (by < 0 || by >= g.nby) continue;
-                const bool edge_row = (by == by0 - ring) || (by == by0 + ring);
-                const double gy = fmax(0.0, fmax(by * g.w - py, py - (by + 1) * g.w) - eps);
-                const double gy2 = gy * gy;
-                const int step = edge_row ? 1 : max(xb - xa, 1);   // inner rows of a ring: only its two end columns
-                for (int bx = xa; bx <= xb; bx += step) {
-                    if (bx < 0 || bx >= g.nbx) continue;
-                    const double gx = fmax(0.0, fmax(bx * g.w - px, px - (bx + 1) * g.w) - eps);
-                    const bool want = mine && gx * gx + gy2 <= fmin(bd[KCAP - 1], r2);
-                    if (!__any_sync(FULL, want)) continue;
-                    const i32 b = g.base + by * g.nbx + bx;
-                    const i32 s1 = bin_start[b + 1];
-                    for (i32 s = bin_start[b]; s < s1; s += KNN_CH) {
-                        if (__any_sync(FULL, qn > KNN_Q - KNN_CH)) knn_flush<KCAP>(bd, bj, qn, q_d, q_j, tid);
-                        const double lim = mine ? fmin(bd[KCAP - 1], r2) : -1.0;
-#pragma unroll
-                        for (int c = 0; c < KNN_CH; ++c) {
-                            if (s + c < s1) {
-                                const double2 p = sr_xy[s + c];
-                                const double ddx = __dsub_rn(p.x, q.x), ddy = __dsub_rn(p.y, q.y);
-                                const double d2 = __dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy));
-                                if (d2 <= lim) {
-                                    q_d[qn][tid] = d2;
-                                    q_j[qn][tid] = sr_inst[s + c];
-                                    ++qn;
-                                }
+        for (int dy = -ring; dy <= ring; ++dy) {
+            const int by = cby + dy;
+            const bool row_ok = open && by >= 0 && by < nby;
+            const double gy = fmax(0.0, fmax(by * gw - py, py - (by + 1) * gw) - eps);
+            const double gy2 = gy * gy;
+            const int step = (dy == -ring || dy == ring || ring == 0) ? 1 : 2 * ring;
+            for (int dx = -ring; dx <= ring; dx += step) {
+                const int bx = cbx + dx;
+                const double gx = fmax(0.0, fmax(bx * gw - px, px - (bx + 1) * gw) - eps);
+                const bool want = row_ok && bx >= 0 && bx < nbx && gx * gx + gy2 <= fmin(bd[KCAP - 1], r2);
+                i32 s0 = 0, len = 0;
+                if (want) {
+                    const i32 b = base + by * nbx + bx;
+                    s0 = bin_start[b];
+                    len = bin_start[b + 1] - s0;
+                }
+                const int maxlen = __reduce_max_sync(FULL, len);
+                for (int i = 0; i < maxlen; ++i) {
+                    if (i < len) {
+                        const double2 p = sr_xy[s0 + i];
+                        const double ddx = __dsub_rn(p.x, q.x), ddy = __dsub_rn(p.y, q.y);
+                        const double d2 = __dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy));
+                        if (d2 <= fmin(bd[KCAP - 1], r2)) {
+                            if (qn == KNN_Q) {   // rare: this lane alone filled its queue between two warp-wide drains
+                                for (int r = 0; r < KNN_Q; ++r) topk_insert<KCAP>(bd, bj, q_d[r][tid], q_j[r][tid]);
+                                qn = 0;
                             }
+                            q_d[qn][tid] = d2;
+                            q_j[qn][tid] = sr_inst[s0 + i];
+                            ++qn;
                         }
                     }
                 }

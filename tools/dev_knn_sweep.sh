@@ -1,5 +1,5 @@
 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
-for t in 12 6 8 16 24; do
+for t in ${TARGETS:-12}; do
 SAME_B200_BIN_TARGET=$t python bench.py --steps 5 --no-cpu-baseline --no-e2e > gpurun_out/bench_knn_$t.json 2>gpurun_out/bench_knn_$t.err
 python - <<PY
 import json
