@@ -251,7 +251,11 @@ def main():
     halo = exchange_halo(W, rank, world, device) if world > 1 else None
     rects, grid = window_rects(W, rank, world)
     tri_vid = triangulate(W["a_xy"])            # global (per-strip) Delaunay, the "precomputed triangulation" of the examples
-    stream = torch.cuda.current_stream().cuda_stream
+    # one explicit stream for everything: the library launches on it and the stage events are recorded on it
+    # (the default stream has handle 0, which the library reads as "create your own stream")
+    tstream = torch.cuda.Stream(device=device)
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
     flush_buf = torch.empty(512 << 20, dtype=torch.uint8, device=device)
 
     def pinned(a):

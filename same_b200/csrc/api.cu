@@ -42,6 +42,7 @@ i64 elem_size(int what) {
 }
 
 ArrayView view(Batch *b, int what) {
+    batch_settle(b);
     auto need = [&](int st, const char *m) { REQUIRE(b->stage >= st, SAME_E_STATE, m); };
     const i64 es = elem_size(what);
     switch (what) {
@@ -205,6 +206,7 @@ int same_batch_create(same_section_t *h, int64_t n_windows, const double *rects,
             else b->rects = {-INFINITY, INFINITY, -INFINITY, INFINITY};
             batch_subset(b);
         } catch (...) {
+            batch_pin_release(b);
             delete b;
             throw;
         }
@@ -218,6 +220,7 @@ int same_batch_destroy(same_batch_t *h) {
         if (!b) return;
         CK(cudaSetDevice(b->sec->device));
         cudaStream_t s = b->stream;
+        batch_pin_release(b);
         delete b;
         CK(cudaStreamSynchronize(s));
     });
@@ -316,6 +319,6 @@ int same_pinned_free(void *p) {
     return guarded([&] { if (p) CK(cudaFreeHost(p)); });
 }
 
-int same_batch_sync(same_batch_t *h) { BATCH_CALL(h, CK(cudaStreamSynchronize(b->stream))); }
+int same_batch_sync(same_batch_t *h) { BATCH_CALL(h, batch_sync(b)); }
 
 }  // extern "C"

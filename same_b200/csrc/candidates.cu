@@ -14,14 +14,7 @@
 namespace same {
 
 constexpr int MAX_RINGS = 4;
-static double target_per_bin() {   // reference cells per bin; SAME_B200_BIN_TARGET overrides (tuning only)
-    static const double v = [] {
-        const char *e = getenv("SAME_B200_BIN_TARGET");
-        const double x = e ? atof(e) : 0.0;
-        return x >= 1.0 ? x : 12.0;
-    }();
-    return v;
-}
+constexpr double TARGET_PER_BIN = 12.0;
 constexpr int MAX_BINS_AXIS = 2048;
 
 // ---- binning -------------------------------------------------------------------------
@@ -32,33 +25,60 @@ __device__ __forceinline__ void bin_of(const GridParams &g, double2 p, int &bx, 
     by = min(max(by, 0), g.nby - 1);
 }
 
-__global__ void k_bin_keys(const i32 *__restrict__ src, const double2 *__restrict__ sec_xy, i64 n, const i32 *__restrict__ off, int W,
-                           const GridParams *__restrict__ grids, unsigned *__restrict__ keys, i32 *__restrict__ vals) {
-    i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int w = find_window(off, W, (i32)i);
-    const GridParams g = grids[w];
+// Counting sort of BOTH frames' window instances by bin (item < nAi: aligned instance, else reference instance
+// item - nAi): pass 1 computes the bin of every instance and counts bin populations (counter [frame][bin]); the
+// counters are scanned in one launch (scan.cuh); pass 2 scatters (xy, instance) to start[bin] + a slot taken from the
+// same counter.  The order of the cells INSIDE a bin is arbitrary; the search ranks candidates by the total order
+// (d2, reference instance), so its result does not depend on it.
+__global__ void k_bin_count(const i32 *__restrict__ a_src, const i32 *__restrict__ r_src, const double2 *__restrict__ a_xy,
+                            const double2 *__restrict__ r_xy, i64 nAi, i64 nRi, const i32 *__restrict__ a_off, const i32 *__restrict__ r_off, int W,
+                            const GridParams *__restrict__ grids, i64 nb1, i32 *__restrict__ bkey, i32 *__restrict__ bcnt) {
+    const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nAi + nRi) return;
+    const bool ref = i >= nAi;
+    const i32 inst = (i32)(ref ? i - nAi : i);
+    const GridParams &g = grids[find_window(ref ? r_off : a_off, W, inst)];
     int bx, by;
-    bin_of(g, sec_xy[src[i]], bx, by);
-    keys[i] = (unsigned)(g.base + by * g.nbx + bx);
-    vals[i] = (i32)i;
+    bin_of(g, ref ? r_xy[r_src[inst]] : a_xy[a_src[inst]], bx, by);
+    const i32 key = g.base + by * g.nbx + bx;
+    bkey[i] = key;
+    atomicAdd(bcnt + (ref ? nb1 : 0) + key, 1);
 }
 
-__global__ void k_bin_starts(const unsigned *__restrict__ sorted_keys, i64 n, i64 nbins, i32 *__restrict__ start) {
-    i64 b = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (b > nbins) return;
-    i64 lo = 0, hi = n;  // lower bound of key b
-    while (lo < hi) {
-        const i64 mid = (lo + hi) >> 1;
-        if ((i64)sorted_keys[mid] < b) lo = mid + 1; else hi = mid;
+__global__ void k_bin_scatter(const i32 *__restrict__ a_src, const i32 *__restrict__ r_src, const double2 *__restrict__ a_xy,
+                              const double2 *__restrict__ r_xy, i64 nAi, i64 nRi, i64 nb1, const i32 *__restrict__ bkey,
+                              const i32 *__restrict__ bstart, i32 *__restrict__ bcnt, double2 *__restrict__ sorted_xy, i32 *__restrict__ sorted_inst) {
+    const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nAi + nRi) return;
+    const bool ref = i >= nAi;
+    const i32 inst = (i32)(ref ? i - nAi : i);
+    const i64 c = (ref ? nb1 : 0) + bkey[i];
+    const i32 dst = bstart[c] + atomicSub(bcnt + c, 1) - 1;
+    sorted_xy[dst] = ref ? r_xy[r_src[inst]] : a_xy[a_src[inst]];
+    sorted_inst[dst] = inst;
+}
+
+// out[i] = sum of in[0 .. i-1] for i in [0, n): one launch, 4 items per thread
+constexpr int SCAN_THREADS = 1024, SCAN_ITEMS = 8;   // big tiles: one L2 round trip of look-back per 32 tiles
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_i32(const i32 *__restrict__ in, i32 *__restrict__ out, i64 n, ScanCtx sc) {
+    __shared__ int smem[SCAN_THREADS / 32 + 1];
+    const i64 base = ((i64)blockIdx.x * SCAN_THREADS + threadIdx.x) * SCAN_ITEMS;
+    int v[SCAN_ITEMS], sum[1] = {0};
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) { v[k] = base + k < n ? in[base + k] : 0; sum[0] += v[k]; }
+    int excl[1], tot[1], pre[1];
+    device_exclusive_scan<1, SCAN_THREADS>(sc, (int)blockIdx.x, sum, excl, tot, pre, smem);
+    int run = excl[0];
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        if (base + k < n) out[base + k] = run;
+        run += v[k];
     }
-    start[b] = (i32)lo;
 }
-
-__global__ void k_gather_xy(const i32 *__restrict__ inst, const i32 *__restrict__ src, const double2 *__restrict__ sec_xy, i64 n,
-                            double2 *__restrict__ out) {
-    i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = sec_xy[src[inst[i]]];
+void scan_i32(Section *sec, const i32 *in, i32 *out, i64 n, cudaStream_t s) {
+    if (n <= 0) return;
+    const unsigned tiles = blocks_for(n, SCAN_THREADS * SCAN_ITEMS);
+    LAUNCH(k_scan_i32, tiles, SCAN_THREADS, 0, s, in, out, n, scan_ctx(sec, tiles, 1, s));
 }
 
 // ---- top-k search ----------------------------------------------------------------------
@@ -66,135 +86,82 @@ __global__ void k_gather_xy(const i32 *__restrict__ inst, const i32 *__restrict_
 // short-circuit form compiled to divergent branches inside the insertion: 180 SASS instructions at ~3 active lanes)
 __device__ __forceinline__ bool cand_less(double d, i32 j, double bd, i32 bj) { return (d < bd) | ((d == bd) & (j < bj)); }
 
-// Sorted top-k of one query in registers, right-aligned: slots [KCAP-knn, KCAP) hold the list (ascending), the
-// slots before it are -inf sentinels that never move, so the k-th best is always the LAST slot (a static register
-// index; a runtime index would push the arrays into local memory).  Branch-free: lt[u] = candidate sorts before
-// slot u (on the old values); slot u takes slot u-1 if lt[u-1], the candidate if only lt[u], else keeps its value.
-// A candidate that does not beat the last slot — e.g. the (inf, INT_MAX) filler of an idle lane — is a no-op.
-template <int KCAP>
-__device__ __forceinline__ void topk_insert(double (&bd)[KCAP], i32 (&bj)[KCAP], double d2, i32 j) {
-    bool lt[KCAP];
-#pragma unroll
-    for (int u = 0; u < KCAP; ++u) lt[u] = cand_less(d2, j, bd[u], bj[u]);
-#pragma unroll
-    for (int u = KCAP - 1; u > 0; --u) {
-        bd[u] = lt[u - 1] ? bd[u - 1] : (lt[u] ? d2 : bd[u]);
-        bj[u] = lt[u - 1] ? bj[u - 1] : (lt[u] ? j : bj[u]);
-    }
-    bd[0] = lt[0] ? d2 : bd[0];
-    bj[0] = lt[0] ? j : bj[0];
-}
-
-// Search kernel.  Thread = query; every lane walks the bins around ITS OWN bin, nearest ring first, and skips bins and
-// rings that cannot beat min(r^2, current k-th best) (conservative bounds; the exact fp64 predicate decides each
-// candidate).  What is shared by the warp is the CONTROL FLOW: all lanes step through the same (ring, dy, dx)
-// offsets and the same candidate slots of "their" bin, a lane whose bin is pruned or shorter is just predicated off.
-// That keeps the warp converged, which lets a lane postpone its insertions: the sorted insertion is ~80
-// instructions and only ~1 candidate in 6 needs it (ncu on the divergent version: 47 % of all warp instructions ran
-// with 3 of 32 lanes active), so a lane appends a passing candidate to a small queue in shared memory and the warp
-// drains all queues together when one is nearly full — the insertion network then runs with most lanes busy.
-// A warp-wide shared candidate stream was tried and rejected: 30/32 lanes active, but 3-4x the distance evaluations
-// and insertions in stream order (profiles/r1j_knn_warp_stream_experiment.md).
-constexpr int KNN_Q = 8;      // queue slots per lane
-
-// drain every lane's queue: as many insertion rounds as the fullest queue of the warp holds
-template <int KCAP>
-__device__ __forceinline__ void knn_flush(double (&bd)[KCAP], i32 (&bj)[KCAP], int &qn, const double (*q_d)[128], const i32 (*q_j)[128], int tid) {
-    const int rounds = __reduce_max_sync(0xffffffffu, qn);
-    for (int r = 0; r < rounds; ++r) {
-        const bool have = r < qn;
-        const double d2 = have ? q_d[r][tid] : INFINITY;
-        const i32 j = have ? q_j[r][tid] : 0x7fffffff;
-        topk_insert<KCAP>(bd, bj, d2, j);
-    }
-    qn = 0;
-}
-
 template <int KCAP>
 __global__ void __launch_bounds__(128) k_knn(const double2 *__restrict__ sa_xy, const i32 *__restrict__ sa_inst, i64 nAi,
                                              const i32 *__restrict__ a_off, int W, const GridParams *__restrict__ grids,
                                              const i32 *__restrict__ bin_start, const double2 *__restrict__ sr_xy,
                                              const i32 *__restrict__ sr_inst, double r2, int knn, i32 *__restrict__ cand,
                                              i32 *__restrict__ cnt, i32 *__restrict__ r_used) {
-    __shared__ double q_d[KNN_Q][128];
-    __shared__ i32 q_j[KNN_Q][128];
-    constexpr unsigned FULL = 0xffffffffu;
-    const int tid = threadIdx.x;
-    const i64 t = (i64)blockIdx.x * blockDim.x + tid;
-    const bool live = t < nAi;
-    i32 inst = 0;
-    double2 q = make_double2(0.0, 0.0);
-    double gw = 1.0, px = 0.0, py = 0.0;
-    int nbx = 0, nby = 0, base = 0, rings = -1, cbx = 0, cby = 0;
-    if (live) {
-        inst = sa_inst[t];
-        q = sa_xy[t];
-        const GridParams *gp = grids + find_window(a_off, W, inst);
-        gw = gp->w; nbx = gp->nbx; nby = gp->nby; base = gp->base; rings = gp->rings;
-        px = q.x - gp->x0; py = q.y - gp->y0;
-        cbx = min(max((int)floor(px * gp->inv_w), 0), nbx - 1);
-        cby = min(max((int)floor(py * gp->inv_w), 0), nby - 1);
-    }
-    const double eps = 1e-7 * gw;
-    const double fx = px - cbx * gw, fy = py - cby * gw;
-    const double edge = fmin(fmin(fx, gw - fx), fmin(fy, gw - fy)) - eps;   // distance to the nearest side of the own bin
+    const i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nAi) return;
+    const i32 inst = sa_inst[t];
+    const double2 q = sa_xy[t];
+    const GridParams g = grids[find_window(a_off, W, inst)];
+    int cbx, cby;
+    bin_of(g, q, cbx, cby);
+    const double px = q.x - g.x0, py = q.y - g.y0;
+    const double eps = 1e-7 * g.w;
+
+    // Sorted top-k in registers, right-aligned: slots [KCAP-knn, KCAP) hold the list (ascending), the slots
+    // before it are -inf sentinels that never move, so the k-th best is always the LAST slot (a static
+    // register index; a runtime index would push the arrays into local memory).
     double bd[KCAP];
     i32 bj[KCAP];
     const int head = KCAP - knn;
 #pragma unroll
     for (int s = 0; s < KCAP; ++s) { bd[s] = (s < head) ? -INFINITY : INFINITY; bj[s] = 0x7fffffff; }
-    int qn = 0;
-    bool open = live;   // this lane still has rings to visit
-    const int max_rings = __reduce_max_sync(FULL, rings);
-    for (int ring = 0; ring <= max_rings; ++ring) {
+#define tau_d bd[KCAP - 1]
+#define tau_j bj[KCAP - 1]
+    int found = 0;
+
+    for (int ring = 0; ring <= g.rings; ++ring) {
+        const double lim = fmin(tau_d, r2);
         if (ring > 0) {
-            // nearest possible point of this ring (Chebyshev distance `ring` bins from the own bin)
-            if (__any_sync(FULL, qn > 0)) knn_flush<KCAP>(bd, bj, qn, q_d, q_j, tid);   // the ring test wants the true k-th best
-            const double gap = (ring - 1) * gw + edge;
-            open = open && ring <= rings && !(gap > 0.0 && gap * gap > fmin(bd[KCAP - 1], r2));
-            if (!__any_sync(FULL, open)) break;
+            // nearest possible point of this ring (Chebyshev distance `ring` bins from the centre bin)
+            const double fx = px - cbx * g.w, fy = py - cby * g.w;
+            const double gap = (ring - 1) * g.w + fmin(fmin(fx, g.w - fx), fmin(fy, g.w - fy)) - eps;
+            if (gap > 0.0 && gap * gap > lim) break;
         }
         for (int dy = -ring; dy <= ring; ++dy) {
             const int by = cby + dy;
-            const bool row_ok = open && by >= 0 && by < nby;
-            const double gy = fmax(0.0, fmax(by * gw - py, py - (by + 1) * gw) - eps);
-            const double gy2 = gy * gy;
+            if (by < 0 || by >= g.nby) continue;
             const int step = (dy == -ring || dy == ring || ring == 0) ? 1 : 2 * ring;
+            const double ylo = by * g.w, yhi = ylo + g.w;
+            const double gy = fmax(0.0, fmax(ylo - py, py - yhi) - eps);
             for (int dx = -ring; dx <= ring; dx += step) {
                 const int bx = cbx + dx;
-                const double gx = fmax(0.0, fmax(bx * gw - px, px - (bx + 1) * gw) - eps);
-                const bool want = row_ok && bx >= 0 && bx < nbx && gx * gx + gy2 <= fmin(bd[KCAP - 1], r2);
-                i32 s0 = 0, len = 0;
-                if (want) {
-                    const i32 b = base + by * nbx + bx;
-                    s0 = bin_start[b];
-                    len = bin_start[b + 1] - s0;
-                }
-                const int maxlen = __reduce_max_sync(FULL, len);
-                for (int i = 0; i < maxlen; ++i) {
-                    if (i < len) {
-                        const double2 p = sr_xy[s0 + i];
-                        const double ddx = __dsub_rn(p.x, q.x), ddy = __dsub_rn(p.y, q.y);
-                        const double d2 = __dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy));
-                        if (d2 <= fmin(bd[KCAP - 1], r2)) {
-                            if (qn == KNN_Q) {   // rare: this lane alone filled its queue between two warp-wide drains
-                                for (int r = 0; r < KNN_Q; ++r) topk_insert<KCAP>(bd, bj, q_d[r][tid], q_j[r][tid]);
-                                qn = 0;
+                if (bx < 0 || bx >= g.nbx) continue;
+                const double xlo = bx * g.w, xhi = xlo + g.w;
+                const double gx = fmax(0.0, fmax(xlo - px, px - xhi) - eps);
+                if (gx * gx + gy * gy > fmin(tau_d, r2)) continue;
+                const i32 b = g.base + by * g.nbx + bx;
+                const i32 s1 = bin_start[b + 1];
+                for (i32 s = bin_start[b]; s < s1; ++s) {
+                    const double2 p = sr_xy[s];
+                    const double ddx = __dsub_rn(p.x, q.x), ddy = __dsub_rn(p.y, q.y);
+                    const double d2 = __dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy));
+                    if ((d2 <= r2) & (d2 <= tau_d)) {
+                        const i32 j = sr_inst[s];
+                        if (cand_less(d2, j, tau_d, tau_j)) {
+                            // branch-free sorted insertion: lt[u] = candidate sorts before slot u (computed on the old
+                            // values); slot u takes slot u-1 if lt[u-1], the candidate if lt[u] only, else keeps its value
+                            bool lt[KCAP];
+#pragma unroll
+                            for (int u = 0; u < KCAP; ++u) lt[u] = cand_less(d2, j, bd[u], bj[u]);
+#pragma unroll
+                            for (int u = KCAP - 1; u > 0; --u) {
+                                bd[u] = lt[u - 1] ? bd[u - 1] : (lt[u] ? d2 : bd[u]);
+                                bj[u] = lt[u - 1] ? bj[u - 1] : (lt[u] ? j : bj[u]);
                             }
-                            q_d[qn][tid] = d2;
-                            q_j[qn][tid] = sr_inst[s0 + i];
-                            ++qn;
+                            bd[0] = lt[0] ? d2 : bd[0];
+                            bj[0] = lt[0] ? j : bj[0];
+                            found = min(found + 1, knn);
                         }
                     }
                 }
             }
         }
     }
-    knn_flush<KCAP>(bd, bj, qn, q_d, q_j, tid);
-    if (!live) return;
-    int found = 0;
-#pragma unroll
-    for (int u = 0; u < KCAP; ++u) found += (u >= head) && (bd[u] < INFINITY);
     cnt[inst] = found;
     i32 *out = cand + (i64)inst * knn;
 #pragma unroll
@@ -204,6 +171,8 @@ __global__ void __launch_bounds__(128) k_knn(const double2 *__restrict__ sa_xy, 
             out[u - head] = ok ? bj[u] : -1;
             if (ok) r_used[bj[u]] = 1;
         }
+#undef tau_d
+#undef tau_j
 }
 
 // generic path for knn > 32: top-k lives in global scratch ([slot][query] so threads coalesce)
@@ -292,11 +261,6 @@ __global__ void k_eff(const i32 *__restrict__ cand, const i32 *__restrict__ cnt,
 }
 
 // ---- compaction + emission ----------------------------------------------------------------
-__global__ void k_flag_pos(const i32 *__restrict__ v, i64 n, i32 *__restrict__ f) {
-    i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) f[i] = v[i] > 0;
-    if (i == n) f[i] = 0;
-}
 __global__ void k_fill_i32(i32 *p, i64 n, i32 v) {
     i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
@@ -311,29 +275,74 @@ __global__ void k_window_offsets(const i32 *__restrict__ newA, const i32 *__rest
     off3[2 * (W + 1) + w] = poff[a_off[w]];
 }
 
-__global__ void k_emit_aligned(const i32 *__restrict__ cnt, const i32 *__restrict__ newA, const i32 *__restrict__ poff, i64 nAi,
-                               const i32 *__restrict__ a_src, const double2 *__restrict__ sec_xy, const i32 *__restrict__ sec_type,
-                               const double *__restrict__ sec_size, i32 *__restrict__ keepA, double2 *__restrict__ ka_xy,
-                               i32 *__restrict__ ka_type, double *__restrict__ ka_size, i32 *__restrict__ row_ptr, i64 nKA, i32 P) {
-    i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i == 0) row_ptr[nKA] = P;
-    if (i >= nAi || cnt[i] == 0) return;
-    const i32 k = newA[i], row = a_src[i];
-    keepA[k] = row;
-    ka_xy[k] = sec_xy[row];
-    ka_type[k] = sec_type[row];
-    ka_size[k] = sec_size[row];
-    row_ptr[k] = poff[i];
-}
-__global__ void k_emit_ref(const i32 *__restrict__ used, const i32 *__restrict__ newR, i64 nRi, const i32 *__restrict__ r_src,
-                           const double2 *__restrict__ sec_xy, const double *__restrict__ sec_size, i32 *__restrict__ keepR,
-                           double2 *__restrict__ kr_xy, double *__restrict__ kr_size) {
-    i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nRi || used[i] == 0) return;
-    const i32 k = newR[i], row = r_src[i];
-    keepR[k] = row;
-    kr_xy[k] = sec_xy[row];
-    kr_size[k] = sec_size[row];
+// Frame compaction in one launch (src/utils.py:734-741): blocks [0, tilesA) scan the aligned instances — kept flag
+// (cnt > 0) and emitted pairs (eff) together — and write the kept aligned rows; blocks [tilesA, ..) scan the used flag of
+// the reference instances and write the kept reference rows.  Item nAi / nRi is a sentinel that receives the totals.
+constexpr int COMPACT_THREADS = 1024, COMPACT_ITEMS = 4;   // big tiles: one L2 round trip of look-back per 32 tiles
+__global__ void __launch_bounds__(COMPACT_THREADS) k_compact_frames(
+    const i32 *__restrict__ cnt, const i32 *__restrict__ eff, const i32 *__restrict__ r_used, i64 nAi, i64 nRi, unsigned tilesA, ScanCtx scA, ScanCtx scR,
+    const i32 *__restrict__ a_src, const i32 *__restrict__ r_src, const double2 *__restrict__ a_xy, const double2 *__restrict__ r_xy,
+    const i32 *__restrict__ a_type, const double *__restrict__ a_size, const double *__restrict__ r_size, i32 *__restrict__ newA,
+    i32 *__restrict__ newR, i32 *__restrict__ poff, i32 *__restrict__ keepA, double2 *__restrict__ ka_xy, i32 *__restrict__ ka_type,
+    double *__restrict__ ka_size, i32 *__restrict__ row_ptr, i32 *__restrict__ keepR, double2 *__restrict__ kr_xy, double *__restrict__ kr_size) {
+    __shared__ int smem[2 * (COMPACT_THREADS / 32) + 2];
+    int f[COMPACT_ITEMS], e[COMPACT_ITEMS], sum[2] = {0, 0}, excl[2], tot[2], pre[2];
+    if (blockIdx.x < tilesA) {
+        const i64 base = ((i64)blockIdx.x * COMPACT_THREADS + threadIdx.x) * COMPACT_ITEMS;
+#pragma unroll
+        for (int k = 0; k < COMPACT_ITEMS; ++k) {
+            const bool in = base + k < nAi;
+            f[k] = in ? cnt[base + k] > 0 : 0;
+            e[k] = in ? eff[base + k] : 0;
+            sum[0] += f[k];
+            sum[1] += e[k];
+        }
+        device_exclusive_scan<2, COMPACT_THREADS>(scA, (int)blockIdx.x, sum, excl, tot, pre, smem);
+        i32 kpos = excl[0], ppos = excl[1];
+#pragma unroll
+        for (int k = 0; k < COMPACT_ITEMS; ++k) {
+            const i64 i = base + k;
+            if (i <= nAi) {
+                newA[i] = kpos;
+                poff[i] = ppos;
+                if (i == nAi) row_ptr[kpos] = ppos;   // row_ptr[nKA] = P
+                if (f[k]) {
+                    const i32 row = a_src[i];
+                    keepA[kpos] = row;
+                    ka_xy[kpos] = a_xy[row];
+                    ka_type[kpos] = a_type[row];
+                    ka_size[kpos] = a_size[row];
+                    row_ptr[kpos] = ppos;
+                }
+            }
+            kpos += f[k];
+            ppos += e[k];
+        }
+    } else {
+        const unsigned tile = blockIdx.x - tilesA;
+        const i64 base = ((i64)tile * COMPACT_THREADS + threadIdx.x) * COMPACT_ITEMS;
+#pragma unroll
+        for (int k = 0; k < COMPACT_ITEMS; ++k) {
+            f[k] = base + k < nRi ? r_used[base + k] != 0 : 0;
+            sum[0] += f[k];
+        }
+        device_exclusive_scan<2, COMPACT_THREADS>(scR, (int)tile, sum, excl, tot, pre, smem);
+        i32 kpos = excl[0];
+#pragma unroll
+        for (int k = 0; k < COMPACT_ITEMS; ++k) {
+            const i64 i = base + k;
+            if (i <= nRi) {
+                newR[i] = kpos;
+                if (f[k]) {
+                    const i32 row = r_src[i];
+                    keepR[kpos] = row;
+                    kr_xy[kpos] = r_xy[row];
+                    kr_size[kpos] = r_size[row];
+                }
+            }
+            kpos += f[k];
+        }
+    }
 }
 
 // one thread per (aligned instance, slot): pair indices + cost (src/same.py:1183-1188)
@@ -387,7 +396,7 @@ void batch_candidates(Batch *b, double radius, int knn, int priority, double dis
         if (!(y1 > y0)) y1 = y0;
         const double ex = x1 - x0, ey = y1 - y0;
         const i64 nref = b->r_off[w + 1] - b->r_off[w];
-        double bw = std::sqrt(target_per_bin() * std::max(ex, 1e-300) * std::max(ey, 1e-300) / (double)std::max<i64>(nref, 1));
+        double bw = std::sqrt(TARGET_PER_BIN * std::max(ex, 1e-300) * std::max(ey, 1e-300) / (double)std::max<i64>(nref, 1));
         bw = std::max(bw, radius * (1.0 + 1e-9) / MAX_RINGS);
         bw = std::max(bw, std::max(ex, ey) / MAX_BINS_AXIS);
         if (!(bw > 0.0) || !std::isfinite(bw)) bw = 1.0;
@@ -406,34 +415,22 @@ void batch_candidates(Batch *b, double radius, int knn, int priority, double dis
     d_grids.alloc(W, s);
     CK(cudaMemcpyAsync(d_grids.p, grids.data(), sizeof(GridParams) * W, cudaMemcpyHostToDevice, s));
 
-    // sort both frames' instances by bin
-    DevBuf<unsigned> keys_in, keys_out;
-    DevBuf<i32> vals_in, sr_inst, sa_inst, bin_start;
-    DevBuf<double2> sr_xy, sa_xy;
-    const i64 nmax = std::max(nAi, nRi);
-    keys_in.alloc(nmax, s); keys_out.alloc(nmax, s); vals_in.alloc(nmax, s);
-    sr_inst.alloc(nRi, s); sa_inst.alloc(nAi, s); sr_xy.alloc(nRi, s); sa_xy.alloc(nAi, s);
-    bin_start.alloc(nbins + 1, s);
-    const int kb = bits_for(nbins + 1);
-    auto sort_frame = [&](const DevBuf<i32> &src, const DevBuf<double2> &xy, i64 n, const DevBuf<i32> &off, DevBuf<i32> &out_inst,
-                          DevBuf<double2> &out_xy) {
-        if (n == 0) return;
-        LAUNCH(k_bin_keys, blocks_for(n, 256), 256, 0, s, src.p, xy.p, n, off.p, (int)W, d_grids.p, keys_in.p, vals_in.p);
-        size_t bytes = 0;
-        CK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, keys_in.p, keys_out.p, vals_in.p, out_inst.p, (int)n, 0, kb, s));
-        void *tmp = b->scratch.get(bytes, s);
-        {
-            ProfScope prof("cub::DeviceRadixSort::SortPairs(bins)", s);
-            CK(cub::DeviceRadixSort::SortPairs(tmp, bytes, keys_in.p, keys_out.p, vals_in.p, out_inst.p, (int)n, 0, kb, s));
-        }
-        g_launches.fetch_add(1, std::memory_order_relaxed);
-        LAUNCH(k_gather_xy, blocks_for(n, 256), 256, 0, s, out_inst.p, src.p, xy.p, n, out_xy.p);
-    };
-    sort_frame(b->r_src, sec->r_xy, nRi, b->d_r_off, sr_inst, sr_xy);
-    LAUNCH(k_bin_starts, blocks_for(nbins + 1, 256), 256, 0, s, keys_out.p, nRi, nbins, bin_start.p);
-    sort_frame(b->a_src, sec->a_xy, nAi, b->d_a_off, sa_inst, sa_xy);
+    // counting sort of both frames' instances by bin
+    const i64 nb1 = nbins + 1, nI = nAi + nRi;
+    DevBuf<i32> bkey, bcnt, bstart, sorted_inst;
+    DevBuf<double2> sorted_xy;
+    bkey.alloc(nI, s); bcnt.alloc(2 * nb1, s); bstart.alloc(2 * nb1, s); sorted_inst.alloc(nI, s); sorted_xy.alloc(nI, s);
+    bcnt.zero(s);
+    if (nI > 0)
+        LAUNCH(k_bin_count, blocks_for(nI, 256), 256, 0, s, b->a_src.p, b->r_src.p, sec->a_xy.p, sec->r_xy.p, nAi, nRi, b->d_a_off.p, b->d_r_off.p, (int)W,
+               d_grids.p, nb1, bkey.p, bcnt.p);
+    scan_i32(sec, bcnt.p, bstart.p, 2 * nb1, s);
+    if (nI > 0)
+        LAUNCH(k_bin_scatter, blocks_for(nI, 256), 256, 0, s, b->a_src.p, b->r_src.p, sec->a_xy.p, sec->r_xy.p, nAi, nRi, nb1, bkey.p, bstart.p, bcnt.p,
+               sorted_xy.p, sorted_inst.p);
 
-    // top-k search
+    // top-k search: aligned instances are sorted[0, nAi), reference instances sorted[nAi, nAi + nRi); the bin starts of
+    // the reference frame (second half of bstart) are positions in the whole sorted array
     b->cand.alloc(nAi * knn, s);
     b->cnt.alloc(nAi + 1, s);
     b->r_used.alloc(nRi + 1, s);
@@ -441,7 +438,7 @@ void batch_candidates(Batch *b, double radius, int knn, int priority, double dis
     const double r2 = radius * radius;
     if (nAi > 0) {
         const unsigned grid = blocks_for(nAi, 128);
-#define KNN_ARGS sa_xy.p, sa_inst.p, nAi, b->d_a_off.p, (int)W, d_grids.p, bin_start.p, sr_xy.p, sr_inst.p, r2, knn
+#define KNN_ARGS sorted_xy.p, sorted_inst.p, nAi, b->d_a_off.p, (int)W, d_grids.p, bstart.p + nb1, sorted_xy.p, sorted_inst.p, r2, knn
         if (knn <= 4) LAUNCH(k_knn<4>, grid, 128, 0, s, KNN_ARGS, b->cand.p, b->cnt.p, b->r_used.p);
         else if (knn <= 8) LAUNCH(k_knn<8>, grid, 128, 0, s, KNN_ARGS, b->cand.p, b->cnt.p, b->r_used.p);
         else if (knn <= 16) LAUNCH(k_knn<16>, grid, 128, 0, s, KNN_ARGS, b->cand.p, b->cnt.p, b->r_used.p);
@@ -468,42 +465,35 @@ void batch_candidates(Batch *b, double radius, int knn, int priority, double dis
         eff = b->eff.p;
     }
 
-    // compaction maps
-    DevBuf<i32> flagA, newA, newR, poff, off3;
-    flagA.alloc(nAi + 1, s); newA.alloc(nAi + 1, s); newR.alloc(nRi + 1, s); poff.alloc(nAi + 1, s); off3.alloc(3 * (W + 1), s);
-    LAUNCH(k_flag_pos, blocks_for(nAi + 1, 256), 256, 0, s, b->cnt.p, nAi, flagA.p);
-    exclusive_scan_i32(flagA.p, newA.p, nAi + 1, b->scratch, s);
-    exclusive_scan_i32(b->r_used.p, newR.p, nRi + 1, b->scratch, s);   // r_used[nRi] == 0 from the memset
-    LAUNCH(k_flag_pos, 1, 1, 0, s, (const i32 *)nullptr, (i64)0, (i32 *)eff + nAi);  // sentinel: eff[nAi] = 0
-    exclusive_scan_i32(eff, poff.p, nAi + 1, b->scratch, s);
-    LAUNCH(k_window_offsets, blocks_for(W + 1, 128), 128, 0, s, newA.p, newR.p, poff.p, b->d_a_off.p, b->d_r_off.p, (int)W, off3.p);
-    std::vector<i32> h(3 * (W + 1));
-    CK(cudaMemcpyAsync(h.data(), off3.p, sizeof(i32) * h.size(), cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
-    b->ka_off.assign(h.begin(), h.begin() + W + 1);
-    b->kr_off.assign(h.begin() + W + 1, h.begin() + 2 * (W + 1));
-    b->p_off.assign(h.begin() + 2 * (W + 1), h.end());
-    b->nKA = b->ka_off[W]; b->nKR = b->kr_off[W]; b->P = b->p_off[W];
+    // compaction + emission without a host round trip: outputs are sized by their upper bounds (kept rows <= instances,
+    // pairs <= knn per aligned instance); the per-window offsets come back once, at the end
+    DevBuf<i32> newR, poff, off3;
+    b->newA.alloc(nAi + 1, s); newR.alloc(nRi + 1, s); poff.alloc(nAi + 1, s); off3.alloc(3 * (W + 1), s);
+    b->keepA.alloc(nAi, s); b->ka_xy.alloc(nAi, s); b->ka_type.alloc(nAi, s); b->ka_size.alloc(nAi, s);
+    b->row_ptr.alloc(nAi + 1, s);
+    b->keepR.alloc(nRi, s); b->kr_xy.alloc(nRi, s); b->kr_size.alloc(nRi, s);
+    b->pairs.alloc(nAi * knn, s); b->cost.alloc(nAi * knn, s);
+    const unsigned tilesA = blocks_for(nAi + 1, COMPACT_THREADS * COMPACT_ITEMS), tilesR = blocks_for(nRi + 1, COMPACT_THREADS * COMPACT_ITEMS);
+    {
+        scan_reserve(sec, 2 * ((i64)tilesA + tilesR), s);   // two independent scans in one launch: disjoint tile-state words
+        const ScanCtx scA = scan_ctx_at(sec, 0, tilesA), scR = scan_ctx_at(sec, 2 * (i64)tilesA, tilesR);
+        LAUNCH(k_compact_frames, tilesA + tilesR, COMPACT_THREADS, 0, s, b->cnt.p, eff, b->r_used.p, nAi, nRi, tilesA, scA, scR, b->a_src.p, b->r_src.p,
+               sec->a_xy.p, sec->r_xy.p, sec->a_type.p, sec->a_size.p, sec->r_size.p, b->newA.p, newR.p, poff.p, b->keepA.p, b->ka_xy.p, b->ka_type.p,
+               b->ka_size.p, b->row_ptr.p, b->keepR.p, b->kr_xy.p, b->kr_size.p);
+    }
+    LAUNCH(k_window_offsets, blocks_for(W + 1, 128), 128, 0, s, b->newA.p, newR.p, poff.p, b->d_a_off.p, b->d_r_off.p, (int)W, off3.p);
     b->d_ka_off.alloc(W + 1, s); b->d_kr_off.alloc(W + 1, s); b->d_p_off.alloc(W + 1, s);
     CK(cudaMemcpyAsync(b->d_ka_off.p, off3.p, sizeof(i32) * (W + 1), cudaMemcpyDeviceToDevice, s));
     CK(cudaMemcpyAsync(b->d_kr_off.p, off3.p + (W + 1), sizeof(i32) * (W + 1), cudaMemcpyDeviceToDevice, s));
     CK(cudaMemcpyAsync(b->d_p_off.p, off3.p + 2 * (W + 1), sizeof(i32) * (W + 1), cudaMemcpyDeviceToDevice, s));
-
-    // emission
-    b->keepA.alloc(b->nKA, s); b->ka_xy.alloc(b->nKA, s); b->ka_type.alloc(b->nKA, s); b->ka_size.alloc(b->nKA, s);
-    b->row_ptr.alloc(b->nKA + 1, s);
-    b->keepR.alloc(b->nKR, s); b->kr_xy.alloc(b->nKR, s); b->kr_size.alloc(b->nKR, s);
-    b->pairs.alloc(b->P, s); b->cost.alloc(b->P, s);
-    LAUNCH(k_emit_aligned, blocks_for(std::max<i64>(nAi, 1), 256), 256, 0, s, b->cnt.p, newA.p, poff.p, nAi, b->a_src.p, sec->a_xy.p, sec->a_type.p,
-           sec->a_size.p, b->keepA.p, b->ka_xy.p, b->ka_type.p, b->ka_size.p, b->row_ptr.p, b->nKA, (i32)b->P);
-    if (nRi > 0)
-        LAUNCH(k_emit_ref, blocks_for(nRi, 256), 256, 0, s, b->r_used.p, newR.p, nRi, b->r_src.p, sec->r_xy.p, sec->r_size.p, b->keepR.p,
-               b->kr_xy.p, b->kr_size.p);
-    if (nAi > 0 && b->P > 0)
-        LAUNCH(k_emit_pairs, blocks_for(nAi * knn, 256), 256, 0, s, b->cand.p, eff, knn, nAi, newA.p, newR.p, poff.p, b->d_a_off.p, (int)W,
+    if (nAi > 0)
+        LAUNCH(k_emit_pairs, blocks_for(nAi * knn, 256), 256, 0, s, b->cand.p, eff, knn, nAi, b->newA.p, newR.p, poff.p, b->d_a_off.p, (int)W,
                b->d_ka_off.p, b->d_kr_off.p, b->a_src.p, b->r_src.p, sec->a_xy.p, sec->r_xy.p, sec->a_prob.p, sec->r_prob.p, sec->K,
                dist_ct_coeff, dist_ct_coeff * 0.001, b->pairs.p, b->cost.p);
-    CK(cudaStreamSynchronize(s));  // temporaries (DevBuf) are released stream-ordered, but keep the stage boundary simple
+    // the window offsets come back asynchronously; whoever needs them on the host first waits for them (batch_settle)
+    CK(cudaMemcpyAsync(b->pin_cand(), off3.p, sizeof(i32) * 3 * (W + 1), cudaMemcpyDeviceToHost, s));
+    b->pend_cand = true;
+    b->pend_renum = false;
     b->stage = 1;
     b->have_groups = false;
     b->Tin = b->T = 0;
@@ -540,10 +530,9 @@ __global__ void k_window_max_size(const double *__restrict__ kr_size, i64 nKR, c
 // one thread per kept ref: its group id, node, size and limit
 __global__ void k_group_setup(i64 nKR, const i32 *__restrict__ kr_off, int W, const i32 *__restrict__ first, const i32 *__restrict__ cnt,
                               const i32 *__restrict__ gid_at, const double *__restrict__ kr_size, const unsigned long long *__restrict__ wmax,
-                              int max_matches, int multiplier, i32 *__restrict__ ref_gid, i32 *__restrict__ g_node, i32 *__restrict__ g_cnt,
-                              i32 *__restrict__ g_limit, i64 G) {
+                              int max_matches, int multiplier, i32 *__restrict__ ref_gid, i32 *__restrict__ g_node, i32 *__restrict__ g_cnt /* zeroed */,
+                              i32 *__restrict__ g_limit) {
     i64 r = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r == 0) g_cnt[G] = 0;
     if (r >= nKR) return;
     if (first[r] == 0x7fffffff) { ref_gid[r] = -1; return; }
     const int w = find_window(kr_off, W, (i32)r);
@@ -568,9 +557,9 @@ __global__ void k_group_fill(const int2 *__restrict__ pairs, i64 P, const i32 *_
     g_idx[g_ptr[g] + atomicAdd(cursor + g, 1)] = (i32)p - p_off[w];
 }
 // ascending pair index inside every group (insertion sort; groups hold ~knn entries)
-__global__ void k_group_sort(const i32 *__restrict__ g_ptr, i64 G, i32 *__restrict__ g_idx) {
+__global__ void k_group_sort(const i32 *__restrict__ g_ptr, const i32 *__restrict__ n_groups, i32 *__restrict__ g_idx) {
     i64 g = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= G) return;
+    if (g >= *n_groups) return;
     const i32 lo = g_ptr[g], n = g_ptr[g + 1] - lo;
     i32 *a = g_idx + lo;
     if (n <= 32) {
@@ -602,43 +591,42 @@ __global__ void k_pick(const i32 *__restrict__ scanned, const i32 *__restrict__ 
 
 void batch_groups(Batch *b, int max_matches, int multiplier) {
     cudaStream_t s = b->stream;
-    const i64 W = b->W, P = b->P, nKR = b->nKR;
     REQUIRE(b->stage >= 1, SAME_E_STATE, "same_batch_groups before same_batch_candidates");
+    batch_settle(b);
+    const i64 W = b->W, P = b->P, nKR = b->nKR;
     b->g_off.assign(W + 1, 0);
     b->G = 0;
     b->have_groups = true;
+    b->pend_groups = false;
     if (P == 0) {  // keep REF_GROUP_PTR (G + 1 = 1 element) readable
         b->g_ptr.alloc(1, s);
         b->g_ptr.zero(s);
-        CK(cudaStreamSynchronize(s));
         return;
     }
+    // every buffer is sized by its bound (groups <= kept reference rows), so nothing has to come back before the end
     DevBuf<i32> first, cnt, head, gid_at, goff, ref_gid, g_cnt, cursor;
     DevBuf<unsigned long long> wmax;
     first.alloc(nKR, s); cnt.alloc(nKR, s); head.alloc(P + 1, s); gid_at.alloc(P + 1, s); goff.alloc(W + 1, s); ref_gid.alloc(nKR, s);
     wmax.alloc(W, s);
     wmax.zero(s);
     cnt.zero(s);
+    b->g_node.alloc(nKR, s); b->g_ptr.alloc(nKR + 1, s); b->g_idx.alloc(P, s); b->g_limit.alloc(nKR, s);
+    g_cnt.alloc(nKR + 1, s); cursor.alloc(nKR, s);
+    g_cnt.zero(s);
+    cursor.zero(s);
     LAUNCH(k_fill_i32, blocks_for(nKR, 256), 256, 0, s, first.p, nKR, 0x7fffffff);
     LAUNCH(k_group_count, blocks_for(P, 256), 256, 0, s, b->pairs.p, P, b->d_p_off.p, b->d_kr_off.p, (int)W, first.p, cnt.p);
     LAUNCH(k_group_heads, blocks_for(P + 1, 256), 256, 0, s, b->pairs.p, P, b->d_p_off.p, b->d_kr_off.p, (int)W, first.p, head.p);
-    exclusive_scan_i32(head.p, gid_at.p, P + 1, b->scratch, s);
+    scan_i32(b->sec, head.p, gid_at.p, P + 1, s);
     LAUNCH(k_pick, blocks_for(W + 1, 128), 128, 0, s, gid_at.p, b->d_p_off.p, (int)(W + 1), goff.p);
+    CK(cudaMemcpyAsync(b->pin_groups(), goff.p, sizeof(i32) * (W + 1), cudaMemcpyDeviceToHost, s));
+    b->pend_groups = true;
     LAUNCH(k_window_max_size, blocks_for(nKR, 256), 256, 0, s, b->kr_size.p, nKR, b->d_kr_off.p, (int)W, wmax.p);
-    std::vector<i32> h(W + 1);
-    CK(cudaMemcpyAsync(h.data(), goff.p, sizeof(i32) * (W + 1), cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
-    b->g_off.assign(h.begin(), h.end());
-    const i64 G = b->G = b->g_off[W];
-    b->g_node.alloc(G, s); b->g_ptr.alloc(G + 1, s); b->g_idx.alloc(P, s); b->g_limit.alloc(G, s);
-    g_cnt.alloc(G + 1, s); cursor.alloc(G, s);
-    cursor.zero(s);
     LAUNCH(k_group_setup, blocks_for(nKR, 256), 256, 0, s, nKR, b->d_kr_off.p, (int)W, first.p, cnt.p, gid_at.p, b->kr_size.p, wmax.p, max_matches,
-           multiplier, ref_gid.p, b->g_node.p, g_cnt.p, b->g_limit.p, G);
-    exclusive_scan_i32(g_cnt.p, b->g_ptr.p, G + 1, b->scratch, s);
+           multiplier, ref_gid.p, b->g_node.p, g_cnt.p, b->g_limit.p);
+    scan_i32(b->sec, g_cnt.p, b->g_ptr.p, nKR + 1, s);   // entries past the number of groups repeat the total
     LAUNCH(k_group_fill, blocks_for(P, 256), 256, 0, s, b->pairs.p, P, b->d_p_off.p, b->d_kr_off.p, (int)W, ref_gid.p, b->g_ptr.p, cursor.p, b->g_idx.p);
-    LAUNCH(k_group_sort, blocks_for(G, 128), 128, 0, s, b->g_ptr.p, G, b->g_idx.p);
-    CK(cudaStreamSynchronize(s));
+    LAUNCH(k_group_sort, blocks_for(nKR, 128), 128, 0, s, b->g_ptr.p, gid_at.p + P, b->g_idx.p);
 }
 
 }  // namespace same

@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "../../include/same_b200.h"
+#include "scan.cuh"
 
 typedef int64_t i64;
 typedef int32_t i32;
@@ -132,7 +133,22 @@ struct Section {
     i64 Tg = -1;
     DevBuf<i32> tri_rows;  // [Tg*3]
     Scratch scratch;
+    // tile states of the in-kernel prefix sums (scan.cuh): zeroed when (re)allocated, separated by epoch afterwards
+    DevBuf<unsigned long long> scan_state;
+    unsigned scan_epoch = 0;
+    // page-locked staging blocks handed to batches (small device results come back asynchronously, see Batch::pin)
+    std::vector<std::pair<i32 *, i64>> pin_pool;
+    ~Section() {
+        for (auto &b : pin_pool) cudaFreeHost(b.first);
+    }
 };
+
+// tile-state context for one launch of `tiles` blocks scanning `n_streams` sums; a launch that runs several independent
+// scans reserves the words of all of them first and places each with scan_ctx_at
+ScanCtx scan_ctx(Section *sec, i64 tiles, int n_streams, cudaStream_t s);
+void scan_reserve(Section *sec, i64 words, cudaStream_t s);
+ScanCtx scan_ctx_at(Section *sec, i64 word_offset, i64 tiles);
+void scan_i32(Section *sec, const i32 *in, i32 *out, i64 n, cudaStream_t s);   // out[i] = sum(in[0..i-1]), one launch
 
 struct GridParams {  // uniform bin grid of one window (reference side)
     double x0, y0, inv_w, w;
@@ -161,20 +177,37 @@ struct Batch {
     std::vector<double> rects;  // W*4
     DevBuf<double> d_rects;
     DevBuf<i32> ri_ptr, ri_rects;
+    std::vector<i32> h_ri_ptr, h_ri_rects;
     RectIndexDev rindex{};
     Scratch scratch;
     int stage = 0;  // 0 created, 1 candidates, 2 triangles in, 3 classified, 4 finalized
+
+    // Small per-window results (offsets, counts) are copied to this page-locked block asynchronously and parsed into the
+    // host vectors at the next synchronisation (batch_sync): a stage does not have to drain the stream just to return.
+    i32 *pin = nullptr;
+    i64 pin_n = 0;
+    bool pend_cand = false, pend_tin = false, pend_renum = false, pend_groups = false;
+    i32 *pin_cand() const { return pin; }                              // 3(W+1): ka_off, kr_off, p_off
+    i32 *pin_tin() const { return pin + 3 * (W + 1); }                 // W+1
+    i32 *pin_renum() const { return pin + 4 * (W + 1); }               // W+1: p_off after node removal
+    i32 *pin_groups() const { return pin + 5 * (W + 1); }              // W+1
+    i32 *pin_misc() const { return pin + 6 * (W + 1); }                // 4(W+1) + 8 scratch for stages that synchronise themselves
 
     // window instances (subset_data)
     i64 nAi = 0, nRi = 0;
     std::vector<i64> a_off, r_off;      // W+1
     DevBuf<i32> d_a_off, d_r_off;       // W+1
     DevBuf<i32> a_src, r_src;           // section row of each instance
+    // row -> its window instances: entries [row_pos[row], row_pos[row+1]) of row_inst hold (window, instance index
+    // within the frame) in ascending window order; aligned rows first, reference row r at index nA + r
+    DevBuf<i32> row_pos;                // [nA + nR + 1]
+    DevBuf<int2> row_inst;              // [nAi + nRi]
 
     // candidates
     int knn = 0;
     double radius = 0;
     DevBuf<i32> cand, cnt, eff;         // [nAi*knn] ref instance, [nAi], [nAi] pairs emitted (priority)
+    DevBuf<i32> newA;                   // [nAi+1] batch-global kept index of each aligned instance (exclusive scan of cnt > 0)
     DevBuf<i32> r_used;                 // [nRi]
 
     // kept nodes (post-KNN frames), batch-global "kept index" = window offset + local index
@@ -225,12 +258,19 @@ struct Batch {
     // separation / postsolve
     DevBuf<double> x_dev;
     DevBuf<i32> match_j, match_p;       // [nKA]
-    DevBuf<i32> viol_flag, viol_pos, sep_counts, cuts;
+    DevBuf<i32> sep_counts, cuts;
+    std::vector<i32> h_sep;
     DevBuf<i32> t_mask;
     DevBuf<double> area_before, area_after;
     DevBuf<unsigned char> flipped;
     bool have_post = false;
 };
+
+// cudaStreamSynchronize + parse whatever small results were pending; batch_settle only synchronises if something is
+void batch_sync(Batch *b);
+void batch_settle(Batch *b);
+void batch_pin_acquire(Batch *b);
+void batch_pin_release(Batch *b);
 
 // implemented across the .cu files
 void section_build(Section *sec, const double *a_xy, const double *r_xy, const double *a_prob, const double *r_prob,

@@ -27,6 +27,56 @@ void upload_offsets(const std::vector<i64> &h, DevBuf<i32> &d, cudaStream_t s) {
     CK(cudaStreamSynchronize(s));  // t goes out of scope
 }
 
+void batch_pin_acquire(Batch *b) {
+    const i64 need = 10 * (b->W + 1) + 8;
+    auto &pool = b->sec->pin_pool;
+    for (size_t k = 0; k < pool.size(); ++k)
+        if (pool[k].second >= need) {
+            b->pin = pool[k].first; b->pin_n = pool[k].second;
+            pool.erase(pool.begin() + k);
+            return;
+        }
+    b->pin_n = std::max<i64>(need, 4096);
+    CK(cudaHostAlloc((void **)&b->pin, sizeof(i32) * (size_t)b->pin_n, cudaHostAllocDefault));
+}
+void batch_pin_release(Batch *b) {
+    if (b->pin) b->sec->pin_pool.emplace_back(b->pin, b->pin_n);
+    b->pin = nullptr;
+}
+
+void batch_sync(Batch *b) {
+    CK(cudaStreamSynchronize(b->stream));
+    const i64 W = b->W;
+    if (b->pend_cand) {
+        const i32 *h = b->pin_cand();
+        b->ka_off.assign(h, h + W + 1);
+        b->kr_off.assign(h + W + 1, h + 2 * (W + 1));
+        b->p_off.assign(h + 2 * (W + 1), h + 3 * (W + 1));
+        b->nKA = b->ka_off[W]; b->nKR = b->kr_off[W]; b->P = b->p_off[W];
+        b->pend_cand = false;
+    }
+    if (b->pend_tin) {
+        const i32 *h = b->pin_tin();
+        b->tin_off.assign(h, h + W + 1);
+        b->pend_tin = false;
+    }
+    if (b->pend_renum) {
+        const i32 *h = b->pin_renum();
+        b->p_off.assign(h, h + W + 1);
+        b->P = b->p_off[W];
+        b->pend_renum = false;
+    }
+    if (b->pend_groups) {
+        const i32 *h = b->pin_groups();
+        b->g_off.assign(h, h + W + 1);
+        b->G = b->g_off[W];
+        b->pend_groups = false;
+    }
+}
+void batch_settle(Batch *b) {
+    if (b->pend_cand || b->pend_tin || b->pend_renum || b->pend_groups) batch_sync(b);
+}
+
 // ------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned long long enc_f64(double d) {
     unsigned long long b = (unsigned long long)__double_as_longlong(d);
@@ -148,11 +198,6 @@ __global__ void __launch_bounds__(SUB_THREADS) k_rect_fill(const double2 *__rest
     }
 }
 
-__global__ void k_pick_offsets(const i32 *__restrict__ scanned, i64 chunks, i64 W, i32 *__restrict__ off) {
-    i64 w = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (w <= W) off[w] = scanned[w * chunks];
-}
-
 void section_count_rects(Section *sec, i64 m, const double *rects, i64 *cntA, i64 *cntR) {
     cudaStream_t s = sec->stream;
     DevBuf<double> d_r;
@@ -168,46 +213,122 @@ void section_count_rects(Section *sec, i64 m, const double *rects, i64 *cntA, i6
     for (i64 i = 0; i < m; ++i) { cntA[i] = (i64)h[i]; cntR[i] = (i64)h[m + i]; }
 }
 
-// ---- window subsetting: subset_data (src/same.py:293-295) for all windows at once ---------------------------
-// One thread per cell looks up the rectangles overlapping its index-grid cell, tests them exactly (half-open) and
-// appends (window << rowbits | row); a key-only radix sort then yields, per window, the rows in ascending order —
-// exactly `df[mask]` of the reference.  Lanes walk their candidate lists in lockstep so a warp needs one atomic per slot.
-// pass 1: number of windows holding each cell; pass 2 (after an exclusive scan): keys written at scan[i].. in ascending
-// window order.  The key stream is then ordered by (row, window), so ONE stable radix pass over the window bits
-// yields (window, row) order — no atomics, no multi-pass sort.
-template <bool FILL, typename KeyT>
-__global__ void __launch_bounds__(256) k_subset_scan(const double2 *__restrict__ xy, i64 n, const double *__restrict__ rects, RectIndexDev ri,
-                                                     int rowbits, i32 *__restrict__ count, const i32 *__restrict__ pos, KeyT *__restrict__ keys) {
-    const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i > n) return;
-    if (i == n) { if (!FILL) count[i] = 0; return; }
-    const double2 p = xy[i];
-    const int c = rect_cell(ri, p.x, p.y);
-    const i32 lo = ri.cell_ptr[c], hi = ri.cell_ptr[c + 1];
-    i32 out = FILL ? pos[i] : 0;
-    for (i32 k = lo; k < hi; ++k) {
-        const int w = ri.cell_rects[k];
-        if (in_rect(p, rects + 4 * (i64)w)) {
-            if (FILL) keys[out] = (KeyT)(((unsigned long long)w << rowbits) | (unsigned long long)i);
-            ++out;
-        }
+void scan_reserve(Section *sec, i64 words, cudaStream_t s) {
+    if (words > sec->scan_state.n || !sec->scan_state.p) {
+        sec->scan_state.alloc(std::max<i64>(words, 1 << 16), s);
+        sec->scan_state.zero(s);
     }
-    if (!FILL) count[i] = out;
+    if (sec->scan_epoch >= (1u << 30) - 16u) {   // epoch field exhausted: start over on a clean buffer
+        sec->scan_state.zero(s);
+        sec->scan_epoch = 0;
+    }
+}
+ScanCtx scan_ctx_at(Section *sec, i64 word_offset, i64 tiles) {
+    REQUIRE(tiles < (1ll << 31), SAME_E_LIMIT, "too many scan tiles");
+    return ScanCtx{sec->scan_state.p + word_offset, (int)std::max<i64>(tiles, 1), ++sec->scan_epoch};
+}
+ScanCtx scan_ctx(Section *sec, i64 tiles, int n_streams, cudaStream_t s) {
+    scan_reserve(sec, std::max<i64>(tiles, 1) * n_streams, s);
+    return scan_ctx_at(sec, 0, tiles);
+}
+
+// ---- window subsetting: subset_data (src/same.py:293-295) for all windows and BOTH frames at once ------------
+// Item = one row of the aligned frame (items [0, nA)) or of the reference frame (items [nA, nA+nR)).  A thread looks
+// up the rectangles overlapping the index-grid cell of its point and tests them exactly (half-open).  Pass 1 counts
+// the windows holding each row and scans the counts in the same launch (scan.cuh); pass 2 writes, at row_pos[item]..,
+// one key (frame | window | row) per hit in ascending window order.  The key stream is then ordered by
+// (frame, row, window), so ONE stable radix pass over the (frame | window) bits yields, per frame and window, the rows
+// in ascending order — exactly `df[mask]` of the reference — with no atomics and no multi-pass sort.  The sort carries
+// the original key position along, which turns into the row -> instance table the triangle remap looks vertices up in.
+constexpr int SUBSET_THREADS = 256;
+// the counting pass uses big tiles: the look-back chain of scan.cuh costs one L2 round trip per 32 tiles
+constexpr int SUBSET_CT = 1024, SUBSET_CI = 4;
+constexpr i64 SUBSET_HIST_W = 4096;   // up to this many windows the per-window sizes are counted in shared memory
+
+__device__ __forceinline__ double2 subset_point(const double2 *__restrict__ a_xy, i64 nA, const double2 *__restrict__ r_xy, i64 item) {
+    return item < nA ? a_xy[item] : r_xy[item - nA];
+}
+
+__global__ void __launch_bounds__(SUBSET_CT) k_subset_count(const double2 *__restrict__ a_xy, i64 nA, const double2 *__restrict__ r_xy, i64 nR,
+                                                            const double *__restrict__ rects, RectIndexDev ri, ScanCtx sc, i64 W,
+                                                            i32 *__restrict__ row_pos, i32 *__restrict__ wcount /* [2][W] zeroed, then [2] totals */) {
+    __shared__ int smem[SUBSET_CT / 32 + 1];
+    extern __shared__ int hist[];   // [2][W] window sizes of this block when they fit (hist_on), flushed once at the end
+    const bool hist_on = W <= SUBSET_HIST_W;
+    if (hist_on) {
+        for (i64 k = threadIdx.x; k < 2 * W; k += SUBSET_CT) hist[k] = 0;
+        __syncthreads();
+    }
+    const i64 n = nA + nR;
+    const i64 base = ((i64)blockIdx.x * SUBSET_CT + threadIdx.x) * SUBSET_CI;
+    int cnt[SUBSET_CI], sum[1] = {0};
+#pragma unroll
+    for (int k = 0; k < SUBSET_CI; ++k) {
+        cnt[k] = 0;
+        if (base + k < n) {
+            const double2 p = subset_point(a_xy, nA, r_xy, base + k);
+            const int c = rect_cell(ri, p.x, p.y);
+            const i32 hi = ri.cell_ptr[c + 1];
+            const i64 fo = base + k < nA ? 0 : W;
+            for (i32 e = ri.cell_ptr[c]; e < hi; ++e) {
+                const int w = ri.cell_rects[e];
+                if (in_rect(p, rects + 4 * (i64)w)) {   // per-window sizes -> window offsets on the host
+                    ++cnt[k];
+                    atomicAdd((hist_on ? hist : wcount) + fo + w, 1);
+                }
+            }
+        }
+        sum[0] += cnt[k];
+    }
+    int excl[1], tot[1], pre[1];
+    device_exclusive_scan<1, SUBSET_CT>(sc, (int)blockIdx.x, sum, excl, tot, pre, smem);   // (its barriers also complete hist)
+    if (hist_on)
+        for (i64 k = threadIdx.x; k < 2 * W; k += SUBSET_CT)
+            if (hist[k]) atomicAdd(wcount + k, hist[k]);
+    int run = excl[0];
+#pragma unroll
+    for (int k = 0; k < SUBSET_CI; ++k) {
+        const i64 item = base + k;
+        if (item <= n) row_pos[item] = run;
+        if (item == nA) wcount[2 * W + 1] = run;
+        if (item == n) wcount[2 * W] = run;
+        run += cnt[k];
+    }
 }
 
 template <typename KeyT>
-__global__ void k_subset_finish(const KeyT *__restrict__ sorted, i64 total, int rowbits, i64 W, i32 *__restrict__ src, i32 *__restrict__ off) {
-    const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < total) src[i] = (i32)((unsigned long long)sorted[i] & ((1ull << rowbits) - 1ull));
-    if (i <= W) {  // offset of window i = lower bound of key (i << rowbits)
-        const unsigned long long key = (unsigned long long)i << rowbits;
-        i64 lo = 0, hi = total;
-        while (lo < hi) {
-            const i64 mid = (lo + hi) >> 1;
-            if ((unsigned long long)sorted[mid] < key) lo = mid + 1; else hi = mid;
+__global__ void __launch_bounds__(SUBSET_THREADS) k_subset_fill(const double2 *__restrict__ a_xy, i64 nA, const double2 *__restrict__ r_xy, i64 nR,
+                                                                const double *__restrict__ rects, RectIndexDev ri, int rowbits, int fbit,
+                                                                const i32 *__restrict__ row_pos, KeyT *__restrict__ keys, i32 *__restrict__ vals) {
+    const i64 item = (i64)blockIdx.x * SUBSET_THREADS + threadIdx.x;
+    if (item >= nA + nR) return;
+    const double2 p = subset_point(a_xy, nA, r_xy, item);
+    const unsigned long long hi_bits = (item < nA ? 0ull : (1ull << fbit)) | (unsigned long long)(item < nA ? item : item - nA);
+    const int c = rect_cell(ri, p.x, p.y);
+    const i32 hi = ri.cell_ptr[c + 1];
+    i32 out = row_pos[item];
+    for (i32 k = ri.cell_ptr[c]; k < hi; ++k) {
+        const int w = ri.cell_rects[k];
+        if (in_rect(p, rects + 4 * (i64)w)) {
+            keys[out] = (KeyT)(hi_bits | ((unsigned long long)w << rowbits));
+            vals[out] = out;
+            ++out;
         }
-        off[i] = (i32)lo;
     }
+}
+
+// sorted key i -> section row of instance i and the (window, instance) entry of its row
+template <typename KeyT>
+__global__ void k_subset_finish(const KeyT *__restrict__ sorted, const i32 *__restrict__ sorted_vals, i64 total, i64 totalA, int rowbits, int fbit,
+                                i32 *__restrict__ a_src, i32 *__restrict__ r_src, int2 *__restrict__ row_inst) {
+    const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const unsigned long long key = (unsigned long long)sorted[i];
+    const i32 row = (i32)(key & ((1ull << rowbits) - 1ull));
+    const i32 w = (i32)((key >> rowbits) & ((1ull << (fbit - rowbits)) - 1ull));
+    const i32 inst = (i32)(i < totalA ? i : i - totalA);
+    if (i < totalA) a_src[inst] = row; else r_src[inst] = row;
+    row_inst[sorted_vals[i]] = make_int2(w, inst);
 }
 
 static int bits_needed(i64 n) {
@@ -217,46 +338,54 @@ static int bits_needed(i64 n) {
 }
 
 template <typename KeyT>
-static void subset_frame_t(Batch *b, const DevBuf<double2> &xy, i64 n, std::vector<i64> &off, DevBuf<i32> &d_off, DevBuf<i32> &src, i64 &total,
-                           int rowbits, int wbits) {
+static void subset_frames_t(Batch *b, int rowbits, int wbits) {
+    Section *sec = b->sec;
     cudaStream_t s = b->stream;
-    const i64 W = b->W;
-    DevBuf<i32> count, pos;
+    const i64 W = b->W, nA = sec->nA, nR = sec->nR, n = nA + nR;
+    const int fbit = rowbits + wbits;
+    DevBuf<i32> wcount;
+    wcount.alloc(2 * W + 2, s);
+    wcount.zero(s);
+    b->row_pos.alloc(n + 1, s);
+    const unsigned tiles = blocks_for(n + 1, SUBSET_CT * SUBSET_CI);
+    LAUNCH(k_subset_count, tiles, SUBSET_CT, W <= SUBSET_HIST_W ? sizeof(int) * 2 * (size_t)W : 0, s, sec->a_xy.p, nA, sec->r_xy.p, nR, b->d_rects.p, b->rindex, scan_ctx(sec, tiles, 1, s), W, b->row_pos.p,
+           wcount.p);
+    i32 *h = b->pin_misc();   // [2W] window sizes, [2] totals, then [2(W+1)] offsets built here for the upload
+    CK(cudaMemcpyAsync(h, wcount.p, sizeof(i32) * (2 * W + 2), cudaMemcpyDeviceToHost, s));
+    batch_sync(b);
+    const i64 total = h[2 * W], totalA = h[2 * W + 1];
+    REQUIRE(total >= 0 && totalA >= 0, SAME_E_LIMIT, "batch exceeds 2^31 window instances");
+    b->nAi = totalA; b->nRi = total - totalA;
+    i32 *ho = h + 2 * W + 2;
+    b->a_off.assign(W + 1, 0); b->r_off.assign(W + 1, 0);
+    for (i64 w = 0; w < W; ++w) { b->a_off[w + 1] = b->a_off[w] + h[w]; b->r_off[w + 1] = b->r_off[w] + h[W + w]; }
+    for (i64 w = 0; w <= W; ++w) { ho[w] = (i32)b->a_off[w]; ho[W + 1 + w] = (i32)b->r_off[w]; }
+    b->d_a_off.alloc(W + 1, s); b->d_r_off.alloc(W + 1, s);
+    CK(cudaMemcpyAsync(b->d_a_off.p, ho, sizeof(i32) * (W + 1), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(b->d_r_off.p, ho + W + 1, sizeof(i32) * (W + 1), cudaMemcpyHostToDevice, s));
+    b->a_src.alloc(b->nAi, s); b->r_src.alloc(b->nRi, s); b->row_inst.alloc(total, s);
+    if (total == 0) return;
     DevBuf<KeyT> keys, keys_out;
-    count.alloc(n + 1, s); pos.alloc(n + 1, s);
-    LAUNCH((k_subset_scan<false, KeyT>), blocks_for(n + 1, 256), 256, 0, s, xy.p, n, b->d_rects.p, b->rindex, rowbits, count.p, (const i32 *)nullptr,
-           (KeyT *)nullptr);
-    exclusive_scan_i32(count.p, pos.p, n + 1, b->scratch, s);
-    i32 h = 0;
-    CK(cudaMemcpyAsync(&h, pos.p + n, sizeof(h), cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
-    total = (i64)h;
-    REQUIRE(total >= 0, SAME_E_LIMIT, "batch exceeds 2^31 window instances");
-    src.alloc(total, s);
-    d_off.alloc(W + 1, s);
-    keys.alloc(total, s); keys_out.alloc(total, s);
-    if (total > 0) {
-        LAUNCH((k_subset_scan<true, KeyT>), blocks_for(n + 1, 256), 256, 0, s, xy.p, n, b->d_rects.p, b->rindex, rowbits, (i32 *)nullptr, pos.p, keys.p);
-        size_t bytes = 0;
-        CK(cub::DeviceRadixSort::SortKeys(nullptr, bytes, keys.p, keys_out.p, (int)total, rowbits, rowbits + wbits, s));
-        void *tmp = b->scratch.get(bytes, s);
-        {
-            ProfScope prof("cub::DeviceRadixSort::SortKeys(subset)", s);
-            CK(cub::DeviceRadixSort::SortKeys(tmp, bytes, keys.p, keys_out.p, (int)total, rowbits, rowbits + wbits, s));
-        }
-        g_launches.fetch_add(1, std::memory_order_relaxed);
+    DevBuf<i32> vals, vals_out;
+    keys.alloc(total, s); keys_out.alloc(total, s); vals.alloc(total, s); vals_out.alloc(total, s);
+    LAUNCH((k_subset_fill<KeyT>), blocks_for(n, SUBSET_THREADS), SUBSET_THREADS, 0, s, sec->a_xy.p, nA, sec->r_xy.p, nR, b->d_rects.p, b->rindex, rowbits,
+           fbit, b->row_pos.p, keys.p, vals.p);
+    size_t bytes = 0;
+    CK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, keys.p, keys_out.p, vals.p, vals_out.p, (int)total, rowbits, fbit + 1, s));
+    void *tmp = b->scratch.get(bytes, s);
+    {
+        ProfScope prof("cub::DeviceRadixSort::SortPairs(subset)", s);
+        CK(cub::DeviceRadixSort::SortPairs(tmp, bytes, keys.p, keys_out.p, vals.p, vals_out.p, (int)total, rowbits, fbit + 1, s));
     }
-    LAUNCH((k_subset_finish<KeyT>), blocks_for(std::max<i64>(total, W + 1), 256), 256, 0, s, keys_out.p, total, rowbits, W, src.p, d_off.p);
-    std::vector<i32> ho(W + 1);
-    CK(cudaMemcpyAsync(ho.data(), d_off.p, sizeof(i32) * (W + 1), cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
-    off.assign(ho.begin(), ho.end());
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    LAUNCH((k_subset_finish<KeyT>), blocks_for(total, 256), 256, 0, s, keys_out.p, vals_out.p, total, totalA, rowbits, fbit, b->a_src.p, b->r_src.p,
+           b->row_inst.p);
 }
 
-static void subset_frame(Batch *b, const DevBuf<double2> &xy, i64 n, std::vector<i64> &off, DevBuf<i32> &d_off, DevBuf<i32> &src, i64 &total) {
-    const int rowbits = bits_needed(std::max<i64>(n, 2)), wbits = bits_needed(b->W + 1);
-    if (rowbits + wbits <= 32) subset_frame_t<unsigned>(b, xy, n, off, d_off, src, total, rowbits, wbits);
-    else subset_frame_t<unsigned long long>(b, xy, n, off, d_off, src, total, rowbits, wbits);
+static void subset_frames(Batch *b) {
+    const int rowbits = bits_needed(std::max<i64>(std::max(b->sec->nA, b->sec->nR), 2)), wbits = bits_needed(b->W + 1);
+    if (rowbits + wbits + 1 <= 32) subset_frames_t<unsigned>(b, rowbits, wbits);
+    else subset_frames_t<unsigned long long>(b, rowbits, wbits);
 }
 
 // host: uniform index grid over the section bbox, each rectangle registered in every grid cell it overlaps (+1 cell of slack)
@@ -267,7 +396,7 @@ static void build_rect_index(Batch *b) {
     const double bx0 = sec->bbox[0], bx1 = sec->bbox[1], by0 = sec->bbox[2], by1 = sec->bbox[3];
     const double ext = std::max(std::max(bx1 - bx0, by1 - by0), 1e-300);
     int G = (int)std::min<i64>(256, std::max<i64>(1, (i64)std::ceil(std::sqrt((double)W)) * 4));
-    std::vector<i32> ptr, lst;
+    std::vector<i32> &ptr = b->h_ri_ptr, &lst = b->h_ri_rects;   // batch members: the async uploads below read them
     double cs = 1.0, inv = 1.0;
     int nx = 1, ny = 1, max_len = 0;
     for (;; G = std::max(1, G / 2)) {
@@ -309,18 +438,17 @@ static void build_rect_index(Batch *b) {
     b->ri_rects.alloc((i64)lst.size(), s);
     CK(cudaMemcpyAsync(b->ri_ptr.p, ptr.data(), sizeof(i32) * ptr.size(), cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(b->ri_rects.p, lst.data(), sizeof(i32) * lst.size(), cudaMemcpyHostToDevice, s));
-    CK(cudaStreamSynchronize(s));
     b->rindex = RectIndexDev{bx0, by0, inv, nx, ny, max_len, b->ri_ptr.p, b->ri_rects.p};
 }
 
 void batch_subset(Batch *b) {
     Section *sec = b->sec;
     cudaStream_t s = b->stream;
+    batch_pin_acquire(b);
     b->d_rects.alloc(4 * b->W, s);
     CK(cudaMemcpyAsync(b->d_rects.p, b->rects.data(), sizeof(double) * 4 * b->W, cudaMemcpyHostToDevice, s));
     build_rect_index(b);
-    subset_frame(b, sec->a_xy, sec->nA, b->a_off, b->d_a_off, b->a_src, b->nAi);
-    subset_frame(b, sec->r_xy, sec->nR, b->r_off, b->d_r_off, b->r_src, b->nRi);
+    subset_frames(b);
 }
 
 // ---- vertex ids -> section rows ------------------------------------------------------

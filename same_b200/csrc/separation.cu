@@ -8,75 +8,118 @@
 
 namespace same {
 
-// matching[i] = j of the LAST pair of row i with x > 0.5 (dict overwrite, src/same.py:636-639)
-__global__ void k_match_rows(const double *__restrict__ x, i32 x_base, const int2 *__restrict__ pairs, const i32 *__restrict__ row_ptr,
-                             const i32 *__restrict__ ka_off, const i32 *__restrict__ p_off, int W, i32 k_lo, i32 k_hi,
-                             i32 *__restrict__ match_j, i32 *__restrict__ match_p) {
-    const i32 k = k_lo + blockIdx.x * blockDim.x + threadIdx.x;
+// matching[i] = j of the LAST pair of row i with x > 0.5 (dict overwrite, src/same.py:636-639).  A block owns
+// MATCH_ROWS consecutive rows; their pairs are one contiguous range of x, which the block reads coalesced and reduces
+// to one flag per pair in shared memory; every thread then scans the flags of its own row.
+constexpr int MATCH_ROWS = 256, MATCH_CHUNK = 2048;
+__global__ void __launch_bounds__(MATCH_ROWS) k_match_rows(const double *__restrict__ x, i32 x_base, const int2 *__restrict__ pairs,
+                                                           const i32 *__restrict__ row_ptr, const i32 *__restrict__ ka_off, const i32 *__restrict__ p_off,
+                                                           int W, i32 k_lo, i32 k_hi, i32 *__restrict__ match_j, i32 *__restrict__ match_p) {
+    __shared__ unsigned char flag[MATCH_CHUNK];
+    __shared__ i32 range[2];
+    const i32 k0 = k_lo + (i32)blockIdx.x * MATCH_ROWS;
+    const i32 k = k0 + threadIdx.x;
+    if (threadIdx.x == 0) { range[0] = row_ptr[k0]; range[1] = row_ptr[min(k0 + MATCH_ROWS, k_hi)]; }
+    i32 rs = 0, re = 0;
+    if (k < k_hi) { rs = row_ptr[k]; re = row_ptr[k + 1]; }
+    __syncthreads();
+    const i32 pb = range[0], pe = range[1];
+    i32 mp = -1;
+    for (i32 c = pb; c < pe; c += MATCH_CHUNK) {
+        for (i32 q = threadIdx.x; q < MATCH_CHUNK; q += MATCH_ROWS) flag[q] = (c + q < pe) && (x[c + q - x_base] > 0.5);
+        __syncthreads();
+        const i32 lo = max(rs, c), hi = min(re, c + MATCH_CHUNK);
+        for (i32 p = lo; p < hi; ++p)
+            if (flag[p - c]) mp = p;
+        __syncthreads();
+    }
     if (k >= k_hi) return;
-    i32 mp = -1, mj = -1;
-    const i32 e = row_ptr[k + 1];
-    for (i32 p = row_ptr[k]; p < e; ++p)
-        if (x[p - x_base] > 0.5) { mp = p; mj = pairs[p].y; }
-    if (mp >= 0) mp -= p_off[find_window(ka_off, W, k)];
+    i32 mj = -1;
+    if (mp >= 0) { mj = pairs[mp].y; mp -= p_off[find_window(ka_off, W, k)]; }
     match_j[k] = mj;
     match_p[k] = mp;
 }
 
-__global__ void __launch_bounds__(256) k_separation(const int3 *__restrict__ tri, const signed char *__restrict__ src_sign, i32 t_lo, i32 t_hi,
-                                                    const i32 *__restrict__ t_off, const i32 *__restrict__ ka_off, const i32 *__restrict__ kr_off,
-                                                    int W, const i32 *__restrict__ match_j, const double2 *__restrict__ kr_xy,
-                                                    i32 *__restrict__ viol_flag, i32 *__restrict__ checked /* per window */) {
-    const i32 t = t_lo + blockIdx.x * blockDim.x + threadIdx.x;
-    int ck = 0, w = 0;
-    if (t < t_hi) {
-        w = find_window(t_off, W, t);
-        const i32 nb = ka_off[w], rb = kr_off[w];
-        const int3 v = tri[t];
-        const i32 ja = match_j[nb + v.x], jb = match_j[nb + v.y], jc = match_j[nb + v.z];
-        int viol = 0;
-        if (ja >= 0 && jb >= 0 && jc >= 0) {  // same.py:649-651
-            const double2 A = kr_xy[rb + ja], B = kr_xy[rb + jb], C = kr_xy[rb + jc];
-            const int rs = sign_of(orient_naive(A.x, A.y, B.x, B.y, C.x, C.y));  // same.py:658
-            const int ss = src_sign[t];
-            if (ss != 0 && rs != 0) {  // same.py:663-664
-                ck = 1;
-                viol = ss != rs;  // same.py:669
+// Separation of one incumbent in ONE launch: orientation test per triangle, ranks of the violated triangles inside
+// their window (exclusive scan that restarts at every window, scan.cuh), the first `cap` cuts of every window in
+// ascending triangle order and the per-window counts.  A block owns SEP_TILE consecutive triangles; the geometry
+// phase is striped (coalesced, independent gathers), the scan phase blocked.
+constexpr int SEP_THREADS = 256, SEP_ITEMS = 8, SEP_TILE = SEP_THREADS * SEP_ITEMS;
+
+__global__ void __launch_bounds__(SEP_THREADS) k_separation(const int3 *__restrict__ tri, const signed char *__restrict__ src_sign, i32 t_lo, i32 t_hi,
+                                                            const i32 *__restrict__ t_off, const i32 *__restrict__ ka_off, const i32 *__restrict__ kr_off,
+                                                            int W, int w_lo, const i32 *__restrict__ match_j, const i32 *__restrict__ match_p,
+                                                            const double2 *__restrict__ kr_xy, i64 cap, ScanCtx sc,
+                                                            i32 *__restrict__ counts /* [2*nw] zeroed: n_viol, n_checked */, i32 *__restrict__ cuts) {
+    __shared__ int E[SEP_TILE + 1];
+    __shared__ __align__(8) unsigned char V[SEP_TILE];
+    __shared__ int smem[SEP_THREADS / 32 + 2];
+    const i32 t0 = t_lo + (i32)blockIdx.x * SEP_TILE;
+    const i32 tend = min(t0 + SEP_TILE, t_hi);
+    const int wf = find_window(t_off, W, t0), wl = find_window(t_off, W, tend - 1);
+    int wk[SEP_ITEMS];
+    int ck = 0;
+#pragma unroll
+    for (int k = 0; k < SEP_ITEMS; ++k) {
+        const int pos = k * SEP_THREADS + threadIdx.x;
+        const i32 t = t0 + pos;
+        int w = wf;
+        unsigned char vi = 0;
+        if (t < tend) {
+            if (wf != wl) w = find_window(t_off, W, t);
+            const i32 nb = ka_off[w], rb = kr_off[w];
+            const int3 v = tri[t];
+            const i32 ja = match_j[nb + v.x], jb = match_j[nb + v.y], jc = match_j[nb + v.z];
+            if (ja >= 0 && jb >= 0 && jc >= 0) {  // same.py:649-651
+                const double2 A = kr_xy[rb + ja], B = kr_xy[rb + jb], C = kr_xy[rb + jc];
+                const int rs = sign_of(orient_naive(A.x, A.y, B.x, B.y, C.x, C.y));  // same.py:658
+                const int ss = src_sign[t];
+                if (ss != 0 && rs != 0) {  // same.py:663-664
+                    if (wf == wl) ++ck; else atomicAdd(counts + 2 * (w - w_lo) + 1, 1);
+                    vi = ss != rs;  // same.py:669
+                }
             }
         }
-        viol_flag[t - t_lo] = viol;
-    } else if (t == t_hi) viol_flag[t - t_lo] = 0;
-    // block-aggregated count when the whole block sits in one window
-    __shared__ int w0, same_w;
-    if (threadIdx.x == 0) { w0 = w; same_w = 1; }
+        wk[k] = w;
+        V[pos] = vi;
+    }
     __syncthreads();
-    if (t < t_hi && w != w0) same_w = 0;
+    // blocked phase: thread owns flags [8*tid, 8*tid+8)
+    const unsigned long long bits = *reinterpret_cast<const unsigned long long *>(V + threadIdx.x * SEP_ITEMS);
+    int nv[2] = {__popcll(bits), ck}, excl[2], tot[2];
+    block_exclusive_scan<2, SEP_THREADS>(nv, excl, tot, smem);
+    {
+        int run = excl[0];
+#pragma unroll
+        for (int k = 0; k < SEP_ITEMS; ++k) {
+            E[threadIdx.x * SEP_ITEMS + k] = run;
+            run += (int)((bits >> (8 * k)) & 1ull);
+        }
+        if (threadIdx.x == SEP_THREADS - 1) E[SEP_TILE] = run;
+    }
+    if (wf == wl && threadIdx.x == 0 && tot[1]) atomicAdd(counts + 2 * (wf - w_lo) + 1, tot[1]);
     __syncthreads();
-    if (same_w) {
-        const int tot = __syncthreads_count(ck);
-        if (threadIdx.x == 0 && tot) atomicAdd(checked + w0, tot);
-    } else if (ck) atomicAdd(checked + w, 1);
-}
-
-__global__ void k_emit_cuts(const int3 *__restrict__ tri, i32 t_lo, i32 t_hi, const i32 *__restrict__ t_off, const i32 *__restrict__ ka_off, int W,
-                            int w_lo, const i32 *__restrict__ viol_flag, const i32 *__restrict__ vpos, const i32 *__restrict__ match_p, i64 cap,
-                            i32 *__restrict__ cuts) {
-    const i32 t = t_lo + blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= t_hi || !viol_flag[t - t_lo]) return;
-    const int w = find_window(t_off, W, t);
-    const i64 r = vpos[t - t_lo] - vpos[t_off[w] - t_lo];
-    if (r >= cap) return;
-    const i32 nb = ka_off[w];
-    const int3 v = tri[t];
-    reinterpret_cast<int4 *>(cuts)[(i64)(w - w_lo) * cap + r] = make_int4(match_p[nb + v.x], match_p[nb + v.y], match_p[nb + v.z], t - t_off[w]);
-}
-
-__global__ void k_sep_counts(const i32 *__restrict__ vpos, const i32 *__restrict__ t_off, i32 t_lo, int w_lo, int w_hi, const i32 *__restrict__ checked,
-                             i32 *__restrict__ out /* 2*(w_hi-w_lo): n_viol, n_checked */) {
-    const int w = w_lo + blockIdx.x * blockDim.x + threadIdx.x;
-    if (w >= w_hi) return;
-    out[2 * (w - w_lo)] = vpos[t_off[w + 1] - t_lo] - vpos[t_off[w] - t_lo];
-    out[2 * (w - w_lo) + 1] = checked[w];
+    // the tile's last window: does it start at or after the tile's first triangle?  Then later tiles need nothing older.
+    const i32 wl_start = t_off[wl];
+    const bool has_boundary = wl_start >= t0;
+    const int tail = tot[0] - (has_boundary ? E[wl_start - t0] : 0);
+    const int carry = tile_segmented_carry(sc, (int)blockIdx.x, tot[0], has_boundary, tail, smem);
+#pragma unroll
+    for (int k = 0; k < SEP_ITEMS; ++k) {
+        const int pos = k * SEP_THREADS + threadIdx.x;
+        const i32 t = t0 + pos;
+        if (t >= tend) continue;
+        const int ww = wk[k];
+        const i32 ws = t_off[ww];
+        const int rank = ws >= t0 ? E[pos] - E[ws - t0] : carry + E[pos];
+        const bool vi = V[pos] != 0;
+        if (vi && rank < cap) {
+            const i32 nb = ka_off[ww];
+            const int3 v = tri[t];
+            reinterpret_cast<int4 *>(cuts)[(i64)(ww - w_lo) * cap + rank] = make_int4(match_p[nb + v.x], match_p[nb + v.y], match_p[nb + v.z], t - ws);
+        }
+        if (t == t_off[ww + 1] - 1) counts[2 * (ww - w_lo)] = rank + (vi ? 1 : 0);
+    }
 }
 
 // x may be host or device memory; a device-resident solution vector is used in place
@@ -99,7 +142,7 @@ static void run_matching(Batch *b, i64 w_lo, i64 w_hi, const double *xd) {
     b->match_p.alloc(b->nKA, s);
     const i32 k_lo = (i32)b->ka_off[w_lo], k_hi = (i32)b->ka_off[w_hi];
     if (k_hi > k_lo)
-        LAUNCH(k_match_rows, blocks_for(k_hi - k_lo, 256), 256, 0, s, xd, (i32)b->p_off[w_lo], b->pairs.p, b->row_ptr.p, b->d_ka_off.p,
+        LAUNCH(k_match_rows, blocks_for(k_hi - k_lo, MATCH_ROWS), MATCH_ROWS, 0, s, xd, (i32)b->p_off[w_lo], b->pairs.p, b->row_ptr.p, b->d_ka_off.p,
                b->d_p_off.p, (int)b->W, k_lo, k_hi, b->match_j.p, b->match_p.p);
 }
 
@@ -108,38 +151,28 @@ void batch_separation(Batch *b, i64 w_lo, i64 w_hi, const double *x, i64 cap, i6
     REQUIRE(b->stage >= 4, SAME_E_STATE, "same_batch_separation before same_batch_tri_finalize");
     REQUIRE(w_lo >= 0 && w_hi <= b->W && w_lo < w_hi, SAME_E_ARG, "bad window range");
     REQUIRE(cap >= 0, SAME_E_ARG, "cap must be >= 0");
+    batch_settle(b);
     const i64 nw = w_hi - w_lo;
     run_matching(b, w_lo, w_hi, resolve_x(b, w_lo, w_hi, x));
     const i32 t_lo = (i32)b->t_off[w_lo], t_hi = (i32)b->t_off[w_hi];
     const i64 nt = t_hi - t_lo;
-    b->viol_flag.alloc(nt + 1, s); b->viol_pos.alloc(nt + 1, s);
-    b->sep_counts.alloc(b->W + 2 * nw, s);
+    b->sep_counts.alloc(2 * nw, s);
     b->cuts.alloc(std::max<i64>(1, nw * cap * 4), s);
-    CK(cudaMemsetAsync(b->sep_counts.p, 0, sizeof(i32) * (b->W + 2 * nw), s));
-    LAUNCH(k_separation, blocks_for(nt + 1, 256), 256, 0, s, b->tri.p, b->t_sign.p, t_lo, t_hi, b->d_t_off.p, b->d_ka_off.p, b->d_kr_off.p, (int)b->W,
-           b->match_j.p, b->kr_xy.p, b->viol_flag.p, b->sep_counts.p);
-    exclusive_scan_i32(b->viol_flag.p, b->viol_pos.p, nt + 1, b->scratch, s);
-    if (nt > 0 && cap > 0)
-        LAUNCH(k_emit_cuts, blocks_for(nt, 256), 256, 0, s, b->tri.p, t_lo, t_hi, b->d_t_off.p, b->d_ka_off.p, (int)b->W, (int)w_lo, b->viol_flag.p,
-               b->viol_pos.p, b->match_p.p, cap, b->cuts.p);
-    i32 *out = b->sep_counts.p + b->W;
-    LAUNCH(k_sep_counts, blocks_for(nw, 128), 128, 0, s, b->viol_pos.p, b->d_t_off.p, t_lo, (int)w_lo, (int)w_hi, b->sep_counts.p, out);
-    std::vector<i32> h(2 * nw);
-    CK(cudaMemcpyAsync(h.data(), out, sizeof(i32) * 2 * nw, cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
-    i64 max_fill = 0;
-    for (i64 w = 0; w < nw; ++w) {
-        n_viol[w] = h[2 * w];
-        n_checked[w] = h[2 * w + 1];
-        max_fill = std::max<i64>(max_fill, std::min<i64>(h[2 * w], cap));
+    CK(cudaMemsetAsync(b->sep_counts.p, 0, sizeof(i32) * 2 * nw, s));
+    if (nt > 0) {
+        const unsigned tiles = blocks_for(nt, SEP_TILE);
+        LAUNCH(k_separation, tiles, SEP_THREADS, 0, s, b->tri.p, b->t_sign.p, t_lo, t_hi, b->d_t_off.p, b->d_ka_off.p, b->d_kr_off.p, (int)b->W, (int)w_lo,
+               b->match_j.p, b->match_p.p, b->kr_xy.p, cap, scan_ctx(b->sec, tiles, 1, s), b->sep_counts.p, b->cuts.p);
     }
-    if (cuts && cap > 0 && max_fill > 0) {
-        if (nw == 1) {  // the callback case: copy only what was filled
-            CK(cudaMemcpyAsync(cuts, b->cuts.p, sizeof(i32) * 4 * (size_t)max_fill, cudaMemcpyDefault, s));
-        } else {
-            CK(cudaMemcpyAsync(cuts, b->cuts.p, sizeof(i32) * 4 * (size_t)(nw * cap), cudaMemcpyDefault, s));
-        }
-        CK(cudaStreamSynchronize(s));
+    // counts and cuts come back behind ONE synchronisation: the cut block is small (cap rows per window), so it is copied
+    // whole instead of waiting for the counts to know how much of it was filled
+    b->h_sep.resize(2 * nw);
+    CK(cudaMemcpyAsync(b->h_sep.data(), b->sep_counts.p, sizeof(i32) * 2 * nw, cudaMemcpyDeviceToHost, s));
+    if (cuts && cap > 0 && nt > 0) CK(cudaMemcpyAsync(cuts, b->cuts.p, sizeof(i32) * 4 * (size_t)(nw * cap), cudaMemcpyDefault, s));
+    batch_sync(b);
+    for (i64 w = 0; w < nw; ++w) {
+        n_viol[w] = b->h_sep[2 * w];
+        n_checked[w] = b->h_sep[2 * w + 1];
     }
 }
 
@@ -196,7 +229,9 @@ void batch_postsolve(Batch *b, i64 w_lo, i64 w_hi, const double *x) {
     cudaStream_t s = b->stream;
     REQUIRE(b->stage >= 4, SAME_E_STATE, "same_batch_postsolve before same_batch_tri_finalize");
     REQUIRE(w_lo >= 0 && w_hi <= b->W && w_lo < w_hi, SAME_E_ARG, "bad window range");
-    run_matching(b, w_lo, w_hi, resolve_x(b, w_lo, w_hi, x));
+    batch_settle(b);
+    const double *xd = resolve_x(b, w_lo, w_hi, x);
+    run_matching(b, w_lo, w_hi, xd);
     if (!b->have_post) {
         b->t_mask.alloc(b->T, s); b->area_before.alloc(b->T, s); b->area_after.alloc(b->T, s); b->flipped.alloc(b->T, s);
         b->have_post = true;
@@ -205,7 +240,7 @@ void batch_postsolve(Batch *b, i64 w_lo, i64 w_hi, const double *x) {
     if (t_hi > t_lo)
         LAUNCH(k_postsolve, blocks_for(t_hi - t_lo, 256), 256, 0, s, b->tri.p, t_lo, t_hi, b->d_t_off.p, b->d_ka_off.p, b->d_kr_off.p, (int)b->W,
                b->match_j.p, b->ka_xy.p, b->kr_xy.p, b->t_mask.p, b->area_before.p, b->area_after.p, b->flipped.p);
-    CK(cudaStreamSynchronize(s));
+    if (xd != x) batch_sync(b);   // the caller's host vector was read asynchronously; a device-resident x needs no wait
 }
 
 void postsolve_arrays(int device, i64 T, const i32 *tri, i64 nA, const double *a_xy, i64 nR, const double *r_xy, const i32 *match_j, i32 *mask,

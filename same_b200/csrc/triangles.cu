@@ -6,58 +6,82 @@
 namespace same {
 
 
-// local (window) index of section row `row` among the window's kept aligned rows, or -1
-__device__ __forceinline__ i32 kept_lookup(const i32 *__restrict__ keepA, i32 lo, i32 hi, i32 row) {
-    const i32 base = lo, end = hi;
-    while (lo < hi) {
-        const i32 mid = (lo + hi) >> 1;
-        if (keepA[mid] < row) lo = mid + 1; else hi = mid;
+// Remap = for every global triangle, every window that holds all three vertices AND whose post-KNN frame kept all
+// three rows.  The subset stage left, per section row, the list of (window, instance) it belongs to (row_inst, ascending
+// window, a handful of entries), and the candidate stage the kept index of every instance (newA, valid where cnt > 0):
+// a thread intersects the three short lists of its triangle — no rectangle tests, no binary searches.  Pass 1 counts the
+// hits per triangle and scans the counts in the same launch (scan.cuh); pass 2 writes (window << tbits | triangle) keys
+// and the window-local vertex triples at pos[t]..; one stable radix pass over the window bits restores the reference's
+// order (window-major, input order inside) and the window offsets are lower bounds in the sorted keys.
+__device__ __forceinline__ i32 inst_in_window(const int2 *__restrict__ row_inst, i32 lo, i32 hi, i32 w) {
+    for (i32 e = lo; e < hi; ++e) {
+        const int2 v = row_inst[e];
+        if (v.x == w) return v.y;
+        if (v.x > w) break;
     }
-    return (lo < end && keepA[lo] == row) ? lo - base : -1;
+    return -1;
 }
 
-// Remap = for every global triangle, every window whose rectangle holds all three vertices AND whose post-KNN
-// frame kept all three rows.  One thread per triangle looks up the rectangles of the index-grid cell of its
-// bounding-box corner (a handful instead of all W), binary-searches the window's kept-row list, and appends
-// (window << tbits | triangle) records; lanes walk their candidate lists in lockstep so a warp needs one atomic per
-// slot.  A first launch only counts (to size the buffers); one radix sort restores the reference's order
-// (window-major, input order inside) and the window offsets are lower bounds in the sorted keys.
-template <bool FILL, typename KeyT>
-__global__ void __launch_bounds__(256) k_remap_scan(const i32 *__restrict__ tri_rows, i64 Tg, const double2 *__restrict__ sec_xy,
-                                                    const double *__restrict__ rects, RectIndexDev ri, const i32 *__restrict__ keepA,
-                                                    const i32 *__restrict__ ka_off, i32 *__restrict__ count, const i32 *__restrict__ pos,
-                                                    KeyT *__restrict__ keys, int3 *__restrict__ recs, int tbits) {
-    const i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t > Tg) return;
-    if (t == Tg) { if (!FILL) count[t] = 0; return; }
-    i32 out = FILL ? pos[t] : 0;
+constexpr int REMAP_CT = 1024, REMAP_CI = 2;   // counting pass: big tiles for the look-back chain
+
+// visits the hits of triangle t in ascending window order: f(window, local a, local b, local c)
+template <typename F>
+__device__ __forceinline__ void remap_hits(const i32 *__restrict__ tri_rows, i64 t, const i32 *__restrict__ row_pos, const int2 *__restrict__ row_inst,
+                                           const i32 *__restrict__ cnt, const i32 *__restrict__ newA, const i32 *__restrict__ ka_off, F &&f) {
     const i32 ra = tri_rows[3 * t], rb = tri_rows[3 * t + 1], rc = tri_rows[3 * t + 2];
-    if (ra >= 0 && rb >= 0 && rc >= 0) {
-        const double2 A = sec_xy[ra], B = sec_xy[rb], C = sec_xy[rc];
-        const double mnx = fmin(A.x, fmin(B.x, C.x)), mxx = fmax(A.x, fmax(B.x, C.x));
-        const double mny = fmin(A.y, fmin(B.y, C.y)), mxy = fmax(A.y, fmax(B.y, C.y));
-        const int c = rect_cell(ri, mnx, mny);   // a rectangle holding the whole bbox holds this corner
-        const i32 hi = ri.cell_ptr[c + 1];
-        for (i32 k = ri.cell_ptr[c]; k < hi; ++k) {
-            const int w = ri.cell_rects[k];
-            const double *r = rects + 4 * (i64)w;   // x_min, x_max, y_min, y_max ; half-open (same.py:293-295)
-            if (!(mnx >= r[0] && mxx < r[1] && mny >= r[2] && mxy < r[3])) continue;
-            const i32 klo = ka_off[w], khi = ka_off[w + 1];
-            int3 v;
-            v.x = kept_lookup(keepA, klo, khi, ra);
-            if (v.x < 0) continue;
-            v.y = kept_lookup(keepA, klo, khi, rb);
-            if (v.y < 0) continue;
-            v.z = kept_lookup(keepA, klo, khi, rc);
-            if (v.z < 0) continue;
-            if (FILL) {
-                keys[out] = (KeyT)(((unsigned long long)w << tbits) | (unsigned long long)t);
-                recs[out] = v;
-            }
-            ++out;
-        }
+    if (ra < 0 || rb < 0 || rc < 0) return;
+    const i32 a0 = row_pos[ra], a1 = row_pos[ra + 1];
+    if (a0 == a1) return;
+    const i32 b0 = row_pos[rb], b1 = row_pos[rb + 1], c0 = row_pos[rc], c1 = row_pos[rc + 1];
+    for (i32 e = a0; e < a1; ++e) {
+        const int2 va = row_inst[e];
+        if (cnt[va.y] == 0) continue;
+        const i32 ib = inst_in_window(row_inst, b0, b1, va.x);
+        if (ib < 0 || cnt[ib] == 0) continue;
+        const i32 ic = inst_in_window(row_inst, c0, c1, va.x);
+        if (ic < 0 || cnt[ic] == 0) continue;
+        const i32 kb = ka_off[va.x];
+        f(va.x, newA[va.y] - kb, newA[ib] - kb, newA[ic] - kb);
     }
-    if (!FILL) count[t] = out;
+}
+
+__global__ void __launch_bounds__(REMAP_CT) k_remap_count(const i32 *__restrict__ tri_rows, i64 Tg, const i32 *__restrict__ row_pos,
+                                                          const int2 *__restrict__ row_inst, const i32 *__restrict__ cnt, const i32 *__restrict__ newA,
+                                                          const i32 *__restrict__ ka_off, ScanCtx sc, i32 *__restrict__ pos) {
+    __shared__ int smem[REMAP_CT / 32 + 1];
+    const i64 base = ((i64)blockIdx.x * REMAP_CT + threadIdx.x) * REMAP_CI;
+    int c[REMAP_CI], sum[1] = {0};
+#pragma unroll
+    for (int k = 0; k < REMAP_CI; ++k) {
+        c[k] = 0;
+        if (base + k < Tg) remap_hits(tri_rows, base + k, row_pos, row_inst, cnt, newA, ka_off, [&](i32, i32, i32, i32) { ++c[k]; });
+        sum[0] += c[k];
+    }
+    int excl[1], tot[1], pre[1];
+    device_exclusive_scan<1, REMAP_CT>(sc, (int)blockIdx.x, sum, excl, tot, pre, smem);
+    int run = excl[0];
+#pragma unroll
+    for (int k = 0; k < REMAP_CI; ++k) {
+        if (base + k <= Tg) pos[base + k] = run;
+        run += c[k];
+    }
+}
+
+template <typename KeyT>
+__global__ void __launch_bounds__(256) k_remap_fill(const i32 *__restrict__ tri_rows, i64 Tg, const i32 *__restrict__ row_pos,
+                                                    const int2 *__restrict__ row_inst, const i32 *__restrict__ cnt, const i32 *__restrict__ newA,
+                                                    const i32 *__restrict__ ka_off, const i32 *__restrict__ pos, int tbits, KeyT *__restrict__ keys,
+                                                    i32 *__restrict__ idx, int3 *__restrict__ recs) {
+    const i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= Tg) return;
+    i32 out = pos[t];
+    if (out == pos[t + 1]) return;
+    remap_hits(tri_rows, t, row_pos, row_inst, cnt, newA, ka_off, [&](i32 w, i32 la, i32 lb, i32 lc) {
+        keys[out] = (KeyT)(((unsigned long long)w << tbits) | (unsigned long long)t);
+        idx[out] = out;
+        recs[out] = make_int3(la, lb, lc);
+        ++out;
+    });
 }
 
 template <typename KeyT>
@@ -80,11 +104,6 @@ __global__ void k_remap_gather(const KeyT *__restrict__ sorted_keys, const i32 *
     }
 }
 
-__global__ void k_iota_tri(i32 *p, i64 n) {
-    i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) p[i] = (i32)i;
-}
-
 static void reset_triangles(Batch *b) {
     b->Tin = 0; b->T = 0; b->n_band = 0; b->tin_has_src = false; b->have_post = false;
 }
@@ -94,42 +113,44 @@ static void remap_t(Batch *b, int tbits, int wbits) {
     Section *sec = b->sec;
     cudaStream_t s = b->stream;
     const i64 W = b->W, Tg = sec->Tg;
-    // count -> exclusive scan -> fill in (triangle, window) order -> ONE stable radix pass over the window bits
-    DevBuf<i32> count, pos;
-    count.alloc(Tg + 1, s); pos.alloc(Tg + 1, s);
-    LAUNCH((k_remap_scan<false, KeyT>), blocks_for(Tg + 1, 256), 256, 0, s, sec->tri_rows.p, Tg, sec->a_xy.p, b->d_rects.p, b->rindex, b->keepA.p,
-           b->d_ka_off.p, count.p, (const i32 *)nullptr, (KeyT *)nullptr, (int3 *)nullptr, tbits);
-    exclusive_scan_i32(count.p, pos.p, Tg + 1, b->scratch, s);
-    i32 h = 0;
-    CK(cudaMemcpyAsync(&h, pos.p + Tg, sizeof(h), cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
-    b->Tin = (i64)h;
+    DevBuf<i32> pos;
+    pos.alloc(Tg + 1, s);
+    const unsigned tiles = blocks_for(Tg + 1, REMAP_CT * REMAP_CI);
+    LAUNCH(k_remap_count, tiles, REMAP_CT, 0, s, sec->tri_rows.p, Tg, b->row_pos.p, b->row_inst.p, b->cnt.p, b->newA.p, b->d_ka_off.p,
+           scan_ctx(sec, tiles, 1, s), pos.p);
+    CK(cudaMemcpyAsync(b->pin_misc(), pos.p + Tg, sizeof(i32), cudaMemcpyDeviceToHost, s));
+    batch_sync(b);   // also brings in the candidate stage's window offsets
+    b->Tin = (i64)b->pin_misc()[0];
     REQUIRE(b->Tin >= 0, SAME_E_LIMIT, "too many window triangles");
     DevBuf<KeyT> keys, keys_out;
     DevBuf<int3> recs;
     DevBuf<i32> idx, idx_out;
     b->tin.alloc(b->Tin, s); b->tin_src.alloc(b->Tin, s);
     b->d_tin_off.alloc(W + 1, s);
-    keys.alloc(b->Tin, s); recs.alloc(b->Tin, s); keys_out.alloc(b->Tin, s); idx.alloc(b->Tin, s); idx_out.alloc(b->Tin, s);
+    keys.alloc(b->Tin, s); recs.alloc(b->Tin, s); idx.alloc(b->Tin, s);
+    const KeyT *sorted_keys = keys.p;
+    const i32 *sorted_idx = idx.p;
     if (b->Tin > 0) {
-        LAUNCH((k_remap_scan<true, KeyT>), blocks_for(Tg + 1, 256), 256, 0, s, sec->tri_rows.p, Tg, sec->a_xy.p, b->d_rects.p, b->rindex, b->keepA.p,
-               b->d_ka_off.p, (i32 *)nullptr, pos.p, keys.p, recs.p, tbits);
-        LAUNCH(k_iota_tri, blocks_for(b->Tin, 256), 256, 0, s, idx.p, b->Tin);
-        size_t bytes = 0;
-        CK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, keys.p, keys_out.p, idx.p, idx_out.p, (int)b->Tin, tbits, tbits + wbits, s));
-        void *tmp = b->scratch.get(bytes, s);
-        {
-            ProfScope prof("cub::DeviceRadixSort::SortPairs(remap)", s);
-            CK(cub::DeviceRadixSort::SortPairs(tmp, bytes, keys.p, keys_out.p, idx.p, idx_out.p, (int)b->Tin, tbits, tbits + wbits, s));
+        LAUNCH((k_remap_fill<KeyT>), blocks_for(Tg, 256), 256, 0, s, sec->tri_rows.p, Tg, b->row_pos.p, b->row_inst.p, b->cnt.p, b->newA.p, b->d_ka_off.p,
+               pos.p, tbits, keys.p, idx.p, recs.p);
+        if (W > 1) {   // a single window is already in input order
+            keys_out.alloc(b->Tin, s); idx_out.alloc(b->Tin, s);
+            size_t bytes = 0;
+            CK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, keys.p, keys_out.p, idx.p, idx_out.p, (int)b->Tin, tbits, tbits + wbits, s));
+            void *tmp = b->scratch.get(bytes, s);
+            {
+                ProfScope prof("cub::DeviceRadixSort::SortPairs(remap)", s);
+                CK(cub::DeviceRadixSort::SortPairs(tmp, bytes, keys.p, keys_out.p, idx.p, idx_out.p, (int)b->Tin, tbits, tbits + wbits, s));
+            }
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+            sorted_keys = keys_out.p;
+            sorted_idx = idx_out.p;
         }
-        g_launches.fetch_add(1, std::memory_order_relaxed);
     }
-    LAUNCH((k_remap_gather<KeyT>), blocks_for(std::max<i64>(b->Tin, W + 1), 256), 256, 0, s, keys_out.p, idx_out.p, recs.p, b->Tin, tbits, W, b->tin.p,
+    LAUNCH((k_remap_gather<KeyT>), blocks_for(std::max<i64>(b->Tin, W + 1), 256), 256, 0, s, sorted_keys, sorted_idx, recs.p, b->Tin, tbits, W, b->tin.p,
            b->tin_src.p, b->d_tin_off.p);
-    std::vector<i32> ho(W + 1);
-    CK(cudaMemcpyAsync(ho.data(), b->d_tin_off.p, sizeof(i32) * (W + 1), cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
-    b->tin_off.assign(ho.begin(), ho.end());
+    CK(cudaMemcpyAsync(b->pin_tin(), b->d_tin_off.p, sizeof(i32) * (W + 1), cudaMemcpyDeviceToHost, s));
+    b->pend_tin = true;
 }
 
 void batch_triangles_remap(Batch *b) {
@@ -149,7 +170,9 @@ void batch_triangles_remap(Batch *b) {
 void batch_triangles_set(Batch *b, const i32 *tri, const i64 *tri_off) {
     cudaStream_t s = b->stream;
     REQUIRE(b->stage >= 1, SAME_E_STATE, "same_batch_triangles_set before same_batch_candidates");
+    batch_settle(b);
     reset_triangles(b);
+    b->pend_tin = false;
     const i64 W = b->W;
     b->tin_off.assign(tri_off, tri_off + W + 1);
     REQUIRE(b->tin_off[0] == 0, SAME_E_ARG, "tri_off[0] must be 0");
@@ -221,10 +244,9 @@ void batch_tri_classify(Batch *b, double radius, int use_angle, double min_angle
     if (Tin > 0)
         LAUNCH(k_tri_classify, blocks_for(Tin, 256), 256, 0, s, b->tin.p, Tin, b->d_tin_off.p, b->d_ka_off.p, (int)b->W, b->ka_xy.p, b->ka_type.p,
                radius, use_angle, min_angle_deg, ignore_same_type, b->cls.p, b->score.p, b->band_idx.p, bc.p);
-    i32 h = 0;
-    CK(cudaMemcpyAsync(&h, bc.p, sizeof(i32), cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
-    b->n_band = h;
+    CK(cudaMemcpyAsync(b->pin_misc(), bc.p, sizeof(i32), cudaMemcpyDeviceToHost, s));
+    batch_sync(b);   // also brings in the remap's window offsets
+    b->n_band = b->pin_misc()[0];
     b->stage = 3;
 }
 
@@ -303,25 +325,17 @@ __global__ void k_addback(i64 nKA, const i32 *__restrict__ ka_off, int W, const 
     ab_flag[v] = f;
 }
 
-// single block: per-window output offsets
+// per-window output offsets: the triangles of window w start after every kept triangle and every add-back of the earlier
+// windows, i.e. at kpos[first input triangle of w] + abpos[first node of w]
 __global__ void k_tri_window_offsets(const i32 *__restrict__ kpos, const i32 *__restrict__ abpos, const i32 *__restrict__ uncpos,
                                      const i32 *__restrict__ validpos, const i32 *__restrict__ tin_off, const i32 *__restrict__ ka_off, int W,
                                      i32 *__restrict__ out /* 4*(W+1): t_off, nkept(per window), unc_off, new ka_off */) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    i32 acc = 0;
-    for (int w = 0; w < W; ++w) {
-        const i32 nk = kpos[tin_off[w + 1]] - kpos[tin_off[w]];
-        const i32 na = abpos[ka_off[w + 1]] - abpos[ka_off[w]];
-        out[w] = acc;
-        out[(W + 1) + w] = nk;
-        acc += nk + na;
-    }
-    out[W] = acc;
-    out[(W + 1) + W] = 0;
-    for (int w = 0; w <= W; ++w) {
-        out[2 * (W + 1) + w] = uncpos[ka_off[w]];
-        out[3 * (W + 1) + w] = validpos[ka_off[w]];
-    }
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w > W) return;
+    out[w] = kpos[tin_off[w]] + abpos[ka_off[w]];
+    out[(W + 1) + w] = w < W ? kpos[tin_off[w + 1]] - kpos[tin_off[w]] : 0;
+    out[2 * (W + 1) + w] = uncpos[ka_off[w]];
+    out[3 * (W + 1) + w] = validpos[ka_off[w]];
 }
 
 __global__ void k_tri_emit_kept(const int3 *__restrict__ tin, i64 Tin, const i32 *__restrict__ tin_off, const i32 *__restrict__ ka_off, int W,
@@ -393,11 +407,19 @@ __global__ void k_compact_pairs(const int2 *__restrict__ pairs, const double *__
     cost2[ppos[p]] = cost[p];
 }
 __global__ void k_compact_rowptr(i64 nKA, const i32 *__restrict__ node_valid, const i32 *__restrict__ validpos, const i32 *__restrict__ row_ptr,
-                                 const i32 *__restrict__ ppos, i32 *__restrict__ row_ptr2, i64 nKA2, i32 P2) {
+                                 const i32 *__restrict__ ppos, i32 *__restrict__ row_ptr2, i64 nKA2, const i32 *__restrict__ P2) {
     const i64 n = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (n == 0) row_ptr2[nKA2] = P2;
+    if (n == 0) row_ptr2[nKA2] = *P2;
     if (n >= nKA || !node_valid[n]) return;
     row_ptr2[validpos[n]] = ppos[row_ptr[n]];
+}
+// keep the instance -> kept-index map of the remap in step with the renumbered nodes
+__global__ void k_renumber_instances(i64 nAi, const i32 *__restrict__ node_valid, const i32 *__restrict__ validpos, i32 *__restrict__ cnt,
+                                     i32 *__restrict__ newA) {
+    const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nAi || cnt[i] == 0) return;
+    const i32 k = newA[i];
+    if (node_valid[k]) newA[i] = validpos[k]; else cnt[i] = 0;
 }
 __global__ void k_fill_i32_tri(i32 *p, i64 n, i32 v) {
     i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
@@ -437,6 +459,7 @@ __global__ void k_tri_tables(const int3 *__restrict__ tri, i64 T, const i32 *__r
 void batch_tri_finalize(Batch *b, int ignore_same_type, int ensure_min, int remove_unconstrained) {
     cudaStream_t s = b->stream;
     REQUIRE(b->stage >= 3, SAME_E_STATE, "same_batch_tri_finalize before same_batch_tri_classify");
+    batch_settle(b);
     const i64 W = b->W, Tin = b->Tin, nKA = b->nKA, P = b->P;
     const int addback = ignore_same_type && ensure_min;
     DevBuf<i32> node_valid, has_tri, best_tri, kept_flag, kpos, ab_flag, abpos, unc_flag, uncpos, validpos, woff;
@@ -459,13 +482,13 @@ void batch_tri_finalize(Batch *b, int ignore_same_type, int ensure_min, int remo
     exclusive_scan_i32(ab_flag.p, abpos.p, nKA + 1, b->scratch, s);
     exclusive_scan_i32(unc_flag.p, uncpos.p, nKA + 1, b->scratch, s);
     exclusive_scan_i32(node_valid.p, validpos.p, nKA + 1, b->scratch, s);  // node_valid[nKA] == 0 from the memset
-    LAUNCH(k_tri_window_offsets, 1, 32, 0, s, kpos.p, abpos.p, uncpos.p, validpos.p, b->d_tin_off.p, b->d_ka_off.p, (int)W, woff.p);
-    std::vector<i32> h(4 * (W + 1));
-    CK(cudaMemcpyAsync(h.data(), woff.p, sizeof(i32) * h.size(), cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
-    b->t_off.assign(h.begin(), h.begin() + W + 1);
-    b->unc_off.assign(h.begin() + 2 * (W + 1), h.begin() + 3 * (W + 1));
-    std::vector<i64> new_ka(h.begin() + 3 * (W + 1), h.end());
+    LAUNCH(k_tri_window_offsets, blocks_for(W + 1, 128), 128, 0, s, kpos.p, abpos.p, uncpos.p, validpos.p, b->d_tin_off.p, b->d_ka_off.p, (int)W, woff.p);
+    const i32 *h = b->pin_misc();
+    CK(cudaMemcpyAsync(b->pin_misc(), woff.p, sizeof(i32) * 4 * (W + 1), cudaMemcpyDeviceToHost, s));
+    batch_sync(b);   // the one host decision of this stage: sizes, and whether any node has to go
+    b->t_off.assign(h, h + W + 1);
+    b->unc_off.assign(h + 2 * (W + 1), h + 3 * (W + 1));
+    std::vector<i64> new_ka(h + 3 * (W + 1), h + 4 * (W + 1));
     b->T = b->t_off[W];
     b->nUnc = b->unc_off[W];
     const int renumber = remove_unconstrained && b->nUnc > 0;
@@ -496,24 +519,23 @@ void batch_tri_finalize(Batch *b, int ignore_same_type, int ensure_min, int remo
         LAUNCH(k_pair_flags, blocks_for(P + 1, 256), 256, 0, s, b->pairs.p, P, b->d_p_off.p, b->d_ka_off.p, (int)W, node_valid.p, pf.p);
         exclusive_scan_i32(pf.p, ppos.p, P + 1, b->scratch, s);
         LAUNCH(k_pick2, blocks_for(W + 1, 128), 128, 0, s, ppos.p, b->d_p_off.p, (int)(W + 1), poff2.p);
-        std::vector<i32> hp(W + 1);
-        CK(cudaMemcpyAsync(hp.data(), poff2.p, sizeof(i32) * (W + 1), cudaMemcpyDeviceToHost, s));
-        CK(cudaStreamSynchronize(s));
-        const i64 P2 = hp[W];
-        pairs2.alloc(P2, s); cost2.alloc(P2, s); row_ptr2.alloc(nKA2 + 1, s);
+        // pairs shrink: the new per-window offsets reach the host with the next synchronisation, the device copies are
+        // made in place; outputs are sized by the old pair count
+        CK(cudaMemcpyAsync(b->pin_renum(), poff2.p, sizeof(i32) * (W + 1), cudaMemcpyDeviceToHost, s));
+        b->pend_renum = true;
+        pairs2.alloc(P, s); cost2.alloc(P, s); row_ptr2.alloc(nKA2 + 1, s);
         if (P > 0)
             LAUNCH(k_compact_pairs, blocks_for(P, 256), 256, 0, s, b->pairs.p, b->cost.p, P, b->d_p_off.p, b->d_ka_off.p, (int)W, pf.p, ppos.p, validpos.p,
                    pairs2.p, cost2.p);
         LAUNCH(k_compact_rowptr, blocks_for(std::max<i64>(nKA, 1), 256), 256, 0, s, nKA, node_valid.p, validpos.p, b->row_ptr.p, ppos.p, row_ptr2.p, nKA2,
-               (i32)P2);
-        CK(cudaStreamSynchronize(s));
+               poff2.p + W);
+        if (b->nAi > 0) LAUNCH(k_renumber_instances, blocks_for(b->nAi, 256), 256, 0, s, b->nAi, node_valid.p, validpos.p, b->cnt.p, b->newA.p);
         b->keepA.swap(keepA2); b->ka_xy.swap(xy2); b->ka_type.swap(type2); b->ka_size.swap(size2);
         b->pairs.swap(pairs2); b->cost.swap(cost2); b->row_ptr.swap(row_ptr2);
-        b->nKA = nKA2; b->P = P2;
+        b->nKA = nKA2;
         b->ka_off = new_ka;
-        b->p_off.assign(hp.begin(), hp.end());
-        upload_offsets(b->ka_off, b->d_ka_off, s);
-        upload_offsets(b->p_off, b->d_p_off, s);
+        CK(cudaMemcpyAsync(b->d_ka_off.p, woff.p + 3 * (W + 1), sizeof(i32) * (W + 1), cudaMemcpyDeviceToDevice, s));
+        CK(cudaMemcpyAsync(b->d_p_off.p, poff2.p, sizeof(i32) * (W + 1), cudaMemcpyDeviceToDevice, s));
         b->have_groups = false;
     }
 
@@ -521,7 +543,6 @@ void batch_tri_finalize(Batch *b, int ignore_same_type, int ensure_min, int remo
     if (b->T > 0)
         LAUNCH(k_tri_tables, blocks_for(b->T, 256), 256, 0, s, b->tri.p, b->T, b->d_t_off.p, b->d_ka_off.p, (int)W, b->ka_xy.p, b->ka_size.p, b->t_weight.p,
                b->t_sign.p, b->t_bounds.p, b->t_argv.p);
-    CK(cudaStreamSynchronize(s));
     b->stage = 4;
     b->have_post = false;
 }
