@@ -58,21 +58,37 @@ __global__ void k_bin_scatter(const i32 *__restrict__ a_src, const i32 *__restri
     sorted_inst[dst] = inst;
 }
 
-// out[i] = sum of in[0 .. i-1] for i in [0, n): one launch, 4 items per thread
-constexpr int SCAN_THREADS = 1024, SCAN_ITEMS = 8;   // big tiles: one L2 round trip of look-back per 32 tiles
+// out[i] = sum of in[0 .. i-1] for i in [0, n): one launch.  A thread owns 16 consecutive values (four 16-byte loads);
+// 256-thread blocks keep eight tiles per SM in flight, so one tile's look-back wait overlaps the others' loads.
+constexpr int SCAN_THREADS = 256, SCAN_ITEMS = 16;
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan_i32(const i32 *__restrict__ in, i32 *__restrict__ out, i64 n, ScanCtx sc) {
     __shared__ int smem[SCAN_THREADS / 32 + 1];
     const i64 base = ((i64)blockIdx.x * SCAN_THREADS + threadIdx.x) * SCAN_ITEMS;
     int v[SCAN_ITEMS], sum[1] = {0};
+    if (base + SCAN_ITEMS <= n) {
 #pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; ++k) { v[k] = base + k < n ? in[base + k] : 0; sum[0] += v[k]; }
+        for (int k = 0; k < SCAN_ITEMS; k += 4) {
+            const int4 q = *reinterpret_cast<const int4 *>(in + base + k);
+            v[k] = q.x; v[k + 1] = q.y; v[k + 2] = q.z; v[k + 3] = q.w;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; ++k) v[k] = base + k < n ? in[base + k] : 0;
+    }
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) sum[0] += v[k];
     int excl[1], tot[1], pre[1];
     device_exclusive_scan<1, SCAN_THREADS>(sc, (int)blockIdx.x, sum, excl, tot, pre, smem);
     int run = excl[0];
 #pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; ++k) {
-        if (base + k < n) out[base + k] = run;
-        run += v[k];
+    for (int k = 0; k < SCAN_ITEMS; ++k) { const int x = v[k]; v[k] = run; run += x; }
+    if (base + SCAN_ITEMS <= n) {
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; k += 4) *reinterpret_cast<int4 *>(out + base + k) = make_int4(v[k], v[k + 1], v[k + 2], v[k + 3]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; ++k)
+            if (base + k < n) out[base + k] = v[k];
     }
 }
 void scan_i32(Section *sec, const i32 *in, i32 *out, i64 n, cudaStream_t s) {

@@ -387,31 +387,71 @@ __global__ void k_compact_nodes(i64 nKA, const i32 *__restrict__ node_valid, con
     const i32 k = validpos[n];
     keepA2[k] = keepA[n]; xy2[k] = xy[n]; type2[k] = type[n]; size2[k] = size[n];
 }
-__global__ void k_pair_flags(const int2 *__restrict__ pairs, i64 P, const i32 *__restrict__ p_off, const i32 *__restrict__ ka_off, int W,
-                             const i32 *__restrict__ node_valid, i32 *__restrict__ pf) {
-    const i64 p = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p == P) pf[p] = 0;
-    if (p >= P) return;
-    const int w = find_window(p_off, W, (i32)p);
-    pf[p] = node_valid[ka_off[w] + pairs[p].x];
-}
-__global__ void k_compact_pairs(const int2 *__restrict__ pairs, const double *__restrict__ cost, i64 P, const i32 *__restrict__ p_off,
-                                const i32 *__restrict__ ka_off, int W, const i32 *__restrict__ pf, const i32 *__restrict__ ppos,
-                                const i32 *__restrict__ validpos, int2 *__restrict__ pairs2, double *__restrict__ cost2) {
-    const i64 p = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= P || !pf[p]) return;
-    const int w = find_window(p_off, W, (i32)p);
-    const i32 nb = ka_off[w];
-    const int2 q = pairs[p];
-    pairs2[ppos[p]] = make_int2(validpos[nb + q.x] - validpos[nb], q.y);
-    cost2[ppos[p]] = cost[p];
-}
-__global__ void k_compact_rowptr(i64 nKA, const i32 *__restrict__ node_valid, const i32 *__restrict__ validpos, const i32 *__restrict__ row_ptr,
-                                 const i32 *__restrict__ ppos, i32 *__restrict__ row_ptr2, i64 nKA2, const i32 *__restrict__ P2) {
-    const i64 n = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (n == 0) row_ptr2[nKA2] = *P2;
-    if (n >= nKA || !node_valid[n]) return;
-    row_ptr2[validpos[n]] = ppos[row_ptr[n]];
+// Pairs of removed nodes go, the others are renumbered (src/same.py:1066-1070) — flag, scan and write in ONE launch
+// (scan.cuh).  A block owns CP_TILE consecutive pairs (pair P is a sentinel that receives the totals): striped,
+// coalesced passes compute the keep flags and later move the pairs; the scan in between is blocked over the flags in
+// shared memory.  The thread that holds the first pair of a window / of a row also writes the window's new pair offset /
+// the row's new row pointer.
+constexpr int CP_THREADS = 256, CP_ITEMS = 8, CP_TILE = CP_THREADS * CP_ITEMS;
+__global__ void __launch_bounds__(CP_THREADS) k_compact_pairs(const int2 *__restrict__ pairs, const double *__restrict__ cost, i64 P,
+                                                              const i32 *__restrict__ p_off, const i32 *__restrict__ ka_off, int W,
+                                                              const i32 *__restrict__ node_valid, const i32 *__restrict__ validpos,
+                                                              const i32 *__restrict__ row_ptr, i64 nKA, ScanCtx sc, int2 *__restrict__ pairs2,
+                                                              double *__restrict__ cost2, i32 *__restrict__ row_ptr2, i32 *__restrict__ poff2) {
+    __shared__ int E[CP_TILE];
+    __shared__ __align__(8) unsigned char V[CP_TILE];
+    __shared__ int smem[CP_THREADS / 32 + 1];
+    const i64 p0 = (i64)blockIdx.x * CP_TILE;
+    const i64 pend = min(p0 + CP_TILE, P);   // real pairs of this tile: [p0, pend)
+    const int wf = p0 < P ? find_window(p_off, W, (i32)p0) : 0, wl = pend > p0 ? find_window(p_off, W, (i32)(pend - 1)) : wf;
+#pragma unroll
+    for (int k = 0; k < CP_ITEMS; ++k) {
+        const int pos = k * CP_THREADS + threadIdx.x;
+        const i64 p = p0 + pos;
+        unsigned char f = 0;
+        if (p < pend) {
+            const int w = wf == wl ? wf : find_window(p_off, W, (i32)p);
+            f = node_valid[ka_off[w] + pairs[p].x] != 0;
+        }
+        V[pos] = f;
+    }
+    __syncthreads();
+    const unsigned long long bits = *reinterpret_cast<const unsigned long long *>(V + threadIdx.x * CP_ITEMS);
+    int sum[1] = {__popcll(bits)}, excl[1], tot[1], pre[1];
+    device_exclusive_scan<1, CP_THREADS>(sc, (int)blockIdx.x, sum, excl, tot, pre, smem);
+    {
+        int run = excl[0];
+#pragma unroll
+        for (int k = 0; k < CP_ITEMS; ++k) {
+            E[threadIdx.x * CP_ITEMS + k] = run;
+            run += (int)((bits >> (8 * k)) & 1ull);
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < CP_ITEMS; ++k) {
+        const int pos = k * CP_THREADS + threadIdx.x;
+        const i64 p = p0 + pos;
+        if (p > P) continue;
+        if (p == P) {   // totals: windows that end the pair list, and the row pointer past the last kept row
+            const i32 end = pos > 0 ? E[pos - 1] + V[pos - 1] : pre[0];   // pairs kept in total
+            for (int ww = W; ww >= 0 && p_off[ww] == (i32)P; --ww) poff2[ww] = end;
+            row_ptr2[validpos[nKA]] = end;
+            continue;
+        }
+        const i32 dst = E[pos];
+        const int w = wf == wl ? wf : find_window(p_off, W, (i32)p);
+        if (p == p_off[w])
+            for (int ww = w; ww >= 0 && p_off[ww] == (i32)p; --ww) poff2[ww] = dst;   // (empty windows share the start)
+        if (V[pos]) {
+            const i32 nb = ka_off[w];
+            const int2 q = pairs[p];
+            const i32 row = nb + q.x;
+            pairs2[dst] = make_int2(validpos[row] - validpos[nb], q.y);
+            cost2[dst] = cost[p];
+            if (p == row_ptr[row]) row_ptr2[validpos[row]] = dst;
+        }
+    }
 }
 // keep the instance -> kept-index map of the remap in step with the renumbered nodes
 __global__ void k_renumber_instances(i64 nAi, const i32 *__restrict__ node_valid, const i32 *__restrict__ validpos, i32 *__restrict__ cnt,
@@ -424,10 +464,6 @@ __global__ void k_renumber_instances(i64 nAi, const i32 *__restrict__ node_valid
 __global__ void k_fill_i32_tri(i32 *p, i64 n, i32 v) {
     i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
-}
-__global__ void k_pick2(const i32 *__restrict__ scanned, const i32 *__restrict__ at, int n, i32 *__restrict__ out) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = scanned[at[i]];
 }
 
 // ---- a8 + a9 ------------------------------------------------------------------------------------------
@@ -508,27 +544,22 @@ void batch_tri_finalize(Batch *b, int ignore_same_type, int ensure_min, int remo
 
     if (renumber) {
         const i64 nKA2 = new_ka[W];
-        DevBuf<i32> keepA2, type2, pf, ppos, row_ptr2, poff2;
+        DevBuf<i32> keepA2, type2, row_ptr2, poff2;
         DevBuf<double2> xy2;
         DevBuf<double> size2, cost2;
         DevBuf<int2> pairs2;
         keepA2.alloc(nKA2, s); type2.alloc(nKA2, s); xy2.alloc(nKA2, s); size2.alloc(nKA2, s);
-        pf.alloc(P + 1, s); ppos.alloc(P + 1, s); poff2.alloc(W + 1, s);
+        poff2.alloc(W + 1, s); pairs2.alloc(P, s); cost2.alloc(P, s); row_ptr2.alloc(nKA2 + 1, s);   // pairs only shrink: sized by the old count
         LAUNCH(k_compact_nodes, blocks_for(nKA, 256), 256, 0, s, nKA, node_valid.p, validpos.p, b->keepA.p, b->ka_xy.p, b->ka_type.p, b->ka_size.p,
                keepA2.p, xy2.p, type2.p, size2.p);
-        LAUNCH(k_pair_flags, blocks_for(P + 1, 256), 256, 0, s, b->pairs.p, P, b->d_p_off.p, b->d_ka_off.p, (int)W, node_valid.p, pf.p);
-        exclusive_scan_i32(pf.p, ppos.p, P + 1, b->scratch, s);
-        LAUNCH(k_pick2, blocks_for(W + 1, 128), 128, 0, s, ppos.p, b->d_p_off.p, (int)(W + 1), poff2.p);
-        // pairs shrink: the new per-window offsets reach the host with the next synchronisation, the device copies are
-        // made in place; outputs are sized by the old pair count
+        {
+            const unsigned tiles = blocks_for(P + 1, CP_TILE);
+            LAUNCH(k_compact_pairs, tiles, CP_THREADS, 0, s, b->pairs.p, b->cost.p, P, b->d_p_off.p, b->d_ka_off.p, (int)W, node_valid.p, validpos.p,
+                   b->row_ptr.p, nKA, scan_ctx(b->sec, tiles, 1, s), pairs2.p, cost2.p, row_ptr2.p, poff2.p);
+        }
+        // the new per-window pair offsets reach the host with the next synchronisation; the device copies are made in place
         CK(cudaMemcpyAsync(b->pin_renum(), poff2.p, sizeof(i32) * (W + 1), cudaMemcpyDeviceToHost, s));
         b->pend_renum = true;
-        pairs2.alloc(P, s); cost2.alloc(P, s); row_ptr2.alloc(nKA2 + 1, s);
-        if (P > 0)
-            LAUNCH(k_compact_pairs, blocks_for(P, 256), 256, 0, s, b->pairs.p, b->cost.p, P, b->d_p_off.p, b->d_ka_off.p, (int)W, pf.p, ppos.p, validpos.p,
-                   pairs2.p, cost2.p);
-        LAUNCH(k_compact_rowptr, blocks_for(std::max<i64>(nKA, 1), 256), 256, 0, s, nKA, node_valid.p, validpos.p, b->row_ptr.p, ppos.p, row_ptr2.p, nKA2,
-               poff2.p + W);
         if (b->nAi > 0) LAUNCH(k_renumber_instances, blocks_for(b->nAi, 256), 256, 0, s, b->nAi, node_valid.p, validpos.p, b->cnt.p, b->newA.p);
         b->keepA.swap(keepA2); b->ka_xy.swap(xy2); b->ka_type.swap(type2); b->ka_size.swap(size2);
         b->pairs.swap(pairs2); b->cost.swap(cost2); b->row_ptr.swap(row_ptr2);
