@@ -14,7 +14,10 @@
 namespace same {
 
 constexpr int MAX_RINGS = 4;
-constexpr double TARGET_PER_BIN = 12.0;
+// reference cells per bin: the own bin plus ring 1 (nine bins) should hold the k nearest with room to spare, and no more —
+// smaller bins prune better (measured at knn = 8 on the 1 M-cell section: 4/bin 250 us, 6/bin 234 us, 8/bin 254 us, 12/bin
+// 279 us, 24/bin 359 us)
+static double target_per_bin(int knn) { return std::max(4.0, 0.75 * knn); }
 constexpr int MAX_BINS_AXIS = 2048;
 
 // ---- binning -------------------------------------------------------------------------
@@ -130,49 +133,55 @@ __global__ void __launch_bounds__(128) k_knn(const double2 *__restrict__ sa_xy, 
 #define tau_j bj[KCAP - 1]
     int found = 0;
 
+    const double fx = px - cbx * g.w, fy = py - cby * g.w;
+    const double edge = fmin(fmin(fx, g.w - fx), fmin(fy, g.w - fy)) - eps;   // distance to the nearest side of the own bin
+    // ring 1 is walked nearest first — the side neighbours on the query's side of its bin, the other two, then the
+    // corners — so that the k-th best tightens early and the far corner bins are pruned without a single evaluation
+    const int sx = (fx + fx < g.w) ? -1 : 1, sy = (fy + fy < g.w) ? -1 : 1;
     for (int ring = 0; ring <= g.rings; ++ring) {
-        const double lim = fmin(tau_d, r2);
         if (ring > 0) {
             // nearest possible point of this ring (Chebyshev distance `ring` bins from the centre bin)
-            const double fx = px - cbx * g.w, fy = py - cby * g.w;
-            const double gap = (ring - 1) * g.w + fmin(fmin(fx, g.w - fx), fmin(fy, g.w - fy)) - eps;
-            if (gap > 0.0 && gap * gap > lim) break;
+            const double gap = (ring - 1) * g.w + edge;
+            if (gap > 0.0 && gap * gap > fmin(tau_d, r2)) break;
         }
-        for (int dy = -ring; dy <= ring; ++dy) {
-            const int by = cby + dy;
-            if (by < 0 || by >= g.nby) continue;
-            const int step = (dy == -ring || dy == ring || ring == 0) ? 1 : 2 * ring;
-            const double ylo = by * g.w, yhi = ylo + g.w;
-            const double gy = fmax(0.0, fmax(ylo - py, py - yhi) - eps);
-            for (int dx = -ring; dx <= ring; dx += step) {
-                const int bx = cbx + dx;
-                if (bx < 0 || bx >= g.nbx) continue;
-                const double xlo = bx * g.w, xhi = xlo + g.w;
-                const double gx = fmax(0.0, fmax(xlo - px, px - xhi) - eps);
-                if (gx * gx + gy * gy > fmin(tau_d, r2)) continue;
-                const i32 b = g.base + by * g.nbx + bx;
-                const i32 s1 = bin_start[b + 1];
-                for (i32 s = bin_start[b]; s < s1; ++s) {
-                    const double2 p = sr_xy[s];
-                    const double ddx = __dsub_rn(p.x, q.x), ddy = __dsub_rn(p.y, q.y);
-                    const double d2 = __dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy));
-                    if ((d2 <= r2) & (d2 <= tau_d)) {
-                        const i32 j = sr_inst[s];
-                        if (cand_less(d2, j, tau_d, tau_j)) {
-                            // branch-free sorted insertion: lt[u] = candidate sorts before slot u (computed on the old
-                            // values); slot u takes slot u-1 if lt[u-1], the candidate if lt[u] only, else keeps its value
-                            bool lt[KCAP];
+        const int n_slots = ring == 0 ? 1 : 8 * ring;
+        for (int slot = 0; slot < n_slots; ++slot) {
+            int dx = 0, dy = 0;
+            if (ring == 1) {
+                dx = (slot == 0 || slot == 4 || slot == 5) ? sx : ((slot == 2 || slot == 6 || slot == 7) ? -sx : 0);
+                dy = (slot == 1 || slot == 4 || slot == 6) ? sy : ((slot == 3 || slot == 5 || slot == 7) ? -sy : 0);
+            } else if (ring > 1) {   // perimeter walk: four sides of 2*ring bins each
+                const int side = slot / (2 * ring), k = slot - side * 2 * ring;
+                dx = side == 0 ? -ring + k : (side == 1 ? ring : (side == 2 ? ring - k : -ring));
+                dy = side == 0 ? -ring : (side == 1 ? -ring + k : (side == 2 ? ring : ring - k));
+            }
+            const int bx = cbx + dx, by = cby + dy;
+            if (bx < 0 || bx >= g.nbx || by < 0 || by >= g.nby) continue;
+            const double gx = fmax(0.0, fmax(bx * g.w - px, px - (bx + 1) * g.w) - eps);
+            const double gy = fmax(0.0, fmax(by * g.w - py, py - (by + 1) * g.w) - eps);
+            if (gx * gx + gy * gy > fmin(tau_d, r2)) continue;
+            const i32 b = g.base + by * g.nbx + bx;
+            const i32 s1 = bin_start[b + 1];
+            for (i32 s = bin_start[b]; s < s1; ++s) {
+                const double2 p = sr_xy[s];
+                const double ddx = __dsub_rn(p.x, q.x), ddy = __dsub_rn(p.y, q.y);
+                const double d2 = __dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy));
+                if ((d2 <= r2) & (d2 <= tau_d)) {
+                    const i32 j = sr_inst[s];
+                    if (cand_less(d2, j, tau_d, tau_j)) {
+                        // branch-free sorted insertion: lt[u] = candidate sorts before slot u (computed on the old
+                        // values); slot u takes slot u-1 if lt[u-1], the candidate if lt[u] only, else keeps its value
+                        bool lt[KCAP];
 #pragma unroll
-                            for (int u = 0; u < KCAP; ++u) lt[u] = cand_less(d2, j, bd[u], bj[u]);
+                        for (int u = 0; u < KCAP; ++u) lt[u] = cand_less(d2, j, bd[u], bj[u]);
 #pragma unroll
-                            for (int u = KCAP - 1; u > 0; --u) {
-                                bd[u] = lt[u - 1] ? bd[u - 1] : (lt[u] ? d2 : bd[u]);
-                                bj[u] = lt[u - 1] ? bj[u - 1] : (lt[u] ? j : bj[u]);
-                            }
-                            bd[0] = lt[0] ? d2 : bd[0];
-                            bj[0] = lt[0] ? j : bj[0];
-                            found = min(found + 1, knn);
+                        for (int u = KCAP - 1; u > 0; --u) {
+                            bd[u] = lt[u - 1] ? bd[u - 1] : (lt[u] ? d2 : bd[u]);
+                            bj[u] = lt[u - 1] ? bj[u - 1] : (lt[u] ? j : bj[u]);
                         }
+                        bd[0] = lt[0] ? d2 : bd[0];
+                        bj[0] = lt[0] ? j : bj[0];
+                        found = min(found + 1, knn);
                     }
                 }
             }
@@ -412,7 +421,7 @@ void batch_candidates(Batch *b, double radius, int knn, int priority, double dis
         if (!(y1 > y0)) y1 = y0;
         const double ex = x1 - x0, ey = y1 - y0;
         const i64 nref = b->r_off[w + 1] - b->r_off[w];
-        double bw = std::sqrt(TARGET_PER_BIN * std::max(ex, 1e-300) * std::max(ey, 1e-300) / (double)std::max<i64>(nref, 1));
+        double bw = std::sqrt(target_per_bin(knn) * std::max(ex, 1e-300) * std::max(ey, 1e-300) / (double)std::max<i64>(nref, 1));
         bw = std::max(bw, radius * (1.0 + 1e-9) / MAX_RINGS);
         bw = std::max(bw, std::max(ex, ey) / MAX_BINS_AXIS);
         if (!(bw > 0.0) || !std::isfinite(bw)) bw = 1.0;
