@@ -38,6 +38,11 @@ def lib():
     return _lib
 
 
+def set_threads(n: int = 0) -> int:
+    """OpenMP worker threads of the oracle's loops (n <= 0: just report).  -> threads in effect."""
+    return int(lib().oracle_set_threads(C.c_int(int(n))))
+
+
 def _p(a):
     return a.ctypes.data_as(C.c_void_p)
 

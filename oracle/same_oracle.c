@@ -27,6 +27,18 @@ typedef int32_t i32;
 
 #define ORACLE_API __attribute__((visibility("default")))
 
+/* Worker threads of the OpenMP loops below (bench.py: torchrun exports OMP_NUM_THREADS=1 to every rank, which would
+ * silently time the CPU arm on one core).  n <= 0 leaves the setting alone; returns the thread count in effect. */
+#ifdef _OPENMP
+#include <omp.h>
+ORACLE_API int oracle_set_threads(int n) {
+    if (n > 0) omp_set_num_threads(n);
+    return omp_get_max_threads();
+}
+#else
+ORACLE_API int oracle_set_threads(int n) { (void)n; return 1; }
+#endif
+
 /* ------------------------------------------------------------------------- */
 /* a1  find_knn_within_radius                      src/utils.py:709-742       */
 /* ------------------------------------------------------------------------- */

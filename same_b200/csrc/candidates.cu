@@ -105,6 +105,78 @@ void scan_i32(Section *sec, const i32 *in, i32 *out, i64 n, cudaStream_t s) {
 // short-circuit form compiled to divergent branches inside the insertion: 180 SASS instructions at ~3 active lanes)
 __device__ __forceinline__ bool cand_less(double d, i32 j, double bd, i32 bj) { return (d < bd) | ((d == bd) & (j < bj)); }
 
+// walk order of the 8 bins of ring 1: the side neighbours on the query's side of its bin, the other two, the corners
+__device__ __forceinline__ void ring1_slot(int slot, int sx, int sy, int &dx, int &dy) {
+    dx = (slot == 0 || slot == 4 || slot == 5) ? sx : ((slot == 2 || slot == 6 || slot == 7) ? -sx : 0);
+    dy = (slot == 1 || slot == 4 || slot == 6) ? sy : ((slot == 3 || slot == 5 || slot == 7) ? -sy : 0);
+}
+__device__ __forceinline__ void ring_slot(int ring, int slot, int &dx, int &dy) {   // perimeter walk: four sides of 2*ring bins
+    const int side = slot / (2 * ring), k = slot - side * 2 * ring;
+    dx = side == 0 ? -ring + k : (side == 1 ? ring : (side == 2 ? ring - k : -ring));
+    dy = side == 0 ? -ring : (side == 1 ? -ring + k : (side == 2 ? ring : ring - k));
+}
+
+// Exact search of ONE query with the (d2, ref instance) list in local memory: the path a query takes when the bucketed
+// search below cannot decide its k-th neighbour (two candidates in the same 2^-20-relative distance bucket at the
+// boundary — in practice only on exact lattices).  Writes the query's outputs itself.
+__device__ __noinline__ void knn_exact_one(double2 q, const GridParams &g, int cbx, int cby, const i32 *__restrict__ bin_start,
+                                           const double2 *__restrict__ sr_xy, const i32 *__restrict__ sr_inst, double r2, int knn,
+                                           i32 *__restrict__ out, i32 *__restrict__ cnt_out, i32 *__restrict__ r_used) {
+    double ld[32];
+    i32 lj[32];
+    const double px = q.x - g.x0, py = q.y - g.y0;
+    const double eps = 1e-7 * g.w;
+    const double fx = px - cbx * g.w, fy = py - cby * g.w;
+    const double edge = fmin(fmin(fx, g.w - fx), fmin(fy, g.w - fy)) - eps;
+    int found = 0;
+    double tau_d = INFINITY;
+    i32 tau_j = 0x7fffffff;
+    for (int ring = 0; ring <= g.rings; ++ring) {
+        if (ring > 0) {
+            const double gap = (ring - 1) * g.w + edge;
+            if (gap > 0.0 && gap * gap > fmin(tau_d, r2)) break;
+        }
+        const int n_slots = ring == 0 ? 1 : 8 * ring;
+        for (int slot = 0; slot < n_slots; ++slot) {
+            int dx = 0, dy = 0;
+            if (ring > 0) ring_slot(ring, slot, dx, dy);
+            const int bx = cbx + dx, by = cby + dy;
+            if (bx < 0 || bx >= g.nbx || by < 0 || by >= g.nby) continue;
+            const double gx = fmax(0.0, fmax(bx * g.w - px, px - (bx + 1) * g.w) - eps);
+            const double gy = fmax(0.0, fmax(by * g.w - py, py - (by + 1) * g.w) - eps);
+            if (gx * gx + gy * gy > fmin(tau_d, r2)) continue;
+            const i32 b = g.base + by * g.nbx + bx;
+            const i32 s1 = bin_start[b + 1];
+            for (i32 s = bin_start[b]; s < s1; ++s) {
+                const double2 p = sr_xy[s];
+                const double ddx = __dsub_rn(p.x, q.x), ddy = __dsub_rn(p.y, q.y);
+                const double d2 = __dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy));
+                if (d2 > r2) continue;
+                const i32 j = sr_inst[s];
+                if (found == knn && !cand_less(d2, j, tau_d, tau_j)) continue;
+                int u = (found == knn) ? knn - 1 : found;
+                while (u > 0 && cand_less(d2, j, ld[u - 1], lj[u - 1])) { ld[u] = ld[u - 1]; lj[u] = lj[u - 1]; --u; }
+                ld[u] = d2; lj[u] = j;
+                if (found < knn) ++found;
+                if (found == knn) { tau_d = ld[knn - 1]; tau_j = lj[knn - 1]; }
+            }
+        }
+    }
+    *cnt_out = found;
+    for (int u = 0; u < knn; ++u) {
+        out[u] = (u < found) ? lj[u] : -1;
+        if (u < found) r_used[lj[u]] = 1;
+    }
+}
+
+// One thread per aligned instance.  The running top-k is kept on a 32-bit KEY — the high word of the fp64 d2, a monotone
+// 2^-20-relative bucket of the distance — with the candidate's position in the sorted array beside it: an insertion is
+// one integer compare and four selects per slot instead of a (double, index) lexicographic compare and six selects
+// (the fp64 list spent 52 % of the kernel's warp instructions inserting at 11 of 32 active lanes, profiles/r1k).
+// The k candidates with the smallest keys ARE the k nearest unless the k-th and a dropped candidate share a bucket
+// (`tie`): those queries take knn_exact_one.  The survivors' exact d2 are recomputed once at the end and put in
+// (d2, ref instance) order by an odd-even transposition pass over an almost sorted list.
+constexpr unsigned KEY_NONE = 0x7ff00000u;   // high word of +inf: above the key of every finite d2
 template <int KCAP>
 __global__ void __launch_bounds__(128) k_knn(const double2 *__restrict__ sa_xy, const i32 *__restrict__ sa_inst, i64 nAi,
                                              const i32 *__restrict__ a_off, int W, const GridParams *__restrict__ grids,
@@ -119,76 +191,125 @@ __global__ void __launch_bounds__(128) k_knn(const double2 *__restrict__ sa_xy, 
     int cbx, cby;
     bin_of(g, q, cbx, cby);
     const double px = q.x - g.x0, py = q.y - g.y0;
-    const double eps = 1e-7 * g.w;
 
-    // Sorted top-k in registers, right-aligned: slots [KCAP-knn, KCAP) hold the list (ascending), the slots
-    // before it are -inf sentinels that never move, so the k-th best is always the LAST slot (a static
-    // register index; a runtime index would push the arrays into local memory).
-    double bd[KCAP];
-    i32 bj[KCAP];
+    // Sorted keys in registers, right-aligned: slots [KCAP-knn, KCAP) hold the list (ascending), the slots before it
+    // are zero keys that never move (no key is < 0), so the k-th best is always the LAST slot (a static register
+    // index; a runtime index would push the arrays into local memory).
+    unsigned bk[KCAP];
+    i32 bs[KCAP];
     const int head = KCAP - knn;
 #pragma unroll
-    for (int s = 0; s < KCAP; ++s) { bd[s] = (s < head) ? -INFINITY : INFINITY; bj[s] = 0x7fffffff; }
-#define tau_d bd[KCAP - 1]
-#define tau_j bj[KCAP - 1]
-    int found = 0;
-
-    const double fx = px - cbx * g.w, fy = py - cby * g.w;
-    const double edge = fmin(fmin(fx, g.w - fx), fmin(fy, g.w - fy)) - eps;   // distance to the nearest side of the own bin
-    // ring 1 is walked nearest first — the side neighbours on the query's side of its bin, the other two, then the
-    // corners — so that the k-th best tightens early and the far corner bins are pruned without a single evaluation
-    const int sx = (fx + fx < g.w) ? -1 : 1, sy = (fy + fy < g.w) ? -1 : 1;
+    for (int s = 0; s < KCAP; ++s) { bk[s] = (s < head) ? 0u : KEY_NONE; bs[s] = 0; }
+#define last_k bk[KCAP - 1]
+    bool tie = false;
+    // Candidates with d2 > thr cannot enter: thr = min(r2, upper edge of the k-th key's bucket), kept as its two words
+    // (upper edge = high word last_k + 1, low word 0; it is below r2 exactly when last_k + 1 <= high word of r2).
+    const unsigned r2_hi = (unsigned)__double2hiint(r2), r2_lo = (unsigned)__double2loint(r2);
+    double thr = r2;
+    // Bin pruning runs in fp32 on lower bounds of the point-to-bin distance: fx, fy (position inside the own bin) and the
+    // bin width are O(w), so fp32 rounding is ~1e-7 w per term; 1e-5 w of slack on every gap and thr rounded up keep the
+    // test conservative.  The exact predicate is always the fp64 one on the candidate itself.
+    const float wf = (float)g.w, epsf = 1e-5f * wf;
+    const float fxf = (float)(px - cbx * g.w), fyf = (float)(py - cby * g.w);
+    float thrf = __double2float_ru(thr);
+    const float edge = fminf(fminf(fxf, wf - fxf), fminf(fyf, wf - fyf)) - epsf;   // distance to the nearest side of the own bin
+    // ring 1 is walked nearest first so that the k-th best tightens early and the far corner bins are pruned without a
+    // single evaluation
+    const int sx = (fxf + fxf < wf) ? -1 : 1, sy = (fyf + fyf < wf) ? -1 : 1;
     for (int ring = 0; ring <= g.rings; ++ring) {
         if (ring > 0) {
             // nearest possible point of this ring (Chebyshev distance `ring` bins from the centre bin)
-            const double gap = (ring - 1) * g.w + edge;
-            if (gap > 0.0 && gap * gap > fmin(tau_d, r2)) break;
+            const float gap = (float)(ring - 1) * wf + edge;
+            if (gap > 0.f && gap * gap > thrf) break;
         }
         const int n_slots = ring == 0 ? 1 : 8 * ring;
         for (int slot = 0; slot < n_slots; ++slot) {
             int dx = 0, dy = 0;
-            if (ring == 1) {
-                dx = (slot == 0 || slot == 4 || slot == 5) ? sx : ((slot == 2 || slot == 6 || slot == 7) ? -sx : 0);
-                dy = (slot == 1 || slot == 4 || slot == 6) ? sy : ((slot == 3 || slot == 5 || slot == 7) ? -sy : 0);
-            } else if (ring > 1) {   // perimeter walk: four sides of 2*ring bins each
-                const int side = slot / (2 * ring), k = slot - side * 2 * ring;
-                dx = side == 0 ? -ring + k : (side == 1 ? ring : (side == 2 ? ring - k : -ring));
-                dy = side == 0 ? -ring : (side == 1 ? -ring + k : (side == 2 ? ring : ring - k));
-            }
+            if (ring == 1) ring1_slot(slot, sx, sy, dx, dy);
+            else if (ring > 1) ring_slot(ring, slot, dx, dy);
             const int bx = cbx + dx, by = cby + dy;
             if (bx < 0 || bx >= g.nbx || by < 0 || by >= g.nby) continue;
-            const double gx = fmax(0.0, fmax(bx * g.w - px, px - (bx + 1) * g.w) - eps);
-            const double gy = fmax(0.0, fmax(by * g.w - py, py - (by + 1) * g.w) - eps);
-            if (gx * gx + gy * gy > fmin(tau_d, r2)) continue;
+            // gap along one axis to a bin d bins away: d > 0: d*w - f;  d < 0: f + (-d - 1)*w;  own row/column: 0
+            const float gx = dx == 0 ? 0.f : fmaxf(0.f, (dx > 0 ? (float)dx * wf - fxf : fxf - (float)(dx + 1) * wf) - epsf);
+            const float gy = dy == 0 ? 0.f : fmaxf(0.f, (dy > 0 ? (float)dy * wf - fyf : fyf - (float)(dy + 1) * wf) - epsf);
+            if (gx * gx + gy * gy > thrf) continue;
             const i32 b = g.base + by * g.nbx + bx;
             const i32 s1 = bin_start[b + 1];
-            for (i32 s = bin_start[b]; s < s1; ++s) {
-                const double2 p = sr_xy[s];
-                const double ddx = __dsub_rn(p.x, q.x), ddy = __dsub_rn(p.y, q.y);
-                const double d2 = __dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy));
-                if ((d2 <= r2) & (d2 <= tau_d)) {
-                    const i32 j = sr_inst[s];
-                    if (cand_less(d2, j, tau_d, tau_j)) {
-                        // branch-free sorted insertion: lt[u] = candidate sorts before slot u (computed on the old
-                        // values); slot u takes slot u-1 if lt[u-1], the candidate if lt[u] only, else keeps its value
-                        bool lt[KCAP];
+            for (i32 s0 = bin_start[b]; s0 < s1; s0 += 2) {
+                // two candidates per trip: both loads are in flight before either is used (the second one re-reads the
+                // first when the bin ends on an odd count and is then skipped)
+                const bool two = s0 + 1 < s1;
+                const double2 pA = sr_xy[s0], pB = sr_xy[two ? s0 + 1 : s0];
+                const double ax = __dsub_rn(pA.x, q.x), ay = __dsub_rn(pA.y, q.y), bx2 = __dsub_rn(pB.x, q.x), by2 = __dsub_rn(pB.y, q.y);
+                const double dA = __dadd_rn(__dmul_rn(ax, ax), __dmul_rn(ay, ay));
+                const double dB = two ? __dadd_rn(__dmul_rn(bx2, bx2), __dmul_rn(by2, by2)) : INFINITY;
 #pragma unroll
-                        for (int u = 0; u < KCAP; ++u) lt[u] = cand_less(d2, j, bd[u], bj[u]);
+                for (int h = 0; h < 2; ++h) {
+                    const double d2 = h ? dB : dA;
+                    const i32 s = s0 + h;
+                    if (d2 <= thr) {
+                        const unsigned key = (unsigned)__double2hiint(d2);
+                        if (key < last_k) {
+                            // branch-free sorted insertion: lt[u] = candidate sorts before slot u (computed on the old
+                            // values); slot u takes slot u-1 if lt[u-1], the candidate if lt[u] only, else keeps its value
+                            const unsigned old_last = last_k;
+                            bool lt[KCAP];
 #pragma unroll
-                        for (int u = KCAP - 1; u > 0; --u) {
-                            bd[u] = lt[u - 1] ? bd[u - 1] : (lt[u] ? d2 : bd[u]);
-                            bj[u] = lt[u - 1] ? bj[u - 1] : (lt[u] ? j : bj[u]);
+                            for (int u = 0; u < KCAP; ++u) lt[u] = key < bk[u];
+#pragma unroll
+                            for (int u = KCAP - 1; u > 0; --u) {
+                                bk[u] = lt[u - 1] ? bk[u - 1] : (lt[u] ? key : bk[u]);
+                                bs[u] = lt[u - 1] ? bs[u - 1] : (lt[u] ? s : bs[u]);
+                            }
+                            bk[0] = lt[0] ? key : bk[0];
+                            bs[0] = lt[0] ? s : bs[0];
+                            tie = last_k == old_last;   // the dropped candidate shares the new k-th's bucket (or the list is not full yet)
+                            const bool below = last_k + 1u <= r2_hi;   // never for KEY_NONE: r2 is finite
+                            thr = __hiloint2double((int)(below ? last_k + 1u : r2_hi), (int)(below ? 0u : r2_lo));
+                            thrf = __double2float_ru(thr);
+                        } else if (key == last_k) {
+                            tie = true;
                         }
-                        bd[0] = lt[0] ? d2 : bd[0];
-                        bj[0] = lt[0] ? j : bj[0];
-                        found = min(found + 1, knn);
                     }
                 }
             }
         }
     }
-    cnt[inst] = found;
     i32 *out = cand + (i64)inst * knn;
+    if (tie && last_k != KEY_NONE) {
+        knn_exact_one(q, g, cbx, cby, bin_start, sr_xy, sr_inst, r2, knn, out, cnt + inst, r_used);
+        return;
+    }
+    // exact d2 of the survivors; unused slots sort last
+    double bd[KCAP];
+    i32 bj[KCAP];
+    int found = 0;
+#pragma unroll
+    for (int u = 0; u < KCAP; ++u) {
+        const bool ok = (u >= head) & (bk[u] != KEY_NONE);
+        const double2 p = sr_xy[bs[u]];
+        const double ddx = __dsub_rn(p.x, q.x), ddy = __dsub_rn(p.y, q.y);
+        bd[u] = ok ? __dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy)) : ((u < head) ? -INFINITY : INFINITY);
+        bj[u] = ok ? sr_inst[bs[u]] : ((u < head) ? (i32)0x80000000 : 0x7fffffff);
+        found += ok;
+    }
+    // the list is sorted by bucket; inside a bucket the exact (d2, instance) order is restored here
+    bool swapped = true;
+    while (swapped) {
+        swapped = false;
+#pragma unroll
+        for (int par = 0; par < 2; ++par)
+#pragma unroll
+            for (int u = par; u + 1 < KCAP; u += 2) {
+                const bool sw = cand_less(bd[u + 1], bj[u + 1], bd[u], bj[u]);
+                const double d0 = bd[u], d1 = bd[u + 1];
+                const i32 j0 = bj[u], j1 = bj[u + 1];
+                bd[u] = sw ? d1 : d0; bd[u + 1] = sw ? d0 : d1;
+                bj[u] = sw ? j1 : j0; bj[u + 1] = sw ? j0 : j1;
+                swapped |= sw;
+            }
+    }
+    cnt[inst] = found;
 #pragma unroll
     for (int u = 0; u < KCAP; ++u)
         if (u >= head) {
@@ -196,8 +317,7 @@ __global__ void __launch_bounds__(128) k_knn(const double2 *__restrict__ sa_xy, 
             out[u - head] = ok ? bj[u] : -1;
             if (ok) r_used[bj[u]] = 1;
         }
-#undef tau_d
-#undef tau_j
+#undef last_k
 }
 
 // generic path for knn > 32: top-k lives in global scratch ([slot][query] so threads coalesce)
@@ -511,6 +631,8 @@ void batch_candidates(Batch *b, double radius, int knn, int priority, double dis
     CK(cudaMemcpyAsync(b->d_ka_off.p, off3.p, sizeof(i32) * (W + 1), cudaMemcpyDeviceToDevice, s));
     CK(cudaMemcpyAsync(b->d_kr_off.p, off3.p + (W + 1), sizeof(i32) * (W + 1), cudaMemcpyDeviceToDevice, s));
     CK(cudaMemcpyAsync(b->d_p_off.p, off3.p + 2 * (W + 1), sizeof(i32) * (W + 1), cudaMemcpyDeviceToDevice, s));
+    // (a one-thread-per-row variant with 8 gather chains in flight per thread was measured at 224 us vs 129 us: the kernel
+    // is bound by L2 sector traffic — ~5 distinct 32-byte sectors per pair — not by chain latency; profiles/r1m)
     if (nAi > 0)
         LAUNCH(k_emit_pairs, blocks_for(nAi * knn, 256), 256, 0, s, b->cand.p, eff, knn, nAi, b->newA.p, newR.p, poff.p, b->d_a_off.p, (int)W,
                b->d_ka_off.p, b->d_kr_off.p, b->a_src.p, b->r_src.p, sec->a_xy.p, sec->r_xy.p, sec->a_prob.p, sec->r_prob.p, sec->K,
