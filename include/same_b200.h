@@ -84,7 +84,9 @@ enum {
     SAME_ARR_TRI_MASK = 25,    /* [i32]   post-solve bits: 0-2 x-order violation of vertex pairs (0,1),(0,2),(1,2); 3-5 y-order; 8-10 vertex matched (src/violationhelper.py:54-121) */
     SAME_ARR_AREA_BEFORE = 26, /* [f64]   calculate_signed_area on aligned XY (src/same.py:1362-1370) */
     SAME_ARR_AREA_AFTER = 27,  /* [f64]   same on matched reference XY, NaN when a vertex is unmatched (src/same.py:1379-1395) */
-    SAME_ARR_FLIPPED = 28      /* [u8]    area_before*area_after < 0 (src/same.py:1398) */
+    SAME_ARR_FLIPPED = 28,     /* [u8]    area_before*area_after < 0 (src/same.py:1398) */
+    SAME_ARR_START_X = 29,     /* [u8]    greedy MIP start: 1 on the chosen pairs (src/init_helpers.py:124-130, x_vars[..].Start) */
+    SAME_ARR_START_UNMATCHED = 30 /* [u8] greedy MIP start: 1 on kept aligned rows left unmatched (src/init_helpers.py:132, no_match_vars[..].Start) */
 };
 
 typedef struct same_section same_section_t;
@@ -164,6 +166,20 @@ SAME_API int same_batch_postsolve(same_batch_t *b, int64_t w_lo, int64_t w_hi, c
 SAME_API int same_postsolve_arrays(int device, int64_t n_tri, const int32_t *tri, int64_t n_aligned, const double *a_xy, int64_t n_ref,
                                    const double *r_xy, const int32_t *match_j, int32_t *mask, double *area_before, double *area_after,
                                    uint8_t *flipped);
+
+/* Greedy MIP start of every window of the batch (compute_mip_start_pairs(init_method='greedy'), src/init_helpers.py:110-132):
+ * pairs in ascending (cost, pair index) order, a pair is chosen iff its aligned row prefers a match (best cost of the row
+ * < no_match_penalty * size) and neither endpoint is taken yet.  Results through same_batch_get(START_X / START_UNMATCHED).
+ * *rounds (may be NULL) = parallel rounds the selection took. */
+SAME_API int same_batch_mip_start(same_batch_t *b, double no_match_penalty, int32_t *rounds);
+
+/* The selection loop on its own, for callers that hold plain arrays: n items with `degree` (1..3) endpoints each
+ * (nodes[n, degree], values in [0, n_nodes)), visited in ascending (key, item index) order; an item is selected iff it is
+ * eligible (eligible == NULL: all are) and none of its endpoints belongs to an item selected earlier.  Used by the greedy
+ * MIP start (degree 2) and by the batch selection of greedy_triangle_collapse (degree 3, key = perimeter,
+ * src/metacell_utils.py:423-433).  nodes/key/eligible HD; selected[n], used[n_nodes] (may be NULL) host, u8. */
+SAME_API int same_greedy_select(int device, int64_t n, int degree, const int32_t *nodes, const double *key, const uint8_t *eligible,
+                                int64_t n_nodes, uint8_t *selected, uint8_t *used, int32_t *rounds);
 
 /* ---- results -------------------------------------------------------------------------- */
 /* W+1 offsets (in elements) of array `what` */

@@ -33,7 +33,7 @@ def lib():
             build()
         _lib = C.CDLL(_LIB_PATH)
         for name in ("oracle_knn_compact", "oracle_knn_priority", "oracle_group_pairs", "oracle_remap_triangles",
-                     "oracle_tri_select", "oracle_separation", "oracle_subset"):
+                     "oracle_tri_select", "oracle_separation", "oracle_subset", "oracle_greedy_select"):
             getattr(_lib, name).restype = C.c_int64
     return _lib
 
@@ -215,3 +215,31 @@ def subset(xy, x_min, x_max, y_min, y_max):
     o = lib().oracle_subset(_p(xy), C.c_int64(len(xy)), C.c_double(x_min), C.c_double(x_max), C.c_double(y_min),
                             C.c_double(y_max), _p(rows))
     return rows[:o].copy()
+
+
+def greedy_select(nodes, key, n_nodes, eligible=None):
+    """Ordered greedy selection with disjoint endpoints (init_helpers.py:110-132, metacell_utils.py:423-433) -> (selected bool [n], used bool [n_nodes])."""
+    nodes = _i32(nodes)
+    if nodes.ndim == 1:
+        nodes = nodes.reshape(-1, 1)
+    n, degree = nodes.shape
+    key = _f64(key).reshape(n)
+    el = None if eligible is None else np.ascontiguousarray(eligible, dtype=np.uint8).reshape(n)
+    sel, used = np.zeros(n, np.uint8), np.zeros(int(n_nodes), np.uint8)
+    lib().oracle_greedy_select(C.c_int64(n), C.c_int(degree), _p(nodes), _p(key), _p(el) if el is not None else None, C.c_int64(int(n_nodes)),
+                               _p(sel), _p(used))
+    return sel.astype(bool), used.astype(bool)
+
+
+def mip_start_greedy(pairs, cost, n_aligned, n_ref, sizes, no_match_penalty):
+    """compute_mip_start_pairs(init_method='greedy') -> (chosen [m,3] (i, j, var_idx) in selection order, unmatched sorted)."""
+    pairs = np.asarray(pairs, dtype=np.int64).reshape(-1, 2)
+    cost = _f64(cost)
+    best = np.full(n_aligned, np.inf)
+    np.minimum.at(best, pairs[:, 0], cost)
+    prefer = best < float(no_match_penalty) * _f64(sizes)
+    nodes = np.stack([pairs[:, 0], n_aligned + pairs[:, 1]], axis=1)
+    sel, used = greedy_select(nodes, cost, n_aligned + n_ref, prefer[pairs[:, 0]])
+    idx = np.flatnonzero(sel)
+    idx = idx[np.argsort(cost[idx], kind="stable")]
+    return np.stack([pairs[idx, 0], pairs[idx, 1], idx], axis=1), np.flatnonzero(~used[:n_aligned])

@@ -466,3 +466,39 @@ ORACLE_API i64 oracle_subset(const double *xy, i64 n, double x_min, double x_max
         if (xy[2 * i] >= x_min && xy[2 * i] < x_max && xy[2 * i + 1] >= y_min && xy[2 * i + 1] < y_max) rows[o++] = (i32)i;
     return o;
 }
+
+/* ------------------------------------------------------------------------- */
+/* f3/f2  ordered greedy selection with disjoint endpoints                   */
+/*        greedy MIP start                     src/init_helpers.py:110-132   */
+/*        batch selection of triangle collapse src/metacell_utils.py:423-433 */
+/* ------------------------------------------------------------------------- */
+typedef struct { double key; i64 idx; } gitem_t;
+static int gitem_cmp(const void *a, const void *b) {
+    const gitem_t *x = (const gitem_t *)a, *y = (const gitem_t *)b;
+    if (x->key < y->key) return -1;
+    if (x->key > y->key) return 1;
+    return (x->idx > y->idx) - (x->idx < y->idx);   /* list.sort is stable: ties stay in index order */
+}
+/* Items in ascending (key, index) order; an item is selected iff it is eligible (eligible == NULL: all) and none of its
+ * `degree` endpoints was used by an earlier selected item.  selected[n], used[n_nodes] out.  Returns the number selected. */
+ORACLE_API i64 oracle_greedy_select(i64 n, int degree, const i32 *nodes, const double *key, const unsigned char *eligible, i64 n_nodes,
+                                    unsigned char *selected, unsigned char *used) {
+    gitem_t *it = (gitem_t *)malloc(sizeof(gitem_t) * (size_t)(n > 0 ? n : 1));
+    for (i64 e = 0; e < n; ++e) { it[e].key = key[e]; it[e].idx = e; }
+    qsort(it, (size_t)n, sizeof(gitem_t), gitem_cmp);
+    memset(selected, 0, (size_t)n);
+    memset(used, 0, (size_t)n_nodes);
+    i64 count = 0;
+    for (i64 r = 0; r < n; ++r) {
+        const i64 e = it[r].idx;
+        if (eligible && !eligible[e]) continue;
+        int hit = 0;
+        for (int d = 0; d < degree; ++d) hit |= used[nodes[e * degree + d]];
+        if (hit) continue;
+        selected[e] = 1;
+        for (int d = 0; d < degree; ++d) used[nodes[e * degree + d]] = 1;
+        ++count;
+    }
+    free(it);
+    return count;
+}

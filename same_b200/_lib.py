@@ -22,6 +22,7 @@ REF_GROUP_NODE, REF_GROUP_PTR, REF_GROUP_IDX, REF_GROUP_LIMIT, ROW_PTR = 7, 8, 9
 TRI_IN, TRI_IN_SRC, TRI_CLASS, TRI_BAND, TRI, TRI_SRC = 12, 13, 14, 15, 16, 17
 TRI_WEIGHT, TRI_SIGN, TRI_BOUNDS, TRI_ARGV, UNCONSTRAINED = 18, 19, 20, 21, 22
 MATCH_J, MATCH_P, TRI_MASK, AREA_BEFORE, AREA_AFTER, FLIPPED = 23, 24, 25, 26, 27, 28
+START_X, START_UNMATCHED = 29, 30
 
 #: numpy dtype and trailing shape of every retrievable array
 ARRAY_SPEC = {
@@ -34,6 +35,7 @@ ARRAY_SPEC = {
     TRI_BOUNDS: (np.float64, (4,)), TRI_ARGV: (np.int32, (4,)), UNCONSTRAINED: (np.int32, ()),
     MATCH_J: (np.int32, ()), MATCH_P: (np.int32, ()), TRI_MASK: (np.int32, ()),
     AREA_BEFORE: (np.float64, ()), AREA_AFTER: (np.float64, ()), FLIPPED: (np.uint8, ()),
+    START_X: (np.uint8, ()), START_UNMATCHED: (np.uint8, ()),
 }
 
 TRI_DROP_RADIUS, TRI_DROP_ANGLE, TRI_SAME_TYPE, TRI_KEEP = 0, 1, 2, 3
@@ -47,7 +49,7 @@ SYMBOLS = [
     "same_batch_groups", "same_batch_separation", "same_batch_postsolve", "same_batch_offsets", "same_batch_length",
     "same_batch_get", "same_elem_size", "same_batch_sync", "same_batch_stream", "same_launch_count",
     "same_profile_enable", "same_profile_report", "same_batch_get_many", "same_pinned_alloc", "same_pinned_free",
-    "same_postsolve_arrays",
+    "same_postsolve_arrays", "same_batch_mip_start", "same_greedy_select",
 ]
 
 
@@ -105,6 +107,8 @@ def load():
     lib.same_pinned_alloc.argtypes = [i64, C.POINTER(vp)]
     lib.same_pinned_free.argtypes = [vp]
     lib.same_postsolve_arrays.argtypes = [i32, i64, vp, i64, vp, i64, vp, vp, vp, vp, vp, vp]
+    lib.same_batch_mip_start.argtypes = [vp, dbl, C.POINTER(C.c_int32)]
+    lib.same_greedy_select.argtypes = [i32, i64, i32, vp, vp, vp, i64, vp, vp, C.POINTER(C.c_int32)]
     lib.same_profile_enable.argtypes = [i32]
     lib.same_profile_report.argtypes = [C.c_char_p, i64]
     lib.same_profile_report.restype = i64

@@ -9,7 +9,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsame_b200.so")
-SOURCES = ["section.cu", "candidates.cu", "triangles.cu", "separation.cu", "api.cu"]
+SOURCES = ["section.cu", "candidates.cu", "triangles.cu", "separation.cu", "greedy.cu", "api.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
     "-fmad=false",            # the reference's scalar Python arithmetic never contracts a*b+c

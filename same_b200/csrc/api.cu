@@ -33,7 +33,7 @@ i64 elem_size(int what) {
         case SAME_ARR_PAIRS: return 8;
         case SAME_ARR_COST: case SAME_ARR_TRI_WEIGHT: case SAME_ARR_AREA_BEFORE: case SAME_ARR_AREA_AFTER: return 8;
         case SAME_ARR_TRI_IN: case SAME_ARR_TRI: return 12;
-        case SAME_ARR_TRI_CLASS: case SAME_ARR_TRI_SIGN: case SAME_ARR_FLIPPED: return 1;
+        case SAME_ARR_TRI_CLASS: case SAME_ARR_TRI_SIGN: case SAME_ARR_FLIPPED: case SAME_ARR_START_X: case SAME_ARR_START_UNMATCHED: return 1;
         case SAME_ARR_TRI_BOUNDS: return 32;
         case SAME_ARR_TRI_ARGV: return 16;
         case SAME_ARR_REF_GROUP_PTR: case SAME_ARR_ROW_PTR: return 4;
@@ -74,6 +74,8 @@ ArrayView view(Batch *b, int what) {
         case SAME_ARR_AREA_BEFORE: REQUIRE(b->have_post, SAME_E_STATE, "postsolve not run"); return {b->area_before.p, b->T, es, &b->t_off};
         case SAME_ARR_AREA_AFTER: REQUIRE(b->have_post, SAME_E_STATE, "postsolve not run"); return {b->area_after.p, b->T, es, &b->t_off};
         case SAME_ARR_FLIPPED: REQUIRE(b->have_post, SAME_E_STATE, "postsolve not run"); return {b->flipped.p, b->T, es, &b->t_off};
+        case SAME_ARR_START_X: REQUIRE(b->have_start, SAME_E_STATE, "mip start not computed"); return {b->start_x.p, b->P, es, &b->p_off};
+        case SAME_ARR_START_UNMATCHED: REQUIRE(b->have_start, SAME_E_STATE, "mip start not computed"); return {b->start_unmatched.p, b->nKA, es, &b->ka_off};
         default: throw same::Error(SAME_E_ARG, "unknown array id");
     }
 }
@@ -259,6 +261,18 @@ int same_batch_separation(same_batch_t *h, int64_t w_lo, int64_t w_hi, const dou
     BATCH_CALL(h, { REQUIRE(n_viol && n_checked, SAME_E_ARG, "NULL output"); batch_separation(b, w_lo, w_hi, x, cap, n_viol, n_checked, cuts); });
 }
 int same_batch_postsolve(same_batch_t *h, int64_t w_lo, int64_t w_hi, const double *x) { BATCH_CALL(h, batch_postsolve(b, w_lo, w_hi, x)); }
+
+int same_batch_mip_start(same_batch_t *h, double no_match_penalty, int32_t *rounds) { BATCH_CALL(h, batch_mip_start(b, no_match_penalty, rounds)); }
+
+int same_greedy_select(int device, int64_t n, int degree, const int32_t *nodes, const double *key, const uint8_t *eligible, int64_t n_nodes,
+                       uint8_t *selected, uint8_t *used, int32_t *rounds) {
+    return guarded([&] {
+        REQUIRE(n >= 0 && n_nodes >= 0 && n < (1ll << 31) && n_nodes < (1ll << 31), SAME_E_ARG, "bad size");
+        REQUIRE(degree >= 1 && degree <= 3, SAME_E_ARG, "degree must be 1, 2 or 3");
+        REQUIRE(n == 0 || (nodes && key && selected), SAME_E_ARG, "NULL argument");
+        greedy_select_arrays(device, n, degree, nodes, key, eligible, n_nodes, selected, used, rounds);
+    });
+}
 
 int same_postsolve_arrays(int device, int64_t n_tri, const int32_t *tri, int64_t n_aligned, const double *a_xy, int64_t n_ref, const double *r_xy,
                           const int32_t *match_j, int32_t *mask, double *area_before, double *area_after, uint8_t *flipped) {

@@ -264,6 +264,10 @@ struct Batch {
     DevBuf<double> area_before, area_after;
     DevBuf<unsigned char> flipped;
     bool have_post = false;
+
+    // greedy MIP start (init_helpers.py:110-132)
+    DevBuf<unsigned char> start_x, start_unmatched;   // [P], [nKA]
+    bool have_start = false;
 };
 
 // cudaStreamSynchronize + parse whatever small results were pending; batch_settle only synchronises if something is
@@ -289,6 +293,10 @@ void batch_separation(Batch *b, i64 w_lo, i64 w_hi, const double *x, i64 cap, i6
 void batch_postsolve(Batch *b, i64 w_lo, i64 w_hi, const double *x);
 void postsolve_arrays(int device, i64 T, const i32 *tri, i64 nA, const double *a_xy, i64 nR, const double *r_xy, const i32 *match_j, i32 *mask,
                       double *area_before, double *area_after, unsigned char *flipped);
+
+void batch_mip_start(Batch *b, double no_match_penalty, i32 *rounds_out);
+void greedy_select_arrays(int device, i64 n, int degree, const i32 *nodes, const double *key, const unsigned char *eligible, i64 n_nodes,
+                          unsigned char *selected, unsigned char *used_out, i32 *rounds_out);
 
 // upload a small host vector of i64 offsets as i32 device array
 void upload_offsets(const std::vector<i64> &h, DevBuf<i32> &d, cudaStream_t s);

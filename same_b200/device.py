@@ -130,6 +130,24 @@ class Section:
         self.close()
 
 
+def greedy_select(nodes, key, n_nodes, eligible=None, device: int = 0, return_rounds=False):
+    """Ordered greedy selection with disjoint endpoints (same_greedy_select): items visited in ascending (key, index) order,
+    an item is taken iff it is eligible and none of its endpoints was taken before.  nodes [n, 1..3] int -> bool [n]."""
+    nodes = np.ascontiguousarray(nodes, dtype=np.int32)
+    if nodes.ndim == 1:
+        nodes = nodes.reshape(-1, 1)
+    n, degree = nodes.shape
+    key = np.ascontiguousarray(key, dtype=np.float64).reshape(n)
+    if n and (nodes.min() < 0 or nodes.max() >= n_nodes):
+        raise ValueError("endpoint out of range")
+    if np.isnan(key).any():
+        raise ValueError("keys must not be NaN")
+    el = None if eligible is None else np.ascontiguousarray(eligible, dtype=np.uint8).reshape(n)
+    sel, used, r = np.zeros(n, np.uint8), np.zeros(int(n_nodes), np.uint8), C.c_int32(0)
+    L.check(L.load().same_greedy_select(device, n, degree, L.ptr(nodes), L.ptr(key), L.ptr(el), int(n_nodes), L.ptr(sel), L.ptr(used), C.byref(r)))
+    return (sel.astype(bool), r.value) if return_rounds else sel.astype(bool)
+
+
 class WindowBatch:
     """A list of windows of one section (same_batch_create).  `rects=None` = the whole section."""
 
@@ -198,6 +216,12 @@ class WindowBatch:
         if not isinstance(x, int):
             x = np.ascontiguousarray(x, dtype=np.float64)
         L.check(L.load().same_batch_postsolve(self._h, w_lo, w_hi, L.ptr(x)))
+
+    def mip_start(self, no_match_penalty):
+        """Greedy MIP start of every window (init_helpers.py:110-132) -> parallel rounds used; results: START_X, START_UNMATCHED."""
+        r = C.c_int32(0)
+        L.check(L.load().same_batch_mip_start(self._h, float(no_match_penalty), C.byref(r)))
+        return r.value
 
     # ---- results ----
     def offsets(self, what):

@@ -163,13 +163,12 @@ def greedy_triangle_collapse(aligned_df, max_metacell_size=3, max_iterations=100
             break
         a, b, c = coords[tri[cand, 0]], coords[tri[cand, 1]], coords[tri[cand, 2]]
         perim = np.linalg.norm(a - b, axis=1) + np.linalg.norm(b - c, axis=1) + np.linalg.norm(c - a, axis=1)
-        used = np.zeros(len(mdf), bool)
-        batch = []
-        for k in np.argsort(perim, kind="stable"):                     # list.sort is stable (src/metacell_utils.py:424)
-            v = tri[cand[k]]
-            if not used[v].any():
-                batch.append(cand[k])
-                used[v] = True
+        # batch mode (src/metacell_utils.py:423-433): candidates in ascending (perimeter, position) order — list.sort is stable —
+        # each taken iff none of its vertices is used yet.  The loop is the ordered greedy selection of csrc/greedy.cu.
+        from .device import greedy_select
+        sel = greedy_select(tri[cand], perim, len(mdf))
+        chosen = np.flatnonzero(sel)
+        batch = cand[chosen[np.argsort(perim[chosen], kind="stable")]].tolist()   # merged metacells are appended in selection order
         merged, remove = [], []
         for t in batch:
             va, vb, vc = tri[t]

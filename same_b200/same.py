@@ -155,8 +155,30 @@ def _solve_window(run: _Run, w: int, aligned_src: pd.DataFrame, ref_src: pd.Data
     if not lazy:
         raise NotImplementedError("lazy_constraints=False (the O(n*k^3) eager builder, src/helpers.py:444-573) is outside the "
                                   "GPU hot path; use lazy_constraints=True (the reference's default)")
-    if gurobi.get("init_method") is not None:
-        raise NotImplementedError("init_method (MIP start, src/init_helpers.py) is not part of the GPU hot path yet")
+    # MIP start (src/same.py:1199-1215, src/init_helpers.py): 'greedy' for every window of the batch in one device pass
+    # (same_batch_mip_start), 'hungarian' through the reference's dense host assignment
+    start = None
+    init_method = gurobi.get("init_method")
+    if init_method is not None:
+        method = str(init_method).lower()
+        if method not in {"greedy", "hungarian"}:
+            raise ValueError(f"Unknown init_method={init_method!r}. Use 'greedy' or 'hungarian'.")
+        if method == "hungarian" and int(optim["max_matches"]) != 1:
+            raise ValueError("init_method='hungarian' requires max_matches == 1.")
+        if method == "greedy":
+            if getattr(run, "_start_penalty", None) != float(optim["no_match_penalty"]):
+                b.mip_start(float(optim["no_match_penalty"]))
+                run._start_penalty = float(optim["no_match_penalty"])
+            x0 = b.get_window(L.START_X, w).astype(np.float64)
+            nm0 = b.get_window(L.START_UNMATCHED, w).astype(np.float64)
+            start = (x0, nm0)
+            print(f"Initialized MIP start (greedy): {int(x0.sum())} matches, {int(nm0.sum())} unmatched")
+        else:
+            from .init_helpers import mip_start_vectors
+            start = mip_start_vectors(valid_pairs=pairs, costs=m["cost"], n_aligned=n_aligned, n_ref=n_ref,
+                                      aligned_sizes=aligned_df["size"].to_numpy(dtype=float), no_match_penalty=optim["no_match_penalty"],
+                                      max_matches=int(optim["max_matches"]), init_method=method, init_big_m=gurobi.get("init_big_m", 1e9),
+                                      init_hungarian_max_n=gurobi.get("init_hungarian_max_n", 5000), verbose=True)
 
     spec = ModelSpec(n_pairs=P, n_ref=n_ref, n_aligned=n_aligned, n_tri=T, cost=m["cost"], row_ptr=m["row_ptr"],
                      ref_group_node=m["ref_group_node"], ref_group_ptr=m["ref_group_ptr"], ref_group_idx=m["ref_group_idx"],
@@ -180,7 +202,10 @@ def _solve_window(run: _Run, w: int, aligned_src: pd.DataFrame, ref_src: pd.Data
             return np.zeros((0, 4), np.int32)
         return cuts[0, :min(viol, cap)].copy()
 
-    res = backend.solve(spec, separate, gurobi, outprefix=outprefix, env_options=_env_options())
+    if start is not None:
+        res = backend.solve(spec, separate, gurobi, outprefix=outprefix, env_options=_env_options(), start=start)
+    else:
+        res = backend.solve(spec, separate, gurobi, outprefix=outprefix, env_options=_env_options())
     time_limit_reached = res.status == "time_limit"
     if res.status not in ("optimal", "time_limit"):
         out_df, var_out = pd.DataFrame(), {}

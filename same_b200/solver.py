@@ -56,7 +56,7 @@ class GurobiBackend:
 
     name = "gurobi"
 
-    def solve(self, spec: ModelSpec, separate: Optional[SeparationFn], gurobi_params: dict, outprefix=None, env_options=None):
+    def solve(self, spec: ModelSpec, separate: Optional[SeparationFn], gurobi_params: dict, outprefix=None, env_options=None, start=None):
         import gurobipy as gp
         from gurobipy import GRB, Model, quicksum
 
@@ -104,6 +104,12 @@ class GurobiBackend:
                 spec.no_match_penalty * quicksum(sizes[i] * no_match_vars[i] for i in range(na)) +
                 spec.delaunay_penalty * quicksum(w[t] * q_tri[t] for t in range(T)),
                 GRB.MINIMIZE)
+            if start is not None:                                                                     # init_helpers.py:229-236
+                x0, nm0 = start
+                for k in range(P):
+                    x[k].Start = float(x0[k])
+                for i in range(na):
+                    no_match_vars[i].Start = float(nm0[i])
             if outprefix:                                                                             # same.py:1218-1224
                 os.makedirs(outprefix, exist_ok=True)
                 model_file = os.path.join(outprefix, "matching_model.lp")
@@ -154,6 +160,116 @@ class GurobiBackend:
                 pass
 
 
+def model_matrices(spec: ModelSpec):
+    """The base model as ONE sparse matrix in the reference's creation order (src/helpers.py:130-158), assembled with array
+    operations straight from the GPU-built CSR (aligned rows) / CSC (reference groups) — no per-row Python expression.
+
+    Variables are numbered as the reference creates them (src/same.py:1116-1149): x[0..P) | penalty[P..P+Nr) | no_match[..+Na) |
+    q_tri[..+T).  Rows: max_matches_<j> per reference group (first-appearance order), one_match_<i> per aligned row,
+    penalty_<j>, no_match_<i>.  -> dict(ptr, idx, val, sense ('<=' / '=='), rhs, names, n_vars, obj)"""
+    P, nr, na, T = spec.n_pairs, spec.n_ref, spec.n_aligned, spec.n_tri
+    gp = np.asarray(spec.ref_group_ptr, dtype=np.int64)
+    gi = np.asarray(spec.ref_group_idx, dtype=np.int64)
+    gn = np.asarray(spec.ref_group_node, dtype=np.int64)
+    rp = np.asarray(spec.row_ptr, dtype=np.int64)
+    G = len(gn)
+    rows = np.flatnonzero(np.diff(rp) > 0)                       # aligned rows that own pairs (all of them after KNN compaction)
+    rsz, gsz = np.diff(rp)[rows], np.diff(gp)
+    R = len(rows)
+    row_members = np.concatenate([np.arange(rp[i], rp[i + 1]) for i in rows]) if R and rsz.sum() != P else np.arange(P, dtype=np.int64)
+    # block 3 / 4: members followed by the row's own penalty / no_match variable
+    def with_tail(members, sizes, tail):
+        n = len(sizes)
+        out = np.empty(len(members) + n, dtype=np.int64)
+        start = np.r_[0, np.cumsum(sizes)][:-1]
+        mpos = np.arange(len(members)) + np.repeat(np.arange(n), sizes)
+        out[mpos] = members
+        out[start + sizes + np.arange(n)] = tail
+        return out
+    idx = np.concatenate([gi, row_members, with_tail(gi, gsz, P + gn), with_tail(row_members, rsz, P + nr + rows)])
+    one_g, one_r = np.ones(len(gi)), np.ones(len(row_members))
+    tail_val = lambda sizes, v: with_tail(np.ones(int(sizes.sum())), sizes, np.full(len(sizes), v)) if len(sizes) else np.zeros(0)
+    val = np.concatenate([one_g, one_r, tail_val(gsz, -1.0), tail_val(rsz, 1.0)])
+    ptr = np.r_[0, np.cumsum(np.concatenate([gsz, rsz, gsz + 1, rsz + 1]))].astype(np.int64)
+    sense = np.asarray(["<="] * (2 * G + R) + ["=="] * R)
+    rhs = np.concatenate([np.asarray(spec.ref_group_limit, dtype=np.float64), np.ones(R), np.ones(G), np.ones(R)])
+    sg, sr = gn.astype(str), rows.astype(str)
+    names = np.concatenate([np.char.add("max_matches_", sg), np.char.add("one_match_", sr), np.char.add("penalty_", sg),
+                            np.char.add("no_match_", sr)]) if (G + R) else np.zeros(0, dtype=str)
+    obj = np.concatenate([np.asarray(spec.cost, dtype=np.float64), np.full(nr, float(spec.penalty_coeff)),
+                          float(spec.no_match_penalty) * np.asarray(spec.aligned_size, dtype=np.float64),
+                          float(spec.delaunay_penalty) * np.asarray(spec.tri_weight, dtype=np.float64)])   # same.py:1191-1197
+    return dict(ptr=ptr, idx=idx, val=val, sense=sense, rhs=rhs, names=names, n_vars=P + nr + na + T, obj=obj)
+
+
+class GurobiMatrixBackend:
+    """Same model, same variable / constraint / cut order and names as `GurobiBackend`, built through gurobipy's matrix API
+    (`addMVar` + one `addMConstr`) from `model_matrices` instead of one `quicksum` per row.  Selected with
+    `set_default_backend('gurobi_matrix')` or SAME_B200_SOLVER=gurobi_matrix.  Needs gurobipy >= 13 like the reference
+    (GRB.METHOD_PDHG, src/same.py:1169-1170); it cannot be exercised in a container without gurobipy — `model_matrices`
+    itself is pinned against the reference's recorded constraint list (tests/test_host_logic.py)."""
+
+    name = "gurobi_matrix"
+
+    def solve(self, spec: ModelSpec, separate: Optional[SeparationFn], gurobi_params: dict, outprefix=None, env_options=None, start=None):
+        import gurobipy as gp
+        from gurobipy import GRB
+        from scipy.sparse import csr_matrix
+
+        log_dir = os.path.join(os.getcwd(), "gurobi_logs")
+        os.makedirs(log_dir, exist_ok=True)
+        options = {"OutputFlag": 1, "LogFile": os.path.join(log_dir, f"gurobi_{os.getpid()}.log")}
+        options.update(env_options or {})
+        env = gp.Env(params=options)
+        model = gp.Model("optimal_matches", env=env)
+        P, nr, na, T = spec.n_pairs, spec.n_ref, spec.n_aligned, spec.n_tri
+        mm = model_matrices(spec)
+        x = model.addMVar(P, vtype=GRB.BINARY, lb=0, ub=1, name="x")
+        pen = model.addMVar(nr, vtype=GRB.CONTINUOUS, lb=0, ub=1000, name="penalty")
+        nom = model.addMVar(na, vtype=GRB.CONTINUOUS, lb=0, ub=1, name="no_match")
+        q = model.addMVar(T, vtype=GRB.CONTINUOUS, lb=0, name="q_tri")
+        model.update()
+        allv = gp.MVar.fromlist(x.tolist() + pen.tolist() + nom.tolist() + q.tolist())
+        A = csr_matrix((mm["val"], mm["idx"], mm["ptr"]), shape=(len(mm["rhs"]), mm["n_vars"]))
+        sense = np.where(mm["sense"] == "==", GRB.EQUAL, GRB.LESS_EQUAL)
+        cons = model.addMConstr(A, allv, sense, mm["rhs"])
+        model.update()
+        for c, nm in zip(cons.tolist(), mm["names"].tolist()):
+            c.ConstrName = nm
+        model.setObjective(mm["obj"] @ allv, GRB.MINIMIZE)
+        model.Params.LazyConstraints = 1
+        model.Params.Method = gp.GRB.METHOD_PDHG
+        model.Params.PDHGGPU = 1
+        if start is not None:                                                  # init_helpers.apply_mip_start
+            x.Start = np.asarray(start[0], dtype=float)
+            nom.Start = np.asarray(start[1], dtype=float)
+        model.write(os.path.join(outprefix, "matching_model.lp") if outprefix else "matching_model.lp")
+        tl = gurobi_params.get("time_limit")
+        model.Params.timeLimit = float(tl) if tl is not None else float("inf")
+        model.Params.MIPGap = float(gurobi_params.get("mip_gap", 0.05))
+        for key, attr, conv in (("mip_focus", "MIPFocus", int), ("cuts", "Cuts", int), ("heuristics", "Heuristics", float)):
+            if gurobi_params.get(key) is not None:
+                setattr(model.Params, attr, conv(gurobi_params[key]))
+        xs, qs = x.tolist(), q.tolist()
+        state = {"cuts": 0}
+        lazy_max = gurobi_params.get("lazy_max_cuts")
+
+        def callback(m, where):
+            if where != GRB.Callback.MIPSOL or (lazy_max is not None and state["cuts"] >= lazy_max):
+                return
+            vals = np.asarray(m.cbGetSolution(xs), dtype=np.float64)
+            for pa, pb, pc, t in separate(vals, state["cuts"]):
+                m.cbLazy(xs[int(pa)] + xs[int(pb)] + xs[int(pc)] <= 2 + qs[int(t)])
+                state["cuts"] += 1
+
+        model.optimize(callback) if separate is not None else model.optimize()
+        status = "optimal" if model.status == GRB.OPTIMAL else ("time_limit" if model.status == GRB.TIME_LIMIT else f"status_{model.status}")
+        if status in ("optimal", "time_limit"):
+            return SolveResult(status, np.asarray(x.X, dtype=np.float64), np.asarray(nom.X, dtype=np.float64), np.asarray(pen.X, dtype=np.float64),
+                               np.asarray(q.X, dtype=np.float64), float(model.Runtime), state["cuts"], model)
+        return SolveResult(status, np.zeros(P), np.zeros(na), np.zeros(nr), np.zeros(T), float(model.Runtime), state["cuts"], model)
+
+
 class HighsCutLoopBackend:
     """scipy.optimize.milp (HiGHS) with an explicit lazy-cut loop.  Variables: x[P] | penalty[Nr] | no_match[Na] | q[T]."""
 
@@ -162,29 +278,18 @@ class HighsCutLoopBackend:
     def __init__(self, max_rounds=50):
         self.max_rounds = max_rounds
 
-    def solve(self, spec: ModelSpec, separate: Optional[SeparationFn], gurobi_params: dict, outprefix=None, env_options=None):
+    def solve(self, spec: ModelSpec, separate: Optional[SeparationFn], gurobi_params: dict, outprefix=None, env_options=None, start=None):
+        # `start` is accepted for interface parity; scipy.optimize.milp has no warm start
         from scipy.optimize import Bounds, LinearConstraint, milp
-        from scipy.sparse import coo_matrix, vstack
+        from scipy.sparse import coo_matrix
 
+        from scipy.sparse import csr_matrix
         P, nr, na, T = spec.n_pairs, spec.n_ref, spec.n_aligned, spec.n_tri
-        n = P + nr + na + T
-        c = np.concatenate([spec.cost, np.full(nr, float(spec.penalty_coeff)), spec.no_match_penalty * spec.aligned_size,
-                            spec.delaunay_penalty * spec.tri_weight])
-        G = len(spec.ref_group_node)
-        gsz = np.diff(spec.ref_group_ptr)
-        grow = np.repeat(np.arange(G), gsz)
-        gcol = spec.ref_group_idx.astype(np.int64)
-        rsz = np.diff(spec.row_ptr)
-        rrow = np.repeat(np.arange(na), rsz)
-        rcol = np.arange(P)
-        one = np.ones(P)
-        A1 = coo_matrix((one, (grow, gcol)), shape=(G, n))                                   # max_matches
-        A2 = coo_matrix((one, (rrow, rcol)), shape=(na, n))                                  # one_match
-        A3 = coo_matrix((np.r_[one, -np.ones(G)], (np.r_[grow, np.arange(G)], np.r_[gcol, P + spec.ref_group_node.astype(np.int64)])), shape=(G, n))
-        A4 = coo_matrix((np.r_[one, np.ones(na)], (np.r_[rrow, np.arange(na)], np.r_[rcol, P + nr + np.arange(na)])), shape=(na, n))
-        A = vstack([A1, A2, A3, A4]).tocsr()
-        lo = np.r_[np.full(G, -np.inf), np.full(na, -np.inf), np.full(G, -np.inf), np.ones(na)]
-        hi = np.r_[spec.ref_group_limit.astype(float), np.ones(na), np.ones(G), np.ones(na)]
+        mm = model_matrices(spec)
+        n, c = mm["n_vars"], mm["obj"]
+        A = csr_matrix((mm["val"], mm["idx"], mm["ptr"]), shape=(len(mm["rhs"]), n))
+        hi = mm["rhs"]
+        lo = np.where(mm["sense"] == "==", mm["rhs"], -np.inf)
         integrality = np.r_[np.ones(P), np.zeros(nr + na + T)]
         bounds = Bounds(np.zeros(n), np.r_[np.ones(P), np.full(nr, 1000.0), np.ones(na), np.full(T, np.inf)])
         cut_rows = []
@@ -222,7 +327,7 @@ class HighsCutLoopBackend:
         return SolveResult(status, sol[:P], sol[P + nr:P + nr + na], sol[P:P + nr], sol[P + nr + na:], rt, cuts_added)
 
 
-_BACKENDS = {"gurobi": GurobiBackend, "highs": HighsCutLoopBackend}
+_BACKENDS = {"gurobi": GurobiBackend, "gurobi_matrix": GurobiMatrixBackend, "highs": HighsCutLoopBackend}
 _default_backend = None
 
 

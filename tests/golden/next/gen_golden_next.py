@@ -1,0 +1,137 @@
+"""Golden vectors for the SURVEY §8(f) rows (MIP start, metacell collapse), produced by the UNMODIFIED reference.
+
+    python tests/golden/next/gen_golden_next.py       # writes tests/golden/next/{mip_start,collapse}.npz
+
+Same rules as gen_golden.py: runs only in the build container (imports /root/reference under oracle/ref_loader.py's
+stubs); the committed .npz files are what the tests read.
+"""
+from __future__ import annotations
+
+import contextlib
+import io
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = os.path.dirname(HERE)                      # the run_same fixtures these cases start from
+ROOT = os.path.dirname(os.path.dirname(GOLD))
+sys.path.insert(0, ROOT)
+
+from oracle import ref_loader  # noqa: E402
+from same_b200 import datagen  # noqa: E402
+
+REF = ref_loader.load_reference()
+import src.init_helpers as rinit  # noqa: E402
+import src.metacell_utils as rmc  # noqa: E402
+
+
+@contextlib.contextmanager
+def quiet():
+    with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
+        yield
+
+
+def mip_start_cases():
+    """compute_mip_start_pairs(init_method='greedy') (src/init_helpers.py:110-132) on recorded candidate pairs + costs."""
+    rec = {}
+    cases = []
+    for name in ("fig2_direct", "uniform_k8", "sparse_merge"):
+        g = np.load(os.path.join(GOLD, f"{name}.npz"), allow_pickle=True)
+        pairs, cost = g["w0_pairs"].astype(np.int64), g["w0_cost"].astype(np.float64)
+        cases.append((name, pairs, cost))
+    # many equal costs: order among ties is the stable sort's (pair index)
+    g = np.load(os.path.join(GOLD, "fig2_direct.npz"), allow_pickle=True)
+    cases.append(("fig2_rounded", g["w0_pairs"].astype(np.int64), np.round(g["w0_cost"].astype(np.float64) / 20.0)))
+    names = []
+    for name, pairs, cost in cases:
+        na, nr = int(pairs[:, 0].max()) + 1, int(pairs[:, 1].max()) + 1
+        rng = np.random.default_rng(len(pairs))
+        sizes = rng.integers(1, 4, na).astype(np.float64)
+        row_min = np.full(na, np.inf)
+        np.minimum.at(row_min, pairs[:, 0], cost)
+        for tag, pen in (("p100", 100.0), ("plow", float(np.median(row_min) / 1.5) + 1e-9)):   # plow: about half of the rows prefer no match
+            with quiet():
+                chosen, unmatched = rinit.compute_mip_start_pairs(valid_pairs=[tuple(p) for p in pairs.tolist()], costs=cost.tolist(), n_aligned=na,
+                                                                  n_ref=nr, aligned_sizes=sizes, no_match_penalty=pen, max_matches=1,
+                                                                  init_method="greedy", verbose=False)
+            key = f"{name}_{tag}"
+            names.append(key)
+            rec[f"{key}__pairs"], rec[f"{key}__cost"], rec[f"{key}__sizes"], rec[f"{key}__penalty"] = pairs, cost, sizes, np.float64(pen)
+            rec[f"{key}__chosen"] = np.asarray(chosen, dtype=np.int64).reshape(-1, 3)
+            rec[f"{key}__unmatched"] = np.asarray(sorted(unmatched), dtype=np.int64)
+            print(key, len(pairs), "pairs ->", len(chosen), "chosen,", len(unmatched), "unmatched")
+    rec["cases"] = np.asarray(names)
+    np.savez_compressed(os.path.join(HERE, "mip_start.npz"), **rec)
+
+
+def collapse_cases():
+    """greedy_triangle_collapse with real collapsing (src/metacell_utils.py:160-561)."""
+    rec, names = {}, []
+    for name, tiles, seed, ms, r_max, ang in (("t2_ms3", 2, 21, 3, 1.5, 10), ("t3_ms10", 3, 22, 10, 2.0, 15), ("t1_ms5_noangle", 1, 23, 5, 1.2, None)):
+        ref, qry, ct = datagen.make_section_pair(n_tiles=tiles, seed=seed)
+        with quiet():
+            mc = rmc.greedy_triangle_collapse(qry, max_metacell_size=ms, r_max=r_max, min_angle_deg=ang, return_object=True)
+        mdf = mc.metacell_df
+        names.append(name)
+        rec[f"{name}__params"] = np.asarray([tiles, seed, ms, r_max, -1.0 if ang is None else ang], dtype=np.float64)
+        rec[f"{name}__xy"] = mdf[["X", "Y"]].to_numpy(np.float64)
+        rec[f"{name}__size"] = mdf["size"].to_numpy(np.int64)
+        rec[f"{name}__type"] = mdf["cell_type"].astype(str).to_numpy()
+        rec[f"{name}__prob"] = mdf[ct].to_numpy(np.float64)
+        rec[f"{name}__members_flat"] = np.asarray([m for ms_ in mdf["members"] for m in ms_], dtype=np.int64)
+        rec[f"{name}__members_ptr"] = np.r_[0, np.cumsum([len(m) for m in mdf["members"]])].astype(np.int64)
+        rec[f"{name}__metacell_id"] = mdf["metacell_id"].to_numpy(np.int64)
+        rec[f"{name}__delaunay"] = np.asarray(mc.metacell_delaunay, dtype=np.int64).reshape(-1, 3)
+        rec[f"{name}__original_delaunay"] = np.asarray(mc.original_delaunay, dtype=np.int64).reshape(-1, 3)
+        print(name, len(qry), "cells ->", len(mdf), "metacells, max size", int(mdf["size"].max()))
+    rec["cases"] = np.asarray(names)
+    np.savez_compressed(os.path.join(HERE, "collapse.npz"), **rec)
+
+
+def run_same_start_cases():
+    """The whole reference pipeline with gurobi_params['init_method']='greedy' (src/same.py:1199-1215): the `.Start` values it
+    leaves on x[...] and no_match[...] of every window's model, recorded from the fake gurobipy."""
+    import tempfile
+    from tests.golden import gen_golden as GG          # installs the recording fake + incumbent rule used by the main fixtures
+    from tests.util import golden_frame, golden_params, load_golden
+    rec, names = {}, []
+    for case, sliding in (("fig2_direct", False), ("tiles4_sliding", True)):
+        g = load_golden(case)
+        ref_df, al_df = golden_frame(g, "ref"), golden_frame(g, "aligned")
+        ct = [str(c) for c in g["commonCT"]]
+        optim, gurobi = golden_params(g, "optim"), golden_params(g, "gurobi")
+        gurobi["init_method"] = "greedy"
+        optim["no_match_penalty"] = 25.0               # low enough that some rows prefer to stay unmatched
+        ref_loader.MODELS.clear()
+        ref_loader.INCUMBENT_FN = GG.make_incumbent_fn(int(g["seed"]))
+        cwd = os.getcwd()
+        with tempfile.TemporaryDirectory() as td:
+            os.chdir(td)
+            try:
+                with quiet():
+                    if sliding:
+                        REF.sliding_window_matching(ref_df, al_df, commonCT=ct, outprefix=os.path.join(td, "out"), optim_params=dict(optim),
+                                                    gurobi_params=dict(gurobi))
+                    else:
+                        REF.run_same(ref_df, al_df, ct, outprefix=None, optim_params=dict(optim), gurobi_params=dict(gurobi))
+            finally:
+                os.chdir(cwd)
+        names.append(case)
+        rec[f"{case}__n_models"] = np.int64(len(ref_loader.MODELS))
+        for w, m in enumerate(ref_loader.MODELS):
+            xs = [v for v in m.vars if v.VarName.startswith("x[")]
+            nm = [v for v in m.vars if v.VarName.startswith("no_match[")]
+            rec[f"{case}__w{w}_start_x"] = np.asarray([np.nan if v.Start is None else v.Start for v in xs], dtype=np.float64)
+            rec[f"{case}__w{w}_start_no_match"] = np.asarray([np.nan if v.Start is None else v.Start for v in nm], dtype=np.float64)
+            print(case, "window", w, int(np.nansum(rec[f"{case}__w{w}_start_x"])), "matches,", int(np.nansum(rec[f"{case}__w{w}_start_no_match"])), "unmatched")
+    rec["cases"] = np.asarray(names)
+    rec["no_match_penalty"] = np.float64(25.0)
+    np.savez_compressed(os.path.join(HERE, "run_same_start.npz"), **rec)
+
+
+if __name__ == "__main__":
+    mip_start_cases()
+    collapse_cases()
+    run_same_start_cases()

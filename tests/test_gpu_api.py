@@ -236,3 +236,34 @@ def test_errors(fake_gurobi):
                            optim_params=dict(cell_id_col="cell_idx"))
     with pytest.raises(ValueError, match="shape"):
         same_b200.run_same(ref_df, al_df, ct, aligned_delaunay=np.zeros((4, 2), int), optim_params=dict(cell_id_col="cell_idx", radius=1.2))
+
+
+@pytest.mark.parametrize("case", ["fig2_direct", "tiles4_sliding"])
+def test_mip_start_through_public_api(case, fake_gurobi, tmp_path):
+    """gurobi_params['init_method']='greedy' (src/same.py:1199-1215): the `.Start` values on x[...] and no_match[...] of every
+    window's model equal the ones the unmodified reference sets (tests/golden/next/run_same_start.npz)."""
+    import same_b200
+    gs = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "next", "run_same_start.npz"))
+    g = load_golden(case)
+    ref_df, al_df = golden_frame(g, "ref"), golden_frame(g, "aligned")
+    ct = [str(c) for c in g["commonCT"]]
+    optim, gurobi = golden_params(g, "optim"), golden_params(g, "gurobi")
+    gurobi["init_method"] = "greedy"
+    optim["no_match_penalty"] = float(gs["no_match_penalty"])
+    fake_gurobi.INCUMBENT_FN = _incumbent_fn(int(g["seed"]))
+    cwd = os.getcwd()
+    os.chdir(tmp_path)
+    try:
+        if case == "tiles4_sliding":
+            same_b200.sliding_window_matching(ref_df, al_df, commonCT=ct, outprefix=str(tmp_path / "out"), optim_params=dict(optim),
+                                              gurobi_params=dict(gurobi))
+        else:
+            same_b200.run_same(ref_df, al_df, ct, outprefix=None, optim_params=dict(optim), gurobi_params=dict(gurobi))
+    finally:
+        os.chdir(cwd)
+    assert len(fake_gurobi.MODELS) == int(gs[f"{case}__n_models"])
+    for w, m in enumerate(fake_gurobi.MODELS):
+        sx = np.asarray([np.nan if v.Start is None else v.Start for v in m.vars if v.VarName.startswith("x[")], dtype=np.float64)
+        sn = np.asarray([np.nan if v.Start is None else v.Start for v in m.vars if v.VarName.startswith("no_match[")], dtype=np.float64)
+        assert np.array_equal(sx, gs[f"{case}__w{w}_start_x"]), (case, w)
+        assert np.array_equal(sn, gs[f"{case}__w{w}_start_no_match"]), (case, w)

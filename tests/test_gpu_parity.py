@@ -340,6 +340,35 @@ def test_ties_on_exact_grid():
         assert np.array_equal(b.get(L.PAIRS), pairs)
 
 
+@pytest.mark.parametrize("knn", [7, 8, 9])
+def test_near_ties_inside_one_distance_bucket(knn):
+    """The search ranks on the high word of d2 first: neighbours whose d2 differ only in the low word (here by one ulp
+    of the coordinate) must still come out in exact (d2, ref index) order — at the k-th boundary (exact fallback),
+    inside the list (re-rank of the survivors) and just outside it."""
+    from same_b200 import _lib as L
+    from same_b200.device import Section
+    rng = np.random.default_rng(5)
+    near = rng.uniform(-1.5, 1.5, size=(6, 2))
+    x1 = 3.0
+    x2 = np.nextafter(x1, 4.0)
+    x3 = np.nextafter(x2, 4.0)
+    # stored farthest first so that memory order and index order both disagree with distance order
+    twins = np.array([[x3, 0.0], [0.0, x2], [-x1, 0.0]])
+    far = rng.uniform(4.0, 6.0, size=(20, 2)) * rng.choice([-1.0, 1.0], size=(20, 2))
+    r = np.concatenate([twins, near, far])
+    a = np.concatenate([np.zeros((1, 2)), rng.uniform(-3, 3, size=(40, 2))])
+    with Section(a, r, np.zeros((len(a), 1)), np.zeros((len(r), 1))) as sec, sec.batch() as b:
+        b.candidates(8.0, knn)
+        keepA, keepR, pairs = O.find_knn_within_radius(a, r, 8.0, knn, brute=True)
+        assert np.array_equal(b.get(L.KEEP_A), keepA) and np.array_equal(b.get(L.KEEP_R), keepR)
+        got = b.get(L.PAIRS)
+        assert np.array_equal(got, pairs)
+        # row 0 really has the three twins at ranks 7, 8, 9 (0-based 6, 7, 8)
+        kr = b.get(L.KEEP_R)
+        mine = kr[got[got[:, 0] == 0][:, 1]]
+        assert mine[6:knn].tolist() == [2, 1, 0][:max(0, knn - 6)]
+
+
 def test_edge_cases():
     from same_b200 import _lib as L
     from same_b200.device import Section

@@ -90,22 +90,6 @@ def test_metacell_size1_triangulation_matches_reference():
     assert mc.metacell_members(3) == [al[str(g["id_col"])].iloc[3]]
 
 
-def test_metacell_collapse_and_unpack_roundtrip():
-    import same_b200
-    from same_b200 import datagen
-    ref, qry, ct = datagen.make_section_pair(n_tiles=1, seed=3)
-    mdf, tri = same_b200.greedy_triangle_collapse(qry, max_metacell_size=3, r_max=1.5, min_angle_deg=10)
-    assert mdf["size"].sum() == len(qry) and mdf["size"].max() <= 3 and len(mdf) < len(qry)
-    members = sorted(m for ms in mdf["members"] for m in ms)
-    assert members == sorted(qry["Cell_Num_Old"].tolist())
-    big = mdf[mdf["size"] == 3].iloc[0]
-    sub = qry.set_index("Cell_Num_Old").loc[big["members"]]
-    assert np.isclose(big["X"], sub["X"].mean()) and np.isclose(big["c1"], sub["c1"].mean()) and len(set(sub["cell_type"])) == 1
-    matches = pd.DataFrame({"Aligned_metacell_id": [0, int(big["metacell_id"])], "Ref_metacell_id": [5, 7]})
-    ind = same_b200.unpack_metacell_matches(matches, mdf, ref)
-    assert len(ind) == len(mdf.iloc[0]["members"]) + 3 and set(ind["Ref_cell_id"]) == {5, 7}
-
-
 def test_merge_window_matches_unique_ref():
     import same_b200
     a = pd.DataFrame({"window_id": [0, 0], "Aligned_Cell_Num_Old": [1, 2], "Ref_Cell_Num_Old": [10, 10], "X": 0.0, "Y": 0.0,
@@ -182,3 +166,54 @@ def test_gloo_halo_exchange_and_gather():
     for r in (0, 1):
         assert res[r][4]["window_id"].tolist() == list(range(7))
         assert res[r][4]["rank"].tolist() == [0, 0, 0, 0, 1, 1, 1]
+
+
+# ---- the host model builder fed from the CSR/CSC arrays ------------------------------------------
+def _spec_from_oracle(case):
+    """ModelSpec of one golden window, its arrays taken from the CPU oracle (the same arrays the GPU batch returns)."""
+    from same_b200.solver import ModelSpec
+    from tests.test_oracle_golden import _pipeline
+    from tests.util import load_golden
+    g = load_golden(case)
+    o, res = _pipeline(g)
+    P, na = len(res["pairs"]), len(res["keepA"])
+    row_ptr = np.searchsorted(res["pairs"][:, 0], np.arange(na + 1)).astype(np.int64)
+    a_size = (g["aligned_size"] if "aligned_size" in g else np.ones(len(g["aligned_xy"])))[res["keepA"]]
+    spec = ModelSpec(n_pairs=P, n_ref=len(res["keepR"]), n_aligned=na, n_tri=len(res["tri"]), cost=res["cost"], row_ptr=row_ptr,
+                     ref_group_node=res["ref_group_node"], ref_group_ptr=res["ref_group_ptr"], ref_group_idx=res["ref_group_idx"],
+                     ref_group_limit=res["ref_group_limit"], aligned_size=a_size, tri_weight=res["weight"],
+                     penalty_coeff=float(o.get("penalty_coeff", 100)), no_match_penalty=float(o.get("no_match_penalty", 100)),
+                     delaunay_penalty=float(o.get("delaunay_penalty", 5)))
+    return g, spec
+
+
+@pytest.mark.parametrize("case", ["fig2_direct", "fig2_priority", "fig2_script", "simulated_st", "uniform_k8"])
+def test_model_matrices_equal_reference_model(case):
+    """model_matrices assembles, with array operations only, exactly the constraint list and objective the reference builds
+    row by row (src/helpers.py:130-158, src/same.py:1191-1197), as recorded from the unmodified reference."""
+    from same_b200.solver import model_matrices
+    g, spec = _spec_from_oracle(case)
+    mm = model_matrices(spec)
+    for key, ref in (("names", "con_name"), ("sense", "con_sense"), ("rhs", "con_rhs"), ("ptr", "con_ptr"), ("idx", "con_idx"), ("val", "con_val")):
+        assert np.array_equal(mm[key], g[f"w0_{ref}"]), key
+    assert mm["n_vars"] == int(g["w0_n_vars"])
+    P, nr, na = spec.n_pairs, spec.n_ref, spec.n_aligned
+    assert np.array_equal(mm["obj"][:P], g["w0_cost"])
+    assert np.array_equal(mm["obj"][P:P + nr], g["w0_obj_penalty"])
+    assert np.array_equal(mm["obj"][P + nr:P + nr + na], g["w0_obj_no_match"])
+    assert np.array_equal(mm["obj"][P + nr + na:], g["w0_obj_q"])
+
+
+def test_highs_backend_solves_from_model_matrices():
+    """The HiGHS stand-in consumes the same matrix; on the 144-cell known-answer fixture it returns a feasible one-to-one matching."""
+    from same_b200.solver import HighsCutLoopBackend, model_matrices
+    g, spec = _spec_from_oracle("simulated_st")
+    res = HighsCutLoopBackend().solve(spec, None, {"time_limit": 60, "mip_gap": 0.05})
+    assert res.status in ("optimal", "time_limit")
+    mm = model_matrices(spec)
+    from scipy.sparse import csr_matrix
+    A = csr_matrix((mm["val"], mm["idx"], mm["ptr"]), shape=(len(mm["rhs"]), mm["n_vars"]))
+    full = np.concatenate([res.x, res.penalty, res.no_match, res.q])
+    lhs = A @ full
+    eq = mm["sense"] == "=="
+    assert np.all(lhs[~eq] <= mm["rhs"][~eq] + 1e-6) and np.allclose(lhs[eq], mm["rhs"][eq], atol=1e-6)

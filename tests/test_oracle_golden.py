@@ -4,6 +4,8 @@ The golden .npz files were produced by running the unmodified reference
 (tests/golden/gen_golden.py).  Integer/index outputs must be bit-exact, costs are
 compared bit-exactly too (the oracle reproduces the reference's operation order;
 the contract in BASELINE.json is 1e-5 relative)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -177,3 +179,20 @@ def test_empty_inputs():
     assert len(keepA) == 0 and len(keepR) == 0 and len(pairs) == 0
     v, ck = O.separation(np.zeros((0, 3), np.int32), np.zeros(0, np.int8), np.zeros(1, np.int32), np.zeros((1, 2)))
     assert len(v) == 0 and ck == 0
+
+
+# ---- greedy MIP start, metacell collapse -------------------------------------------------
+def _next_golden(name):
+    return np.load(os.path.join(os.path.dirname(__file__), "golden", "next", name), allow_pickle=True)
+
+
+def test_oracle_mip_start_equals_reference():
+    """oracle_greedy_select reproduces compute_mip_start_pairs(init_method='greedy') (src/init_helpers.py:110-132): same
+    chosen pairs in the same order, same unmatched set — including the tie-heavy rounded-cost case."""
+    g = _next_golden("mip_start.npz")
+    for case in g["cases"]:
+        pairs, cost, sizes, pen = g[f"{case}__pairs"], g[f"{case}__cost"], g[f"{case}__sizes"], float(g[f"{case}__penalty"])
+        na, nr = int(pairs[:, 0].max()) + 1, int(pairs[:, 1].max()) + 1
+        chosen, unmatched = O.mip_start_greedy(pairs, cost, na, nr, sizes, pen)
+        assert np.array_equal(chosen, g[f"{case}__chosen"]), case
+        assert np.array_equal(unmatched, g[f"{case}__unmatched"]), case
