@@ -131,7 +131,36 @@ def run_same_start_cases():
     np.savez_compressed(os.path.join(HERE, "run_same_start.npz"), **rec)
 
 
+def unpack_cases():
+    """unpack_metacell_matches (src/metacell_utils.py:564-766): both strategies, metacells on the aligned side only and on both sides."""
+    import pandas as pd
+    rec, names = {}, []
+    ref, qry, ct = datagen.make_section_pair(n_tiles=2, seed=31)
+    with quiet():
+        mc_a = rmc.greedy_triangle_collapse(qry, max_metacell_size=4, r_max=1.5, min_angle_deg=10, return_object=True)
+        mc_r = rmc.greedy_triangle_collapse(ref, max_metacell_size=3, r_max=1.5, min_angle_deg=10, return_object=True)
+    rng = np.random.default_rng(31)
+    n = min(len(mc_a.metacell_df), len(mc_r.metacell_df), 400)
+    big_a = np.argsort(-mc_a.metacell_df["size"].to_numpy(), kind="stable")[:n]          # favour merged metacells
+    matches = pd.DataFrame({"Aligned_metacell_id": big_a, "Ref_metacell_id": rng.permutation(len(mc_r.metacell_df))[:n]})
+    rec["match_a"], rec["match_r"] = matches["Aligned_metacell_id"].to_numpy(np.int64), matches["Ref_metacell_id"].to_numpy(np.int64)
+    for name, ref_side, strategy in (("both_distribute", mc_r.metacell_df, "distribute"), ("both_nearest", mc_r.metacell_df, "nearest"),
+                                     ("aligned_only_distribute", ref, "distribute"), ("aligned_only_nearest", ref, "nearest")):
+        m = matches if ref_side is not ref else pd.DataFrame({"Aligned_metacell_id": big_a, "Ref_metacell_id": rng.permutation(len(ref))[:n]})
+        with quiet():
+            out = rmc.unpack_metacell_matches(m, mc_a.metacell_df, ref_side, aligned_df=qry, ref_df=ref, strategy=strategy,
+                                              aligned_original_idx_col="Cell_Num_Old", ref_original_idx_col="Cell_Num_Old")
+        names.append(name)
+        rec[f"{name}__match_r"] = m["Ref_metacell_id"].to_numpy(np.int64)
+        rec[f"{name}__aligned"] = out["Aligned_cell_id"].to_numpy(np.int64)
+        rec[f"{name}__ref"] = out["Ref_cell_id"].to_numpy(np.int64)
+        print("unpack", name, len(m), "metacell matches ->", len(out), "cell matches")
+    rec["cases"] = np.asarray(names)
+    np.savez_compressed(os.path.join(HERE, "unpack.npz"), **rec)
+
+
 if __name__ == "__main__":
+    unpack_cases()
     mip_start_cases()
     collapse_cases()
     run_same_start_cases()

@@ -151,3 +151,21 @@ def test_metacell_collapse_and_unpack_roundtrip():
     assert len(ind) == len(mdf.iloc[0]["members"]) + 3 and set(ind["Ref_cell_id"]) == {5, 7}
 
 
+
+
+def test_unpack_metacell_matches_vs_reference_golden():
+    """unpack_metacell_matches == the unmodified reference (src/metacell_utils.py:564-766) row for row: 'distribute' and 'nearest',
+    metacells on the aligned side only and on both sides.  (The metacells come from greedy_triangle_collapse, hence a GPU test.)"""
+    import same_b200
+    from same_b200 import datagen
+    g = _golden("unpack.npz")
+    ref, qry, ct = datagen.make_section_pair(n_tiles=2, seed=31)
+    mc_a = same_b200.greedy_triangle_collapse(qry, max_metacell_size=4, r_max=1.5, min_angle_deg=10, return_object=True)
+    mc_r = same_b200.greedy_triangle_collapse(ref, max_metacell_size=3, r_max=1.5, min_angle_deg=10, return_object=True)
+    for case in g["cases"]:
+        m = pd.DataFrame({"Aligned_metacell_id": g["match_a"], "Ref_metacell_id": g[f"{case}__match_r"]})
+        ref_side = mc_r.metacell_df if str(case).startswith("both") else ref
+        out = same_b200.unpack_metacell_matches(m, mc_a.metacell_df, ref_side, aligned_df=qry, ref_df=ref, strategy=str(case).split("_")[-1],
+                                                aligned_original_idx_col="Cell_Num_Old", ref_original_idx_col="Cell_Num_Old")
+        assert np.array_equal(out["Aligned_cell_id"].to_numpy(np.int64), g[f"{case}__aligned"]), case
+        assert np.array_equal(out["Ref_cell_id"].to_numpy(np.int64), g[f"{case}__ref"]), case
