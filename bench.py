@@ -468,6 +468,11 @@ def main():
             traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
         except Exception:
             pass
+        ncu_metrics = {}
+        try:
+            ncu_metrics = json.load(open(os.path.join(ROOT, "profiles", "ncu_metrics.json")))
+        except Exception:
+            pass
         kernels = {}
         for name, (cnt, ms) in sorted(prof.items(), key=lambda kv: -kv[1][1]):
             per = ms / cnt
@@ -483,7 +488,14 @@ def main():
         roofline = {"kernel": dom, "bound": "hbm", "achieved": kernels[dom]["achieved_gbs"], "peak": hbm_peak, "unit": "GB/s",
                     "frac": kernels[dom]["frac_of_hbm_peak"], "traffic": traffic.get(dom), "peak_source": peak_src,
                     "avg_launch_ms": kernels[dom]["avg_ms"], "algorithmic_bytes_per_launch": kernels[dom]["algorithmic_bytes"],
-                    "note": "the search kernel is bound by fp64 issue + L1 latency, not HBM (DESIGN.md §4); frac is against the HBM copy peak"}
+                    "note": "the search kernel is bound by instruction issue (see `ncu`), not HBM (DESIGN.md §4); frac is against the HBM copy peak. "
+                            "The largest HBM-bound kernel of the path is reported in `hbm_kernel`."}
+        if dom in ncu_metrics:
+            roofline["ncu"] = dict(ncu_metrics[dom], source="profiles/ncu_metrics.json (ncu --set full of this kernel, same command)")
+        hb = max((n for n in kernels if n in alg and n != dom), key=lambda n: kernels[n]["avg_ms"] * kernels[n]["launches_per_step"])
+        roofline["hbm_kernel"] = {"kernel": hb, "bound": "hbm", "achieved": kernels[hb]["achieved_gbs"], "peak": hbm_peak, "unit": "GB/s",
+                                  "frac": kernels[hb]["frac_of_hbm_peak"], "traffic": traffic.get(hb), "avg_launch_ms": kernels[hb]["avg_ms"],
+                                  "algorithmic_bytes_per_launch": kernels[hb]["algorithmic_bytes"]}
         value = tot[0] / (cand_ms * 1e-3)
         line = {
             "metric": "candidate_pairs_per_s", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),

@@ -181,6 +181,14 @@ SAME_API int same_batch_mip_start(same_batch_t *b, double no_match_penalty, int3
 SAME_API int same_greedy_select(int device, int64_t n, int degree, const int32_t *nodes, const double *key, const uint8_t *eligible,
                                 int64_t n_nodes, uint8_t *selected, uint8_t *used, int32_t *rounds);
 
+/* One collapse iteration of greedy_triangle_collapse (src/metacell_utils.py:388-433) on the current metacells: a triangle is a
+ * candidate iff its three vertices have the same type code and their sizes sum to <= max_size; candidates are visited in
+ * ascending (perimeter, triangle index) order and selected iff no vertex is used yet.  The perimeter reproduces the reference's
+ * arithmetic (np.linalg.norm of each side = sqrt(fma(dy, dy, dx*dx)), summed left to right).  xy[n,2], type[n], size[n],
+ * tri[T,3] HD; selected[T] u8, perimeter[T] (may be NULL) host. */
+SAME_API int same_collapse_select(int device, int64_t n, const double *xy, const int32_t *type, const double *size, int64_t n_tri,
+                                  const int32_t *tri, double max_size, uint8_t *selected, double *perimeter, int32_t *rounds);
+
 /* ---- results -------------------------------------------------------------------------- */
 /* W+1 offsets (in elements) of array `what` */
 SAME_API int same_batch_offsets(same_batch_t *b, int what, int64_t *off);

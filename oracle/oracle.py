@@ -243,3 +243,15 @@ def mip_start_greedy(pairs, cost, n_aligned, n_ref, sizes, no_match_penalty):
     idx = np.flatnonzero(sel)
     idx = idx[np.argsort(cost[idx], kind="stable")]
     return np.stack([pairs[idx, 0], pairs[idx, 1], idx], axis=1), np.flatnonzero(~used[:n_aligned])
+
+
+def collapse_select(xy, type_codes, sizes, tri, max_size):
+    """One collapse iteration of greedy_triangle_collapse (metacell_utils.py:388-433) -> (selected bool [T], perimeter [T])."""
+    xy = _f64(xy).reshape(-1, 2)
+    tri = _i32(tri).reshape(-1, 3)
+    tc, sz = _i32(type_codes), _f64(sizes)
+    T = len(tri)
+    cand, per = np.zeros(T, np.uint8), np.zeros(T, np.float64)
+    lib().oracle_collapse_score(C.c_int64(T), _p(tri), _p(xy), _p(tc), _p(sz), C.c_double(float(max_size)), _p(cand), _p(per))
+    sel, _ = greedy_select(tri, per, len(xy), cand)
+    return sel, per

@@ -502,3 +502,19 @@ ORACLE_API i64 oracle_greedy_select(i64 n, int degree, const i32 *nodes, const d
     free(it);
     return count;
 }
+
+/* f2  candidate test + perimeter of one collapse iteration   src/metacell_utils.py:388-409
+ * np.linalg.norm(1-D) = sqrt(ddot(v, v)); ddot with n = 2 on FMA hosts = fma(vy, vy, vx*vx);
+ * the three norms are added left to right. */
+static double norm2_ref(double vx, double vy) { return sqrt(fma(vy, vy, vx * vx)); }
+ORACLE_API void oracle_collapse_score(i64 n_tri, const i32 *tri, const double *xy, const i32 *type, const double *size, double max_size,
+                                      unsigned char *cand, double *perim) {
+    for (i64 t = 0; t < n_tri; ++t) {
+        const i32 a = tri[3 * t], b = tri[3 * t + 1], c = tri[3 * t + 2];
+        const int same = type[a] == type[b] && type[b] == type[c];
+        const double total = size[a] + size[b] + size[c];
+        const double ax = xy[2 * a], ay = xy[2 * a + 1], bx = xy[2 * b], by = xy[2 * b + 1], cx = xy[2 * c], cy = xy[2 * c + 1];
+        perim[t] = (norm2_ref(ax - bx, ay - by) + norm2_ref(bx - cx, by - cy)) + norm2_ref(cx - ax, cy - ay);
+        cand[t] = same && !(total > max_size);
+    }
+}

@@ -48,7 +48,7 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio", "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio", "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio",
         "smsp__thread_inst_executed_per_inst_executed.ratio", "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
-        "sm__inst_executed_pipe_fp64.sum", "smsp__warps_eligible.avg.per_cycle_active", "l1tex__t_bytes_pipe_lsu_mem_global_op_ld.sum",
+        "sm__inst_executed_pipe_fp64.sum", "smsp__warps_eligible.avg.per_cycle_active", "smsp__issue_active.avg.pct_of_peak_sustained_active", "l1tex__t_bytes_pipe_lsu_mem_global_op_ld.sum",
         "lts__t_bytes.sum", "sm__cycles_elapsed.avg", "smsp__cycles_active.avg"]
 
 
@@ -59,7 +59,7 @@ def full(rep, out, traffic_path=None):
     units = rows[1]
     data = rows[2:]
     ki = hdr.index("Kernel Name")
-    traffic = {}
+    traffic, extra = {}, {}
     with open(out, "w") as f:
         f.write(f"# ncu --set full summary ({rep})\n\n")
         for r in data:
@@ -79,6 +79,16 @@ def full(rep, out, traffic_path=None):
                 traffic.setdefault(short(r[ki]), []).append(tobytes("dram__bytes_read.sum") + tobytes("dram__bytes_write.sum"))
             except Exception:
                 pass
+            for k, name in (("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue_active_pct"),
+                            ("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "fp64_pipe_active_pct"),
+                            ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps_active_pct"),
+                            ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram_throughput_pct"),
+                            ("lts__t_sector_hit_rate.pct", "l2_hit_pct")):
+                if k in hdr:
+                    try:
+                        extra.setdefault(short(r[ki]).replace("void ", ""), {})[name] = float(r[hdr.index(k)].replace(",", ""))
+                    except ValueError:
+                        pass
     if traffic_path:
         old = {}
         try:
@@ -88,6 +98,14 @@ def full(rep, out, traffic_path=None):
         for k, v in traffic.items():
             old[k.replace("void ", "")] = sum(v) / len(v)
         json.dump(old, open(traffic_path, "w"), indent=1, sort_keys=True)
+        mpath = traffic_path.replace("ncu_traffic", "ncu_metrics")
+        oldm = {}
+        try:
+            oldm = json.load(open(mpath))
+        except Exception:
+            pass
+        oldm.update(extra)
+        json.dump(oldm, open(mpath, "w"), indent=1, sort_keys=True)
     print(open(out).read())
 
 

@@ -274,6 +274,15 @@ int same_greedy_select(int device, int64_t n, int degree, const int32_t *nodes, 
     });
 }
 
+int same_collapse_select(int device, int64_t n, const double *xy, const int32_t *type, const double *size, int64_t n_tri, const int32_t *tri,
+                         double max_size, uint8_t *selected, double *perimeter, int32_t *rounds) {
+    return guarded([&] {
+        REQUIRE(n >= 0 && n_tri >= 0 && n < (1ll << 31) && 3 * n_tri < (1ll << 31), SAME_E_ARG, "bad size");
+        REQUIRE(n_tri == 0 || (xy && type && size && tri && selected), SAME_E_ARG, "NULL argument");
+        collapse_select_arrays(device, n, xy, type, size, n_tri, tri, max_size, selected, perimeter, rounds);
+    });
+}
+
 int same_postsolve_arrays(int device, int64_t n_tri, const int32_t *tri, int64_t n_aligned, const double *a_xy, int64_t n_ref, const double *r_xy,
                           const int32_t *match_j, int32_t *mask, double *area_before, double *area_after, uint8_t *flipped) {
     return guarded([&] {

@@ -298,6 +298,9 @@ void batch_mip_start(Batch *b, double no_match_penalty, i32 *rounds_out);
 void greedy_select_arrays(int device, i64 n, int degree, const i32 *nodes, const double *key, const unsigned char *eligible, i64 n_nodes,
                           unsigned char *selected, unsigned char *used_out, i32 *rounds_out);
 
+void collapse_select_arrays(int device, i64 n, const double *xy, const i32 *type, const double *size, i64 T, const i32 *tri, double max_size,
+                            unsigned char *selected, double *perim_out, i32 *rounds_out);
+
 // upload a small host vector of i64 offsets as i32 device array
 void upload_offsets(const std::vector<i64> &h, DevBuf<i32> &d, cudaStream_t s);
 

@@ -184,6 +184,60 @@ void greedy_select_arrays(int device, i64 n, int degree, const i32 *nodes, const
     CK(cudaStreamDestroy(s));
 }
 
+// ---- batch selection of greedy_triangle_collapse (src/metacell_utils.py:388-433) --------------------------------
+// np.linalg.norm of a 2-vector is sqrt(ddot(v, v)); ddot on FMA hosts is fma(vy, vy, vx*vx), the three norms
+// are added left to right.  The perimeter only orders the candidates, but on lattice-like data (ISS spots) many perimeters tie
+// to the last bit, so the order is only reproduced with the reference's own rounding.
+__device__ __forceinline__ double norm2_ref(double vx, double vy) { return __dsqrt_rn(__fma_rn(vy, vy, __dmul_rn(vx, vx))); }
+__global__ void k_collapse_score(const double2 *__restrict__ xy, const i32 *__restrict__ type, const double *__restrict__ size, const i32 *__restrict__ tri,
+                                 i64 T, double max_size, unsigned char *__restrict__ cand, double *__restrict__ perim) {
+    const i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    const i32 a = tri[3 * t], b = tri[3 * t + 1], c = tri[3 * t + 2];
+    const bool same = (type[a] == type[b]) & (type[b] == type[c]);                              // :391-394
+    const double total = __dadd_rn(__dadd_rn(size[a], size[b]), size[c]);                       // :397-399
+    const double2 A = xy[a], B = xy[b], C = xy[c];
+    const double p = __dadd_rn(__dadd_rn(norm2_ref(__dsub_rn(A.x, B.x), __dsub_rn(A.y, B.y)), norm2_ref(__dsub_rn(B.x, C.x), __dsub_rn(B.y, C.y))),
+                               norm2_ref(__dsub_rn(C.x, A.x), __dsub_rn(C.y, A.y)));            // :405-409
+    cand[t] = same && !(total > max_size);
+    perim[t] = p;
+}
+
+// score + select in one call, everything device-resident in between; host or device arrays in, host arrays out
+void collapse_select_arrays(int device, i64 n, const double *xy, const i32 *type, const double *size, i64 T, const i32 *tri, double max_size,
+                            unsigned char *selected, double *perim_out, i32 *rounds_out) {
+    CK(cudaSetDevice(device));
+    cudaStream_t s;
+    CK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    try {
+        DevBuf<double2> d_xy;
+        DevBuf<i32> d_type, d_tri;
+        DevBuf<double> d_size, d_perim;
+        DevBuf<unsigned char> d_cand, d_sel, d_used;
+        d_xy.alloc(n, s); d_type.alloc(n, s); d_size.alloc(n, s); d_tri.alloc(3 * T, s); d_perim.alloc(T, s); d_cand.alloc(T, s); d_sel.alloc(T, s);
+        d_used.alloc(n, s);
+        int rounds = 0;
+        if (T > 0) {
+            CK(cudaMemcpyAsync(d_xy.p, xy, sizeof(double2) * (size_t)n, cudaMemcpyDefault, s));
+            CK(cudaMemcpyAsync(d_type.p, type, sizeof(i32) * (size_t)n, cudaMemcpyDefault, s));
+            CK(cudaMemcpyAsync(d_size.p, size, sizeof(double) * (size_t)n, cudaMemcpyDefault, s));
+            CK(cudaMemcpyAsync(d_tri.p, tri, sizeof(i32) * (size_t)(3 * T), cudaMemcpyDefault, s));
+            LAUNCH(k_collapse_score, blocks_for(T, 256), 256, 0, s, d_xy.p, d_type.p, d_size.p, d_tri.p, T, max_size, d_cand.p, d_perim.p);
+            rounds = greedy_select_dev<3>(d_tri.p, d_perim.p, d_cand.p, T, n, d_sel.p, d_used.p, s);
+            CK(cudaMemcpyAsync(selected, d_sel.p, (size_t)T, cudaMemcpyDefault, s));
+            if (perim_out) CK(cudaMemcpyAsync(perim_out, d_perim.p, sizeof(double) * (size_t)T, cudaMemcpyDefault, s));
+        }
+        CK(cudaStreamSynchronize(s));
+        if (rounds_out) *rounds_out = rounds;
+    } catch (...) {
+        cudaStreamSynchronize(s);
+        cudaStreamDestroy(s);
+        throw;
+    }
+    CK(cudaStreamSynchronize(s));
+    CK(cudaStreamDestroy(s));
+}
+
 // ---- greedy MIP start over a whole batch (src/init_helpers.py:110-132) ---------------------------------------
 // one thread per kept aligned row: prefer_match = (best cost of the row) < no_match_penalty * size
 __global__ void k_start_rows(const i32 *__restrict__ row_ptr, const double *__restrict__ cost, const double *__restrict__ ka_size, i64 nKA,

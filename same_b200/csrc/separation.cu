@@ -44,7 +44,7 @@ __global__ void __launch_bounds__(MATCH_ROWS) k_match_rows(const double *__restr
 // their window (exclusive scan that restarts at every window, scan.cuh), the first `cap` cuts of every window in
 // ascending triangle order and the per-window counts.  A block owns SEP_TILE consecutive triangles; the geometry
 // phase is striped (coalesced, independent gathers), the scan phase blocked.
-constexpr int SEP_THREADS = 256, SEP_ITEMS = 8, SEP_TILE = SEP_THREADS * SEP_ITEMS;
+constexpr int SEP_THREADS = 256, SEP_ITEMS = 4, SEP_TILE = SEP_THREADS * SEP_ITEMS;   // 4 or 8 (flags of a thread are read as one word)
 
 __global__ void __launch_bounds__(SEP_THREADS) k_separation(const int3 *__restrict__ tri, const signed char *__restrict__ src_sign, i32 t_lo, i32 t_hi,
                                                             const i32 *__restrict__ t_off, const i32 *__restrict__ ka_off, const i32 *__restrict__ kr_off,
@@ -85,7 +85,9 @@ __global__ void __launch_bounds__(SEP_THREADS) k_separation(const int3 *__restri
     }
     __syncthreads();
     // blocked phase: thread owns flags [8*tid, 8*tid+8)
-    const unsigned long long bits = *reinterpret_cast<const unsigned long long *>(V + threadIdx.x * SEP_ITEMS);
+    static_assert(SEP_ITEMS == 4 || SEP_ITEMS == 8, "flags of a thread are read as one 32- or 64-bit word");
+    const unsigned long long bits = SEP_ITEMS == 8 ? *reinterpret_cast<const unsigned long long *>(V + threadIdx.x * SEP_ITEMS)
+                                                   : (unsigned long long)*reinterpret_cast<const unsigned *>(V + threadIdx.x * SEP_ITEMS);
     int nv[2] = {__popcll(bits), ck}, excl[2], tot[2];
     block_exclusive_scan<2, SEP_THREADS>(nv, excl, tot, smem);
     {

@@ -148,6 +148,23 @@ def greedy_select(nodes, key, n_nodes, eligible=None, device: int = 0, return_ro
     return (sel.astype(bool), r.value) if return_rounds else sel.astype(bool)
 
 
+def collapse_select(xy, type_codes, sizes, tri, max_size, device: int = 0):
+    """One collapse iteration of greedy_triangle_collapse on the GPU (same_collapse_select): candidate test, perimeter in the
+    reference's arithmetic, ordered disjoint selection.  -> (selected bool [T], perimeter float64 [T])"""
+    xy = np.ascontiguousarray(xy, dtype=np.float64).reshape(-1, 2)
+    n = len(xy)
+    tc = np.ascontiguousarray(type_codes, dtype=np.int32).reshape(n)
+    sz = np.ascontiguousarray(sizes, dtype=np.float64).reshape(n)
+    tri = np.ascontiguousarray(tri, dtype=np.int32).reshape(-1, 3)
+    T = len(tri)
+    if T and (tri.min() < 0 or tri.max() >= n):
+        raise ValueError("triangle vertex out of range")
+    sel, per, r = np.zeros(T, np.uint8), np.zeros(T, np.float64), C.c_int32(0)
+    L.check(L.load().same_collapse_select(device, n, L.ptr(xy), L.ptr(tc), L.ptr(sz), T, L.ptr(tri), float(max_size), L.ptr(sel), L.ptr(per),
+                                          C.byref(r)))
+    return sel.astype(bool), per
+
+
 class WindowBatch:
     """A list of windows of one section (same_batch_create).  `rects=None` = the whole section."""
 

@@ -154,21 +154,20 @@ def greedy_triangle_collapse(aligned_df, max_metacell_size=3, max_iterations=100
         if len(tri) == 0:
             break
         tri = tri.astype(int)
-        types = mdf[cell_type_col].to_numpy()
+        # candidate test, perimeter and batch selection on the GPU (src/metacell_utils.py:388-433, csrc/greedy.cu): same type,
+        # merged size within the limit, candidates in ascending (perimeter, position) order — list.sort is stable — each taken
+        # iff none of its vertices is used yet
+        from .device import collapse_select
         sizes = mdf["size"].to_numpy()
-        same = (types[tri[:, 0]] == types[tri[:, 1]]) & (types[tri[:, 1]] == types[tri[:, 2]])
         tot = sizes[tri[:, 0]] + sizes[tri[:, 1]] + sizes[tri[:, 2]]
-        cand = np.flatnonzero(same & ~(tot > max_metacell_size))
-        if len(cand) == 0:
+        if not (tot <= max_metacell_size).any():            # nothing can merge (always the case for max_metacell_size=1): no device work
             break
-        a, b, c = coords[tri[cand, 0]], coords[tri[cand, 1]], coords[tri[cand, 2]]
-        perim = np.linalg.norm(a - b, axis=1) + np.linalg.norm(b - c, axis=1) + np.linalg.norm(c - a, axis=1)
-        # batch mode (src/metacell_utils.py:423-433): candidates in ascending (perimeter, position) order — list.sort is stable —
-        # each taken iff none of its vertices is used yet.  The loop is the ordered greedy selection of csrc/greedy.cu.
-        from .device import greedy_select
-        sel = greedy_select(tri[cand], perim, len(mdf))
+        codes = pd.factorize(mdf[cell_type_col])[0]
+        sel, perim = collapse_select(coords, codes, sizes, tri, max_metacell_size)
         chosen = np.flatnonzero(sel)
-        batch = cand[chosen[np.argsort(perim[chosen], kind="stable")]].tolist()   # merged metacells are appended in selection order
+        if len(chosen) == 0:
+            break
+        batch = chosen[np.argsort(perim[chosen], kind="stable")].tolist()   # merged metacells are appended in selection order
         merged, remove = [], []
         for t in batch:
             va, vb, vc = tri[t]

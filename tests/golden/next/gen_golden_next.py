@@ -78,7 +78,7 @@ def collapse_cases():
         rec[f"{name}__params"] = np.asarray([tiles, seed, ms, r_max, -1.0 if ang is None else ang], dtype=np.float64)
         rec[f"{name}__xy"] = mdf[["X", "Y"]].to_numpy(np.float64)
         rec[f"{name}__size"] = mdf["size"].to_numpy(np.int64)
-        rec[f"{name}__type"] = mdf["cell_type"].astype(str).to_numpy()
+        rec[f"{name}__type"] = np.asarray(mdf["cell_type"].astype(str).tolist(), dtype="U")
         rec[f"{name}__prob"] = mdf[ct].to_numpy(np.float64)
         rec[f"{name}__members_flat"] = np.asarray([m for ms_ in mdf["members"] for m in ms_], dtype=np.int64)
         rec[f"{name}__members_ptr"] = np.r_[0, np.cumsum([len(m) for m in mdf["members"]])].astype(np.int64)
@@ -159,7 +159,78 @@ def unpack_cases():
     np.savez_compressed(os.path.join(HERE, "unpack.npz"), **rec)
 
 
+def heart_case():
+    """BASELINE configs[2]: the shipped ISS heart serial sections (examples/heart/data, 3,801 / 3,184 spots, K=8) with
+    greedy_triangle_collapse metacells (max_metacell_size=10) through sliding_window_matching, parameters of
+    examples/heart/run_same.sh:40-133 (MS=10).  Recorded with the same machinery as the main fixtures."""
+    import pandas as pd
+    from tests.golden import gen_golden as GG
+    d = os.path.join(ref_loader.REFERENCE_ROOT, "examples", "heart", "data")
+    cts = ['Smooth muscle cells', 'Fibroblast', 'Atrial cardiomyocytes', 'Cardiomyocytes', 'Endothelium', 'Epicardium',
+           'Schwan progenitors', 'Ventricular cardiomyocytes']
+    frames = []
+    for f in ("refAD_valis.csv", "queryAD_valis.csv"):
+        df = pd.read_csv(os.path.join(d, f))
+        df = df.rename(columns={f"{c}_percentage": c for c in cts})
+        df["X"], df["Y"] = df["New_X"].astype(float), df["New_Y"].astype(float)   # the script's spot_x + 75 gives 0 triangles at r_max=50 (SURVEY.md §4)
+        df["cell_type"] = df[cts].idxmax(axis=1)
+        frames.append(df[["X", "Y", "Cell_Num", "cell_type"] + cts].copy())
+    ref, qry = frames
+    ms = 10
+    optim = dict(window_size=4000, overlap=100, min_cells_per_window=30, max_matches=1, radius=50, knn=8, no_match_penalty=10000,
+                 penalty_coeff=100, dist_ct_coeff=1, delaunay_penalty=10, cell_id_col="metacell_id", ref_metacell_match_multiplier=ms,
+                 ignore_same_type_triangles=True, lazy_constraints=True, min_angle_deg=15)
+    gurobi = dict(mip_gap=0.05, lazy_allowed_flip_fraction=0.05, time_limit=7200)
+    mcp = dict(max_metacell_size=ms, r_max=50, min_angle_deg=15, use_alpha_shape=False)
+    rec = {}
+    rec.update(GG.frame_arrays(ref, cts, "Cell_Num", "ref"))
+    rec.update(GG.frame_arrays(qry, cts, "Cell_Num", "aligned"))
+    rec["commonCT"], rec["id_col"], rec["seed"] = np.asarray(cts, dtype="U"), np.asarray("Cell_Num"), np.int64(15)
+    for k, v in optim.items():
+        rec[f"optim_{k}"] = np.asarray(np.nan if v is None else v)
+    for k, v in gurobi.items():
+        rec[f"gurobi_{k}"] = np.asarray(np.nan if v is None else v)
+    for k, v in mcp.items():
+        rec[f"mc_{k}"] = np.asarray(v)
+    with quiet():
+        mc_al = rmc.greedy_triangle_collapse(qry, cell_type_col="cell_type", original_idx_col="Cell_Num", return_object=True, **mcp)
+        mc_rf = rmc.greedy_triangle_collapse(ref, cell_type_col="cell_type", original_idx_col="Cell_Num", return_object=True, **mcp)
+    for tag, mc in (("mca", mc_al), ("mcr", mc_rf)):
+        mdf = mc.metacell_df
+        rec[f"{tag}_xy"], rec[f"{tag}_size"] = mdf[["X", "Y"]].to_numpy(np.float64), mdf["size"].to_numpy(np.int64)
+        rec[f"{tag}_prob"] = mdf[cts].to_numpy(np.float64)
+        rec[f"{tag}_type"] = np.asarray(mdf["cell_type"].astype(str).tolist(), dtype="U")
+        rec[f"{tag}_members_flat"] = np.asarray([m for ms_ in mdf["members"] for m in ms_], dtype=np.int64)
+        rec[f"{tag}_delaunay"] = np.asarray(mc.metacell_delaunay, dtype=np.int64).reshape(-1, 3)
+    print("heart: metacells", len(mc_al.metacell_df), "/", len(mc_rf.metacell_df), "of", len(qry), "/", len(ref), flush=True)
+    ref_loader.MODELS.clear()
+    ref_loader.INCUMBENT_FN = GG.make_incumbent_fn(15)
+    import tempfile
+    cwd = os.getcwd()
+    with tempfile.TemporaryDirectory() as td:
+        os.chdir(td)
+        try:
+            with quiet():
+                matches = REF.sliding_window_matching(mc_rf, mc_al, commonCT=list(cts), outprefix=os.path.join(td, "out"), optim_params=dict(optim),
+                                                      gurobi_params=dict(gurobi))
+        finally:
+            os.chdir(cwd)
+    rec["n_models"] = np.int64(len(ref_loader.MODELS))
+    for w, m in enumerate(ref_loader.MODELS):
+        for k, v in GG.record_model(m, cts).items():
+            rec[f"w{w}_{k}"] = v
+    rec["matches_columns"] = np.asarray(list(matches.columns), dtype="U")
+    for col in matches.columns:
+        v = matches[col].to_numpy()
+        rec[f"matches__{col}"] = np.asarray(v.tolist(), dtype="U") if v.dtype.kind in "OUT" else v
+    np.savez_compressed(os.path.join(HERE, "heart_mc10.npz"), **rec)
+    print("heart:", len(ref_loader.MODELS), "window model(s),", len(matches), "matches,", sum(len(m.lazy) for m in ref_loader.MODELS), "cuts")
+
+
 if __name__ == "__main__":
+    if "--heart" in sys.argv:
+        heart_case()
+        sys.exit(0)
     unpack_cases()
     mip_start_cases()
     collapse_cases()

@@ -267,3 +267,38 @@ def test_mip_start_through_public_api(case, fake_gurobi, tmp_path):
         sn = np.asarray([np.nan if v.Start is None else v.Start for v in m.vars if v.VarName.startswith("no_match[")], dtype=np.float64)
         assert np.array_equal(sx, gs[f"{case}__w{w}_start_x"]), (case, w)
         assert np.array_equal(sn, gs[f"{case}__w{w}_start_no_match"]), (case, w)
+
+
+def test_heart_metacells_vs_reference(fake_gurobi, tmp_path):
+    """BASELINE configs[2]: the ISS heart sections (3,801 / 3,184 spots, K=8) collapsed to metacells of up to 10 cells and matched
+    through sliding_window_matching with the paper script's parameters (examples/heart/run_same.sh): metacell frames, every
+    window's model (pairs, costs, constraints, cuts) and the matches frame equal the unmodified reference's record."""
+    import same_b200
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "next", "heart_mc10.npz")
+    g = dict(np.load(path, allow_pickle=False))
+    ref_df, al_df = golden_frame(g, "ref"), golden_frame(g, "aligned")
+    ct = [str(c) for c in g["commonCT"]]
+    optim, gurobi = golden_params(g, "optim"), golden_params(g, "gurobi")
+    mcp = dict(max_metacell_size=int(g["mc_max_metacell_size"]), r_max=float(g["mc_r_max"]), min_angle_deg=float(g["mc_min_angle_deg"]),
+               use_alpha_shape=False)
+    mc_al = same_b200.greedy_triangle_collapse(al_df, cell_type_col="cell_type", original_idx_col="Cell_Num", return_object=True, **mcp)
+    mc_rf = same_b200.greedy_triangle_collapse(ref_df, cell_type_col="cell_type", original_idx_col="Cell_Num", return_object=True, **mcp)
+    for tag, mc in (("mca", mc_al), ("mcr", mc_rf)):
+        mdf = mc.metacell_df
+        assert np.array_equal(mdf[["X", "Y"]].to_numpy(), g[f"{tag}_xy"]), tag
+        assert np.array_equal(mdf["size"].to_numpy(), g[f"{tag}_size"]), tag
+        assert np.array_equal(mdf[ct].to_numpy(), g[f"{tag}_prob"]), tag
+        assert np.array_equal(mdf["cell_type"].astype(str).to_numpy(), g[f"{tag}_type"]), tag
+        assert np.array_equal(np.asarray([m for ms_ in mdf["members"] for m in ms_]), g[f"{tag}_members_flat"]), tag
+        assert np.array_equal(np.asarray(mc.metacell_delaunay, dtype=np.int64).reshape(-1, 3), g[f"{tag}_delaunay"]), tag
+    assert mc_al.metacell_df["size"].max() > 3
+    fake_gurobi.INCUMBENT_FN = _incumbent_fn(int(g["seed"]))
+    cwd = os.getcwd()
+    os.chdir(tmp_path)
+    try:
+        got = same_b200.sliding_window_matching(mc_rf, mc_al, commonCT=ct, outprefix=str(tmp_path / "out"), optim_params=dict(optim),
+                                                gurobi_params=dict(gurobi))
+    finally:
+        os.chdir(cwd)
+    _compare_models(fake_gurobi, g)
+    _compare_matches(got, g)

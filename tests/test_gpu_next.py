@@ -169,3 +169,30 @@ def test_unpack_metacell_matches_vs_reference_golden():
                                                 aligned_original_idx_col="Cell_Num_Old", ref_original_idx_col="Cell_Num_Old")
         assert np.array_equal(out["Aligned_cell_id"].to_numpy(np.int64), g[f"{case}__aligned"]), case
         assert np.array_equal(out["Ref_cell_id"].to_numpy(np.int64), g[f"{case}__ref"]), case
+
+
+@pytest.mark.parametrize("lattice", [False, True])
+def test_collapse_select_vs_oracle(lattice):
+    """same_collapse_select == oracle: candidate flags, perimeters bit for bit (fma(dy,dy,dx*dx) per side), selection.  The lattice
+    variant puts the points on an integer grid with a few fractional centroids, so most perimeters tie exactly or to the last bit."""
+    from scipy.spatial import Delaunay
+    from same_b200.device import collapse_select
+    rng = np.random.default_rng(3 + lattice)
+    n = 6000
+    if lattice:
+        gx, gy = np.meshgrid(np.arange(80.0) * 17.0, np.arange(75.0) * 17.0)
+        xy = np.stack([gx.ravel(), gy.ravel()], axis=1)[:n]
+        k = rng.choice(n, 600, replace=False)
+        xy[k] += rng.integers(-5, 6, size=(600, 2)) / 3.0
+    else:
+        xy = rng.uniform(0, 1000, size=(n, 2))
+    tri = Delaunay(xy).simplices.astype(np.int32)
+    types = rng.integers(0, 3, n).astype(np.int32)
+    types[: n // 2] = 0                                    # a large same-type region so that many triangles compete
+    sizes = rng.integers(1, 5, n).astype(np.float64)
+    sel, per = collapse_select(xy, types, sizes, tri, 8)
+    want_sel, want_per = O.collapse_select(xy, types, sizes, tri, 8)
+    assert np.array_equal(per, want_per)
+    assert np.array_equal(sel, want_sel) and sel.sum() > 100
+    if lattice:
+        assert len(np.unique(per)) < 0.2 * len(per)

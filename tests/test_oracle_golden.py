@@ -196,3 +196,30 @@ def test_oracle_mip_start_equals_reference():
         chosen, unmatched = O.mip_start_greedy(pairs, cost, na, nr, sizes, pen)
         assert np.array_equal(chosen, g[f"{case}__chosen"]), case
         assert np.array_equal(unmatched, g[f"{case}__unmatched"]), case
+
+
+def test_oracle_collapse_equals_reference(monkeypatch):
+    """oracle_collapse_score + oracle_greedy_select (candidate test, perimeter in the reference's fma arithmetic, ordered disjoint
+    selection) reproduce greedy_triangle_collapse of the unmodified reference: plugged into the host loop of
+    same_b200.metacell_utils in place of the CUDA call, the metacell frames equal the recorded ones bit for bit — on the seeded
+    sections and on the lattice-like ISS heart sections, where perimeters tie to the last bit."""
+    import same_b200
+    from same_b200 import datagen, device
+    from tests.util import golden_frame
+    monkeypatch.setattr(device, "collapse_select", lambda xy, tc, sz, tri, ms, device=0: O.collapse_select(xy, tc, sz, tri, ms))
+    g = _next_golden("collapse.npz")
+    for case in g["cases"]:
+        tiles, seed, ms, r_max, ang = g[f"{case}__params"]
+        ref, qry, ct = datagen.make_section_pair(n_tiles=int(tiles), seed=int(seed))
+        mc = same_b200.greedy_triangle_collapse(qry, max_metacell_size=int(ms), r_max=float(r_max), min_angle_deg=None if ang < 0 else float(ang),
+                                                return_object=True)
+        assert np.array_equal(mc.metacell_df[["X", "Y"]].to_numpy(), g[f"{case}__xy"]), case
+        assert np.array_equal(np.asarray([m for ms_ in mc.metacell_df["members"] for m in ms_]), g[f"{case}__members_flat"]), case
+        assert np.array_equal(np.asarray(mc.metacell_delaunay).reshape(-1, 3), g[f"{case}__delaunay"]), case
+    h = dict(np.load(os.path.join(os.path.dirname(__file__), "golden", "next", "heart_mc10.npz")))
+    for tag, df in (("mca", golden_frame(h, "aligned")), ("mcr", golden_frame(h, "ref"))):
+        mc = same_b200.greedy_triangle_collapse(df, cell_type_col="cell_type", original_idx_col="Cell_Num", return_object=True, max_metacell_size=10,
+                                                r_max=50.0, min_angle_deg=15.0, use_alpha_shape=False)
+        assert np.array_equal(mc.metacell_df[["X", "Y"]].to_numpy(), h[f"{tag}_xy"]), tag
+        assert np.array_equal(mc.metacell_df["size"].to_numpy(), h[f"{tag}_size"]), tag
+        assert np.array_equal(np.asarray(mc.metacell_delaunay, dtype=np.int64).reshape(-1, 3), h[f"{tag}_delaunay"]), tag
