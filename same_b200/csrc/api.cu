@@ -146,7 +146,11 @@ int same_section_create(int device, void *stream, int64_t n_aligned, int64_t n_r
             sec->nA = n_aligned; sec->nR = n_ref; sec->K = n_types;
             section_build(sec, a_xy, r_xy, a_prob, r_prob, a_type, r_type, a_size, r_size);
         } catch (...) {
+            cudaStream_t aux = sec->aux_stream;
+            cudaEvent_t ev = sec->aux_ready;
             delete sec;
+            if (aux) { cudaStreamSynchronize(aux); cudaStreamDestroy(aux); }
+            if (ev) cudaEventDestroy(ev);
             throw;
         }
         *out = (same_section_t *)sec;
@@ -158,10 +162,14 @@ int same_section_destroy(same_section_t *h) {
         Section *sec = (Section *)h;
         if (!sec) return;
         CK(cudaSetDevice(sec->device));
-        cudaStream_t s = sec->stream;
+        cudaStream_t s = sec->stream, aux = sec->aux_stream;
+        cudaEvent_t ev = sec->aux_ready;
         bool own = sec->own_stream;
+        CK(cudaStreamSynchronize(s));   // buffers allocated on the auxiliary stream are freed there: nothing on `s` may still read them
         delete sec;
         CK(cudaStreamSynchronize(s));
+        if (aux) { CK(cudaStreamSynchronize(aux)); CK(cudaStreamDestroy(aux)); }
+        if (ev) CK(cudaEventDestroy(ev));
         if (own) CK(cudaStreamDestroy(s));
     });
 }

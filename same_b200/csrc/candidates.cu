@@ -597,6 +597,9 @@ void batch_candidates(Batch *b, double radius, int knn, int priority, double dis
 #undef KNN_ARGS
     }
 
+    // first use of the columns that section_build uploads on the auxiliary stream (type codes, sizes, probabilities)
+    if (sec->aux_ready) CK(cudaStreamWaitEvent(s, sec->aux_ready, 0));
+
     // a2: priority filter decides how many pairs each aligned row emits; compaction of the frames is
     // still a1's (knn_utils.py:14 re-uses the frames find_knn_within_radius returned)
     const i32 *eff = b->cnt.p;

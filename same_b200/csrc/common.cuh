@@ -123,6 +123,10 @@ struct Section {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    // Columns the search does not read (probabilities, type codes, sizes) are uploaded on a second stream while the window
+    // subsetting, binning and search already run on the coordinates; `aux_ready` is waited for before their first use.
+    cudaStream_t aux_stream = nullptr;
+    cudaEvent_t aux_ready = nullptr;
     i64 nA = 0, nR = 0;
     int K = 0;
     DevBuf<double2> a_xy, r_xy;

@@ -128,14 +128,20 @@ void section_build(Section *sec, const double *a_xy, const double *r_xy, const d
     const int K = sec->K;
     upload(sec->a_xy, a_xy, nA, s);
     upload(sec->r_xy, r_xy, nR, s);
-    upload(sec->a_prob, a_prob, nA * K, s);
-    upload(sec->r_prob, r_prob, nR * K, s);
-    if (a_type) upload(sec->a_type, a_type, nA, s); else { sec->a_type.alloc(nA, s); sec->a_type.zero(s); }
-    if (r_type) upload(sec->r_type, r_type, nR, s); else { sec->r_type.alloc(nR, s); sec->r_type.zero(s); }
-    if (a_size) upload(sec->a_size, a_size, nA, s);
-    else { sec->a_size.alloc(nA, s); LAUNCH(k_fill_f64, blocks_for(nA, 256), 256, 0, s, sec->a_size.p, nA, 1.0); }
-    if (r_size) upload(sec->r_size, r_size, nR, s);
-    else { sec->r_size.alloc(nR, s); LAUNCH(k_fill_f64, blocks_for(nR, 256), 256, 0, s, sec->r_size.p, nR, 1.0); }
+    // everything else goes up on the auxiliary stream: the synchronisation below (bounding box) then waits for the
+    // coordinates only, and the first stages of a batch overlap the rest of the upload
+    CK(cudaStreamCreateWithFlags(&sec->aux_stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&sec->aux_ready, cudaEventDisableTiming));
+    cudaStream_t x = sec->aux_stream;
+    upload(sec->a_prob, a_prob, nA * K, x);
+    upload(sec->r_prob, r_prob, nR * K, x);
+    if (a_type) upload(sec->a_type, a_type, nA, x); else { sec->a_type.alloc(nA, x); sec->a_type.zero(x); }
+    if (r_type) upload(sec->r_type, r_type, nR, x); else { sec->r_type.alloc(nR, x); sec->r_type.zero(x); }
+    if (a_size) upload(sec->a_size, a_size, nA, x);
+    else { sec->a_size.alloc(nA, x); LAUNCH(k_fill_f64, blocks_for(nA, 256), 256, 0, x, sec->a_size.p, nA, 1.0); }
+    if (r_size) upload(sec->r_size, r_size, nR, x);
+    else { sec->r_size.alloc(nR, x); LAUNCH(k_fill_f64, blocks_for(nR, 256), 256, 0, x, sec->r_size.p, nR, 1.0); }
+    CK(cudaEventRecord(sec->aux_ready, x));
     // bounding box of both frames (src/same.py:481-482)
     DevBuf<unsigned long long> bb;
     bb.alloc(4, s);
