@@ -105,11 +105,6 @@ void scan_i32(Section *sec, const i32 *in, i32 *out, i64 n, cudaStream_t s) {
 // short-circuit form compiled to divergent branches inside the insertion: 180 SASS instructions at ~3 active lanes)
 __device__ __forceinline__ bool cand_less(double d, i32 j, double bd, i32 bj) { return (d < bd) | ((d == bd) & (j < bj)); }
 
-// walk order of the 8 bins of ring 1: the side neighbours on the query's side of its bin, the other two, the corners
-__device__ __forceinline__ void ring1_slot(int slot, int sx, int sy, int &dx, int &dy) {
-    dx = (slot == 0 || slot == 4 || slot == 5) ? sx : ((slot == 2 || slot == 6 || slot == 7) ? -sx : 0);
-    dy = (slot == 1 || slot == 4 || slot == 6) ? sy : ((slot == 3 || slot == 5 || slot == 7) ? -sy : 0);
-}
 __device__ __forceinline__ void ring_slot(int ring, int slot, int &dx, int &dy) {   // perimeter walk: four sides of 2*ring bins
     const int side = slot / (2 * ring), k = slot - side * 2 * ring;
     dx = side == 0 ? -ring + k : (side == 1 ? ring : (side == 2 ? ring - k : -ring));
@@ -212,27 +207,47 @@ __global__ void __launch_bounds__(128) k_knn(const double2 *__restrict__ sa_xy, 
     const float wf = (float)g.w, epsf = 1e-5f * wf;
     const float fxf = (float)(px - cbx * g.w), fyf = (float)(py - cby * g.w);
     float thrf = __double2float_ru(thr);
-    const float edge = fminf(fminf(fxf, wf - fxf), fminf(fyf, wf - fyf)) - epsf;   // distance to the nearest side of the own bin
-    // ring 1 is walked nearest first so that the k-th best tightens early and the far corner bins are pruned without a
-    // single evaluation
+    // The own bin and ring 1 — where nearly all the work is — are nine bins whose squared gaps are sums of four numbers: the
+    // gap to the NEAR neighbour column / row (the one on the query's side of its bin) and to the FAR one.  They are walked
+    // nearest first (own, near column, near row, far column, far row, then the corners) from a packed 2-bit code table, so
+    // the k-th best tightens early and the far bins are pruned without an evaluation.  Rings >= 2 use the general walker.
     const int sx = (fxf + fxf < wf) ? -1 : 1, sy = (fyf + fyf < wf) ? -1 : 1;
-    for (int ring = 0; ring <= g.rings; ++ring) {
-        if (ring > 0) {
-            // nearest possible point of this ring (Chebyshev distance `ring` bins from the centre bin)
-            const float gap = (float)(ring - 1) * wf + edge;
-            if (gap > 0.f && gap * gap > thrf) break;
-        }
-        const int n_slots = ring == 0 ? 1 : 8 * ring;
-        for (int slot = 0; slot < n_slots; ++slot) {
-            int dx = 0, dy = 0;
-            if (ring == 1) ring1_slot(slot, sx, sy, dx, dy);
-            else if (ring > 1) ring_slot(ring, slot, dx, dy);
-            const int bx = cbx + dx, by = cby + dy;
-            if (bx < 0 || bx >= g.nbx || by < 0 || by >= g.nby) continue;
+    const float nxg = fmaxf(0.f, fminf(fxf, wf - fxf) - epsf), fxg = fmaxf(0.f, fmaxf(fxf, wf - fxf) - epsf);
+    const float nyg = fmaxf(0.f, fminf(fyf, wf - fyf) - epsf), fyg = fmaxf(0.f, fmaxf(fyf, wf - fyf) - epsf);
+    const float nx2 = nxg * nxg, fx2 = fxg * fxg, ny2 = nyg * nyg, fy2 = fyg * fyg;
+    const float edge = fminf(nxg, nyg);                     // distance to the nearest side of the own bin (lower bound)
+    // codes 0 = own column/row, 1 = near, 2 = far; slot order: own, (N,0), (0,N), (F,0), (0,F), (N,N), (N,F), (F,N), (F,F)
+    constexpr unsigned XC = 0u | 1u << 2 | 0u << 4 | 2u << 6 | 0u << 8 | 1u << 10 | 1u << 12 | 2u << 14 | 2u << 16;
+    constexpr unsigned YC = 0u | 0u << 2 | 1u << 4 | 0u << 6 | 2u << 8 | 1u << 10 | 2u << 12 | 1u << 14 | 2u << 16;
+    int ring = 1, slot = 8;                                 // general walker state; the first general step moves to ring 2
+    for (int it = 0;; ++it) {
+        int dx, dy;
+        float g2;
+        if (it < 9) {
+            const unsigned cx = (XC >> (2 * it)) & 3u, cy = (YC >> (2 * it)) & 3u;
+            dx = cx == 0u ? 0 : (cx == 1u ? sx : -sx);
+            dy = cy == 0u ? 0 : (cy == 1u ? sy : -sy);
+            g2 = (cx == 0u ? 0.f : (cx == 1u ? nx2 : fx2)) + (cy == 0u ? 0.f : (cy == 1u ? ny2 : fy2));
+            if (it == 1 && edge * edge > thrf) break;       // nothing outside the own bin can enter any more
+        } else {
+            if (slot >= 8 * ring) { ++ring; slot = 0; }
+            if (ring > g.rings) break;
+            if (slot == 0) {
+                // nearest possible point of this ring (Chebyshev distance `ring` bins from the centre bin)
+                const float gap = (float)(ring - 1) * wf + edge;
+                if (gap * gap > thrf) break;
+            }
+            ring_slot(ring, slot, dx, dy);
+            ++slot;
             // gap along one axis to a bin d bins away: d > 0: d*w - f;  d < 0: f + (-d - 1)*w;  own row/column: 0
             const float gx = dx == 0 ? 0.f : fmaxf(0.f, (dx > 0 ? (float)dx * wf - fxf : fxf - (float)(dx + 1) * wf) - epsf);
             const float gy = dy == 0 ? 0.f : fmaxf(0.f, (dy > 0 ? (float)dy * wf - fyf : fyf - (float)(dy + 1) * wf) - epsf);
-            if (gx * gx + gy * gy > thrf) continue;
+            g2 = gx * gx + gy * gy;
+        }
+        const int bx = cbx + dx, by = cby + dy;
+        if (bx < 0 || bx >= g.nbx || by < 0 || by >= g.nby) continue;
+        if (g2 > thrf) continue;
+        {
             const i32 b = g.base + by * g.nbx + bx;
             const i32 s1 = bin_start[b + 1];
             for (i32 s0 = bin_start[b]; s0 < s1; s0 += 2) {
@@ -634,8 +649,9 @@ void batch_candidates(Batch *b, double radius, int knn, int priority, double dis
     CK(cudaMemcpyAsync(b->d_ka_off.p, off3.p, sizeof(i32) * (W + 1), cudaMemcpyDeviceToDevice, s));
     CK(cudaMemcpyAsync(b->d_kr_off.p, off3.p + (W + 1), sizeof(i32) * (W + 1), cudaMemcpyDeviceToDevice, s));
     CK(cudaMemcpyAsync(b->d_p_off.p, off3.p + 2 * (W + 1), sizeof(i32) * (W + 1), cudaMemcpyDeviceToDevice, s));
-    // (a one-thread-per-row variant with 8 gather chains in flight per thread was measured at 224 us vs 129 us: the kernel
-    // is bound by L2 sector traffic — ~5 distinct 32-byte sectors per pair — not by chain latency; profiles/r1m)
+    // (measured and not kept: one thread per row with 8 gather chains in flight, 224 us vs 129 us; rows visited in bin order so
+    // that neighbouring warps gather the same reference rows, 128 us — the kernel moves 292 MB of scattered 32-byte sectors
+    // through DRAM at 2.3 TB/s either way; profiles/r1m)
     if (nAi > 0)
         LAUNCH(k_emit_pairs, blocks_for(nAi * knn, 256), 256, 0, s, b->cand.p, eff, knn, nAi, b->newA.p, newR.p, poff.p, b->d_a_off.p, (int)W,
                b->d_ka_off.p, b->d_kr_off.p, b->a_src.p, b->r_src.p, sec->a_xy.p, sec->r_xy.p, sec->a_prob.p, sec->r_prob.p, sec->K,
