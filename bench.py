@@ -215,7 +215,7 @@ def run_reference(args, rank, world):
         return
     from oracle import oracle as O
     O.build()
-    cores = O.set_threads(os.cpu_count())       # torchrun exports OMP_NUM_THREADS=1: ask for every host core explicitly
+    cores = O.set_threads(len(os.sched_getaffinity(0)))   # torchrun exports OMP_NUM_THREADS=1: ask for every host core explicitly
     W = make_workload(args.tiles, 0, 1)
     rects, grid = window_rects(W, 0, 1)
     all_w = np.arange(len(rects))
@@ -266,6 +266,16 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: same_b200 has no CPU fallback")
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
+    all_cpus = os.sched_getaffinity(0)
+    if world > 1:
+        # one process per GPU: run on the CPUs next to this rank's GPU so that its pinned buffers are first-touched on the local
+        # NUMA node (eight ranks pushing ~230 MB per step each through one socket halve the PCIe rate otherwise)
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local_rank))
+        except Exception as e:      # affinity is an optimisation only
+            sys.stderr.write(f"[bench] rank {rank}: CPU affinity not set ({e})\n")
     if world > 1:
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # keep stdout = the one JSON line
         dist.init_process_group("nccl", device_id=device)
@@ -522,7 +532,8 @@ def main():
         if not args.no_cpu_baseline:
             from oracle import oracle as O
             O.build()
-            cores = O.set_threads(os.cpu_count())   # torchrun exports OMP_NUM_THREADS=1
+            os.sched_setaffinity(0, all_cpus)       # the CPU arm gets every host core back
+            cores = O.set_threads(len(all_cpus))    # torchrun exports OMP_NUM_THREADS=1
             c = cpu_arm(W, rects, target_s=12.0)
             line["cpu_baseline"] = {"value": c["pairs"] / c["seconds"], "unit": "pairs/s", "cores": cores, "kind": "port",
                                     "sample": f"candidate stage of all {len(rects)} windows x {c['reps']} repetitions = {c['seconds']:.1f} s of CPU work; "

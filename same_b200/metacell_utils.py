@@ -72,15 +72,38 @@ class MetaCell:
                 "n_metacell_triangles": int(getattr(self.metacell_delaunay, "shape", [0])[0])}
 
 
+def _reference_valid(p1, p2, p3, r_max, min_angle_deg):
+    """is_triangle_valid of the reference, expression for expression (src/metacell_utils.py:233-262): 1-D np.linalg.norm / np.dot."""
+    def angle(a, b, c):          # angle at b
+        v1, v2 = a - b, c - b
+        cos_angle = np.dot(v1, v2) / (np.linalg.norm(v1) * np.linalg.norm(v2))
+        return np.degrees(np.arccos(np.clip(cos_angle, -1, 1)))
+    if r_max is not None:
+        if max(np.linalg.norm(p2 - p1), np.linalg.norm(p3 - p2), np.linalg.norm(p1 - p3)) > r_max:
+            return False
+    if min_angle_deg is not None:
+        with np.errstate(invalid="ignore", divide="ignore"):
+            if min(angle(p2, p1, p3), angle(p1, p2, p3), angle(p1, p3, p2)) < min_angle_deg:
+                return False
+    return True
+
+
 def _valid_triangles(coords, tri, r_max, min_angle_deg):
-    """Edge length <= r_max (note: '>' drops, src/metacell_utils.py:251) and min angle >= min_angle_deg (:257-261)."""
+    """Edge length <= r_max (note: '>' drops, src/metacell_utils.py:251) and min angle >= min_angle_deg (:257-261).
+
+    Decided with array operations; the reference evaluates the same quantities through 1-D `np.linalg.norm` / `np.dot` (BLAS
+    ddot, fused multiply-add), which can differ from the array expressions in the last bit, so triangles whose longest edge or
+    smallest angle lies within a relative 1e-9 of a threshold are re-decided with the reference's own scalar expressions."""
     if len(tri) == 0:
         return np.zeros(0, bool)
     p = coords[tri]                                    # (T, 3, 2)
     ok = np.ones(len(tri), bool)
+    band = np.zeros(len(tri), bool)
     e = [np.linalg.norm(p[:, (k + 1) % 3] - p[:, k], axis=1) for k in range(3)]
     if r_max is not None:
-        ok &= ~(np.maximum(np.maximum(e[0], e[1]), e[2]) > r_max)
+        longest = np.maximum(np.maximum(e[0], e[1]), e[2])
+        ok &= ~(longest > r_max)
+        band |= np.abs(longest - r_max) <= 1e-9 * abs(r_max)
     if min_angle_deg is not None:
         angs = []
         for k in range(3):
@@ -90,6 +113,10 @@ def _valid_triangles(coords, tri, r_max, min_angle_deg):
             angs.append(np.degrees(np.arccos(np.clip(c, -1, 1))))
         mn = np.minimum(np.minimum(angs[0], angs[1]), angs[2])
         ok &= ~(mn < min_angle_deg)                    # NaN (degenerate) compares False -> kept, as in the reference
+        with np.errstate(invalid="ignore"):
+            band |= np.abs(mn - min_angle_deg) <= 1e-9 * max(abs(min_angle_deg), 1.0)
+    for t in np.flatnonzero(band):
+        ok[t] = _reference_valid(p[t, 0], p[t, 1], p[t, 2], r_max, min_angle_deg)
     return ok
 
 

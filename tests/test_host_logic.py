@@ -217,3 +217,16 @@ def test_highs_backend_solves_from_model_matrices():
     lhs = A @ full
     eq = mm["sense"] == "=="
     assert np.all(lhs[~eq] <= mm["rhs"][~eq] + 1e-6) and np.allclose(lhs[eq], mm["rhs"][eq], atol=1e-6)
+
+
+def test_metacell_filter_thresholds_follow_reference_expressions():
+    """Triangles exactly on the r_max / min-angle thresholds (a 3-4-5 lattice: edges of exactly r_max, a right isosceles triangle
+    against min_angle_deg=45) are decided by the reference's scalar expressions (src/metacell_utils.py:233-262)."""
+    from same_b200.metacell_utils import _reference_valid, _valid_triangles
+    coords = np.array([[0.0, 0.0], [30.0, 40.0], [30.0, 0.0], [0.0, 40.0], [10.0, 0.0], [0.0, 10.0], [7.3, 9.1], [50.0, 0.0]])
+    tri = np.array([[0, 1, 2], [0, 3, 1], [0, 4, 5], [4, 6, 5], [0, 7, 1]])
+    for r_max, ang in ((50.0, None), (50.0, 45.0), (49.99999999999999, 30.0), (None, 45.0), (50.00000000000001, 36.86989764584402)):
+        got = _valid_triangles(coords, tri, r_max, ang)
+        want = np.array([_reference_valid(coords[a], coords[b], coords[c], r_max, ang) for a, b, c in tri])
+        assert np.array_equal(got, want), (r_max, ang)
+    assert _valid_triangles(coords, tri, 50.0, None)[0] and not _valid_triangles(coords, tri, 49.99999999999999, None)[0]
