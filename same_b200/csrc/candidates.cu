@@ -439,7 +439,7 @@ __global__ void k_window_offsets(const i32 *__restrict__ newA, const i32 *__rest
 // (cnt > 0) and emitted pairs (eff) together — and write the kept aligned rows; blocks [tilesA, ..) scan the used flag of
 // the reference instances and write the kept reference rows.  Item nAi / nRi is a sentinel that receives the totals.
 constexpr int COMPACT_THREADS = 1024, COMPACT_ITEMS = 4;   // big tiles: one L2 round trip of look-back per 32 tiles
-__global__ void __launch_bounds__(COMPACT_THREADS) k_compact_frames(
+__global__ void __launch_bounds__(COMPACT_THREADS, 2) k_compact_frames(
     const i32 *__restrict__ cnt, const i32 *__restrict__ eff, const i32 *__restrict__ r_used, i64 nAi, i64 nRi, unsigned tilesA, ScanCtx scA, ScanCtx scR,
     const i32 *__restrict__ a_src, const i32 *__restrict__ r_src, const double2 *__restrict__ a_xy, const double2 *__restrict__ r_xy,
     const i32 *__restrict__ a_type, const double *__restrict__ a_size, const double *__restrict__ r_size, i32 *__restrict__ newA,

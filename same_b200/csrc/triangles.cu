@@ -198,7 +198,7 @@ __device__ __forceinline__ double angle_at(double2 p1, double2 p2, double2 p3) {
     return __dmul_rn(acos(c), 57.29577951308232);  // np.degrees: x * (180/pi)
 }
 
-__global__ void k_tri_classify(const int3 *__restrict__ tin, i64 Tin, const i32 *__restrict__ tin_off, const i32 *__restrict__ ka_off, int W,
+__global__ void __launch_bounds__(256, 4) k_tri_classify(const int3 *__restrict__ tin, i64 Tin, const i32 *__restrict__ tin_off, const i32 *__restrict__ ka_off, int W,
                                const double2 *__restrict__ ka_xy, const i32 *__restrict__ ka_type, double radius, int use_angle,
                                double min_angle, int ignore_same_type, unsigned char *__restrict__ cls, double *__restrict__ score,
                                i32 *__restrict__ band_idx, i32 *__restrict__ band_count) {
