@@ -263,7 +263,6 @@ struct Batch {
     DevBuf<double> x_dev;
     DevBuf<i32> match_j, match_p;       // [nKA]
     DevBuf<i32> sep_counts, cuts;
-    std::vector<i32> h_sep;
     DevBuf<i32> t_mask;
     DevBuf<double> area_before, area_after;
     DevBuf<unsigned char> flipped;
