@@ -240,6 +240,36 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def run_same_wall(tiles, seed=1):
+    """`run_same` wall clock, solver excluded (BASELINE metric, second half; configs[0] = 5 tiles, configs[1] = 25 tiles): the public
+    API end to end on host DataFrames — frames prepared, GPU stages, model arrays fetched, ONE separation call on a seeded
+    incumbent, post-solve analysis, matches frame + var_out built — with `IncumbentBackend` in place of Gurobi.  The parameters
+    are examples/synthetic/run_same.sh's; tools/time_reference_c2.py times the unmodified reference on the same input."""
+    import same_b200
+    from same_b200 import datagen
+    from same_b200.solver import IncumbentBackend
+    ref, qry, ct = datagen.make_section_pair(n_tiles=tiles, n_types=3, seed=seed)
+    optim = dict(radius=1.0, knn=8, max_matches=2, min_angle_deg=5, cell_id_col="Cell_Num_Old", dist_ct_coeff=1, ignore_same_type_triangles=False,
+                 delaunay_penalty=10, no_match_penalty=10000, penalty_coeff=100, lazy_constraints=True)
+    gurobi = dict(mip_gap=0.025, lazy_allowed_flip_fraction=0.0, time_limit=7200, mip_focus=2)
+
+    def inc(spec):
+        rp = np.asarray(spec.row_ptr, dtype=np.int64)
+        rows = np.repeat(np.arange(len(rp) - 1), np.diff(rp))
+        return incumbent(np.column_stack([rows, rows]), seed=seed)
+
+    import contextlib, io
+    times = []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        with contextlib.redirect_stdout(io.StringIO()):
+            matches, var_out = same_b200.run_same(ref, qry, list(ct), outprefix=None, optim_params=dict(optim), gurobi_params=dict(gurobi),
+                                                  solver=IncumbentBackend(inc))
+        times.append(time.perf_counter() - t0)
+    return {"cells": [len(ref), len(qry)], "pairs": len(var_out["x"]), "triangles": len(var_out["triangle_data"]["triangles"]),
+            "cuts": int(var_out["lazy_cuts_added"]), "matches": len(matches), "seconds": min(times), "seconds_first_call": times[0]}
+
+
 def workload_config(args, world, grid, n_windows):
     return {"workload": f"BASELINE configs[3]: synthetic {args.tiles}-tile section per GPU (~{args.tiles * 411 / 1e6:.2f}M ref / ~{args.tiles * 372 / 1e6:.2f}M query cells, K={N_TYPES}), "
                         f"candidate+cost+triangle+separation kernels, sliding window {grid[0]}x{grid[1]} per GPU",
@@ -529,6 +559,22 @@ def main():
                                                  "from pinned host frames + triangulation + incumbent to everything the host model builder reads"}}
         if halo:
             line["halo_exchange"] = halo
+        if world == 1 and not args.no_e2e:
+            try:
+                ref_cpu = {}
+                for t in (5, 25):
+                    try:
+                        ref_cpu[t] = json.load(open(os.path.join(ROOT, "profiles", f"reference_cpu_c2_{t}tiles.json")))["seconds"]
+                    except Exception:
+                        ref_cpu[t] = None
+                line["run_same_wall_clock"] = {
+                    "note": "public run_same on host DataFrames, solver replaced by one seeded incumbent + one separation call (IncumbentBackend); "
+                            "reference_seconds = the unmodified Python reference on the same input and rule, timed in the build container "
+                            "(tools/time_reference_c2.py; it cannot travel to the GPU box)",
+                    "configs[0] (5 tiles, ~2k cells)": dict(run_same_wall(5), reference_seconds=ref_cpu[5]),
+                    "configs[1] (25 tiles, ~10k cells)": dict(run_same_wall(25), reference_seconds=ref_cpu[25])}
+            except Exception as e:      # an extra, never the reason a bench line is missing
+                line["run_same_wall_clock"] = {"error": repr(e)}
         if not args.no_cpu_baseline:
             from oracle import oracle as O
             O.build()

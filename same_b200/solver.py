@@ -327,6 +327,31 @@ class HighsCutLoopBackend:
         return SolveResult(status, sol[:P], sol[P + nr:P + nr + na], sol[P:P + nr], sol[P + nr + na:], rt, cuts_added)
 
 
+class IncumbentBackend:
+    """No solver: `incumbent(spec) -> x[P]` supplies ONE candidate solution, the separation callback fires once on it (as a
+    MIPSOL event would) and q_t = 1 on every triangle that received a cut.  For timing and testing everything around the MIP
+    (KNN, costs, tables, separation, post-solve, frames) on machines without a Gurobi licence — the same rule the golden
+    fixtures were recorded with.  Never selected by default."""
+
+    name = "incumbent"
+
+    def __init__(self, incumbent):
+        self.incumbent = incumbent
+
+    def solve(self, spec: ModelSpec, separate: Optional[SeparationFn], gurobi_params: dict, outprefix=None, env_options=None, start=None):
+        t0 = time.perf_counter()
+        x = np.asarray(self.incumbent(spec), dtype=np.float64)
+        q = np.zeros(spec.n_tri)
+        cuts = 0
+        if separate is not None:
+            new = separate(x, 0)
+            cuts = len(new)
+            if cuts:
+                q[np.asarray(new)[:, 3].astype(np.int64)] = 1.0
+        rows_matched = np.add.reduceat(x > 0.5, spec.row_ptr[:-1].astype(np.int64)) > 0 if spec.n_pairs else np.zeros(spec.n_aligned, bool)
+        return SolveResult("optimal", x, (~rows_matched).astype(np.float64), np.zeros(spec.n_ref), q, time.perf_counter() - t0, cuts)
+
+
 _BACKENDS = {"gurobi": GurobiBackend, "gurobi_matrix": GurobiMatrixBackend, "highs": HighsCutLoopBackend}
 _default_backend = None
 
