@@ -662,6 +662,7 @@ void batch_candidates(Batch *b, double radius, int knn, int priority, double dis
     b->pend_renum = false;
     b->stage = 1;
     b->have_groups = false;
+    b->have_start = false;
     b->Tin = b->T = 0;
 }
 

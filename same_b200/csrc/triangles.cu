@@ -568,6 +568,7 @@ void batch_tri_finalize(Batch *b, int ignore_same_type, int ensure_min, int remo
         CK(cudaMemcpyAsync(b->d_ka_off.p, woff.p + 3 * (W + 1), sizeof(i32) * (W + 1), cudaMemcpyDeviceToDevice, s));
         CK(cudaMemcpyAsync(b->d_p_off.p, poff2.p, sizeof(i32) * (W + 1), cudaMemcpyDeviceToDevice, s));
         b->have_groups = false;
+        b->have_start = false;   // pairs and rows were renumbered
     }
 
     b->t_weight.alloc(b->T, s); b->t_sign.alloc(b->T, s); b->t_bounds.alloc(4 * b->T, s); b->t_argv.alloc(4 * b->T, s);
