@@ -249,6 +249,14 @@ def _stub(name, **attrs):
     return m
 
 
+def _any_callable(name):
+    """Module-level __getattr__ of the plotting stubs: any public name is a no-op callable; dunder lookups (`__file__`, `__path__`,
+    ...) fail as on a real module, so that tools which walk sys.modules (hypothesis, importlib) are not handed a function."""
+    if name.startswith("__") and name.endswith("__"):
+        raise AttributeError(name)
+    return lambda *a, **k: None
+
+
 def install_stubs():
     g = _stub("gurobipy", Model=Model, GRB=GRB, quicksum=quicksum, Env=Env, LinExpr=LinExpr, Var=Var)
     g.tupledict = tupledict
@@ -265,8 +273,8 @@ def install_stubs():
         for sub in ("pyplot", "patches", "colors", "gridspec", "lines", "cm", "collections"):
             s = _stub(f"matplotlib.{sub}")
             setattr(mp, sub, s)
-            s.__getattr__ = lambda n: (lambda *a, **k: None)  # type: ignore[attr-defined]
-        mp.__getattr__ = lambda n: (lambda *a, **k: None)  # type: ignore[attr-defined]
+            s.__getattr__ = _any_callable  # type: ignore[attr-defined]
+        mp.__getattr__ = _any_callable  # type: ignore[attr-defined]
     try:
         importlib.import_module("shapely.geometry")
     except Exception:

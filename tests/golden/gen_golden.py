@@ -53,7 +53,7 @@ def frame_arrays(df, commonCT, id_col, prefix):
         f"{prefix}_prob": df[list(commonCT)].to_numpy(np.float64),
         f"{prefix}_type_names": types.astype("U"),
         f"{prefix}_type_code": codes.astype(np.int32),
-        f"{prefix}_id": df[id_col].to_numpy(),
+        f"{prefix}_id": (lambda v: np.asarray(v.tolist(), dtype="U") if v.dtype.kind in "OUT" else v)(df[id_col].to_numpy()),
         f"{prefix}_index": df.index.to_numpy(),
     }
     if "size" in df.columns:

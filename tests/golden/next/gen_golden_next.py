@@ -227,7 +227,37 @@ def heart_case():
     print("heart:", len(ref_loader.MODELS), "window model(s),", len(matches), "matches,", sum(len(m.lazy) for m in ref_loader.MODELS), "cuts")
 
 
+def tongue_case():
+    """The shipped tongue sections (examples/tongue/data: 3,608 MERFISH reference / 4,671 protein query cells, K=5, fractional
+    probabilities x100, an int64 id column on one side and UUID strings on the other) through greedy_triangle_collapse(MS=1) +
+    sliding_window_matching with the parameters of examples/tongue/run_same.sh:22-47.  Real cross-modality data: costs with
+    non-integer probabilities, several windows with 300-unit overlaps."""
+    import pandas as pd
+    import shutil
+    from tests.golden import gen_golden as GG
+    d = os.path.join(ref_loader.REFERENCE_ROOT, "examples", "tongue", "data")
+    cts = ['Endothelial cells', 'Epithelial cells', 'Fibroblasts', 'Lymphoid cells', 'Myeloid cells']
+    frames = []
+    for f in ("mer_df.csv", "prot_df.csv"):
+        df = pd.read_csv(os.path.join(d, f), index_col=0)
+        df["X"], df["Y"] = df["transformed_x"], df["transformed_y"]
+        df[cts] = df[cts] * 100
+        df["cell_type"] = df[cts].idxmax(axis=1)
+        frames.append(df[["X", "Y", "Cell_Num", "cell_type"] + cts].copy())
+    ref, qry = frames
+    optim = dict(window_size=4000, overlap=300, min_cells_per_window=30, max_matches=1, radius=300, knn=8, no_match_penalty=10000,
+                 penalty_coeff=100, dist_ct_coeff=1, delaunay_penalty=10, cell_id_col="metacell_id", ref_metacell_match_multiplier=1,
+                 lazy_constraints=True, min_angle_deg=15)
+    gurobi = dict(mip_gap=0.05, lazy_allowed_flip_fraction=0.05)
+    GG.run_case("tongue", ref, qry, cts, optim, gurobi, "Cell_Num", seed=16, use_metacell=True, sliding=True, stage=False,
+                mc_params=dict(max_metacell_size=1, r_max=300, min_angle_deg=15, use_alpha_shape=False))
+    shutil.move(os.path.join(GOLD, "tongue.npz"), os.path.join(HERE, "tongue.npz"))
+
+
 if __name__ == "__main__":
+    if "--tongue" in sys.argv:
+        tongue_case()
+        sys.exit(0)
     if "--heart" in sys.argv:
         heart_case()
         sys.exit(0)

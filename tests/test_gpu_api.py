@@ -18,6 +18,7 @@ pytestmark = pytest.mark.gpu
 def fake_gurobi():
     from oracle import ref_loader
     saved = sys.modules.get("gurobipy")
+    before = set(sys.modules)
     ref_loader.install_stubs()
     Model = ref_loader.Model
     if not hasattr(Model, "_orig_optimize"):
@@ -34,6 +35,9 @@ def fake_gurobi():
     yield ref_loader
     Model.optimize = Model._orig_optimize
     ref_loader.INCUMBENT_FN = None
+    for name in set(sys.modules) - before:       # every stub module the fixture brought in goes away again
+        if name.split(".")[0] in ("gurobipy", "scanpy", "alphashape", "matplotlib", "shapely"):
+            sys.modules.pop(name, None)
     if saved is not None:
         sys.modules["gurobipy"] = saved
     else:
@@ -300,5 +304,34 @@ def test_heart_metacells_vs_reference(fake_gurobi, tmp_path):
                                                 gurobi_params=dict(gurobi))
     finally:
         os.chdir(cwd)
+    _compare_models(fake_gurobi, g)
+    _compare_matches(got, g)
+
+
+def test_tongue_sections_vs_reference(fake_gurobi, tmp_path):
+    """The shipped tongue sections (3,608 MERFISH reference / 4,671 protein query cells, K=5, fractional probabilities, UUID-string
+    ids on one side) through greedy_triangle_collapse(MS=1) + sliding_window_matching with the paper script's parameters
+    (examples/tongue/run_same.sh): every window's model and the matches frame equal the unmodified reference's record."""
+    import same_b200
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "next", "tongue.npz")
+    if not os.path.exists(path):
+        pytest.skip("tongue fixture not generated")
+    g = dict(np.load(path, allow_pickle=False))
+    ref_df, al_df = golden_frame(g, "ref"), golden_frame(g, "aligned")
+    ct = [str(c) for c in g["commonCT"]]
+    optim, gurobi = golden_params(g, "optim"), golden_params(g, "gurobi")
+    mcp = dict(max_metacell_size=1, r_max=300, min_angle_deg=15, use_alpha_shape=False)
+    mc_al = same_b200.greedy_triangle_collapse(al_df, cell_type_col="cell_type", original_idx_col="Cell_Num", return_object=True, **mcp)
+    mc_rf = same_b200.greedy_triangle_collapse(ref_df, cell_type_col="cell_type", original_idx_col="Cell_Num", return_object=True, **mcp)
+    assert np.array_equal(np.asarray(mc_al.metacell_delaunay, dtype=np.int64), g["mc_aligned_delaunay"])
+    fake_gurobi.INCUMBENT_FN = _incumbent_fn(int(g["seed"]))
+    cwd = os.getcwd()
+    os.chdir(tmp_path)
+    try:
+        got = same_b200.sliding_window_matching(mc_rf, mc_al, commonCT=ct, outprefix=str(tmp_path / "out"), optim_params=dict(optim),
+                                                gurobi_params=dict(gurobi))
+    finally:
+        os.chdir(cwd)
+    assert int(g["n_models"]) > 1
     _compare_models(fake_gurobi, g)
     _compare_matches(got, g)
