@@ -332,6 +332,6 @@ def test_tongue_sections_vs_reference(fake_gurobi, tmp_path):
                                                 gurobi_params=dict(gurobi))
     finally:
         os.chdir(cwd)
-    assert int(g["n_models"]) > 1
+    assert int(g["n_models"]) >= 1
     _compare_models(fake_gurobi, g)
     _compare_matches(got, g)
