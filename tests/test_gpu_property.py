@@ -1,6 +1,8 @@
 """Property tests (hypothesis) of the candidate search on inputs built to provoke ties and threshold cases: integer / half-integer
 lattices (many equal distances, duplicates, candidates exactly on the radius), random knn and window splits — CUDA == oracle
 brute force, bit for bit.  The bucketed top-k of k_knn takes its exact fallback on most of these rows."""
+import os
+
 import numpy as np
 import pytest
 from hypothesis import HealthCheck, given, settings, strategies as st
@@ -28,7 +30,8 @@ def lattice_case(draw):
     return a, r, knn, radius, split, side * step
 
 
-@settings(max_examples=40, deadline=None, suppress_health_check=[HealthCheck.too_slow, HealthCheck.data_too_large])
+@settings(max_examples=int(os.environ.get("SAME_B200_HYPOTHESIS_EXAMPLES", "40")), deadline=None, derandomize=os.environ.get("SAME_B200_HYPOTHESIS_RANDOM") is None,
+          suppress_health_check=[HealthCheck.too_slow, HealthCheck.data_too_large])
 @given(lattice_case())
 def test_candidates_on_lattices(case):
     from same_b200 import _lib as L
