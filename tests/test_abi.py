@@ -49,3 +49,25 @@ def test_product_does_not_import_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
                 assert "same_oracle" not in src, f
+
+
+def test_next_rows_have_no_cpu_fallback_either():
+    """The MIP start / metacell collapse entry points fail loudly without a device (no numpy fallback behind them)."""
+    import numpy as np
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import same_b200
+    from same_b200 import _lib as L
+    from same_b200 import datagen, init_helpers
+    from same_b200.device import collapse_select, greedy_select
+    with pytest.raises(L.SameError):
+        greedy_select(np.array([[0, 1], [1, 2]]), np.array([1.0, 2.0]), 3)
+    with pytest.raises(L.SameError):
+        collapse_select(np.zeros((3, 2)), np.zeros(3, np.int32), np.ones(3), np.array([[0, 1, 2]]), 3)
+    with pytest.raises(L.SameError):
+        init_helpers.compute_mip_start_pairs(valid_pairs=[(0, 0)], costs=[1.0], n_aligned=1, n_ref=1, aligned_sizes=np.ones(1), no_match_penalty=5.0,
+                                             max_matches=1, init_method="greedy", verbose=False)
+    ref, qry, ct = datagen.make_section_pair(n_tiles=1, seed=3)
+    with pytest.raises(L.SameError):
+        same_b200.greedy_triangle_collapse(qry, max_metacell_size=3, r_max=1.5, min_angle_deg=10)
