@@ -15,9 +15,13 @@ namespace same {
 
 constexpr int MAX_RINGS = 4;
 // reference cells per bin: the own bin plus ring 1 (nine bins) should hold the k nearest with room to spare, and no more —
-// smaller bins prune better (measured at knn = 8 on the 1 M-cell section: 4/bin 250 us, 6/bin 234 us, 8/bin 254 us, 12/bin
-// 279 us, 24/bin 359 us)
-static double target_per_bin(int knn) { return std::max(4.0, 0.75 * knn); }
+// smaller bins prune better (measured at knn = 8 on the 1 M-cell section with the bucketed top-k: 4/bin 194 us, 5/bin 182 us,
+// 6/bin 179 us, 8/bin 192 us, 10/bin 199 us)
+static double target_per_bin(int knn) {
+    static const char *env = getenv("SAME_B200_BIN_TARGET");   // tuning knob for tools/dev_knn_sweep.sh (cells per bin = value * knn / 8)
+    const double scale = env ? atof(env) / 8.0 : 0.75;
+    return std::max(scale > 0.0 ? 2.0 : 4.0, (scale > 0.0 ? scale : 0.75) * knn);
+}
 constexpr int MAX_BINS_AXIS = 2048;
 
 // ---- binning -------------------------------------------------------------------------
