@@ -430,13 +430,15 @@ __global__ void k_fill_i32(i32 *p, i64 n, i32 v) {
     if (i < n) p[i] = v;
 }
 // off3[0..W] / [W+1..2W+1] / [2W+2..3W+2]: kept-aligned, kept-ref and pair offsets of each window
+// (also written to the three device-side offset arrays the later kernels read, instead of three device-to-device copies)
 __global__ void k_window_offsets(const i32 *__restrict__ newA, const i32 *__restrict__ newR, const i32 *__restrict__ poff,
-                                 const i32 *__restrict__ a_off, const i32 *__restrict__ r_off, int W, i32 *__restrict__ off3) {
+                                 const i32 *__restrict__ a_off, const i32 *__restrict__ r_off, int W, i32 *__restrict__ off3,
+                                 i32 *__restrict__ ka_off, i32 *__restrict__ kr_off, i32 *__restrict__ p_off) {
     int w = blockIdx.x * blockDim.x + threadIdx.x;
     if (w > W) return;
-    off3[w] = newA[a_off[w]];
-    off3[W + 1 + w] = newR[r_off[w]];
-    off3[2 * (W + 1) + w] = poff[a_off[w]];
+    const i32 ka = newA[a_off[w]], kr = newR[r_off[w]], po = poff[a_off[w]];
+    off3[w] = ka; off3[W + 1 + w] = kr; off3[2 * (W + 1) + w] = po;
+    ka_off[w] = ka; kr_off[w] = kr; p_off[w] = po;
 }
 
 // Frame compaction in one launch (src/utils.py:734-741): blocks [0, tilesA) scan the aligned instances — kept flag
@@ -648,11 +650,9 @@ void batch_candidates(Batch *b, double radius, int knn, int priority, double dis
                sec->a_xy.p, sec->r_xy.p, sec->a_type.p, sec->a_size.p, sec->r_size.p, b->newA.p, newR.p, poff.p, b->keepA.p, b->ka_xy.p, b->ka_type.p,
                b->ka_size.p, b->row_ptr.p, b->keepR.p, b->kr_xy.p, b->kr_size.p);
     }
-    LAUNCH(k_window_offsets, blocks_for(W + 1, 128), 128, 0, s, b->newA.p, newR.p, poff.p, b->d_a_off.p, b->d_r_off.p, (int)W, off3.p);
     b->d_ka_off.alloc(W + 1, s); b->d_kr_off.alloc(W + 1, s); b->d_p_off.alloc(W + 1, s);
-    CK(cudaMemcpyAsync(b->d_ka_off.p, off3.p, sizeof(i32) * (W + 1), cudaMemcpyDeviceToDevice, s));
-    CK(cudaMemcpyAsync(b->d_kr_off.p, off3.p + (W + 1), sizeof(i32) * (W + 1), cudaMemcpyDeviceToDevice, s));
-    CK(cudaMemcpyAsync(b->d_p_off.p, off3.p + 2 * (W + 1), sizeof(i32) * (W + 1), cudaMemcpyDeviceToDevice, s));
+    LAUNCH(k_window_offsets, blocks_for(W + 1, 128), 128, 0, s, b->newA.p, newR.p, poff.p, b->d_a_off.p, b->d_r_off.p, (int)W, off3.p, b->d_ka_off.p,
+           b->d_kr_off.p, b->d_p_off.p);
     // (measured and not kept: one thread per row with 8 gather chains in flight, 224 us vs 129 us; rows visited in bin order so
     // that neighbouring warps gather the same reference rows, 128 us — the kernel moves 292 MB of scattered 32-byte sectors
     // through DRAM at 2.3 TB/s either way; profiles/r1m)
