@@ -189,6 +189,13 @@ SAME_API int same_greedy_select(int device, int64_t n, int degree, const int32_t
 SAME_API int same_collapse_select(int device, int64_t n, const double *xy, const int32_t *type, const double *size, int64_t n_tri,
                                   const int32_t *tri, double max_size, uint8_t *selected, double *perimeter, int32_t *rounds);
 
+/* Member means of merged metacells (src/metacell_utils.py:446-474): out[g, c] = mean over the rows pos[ptr[g] .. ptr[g+1]) of
+ * values[row, c], summed in the order pandas / numpy sum them (pairwise summation), divided by the member count; NaN for an
+ * empty group.  values[n_rows, n_cols] row-major, ptr[n_groups + 1], pos[ptr[n_groups]] HD; out[n_groups, n_cols] host.
+ * Inputs must not contain NaN (pandas would skip them; the caller keeps such columns on its own path). */
+SAME_API int same_segment_mean(int device, int64_t n_rows, int64_t n_cols, const double *values, int64_t n_groups, const int64_t *ptr,
+                               const int32_t *pos, double *out);
+
 /* ---- results -------------------------------------------------------------------------- */
 /* W+1 offsets (in elements) of array `what` */
 SAME_API int same_batch_offsets(same_batch_t *b, int what, int64_t *off);

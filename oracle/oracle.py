@@ -255,3 +255,16 @@ def collapse_select(xy, type_codes, sizes, tri, max_size):
     lib().oracle_collapse_score(C.c_int64(T), _p(tri), _p(xy), _p(tc), _p(sz), C.c_double(float(max_size)), _p(cand), _p(per))
     sel, _ = greedy_select(tri, per, len(xy), cand)
     return sel, per
+
+
+def segment_mean(values, ptr, pos):
+    """Member means in pandas' / numpy's summation order (metacell_utils.py:446-474) -> [G, C]."""
+    values = _f64(values)
+    if values.ndim == 1:
+        values = values.reshape(-1, 1)
+    ptr = np.ascontiguousarray(ptr, dtype=np.int64)
+    pos = _i32(pos)
+    G = len(ptr) - 1
+    out = np.empty((G, values.shape[1]))
+    lib().oracle_segment_mean(C.c_int64(values.shape[0]), C.c_int64(values.shape[1]), _p(values), C.c_int64(G), _p(ptr), _p(pos), _p(out))
+    return out

@@ -518,3 +518,34 @@ ORACLE_API void oracle_collapse_score(i64 n_tri, const i32 *tri, const double *x
         cand[t] = same && !(total > max_size);
     }
 }
+
+/* f2  member means of merged metacells                 src/metacell_utils.py:446-474
+ * rows[col].mean() = pandas nanmean = numpy pairwise sum / count (verified against pandas in tests/test_oracle_golden.py). */
+static double pairwise_sum_ref(const double *v, i64 C, i64 c, const i32 *pos, i64 n) {
+    if (n < 8) {
+        double r = 0.0;
+        for (i64 i = 0; i < n; ++i) r += v[(i64)pos[i] * C + c];
+        return r;
+    }
+    if (n <= 128) {
+        double r[8];
+        for (int k = 0; k < 8; ++k) r[k] = v[(i64)pos[k] * C + c];
+        i64 i = 8;
+        for (; i < n - (n % 8); i += 8)
+            for (int k = 0; k < 8; ++k) r[k] += v[(i64)pos[i + k] * C + c];
+        double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+        for (; i < n; ++i) res += v[(i64)pos[i] * C + c];
+        return res;
+    }
+    i64 n2 = n / 2;
+    n2 -= n2 % 8;
+    return pairwise_sum_ref(v, C, c, pos, n2) + pairwise_sum_ref(v, C, c, pos + n2, n - n2);
+}
+ORACLE_API void oracle_segment_mean(i64 n_rows, i64 C, const double *values, i64 G, const i64 *ptr, const i32 *pos, double *out) {
+    (void)n_rows;
+    for (i64 g = 0; g < G; ++g)
+        for (i64 c = 0; c < C; ++c) {
+            const i64 n = ptr[g + 1] - ptr[g];
+            out[g * C + c] = n > 0 ? pairwise_sum_ref(values, C, c, pos + ptr[g], n) / (double)n : NAN;
+        }
+}

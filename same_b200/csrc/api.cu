@@ -291,6 +291,19 @@ int same_collapse_select(int device, int64_t n, const double *xy, const int32_t 
     });
 }
 
+int same_segment_mean(int device, int64_t n_rows, int64_t n_cols, const double *values, int64_t n_groups, const int64_t *ptr, const int32_t *pos,
+                      double *out) {
+    return guarded([&] {
+        REQUIRE(n_rows >= 0 && n_cols >= 0 && n_groups >= 0, SAME_E_ARG, "negative size");
+        REQUIRE(n_rows < (1ll << 31), SAME_E_LIMIT, "at most 2^31 rows");
+        if (n_groups == 0 || n_cols == 0) return;
+        REQUIRE(values && ptr && out, SAME_E_ARG, "NULL argument");
+        const int64_t n_members = ptr[n_groups];    // ptr is host memory in every caller of this stateless form
+        REQUIRE(n_members >= 0 && (n_members == 0 || pos), SAME_E_ARG, "bad member list");
+        segment_mean_arrays(device, n_rows, n_cols, values, n_groups, ptr, n_members, pos, out);
+    });
+}
+
 int same_postsolve_arrays(int device, int64_t n_tri, const int32_t *tri, int64_t n_aligned, const double *a_xy, int64_t n_ref, const double *r_xy,
                           const int32_t *match_j, int32_t *mask, double *area_before, double *area_after, uint8_t *flipped) {
     return guarded([&] {

@@ -304,6 +304,8 @@ void greedy_select_arrays(int device, i64 n, int degree, const i32 *nodes, const
 void collapse_select_arrays(int device, i64 n, const double *xy, const i32 *type, const double *size, i64 T, const i32 *tri, double max_size,
                             unsigned char *selected, double *perim_out, i32 *rounds_out);
 
+void segment_mean_arrays(int device, i64 n_rows, i64 C, const double *values, i64 G, const i64 *ptr, i64 n_members, const i32 *pos, double *out);
+
 // upload a small host vector of i64 offsets as i32 device array
 void upload_offsets(const std::vector<i64> &h, DevBuf<i32> &d, cudaStream_t s);
 

@@ -238,6 +238,69 @@ void collapse_select_arrays(int device, i64 n, const double *xy, const i32 *type
     CK(cudaStreamDestroy(s));
 }
 
+// ---- member means of merged metacells (src/metacell_utils.py:446-474) ---------------------------------------------
+// `rows[col].mean()` of the reference is pandas' nanmean = numpy's pairwise sum of the gathered members divided by their
+// count (checked against pandas in tests/test_oracle_golden.py).  The sum is reproduced operation for operation: fewer than 8
+// values are added left to right starting from 0; up to 128 values go through eight running sums combined as
+// ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) plus a sequential tail; longer lists split in halves (first half rounded down to a
+// multiple of 8).  One thread per (merged metacell, column).
+__device__ double pairwise_sum_ref(const double *__restrict__ V, i64 C, i64 c, const i32 *__restrict__ pos, i64 n) {
+    if (n < 8) {
+        double r = 0.0;
+        for (i64 i = 0; i < n; ++i) r = __dadd_rn(r, V[(i64)pos[i] * C + c]);
+        return r;
+    }
+    if (n <= 128) {
+        double r[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) r[k] = V[(i64)pos[k] * C + c];
+        i64 i = 8;
+        for (; i < n - (n % 8); i += 8)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) r[k] = __dadd_rn(r[k], V[(i64)pos[i + k] * C + c]);
+        double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])), __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+        for (; i < n; ++i) res = __dadd_rn(res, V[(i64)pos[i] * C + c]);
+        return res;
+    }
+    i64 n2 = n / 2;
+    n2 -= n2 % 8;
+    return __dadd_rn(pairwise_sum_ref(V, C, c, pos, n2), pairwise_sum_ref(V, C, c, pos + n2, n - n2));
+}
+__global__ void k_member_mean(const double *__restrict__ V, i64 C, const i32 *__restrict__ pos, const i64 *__restrict__ ptr, i64 G,
+                              double *__restrict__ out) {
+    const i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= G * C) return;
+    const i64 g = t / C, c = t - g * C;
+    const i64 lo = ptr[g], n = ptr[g + 1] - lo;
+    out[t] = n > 0 ? __ddiv_rn(pairwise_sum_ref(V, C, c, pos + lo, n), (double)n) : __longlong_as_double(0x7ff8000000000000ll);
+}
+
+void segment_mean_arrays(int device, i64 n_rows, i64 C, const double *values, i64 G, const i64 *ptr, i64 n_members, const i32 *pos, double *out) {
+    CK(cudaSetDevice(device));
+    cudaStream_t s;
+    CK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    try {
+        DevBuf<double> d_v, d_out;
+        DevBuf<i32> d_pos;
+        DevBuf<i64> d_ptr;
+        d_v.alloc(n_rows * C, s); d_out.alloc(G * C, s); d_pos.alloc(n_members, s); d_ptr.alloc(G + 1, s);
+        if (G > 0 && C > 0) {
+            CK(cudaMemcpyAsync(d_v.p, values, sizeof(double) * (size_t)(n_rows * C), cudaMemcpyDefault, s));
+            if (n_members) CK(cudaMemcpyAsync(d_pos.p, pos, sizeof(i32) * (size_t)n_members, cudaMemcpyDefault, s));
+            CK(cudaMemcpyAsync(d_ptr.p, ptr, sizeof(i64) * (size_t)(G + 1), cudaMemcpyDefault, s));
+            LAUNCH(k_member_mean, blocks_for(G * C, 128), 128, 0, s, d_v.p, C, d_pos.p, d_ptr.p, G, d_out.p);
+            CK(cudaMemcpyAsync(out, d_out.p, sizeof(double) * (size_t)(G * C), cudaMemcpyDefault, s));
+        }
+        CK(cudaStreamSynchronize(s));
+    } catch (...) {
+        cudaStreamSynchronize(s);
+        cudaStreamDestroy(s);
+        throw;
+    }
+    CK(cudaStreamSynchronize(s));
+    CK(cudaStreamDestroy(s));
+}
+
 // ---- greedy MIP start over a whole batch (src/init_helpers.py:110-132) ---------------------------------------
 // one thread per kept aligned row: prefer_match = (best cost of the row) < no_match_penalty * size
 __global__ void k_start_rows(const i32 *__restrict__ row_ptr, const double *__restrict__ cost, const double *__restrict__ ka_size, i64 nKA,

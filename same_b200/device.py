@@ -165,6 +165,21 @@ def collapse_select(xy, type_codes, sizes, tri, max_size, device: int = 0):
     return sel.astype(bool), per
 
 
+def segment_mean(values, ptr, pos, device: int = 0):
+    """out[g] = mean of values[pos[ptr[g]:ptr[g+1]]] per column, in pandas' / numpy's summation order (same_segment_mean)."""
+    values = np.ascontiguousarray(values, dtype=np.float64)
+    if values.ndim == 1:
+        values = values.reshape(-1, 1)
+    ptr = np.ascontiguousarray(ptr, dtype=np.int64)
+    pos = np.ascontiguousarray(pos, dtype=np.int32)
+    G = len(ptr) - 1
+    if len(pos) != ptr[-1] or (len(pos) and (pos.min() < 0 or pos.max() >= len(values))):
+        raise ValueError("member positions out of range")
+    out = np.empty((G, values.shape[1]), dtype=np.float64)
+    L.check(L.load().same_segment_mean(device, values.shape[0], values.shape[1], L.ptr(values), G, L.ptr(ptr), L.ptr(pos), L.ptr(out)))
+    return out
+
+
 class WindowBatch:
     """A list of windows of one section (same_batch_create).  `rects=None` = the whole section."""
 

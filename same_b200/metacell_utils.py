@@ -149,7 +149,13 @@ def greedy_triangle_collapse(aligned_df, max_metacell_size=3, max_iterations=100
     if aligned_df[original_idx_col].duplicated().any():
         dups = aligned_df.loc[aligned_df[original_idx_col].duplicated(), original_idx_col].head(5).tolist()
         raise ValueError(f"'{original_idx_col}' must be unique per original cell. Found duplicates (examples): {dups}")
-    indexed = aligned_df.set_index(original_idx_col, drop=False)
+    id_index = pd.Index(aligned_df[original_idx_col])
+    # numeric columns whose member means run on the GPU: float64 / integer / bool without NaN (pandas sums exactly these in float64,
+    # pairwise); anything else keeps pandas' own per-group mean
+    gpu_cols = [c for c in aligned_df.columns
+                if aligned_df[c].dtype.kind in "iub" or (aligned_df[c].dtype == np.float64 and not aligned_df[c].isna().any())]
+    gpu_col_at = {c: k for k, c in enumerate(gpu_cols)}
+    V = aligned_df[gpu_cols].to_numpy(dtype=np.float64) if gpu_cols else np.zeros((len(aligned_df), 0))
 
     coords0 = aligned_df[[x_col, y_col]].to_numpy()
     if len(coords0) >= 4:
@@ -195,28 +201,38 @@ def greedy_triangle_collapse(aligned_df, max_metacell_size=3, max_iterations=100
         if len(chosen) == 0:
             break
         batch = chosen[np.argsort(perim[chosen], kind="stable")].tolist()   # merged metacells are appended in selection order
-        merged, remove = [], []
-        for t in batch:
-            va, vb, vc = tri[t]
-            remove.extend([va, vb, vc])
-            members = mdf.iloc[va]["members"] + mdf.iloc[vb]["members"] + mdf.iloc[vc]["members"]
-            rows = indexed.loc[members]
-            m = {x_col: rows[x_col].mean(), y_col: rows[y_col].mean(), cell_type_col: mdf.iloc[va][cell_type_col],
-                 "size": tot[t], "members": members}
-            for col in mdf.columns:
-                if col in [x_col, y_col, cell_type_col, "size", "members", metacell_idx_col] + id_cols_present:
-                    continue
-                if pd.api.types.is_numeric_dtype(mdf[col]):
-                    if col in aligned_df.columns:
-                        m[col] = rows[col].mean()
-                    else:
-                        m[col] = np.average([mdf.iloc[i][col] for i in (va, vb, vc)], weights=[mdf.iloc[i]["size"] for i in (va, vb, vc)])
-                else:
-                    m[col] = mdf.iloc[va][col]
-            merged.append(m)
-        mdf = mdf.drop(remove).reset_index(drop=True)
-        if merged:
-            mdf = pd.concat([mdf, pd.DataFrame(merged)], ignore_index=True)
+        # merge step (src/metacell_utils.py:436-489): members of the three vertices concatenated, true means over the ORIGINAL
+        # member cells for every numeric column — on the GPU in pandas' summation order (same_segment_mean) —, first vertex's
+        # value for the others; merged metacells are appended in selection order
+        tb = tri[batch]
+        mem = mdf["members"].tolist()
+        members = [mem[a] + mem[b] + mem[c] for a, b, c in tb.tolist()]
+        ptr = np.r_[0, np.cumsum([len(m) for m in members])].astype(np.int64)
+        pos = id_index.get_indexer([v for m in members for v in m])
+        skip = [x_col, y_col, cell_type_col, "size", "members", metacell_idx_col] + id_cols_present
+        other = [c for c in mdf.columns if c not in skip]
+        mean_cols = [x_col, y_col] + [c for c in other if pd.api.types.is_numeric_dtype(mdf[c]) and c in aligned_df.columns]
+        on_gpu = [c for c in mean_cols if c in gpu_col_at]
+        means = {}
+        if on_gpu:
+            from .device import segment_mean
+            got = segment_mean(V[:, [gpu_col_at[c] for c in on_gpu]], ptr, pos)
+            means = {c: got[:, k] for k, c in enumerate(on_gpu)}
+        for c in mean_cols:
+            if c not in means:      # NaNs present or a dtype pandas sums differently (float32, object numbers): pandas itself, per group
+                ser = aligned_df[c].reset_index(drop=True)
+                means[c] = np.array([ser.iloc[pos[ptr[g]:ptr[g + 1]]].mean() for g in range(len(members))])
+        new = {x_col: means[x_col], y_col: means[y_col], cell_type_col: mdf[cell_type_col].to_numpy()[tb[:, 0]], "size": tot[batch],
+               "members": pd.Series(members, dtype=object)}
+        for c in other:
+            if c in means:
+                new[c] = means[c]
+            elif pd.api.types.is_numeric_dtype(mdf[c]):      # numeric column that the original frame does not have: size-weighted average
+                new[c] = [np.average([mdf.iloc[i][c] for i in v], weights=[mdf.iloc[i]["size"] for i in v]) for v in tb.tolist()]
+            else:
+                new[c] = mdf[c].to_numpy()[tb[:, 0]]
+        mdf = mdf.drop(tb.ravel().tolist()).reset_index(drop=True)
+        mdf = pd.concat([mdf, pd.DataFrame(new)], ignore_index=True)
         mdf[metacell_idx_col] = range(len(mdf))
 
     final_coords = mdf[[x_col, y_col]].values

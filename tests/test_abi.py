@@ -60,11 +60,13 @@ def test_next_rows_have_no_cpu_fallback_either():
     import same_b200
     from same_b200 import _lib as L
     from same_b200 import datagen, init_helpers
-    from same_b200.device import collapse_select, greedy_select
+    from same_b200.device import collapse_select, greedy_select, segment_mean
     with pytest.raises(L.SameError):
         greedy_select(np.array([[0, 1], [1, 2]]), np.array([1.0, 2.0]), 3)
     with pytest.raises(L.SameError):
         collapse_select(np.zeros((3, 2)), np.zeros(3, np.int32), np.ones(3), np.array([[0, 1, 2]]), 3)
+    with pytest.raises(L.SameError):
+        segment_mean(np.ones((3, 2)), np.array([0, 3]), np.array([0, 1, 2], np.int32))
     with pytest.raises(L.SameError):
         init_helpers.compute_mip_start_pairs(valid_pairs=[(0, 0)], costs=[1.0], n_aligned=1, n_ref=1, aligned_sizes=np.ones(1), no_match_penalty=5.0,
                                              max_matches=1, init_method="greedy", verbose=False)

@@ -196,3 +196,15 @@ def test_collapse_select_vs_oracle(lattice):
     assert np.array_equal(sel, want_sel) and sel.sum() > 100
     if lattice:
         assert len(np.unique(per)) < 0.2 * len(per)
+
+
+def test_segment_mean_vs_oracle():
+    """same_segment_mean == oracle (== pandas mean, tests/test_oracle_golden.py) bit for bit, incl. groups beyond 8 and 128 members."""
+    from same_b200.device import segment_mean
+    rng = np.random.default_rng(2)
+    V = rng.uniform(-1, 1, (20000, 5)) * 10.0 ** rng.integers(-3, 4, (20000, 5))
+    sizes = np.r_[rng.integers(1, 12, 5000), [127, 128, 129, 300, 1000, 5000]]
+    ptr = np.r_[0, np.cumsum(sizes)]
+    pos = rng.integers(0, len(V), ptr[-1]).astype(np.int32)
+    assert np.array_equal(segment_mean(V, ptr, pos), O.segment_mean(V, ptr, pos))
+    assert segment_mean(V, np.array([0]), np.zeros(0, np.int32)).shape == (0, 5)

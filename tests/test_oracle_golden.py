@@ -207,6 +207,7 @@ def test_oracle_collapse_equals_reference(monkeypatch):
     from same_b200 import datagen, device
     from tests.util import golden_frame
     monkeypatch.setattr(device, "collapse_select", lambda xy, tc, sz, tri, ms, device=0: O.collapse_select(xy, tc, sz, tri, ms))
+    monkeypatch.setattr(device, "segment_mean", lambda v, ptr, pos, device=0: O.segment_mean(v, ptr, pos))
     g = _next_golden("collapse.npz")
     for case in g["cases"]:
         tiles, seed, ms, r_max, ang = g[f"{case}__params"]
@@ -214,6 +215,7 @@ def test_oracle_collapse_equals_reference(monkeypatch):
         mc = same_b200.greedy_triangle_collapse(qry, max_metacell_size=int(ms), r_max=float(r_max), min_angle_deg=None if ang < 0 else float(ang),
                                                 return_object=True)
         assert np.array_equal(mc.metacell_df[["X", "Y"]].to_numpy(), g[f"{case}__xy"]), case
+        assert np.array_equal(mc.metacell_df[ct].to_numpy(), g[f"{case}__prob"]), case
         assert np.array_equal(np.asarray([m for ms_ in mc.metacell_df["members"] for m in ms_]), g[f"{case}__members_flat"]), case
         assert np.array_equal(np.asarray(mc.metacell_delaunay).reshape(-1, 3), g[f"{case}__delaunay"]), case
     h = dict(np.load(os.path.join(os.path.dirname(__file__), "golden", "next", "heart_mc10.npz")))
@@ -222,4 +224,24 @@ def test_oracle_collapse_equals_reference(monkeypatch):
                                                 r_max=50.0, min_angle_deg=15.0, use_alpha_shape=False)
         assert np.array_equal(mc.metacell_df[["X", "Y"]].to_numpy(), h[f"{tag}_xy"]), tag
         assert np.array_equal(mc.metacell_df["size"].to_numpy(), h[f"{tag}_size"]), tag
+        assert np.array_equal(mc.metacell_df[[str(c) for c in h["commonCT"]]].to_numpy(), h[f"{tag}_prob"]), tag
         assert np.array_equal(np.asarray(mc.metacell_delaunay, dtype=np.int64).reshape(-1, 3), h[f"{tag}_delaunay"]), tag
+
+
+def test_oracle_segment_mean_equals_pandas_mean():
+    """oracle_segment_mean == `rows[col].mean()` as the reference computes member means (src/metacell_utils.py:446-474): pandas
+    nanmean = numpy pairwise sum / count, for group sizes on both sides of numpy's 8- and 128-element thresholds."""
+    import pandas as pd
+    rng = np.random.default_rng(1)
+    V = rng.uniform(-1, 1, (4000, 3)) * 10.0 ** rng.integers(-3, 4, (4000, 3))
+    sizes = np.r_[rng.integers(1, 20, 300), [7, 8, 9, 15, 16, 17, 127, 128, 129, 136, 200, 257, 1000]]
+    ptr = np.r_[0, np.cumsum(sizes)]
+    pos = rng.integers(0, len(V), ptr[-1]).astype(np.int32)
+    out = O.segment_mean(V, ptr, pos)
+    df = pd.DataFrame(V, columns=list("abc"))
+    for g in range(len(sizes)):
+        rows = df.iloc[pos[ptr[g]:ptr[g + 1]]]
+        assert [rows[c].mean() for c in "abc"] == out[g].tolist(), (g, sizes[g])
+    ints = rng.integers(0, 1000, 4000)                       # integer columns are summed in float64 too
+    assert O.segment_mean(ints.astype(np.float64), ptr[:50], pos[:ptr[49]])[:, 0].tolist() == \
+        [pd.Series(ints).iloc[pos[ptr[g]:ptr[g + 1]]].mean() for g in range(49)]
