@@ -532,6 +532,10 @@ def main():
                             "The largest HBM-bound kernel of the path is reported in `hbm_kernel`."}
         if dom in ncu_metrics:
             roofline["ncu"] = dict(ncu_metrics[dom], source="profiles/ncu_metrics.json (ncu --set full of this kernel, same command)")
+        try:        # compute-side denominator, measured in this run: FP64 FMA micro-kernel
+            roofline["fp64_peak_tflops_measured"] = L.fp64_peak_tflops(local_rank)
+        except Exception as e:
+            roofline["fp64_peak_tflops_measured"] = None
         hb = max((n for n in kernels if n in alg and n != dom), key=lambda n: kernels[n]["avg_ms"] * kernels[n]["launches_per_step"])
         roofline["hbm_kernel"] = {"kernel": hb, "bound": "hbm", "achieved": kernels[hb]["achieved_gbs"], "peak": hbm_peak, "unit": "GB/s",
                                   "frac": kernels[hb]["frac_of_hbm_peak"], "traffic": traffic.get(hb), "avg_launch_ms": kernels[hb]["avg_ms"],

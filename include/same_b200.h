@@ -215,6 +215,9 @@ SAME_API int64_t same_elem_size(int what);
 SAME_API int same_batch_sync(same_batch_t *b);
 /* stream the batch runs on (cudaStream_t), for event timing by the caller */
 SAME_API void *same_batch_stream(same_batch_t *b);
+/* FP64 vector peak of the device in TFLOP/s, measured with an FMA micro-kernel (eight independent chains per thread, best of
+ * three launches): the compute-side roofline denominator bench.py records next to the measured HBM copy peak. */
+SAME_API int same_measure_fp64_peak(int device, double *tflops);
 /* number of kernel launches issued by this library in this process (bench.py "gpu_launches") */
 SAME_API int64_t same_launch_count(void);
 /* Per-kernel device timing for bench.py's roofline block: while enabled every launch is bracketed by CUDA

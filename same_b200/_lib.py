@@ -49,7 +49,7 @@ SYMBOLS = [
     "same_batch_groups", "same_batch_separation", "same_batch_postsolve", "same_batch_offsets", "same_batch_length",
     "same_batch_get", "same_elem_size", "same_batch_sync", "same_batch_stream", "same_launch_count",
     "same_profile_enable", "same_profile_report", "same_batch_get_many", "same_pinned_alloc", "same_pinned_free",
-    "same_postsolve_arrays", "same_batch_mip_start", "same_greedy_select", "same_collapse_select", "same_segment_mean",
+    "same_postsolve_arrays", "same_batch_mip_start", "same_greedy_select", "same_collapse_select", "same_segment_mean", "same_measure_fp64_peak",
 ]
 
 
@@ -111,6 +111,7 @@ def load():
     lib.same_greedy_select.argtypes = [i32, i64, i32, vp, vp, vp, i64, vp, vp, C.POINTER(C.c_int32)]
     lib.same_collapse_select.argtypes = [i32, i64, vp, vp, vp, i64, vp, dbl, vp, vp, C.POINTER(C.c_int32)]
     lib.same_segment_mean.argtypes = [i32, i64, i64, vp, i64, vp, vp, vp]
+    lib.same_measure_fp64_peak.argtypes = [i32, C.POINTER(C.c_double)]
     lib.same_profile_enable.argtypes = [i32]
     lib.same_profile_report.argtypes = [C.c_char_p, i64]
     lib.same_profile_report.restype = i64
@@ -131,6 +132,12 @@ def ptr(a):
     if isinstance(a, int):
         return C.c_void_p(a)
     return a.ctypes.data_as(C.c_void_p)
+
+
+def fp64_peak_tflops(device: int = 0) -> float:
+    v = C.c_double(0.0)
+    check(load().same_measure_fp64_peak(device, C.byref(v)))
+    return v.value
 
 
 def launch_count() -> int:

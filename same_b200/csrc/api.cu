@@ -90,6 +90,9 @@ int same_device_count(int *count) {
     return guarded([&] { CK(cudaGetDeviceCount(count)); });
 }
 int64_t same_launch_count(void) { return (int64_t)g_launches.load(); }
+int same_measure_fp64_peak(int device, double *tflops) {
+    return guarded([&] { REQUIRE(tflops, SAME_E_ARG, "NULL output"); *tflops = measure_fp64_peak(device); });
+}
 
 int same_profile_enable(int on) {
     return guarded([&] {

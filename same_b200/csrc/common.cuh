@@ -306,6 +306,8 @@ void collapse_select_arrays(int device, i64 n, const double *xy, const i32 *type
 
 void segment_mean_arrays(int device, i64 n_rows, i64 C, const double *values, i64 G, const i64 *ptr, i64 n_members, const i32 *pos, double *out);
 
+double measure_fp64_peak(int device);
+
 // upload a small host vector of i64 offsets as i32 device array
 void upload_offsets(const std::vector<i64> &h, DevBuf<i32> &d, cudaStream_t s);
 

@@ -459,6 +459,44 @@ void batch_subset(Batch *b) {
     subset_frames(b);
 }
 
+// ---- FP64 vector peak (bench.py: the compute-side denominator SURVEY.md §8d asks to measure in the same run) ---------------
+__global__ void __launch_bounds__(256) k_fp64_fma(double *__restrict__ out, int iters) {
+    double a[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] = 1.0 + 1e-3 * (double)(threadIdx.x + k);
+    const double b = 1.0000001, c = 1e-9;
+    for (int it = 0; it < iters; ++it)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a[k] = __fma_rn(a[k], b, c);     // eight independent chains per thread
+    double r = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r += a[k];
+    out[(i64)blockIdx.x * blockDim.x + threadIdx.x] = r;
+}
+double measure_fp64_peak(int device) {
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    const int blocks = prop.multiProcessorCount * 8, iters = 8192;
+    double *d = nullptr;
+    CK(cudaMalloc((void **)&d, sizeof(double) * (size_t)blocks * 256));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {
+        CK(cudaEventRecord(e0, 0));
+        k_fp64_fma<<<blocks, 256>>>(d, iters);
+        CK(cudaEventRecord(e1, 0));
+        CK(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0) best = std::min(best, ms);
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    CK(cudaFree(d));
+    return 2.0 * 8.0 * (double)iters * 256.0 * (double)blocks / ((double)best * 1e-3) / 1e12;
+}
+
 // ---- vertex ids -> section rows ------------------------------------------------------
 __global__ void k_iota64(i64 *p, i64 n) {
     i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;

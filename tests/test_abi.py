@@ -13,7 +13,7 @@ def test_header_symbols_exported():
     build.build()
     lib = L.load()
     header = open(os.path.join(ROOT, "include", "same_b200.h")).read()
-    declared = sorted(set(re.findall(r"^SAME_API [^;(]*?\b(same_[a-z_]+)\(", header, flags=re.M)))
+    declared = sorted(set(re.findall(r"^SAME_API [^;(]*?\b(same_[a-z0-9_]+)\(", header, flags=re.M)))
     assert declared, "no declarations found in the header"
     for name in declared:
         assert hasattr(lib, name), f"{name} is declared in include/same_b200.h but not exported"
