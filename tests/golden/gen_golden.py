@@ -328,6 +328,21 @@ def main(only=None):
     else:
         print("[golden] simulated_st: probability columns not found, skipped:", list(sa.columns)[:12])
 
+    # ---- simulated_elastic: the reference's second saved run (elastically deformed copy of the same 144 cells) ----
+    ea = pd.read_csv(os.path.join(ex, "simulated_elastic/aligned_df.csv"))
+    er = pd.read_csv(os.path.join(ex, "simulated_elastic/ref_df.csv"))
+    for d in (ea, er):
+        if "cell_type" not in d.columns and "Cell Type" in d.columns:
+            d["cell_type"] = d["Cell Type"].astype(str)
+    el_ct = sorted(set(ea["cell_type"]))
+    if all(c in ea.columns for c in el_ct):
+        idc_e = "Cell_Num_Old" if "Cell_Num_Old" in ea.columns else ea.columns[0]
+        o4e = dict(radius=3, knn=8, cell_id_col=idc_e, min_angle_deg=15, ignore_same_type_triangles=True)
+        cases.append(("simulated_elastic", lambda: run_case(
+            "simulated_elastic", er, ea, el_ct, o4e, dict(lazy_allowed_flip_fraction=0.0), idc_e, seed=18)))
+    else:
+        print("[golden] simulated_elastic: probability columns not found, skipped:", list(ea.columns)[:12])
+
     # ---- seeded datagen section, K=3, sliding window 3x3 with overlap (driver a13) ----
     r5, q5, ct5 = datagen.make_section_pair(n_tiles=4, n_types=3, seed=5)
     o5 = dict(window_size=12, overlap=3, min_cells_per_window=10, radius=1.0, knn=5, max_matches=1,
