@@ -55,12 +55,24 @@ def pinned_empty(shape, dtype):
     return np.frombuffer(raw, dtype=dtype, count=count).reshape(shape)
 
 
+def default_device() -> int:
+    """GPU of this process: SAME_B200_DEVICE if set, else LOCAL_RANK (one process per GPU under torchrun), else 0."""
+    import os
+    for key in ("SAME_B200_DEVICE", "LOCAL_RANK"):
+        v = os.environ.get(key)
+        if v is not None and v.strip().lstrip("-").isdigit():
+            return int(v)
+    return 0
+
+
 class Section:
-    """Both frames of one tissue section pair on the GPU (same_section_create)."""
+    """Both frames of one tissue section pair on the GPU (same_section_create).  `device=None` = `default_device()`."""
 
     def __init__(self, a_xy, r_xy, a_prob, r_prob, a_type=None, r_type=None, a_size=None, r_size=None,
-                 device: int = 0, stream=None):
+                 device=None, stream=None):
         lib = L.load()
+        if device is None:
+            device = default_device()
         self._keep = []
         a_xy, r_xy = _f64(a_xy, (-1, 2)), _f64(r_xy, (-1, 2))
         self.n_aligned, self.n_ref = len(a_xy), len(r_xy)
@@ -130,7 +142,7 @@ class Section:
         self.close()
 
 
-def greedy_select(nodes, key, n_nodes, eligible=None, device: int = 0, return_rounds=False):
+def greedy_select(nodes, key, n_nodes, eligible=None, device=None, return_rounds=False):
     """Ordered greedy selection with disjoint endpoints (same_greedy_select): items visited in ascending (key, index) order,
     an item is taken iff it is eligible and none of its endpoints was taken before.  nodes [n, 1..3] int -> bool [n]."""
     nodes = np.ascontiguousarray(nodes, dtype=np.int32)
@@ -144,11 +156,12 @@ def greedy_select(nodes, key, n_nodes, eligible=None, device: int = 0, return_ro
         raise ValueError("keys must not be NaN")
     el = None if eligible is None else np.ascontiguousarray(eligible, dtype=np.uint8).reshape(n)
     sel, used, r = np.zeros(n, np.uint8), np.zeros(int(n_nodes), np.uint8), C.c_int32(0)
+    device = default_device() if device is None else device
     L.check(L.load().same_greedy_select(device, n, degree, L.ptr(nodes), L.ptr(key), L.ptr(el), int(n_nodes), L.ptr(sel), L.ptr(used), C.byref(r)))
     return (sel.astype(bool), r.value) if return_rounds else sel.astype(bool)
 
 
-def collapse_select(xy, type_codes, sizes, tri, max_size, device: int = 0):
+def collapse_select(xy, type_codes, sizes, tri, max_size, device=None):
     """One collapse iteration of greedy_triangle_collapse on the GPU (same_collapse_select): candidate test, perimeter in the
     reference's arithmetic, ordered disjoint selection.  -> (selected bool [T], perimeter float64 [T])"""
     xy = np.ascontiguousarray(xy, dtype=np.float64).reshape(-1, 2)
@@ -160,12 +173,13 @@ def collapse_select(xy, type_codes, sizes, tri, max_size, device: int = 0):
     if T and (tri.min() < 0 or tri.max() >= n):
         raise ValueError("triangle vertex out of range")
     sel, per, r = np.zeros(T, np.uint8), np.zeros(T, np.float64), C.c_int32(0)
+    device = default_device() if device is None else device
     L.check(L.load().same_collapse_select(device, n, L.ptr(xy), L.ptr(tc), L.ptr(sz), T, L.ptr(tri), float(max_size), L.ptr(sel), L.ptr(per),
                                           C.byref(r)))
     return sel.astype(bool), per
 
 
-def segment_mean(values, ptr, pos, device: int = 0):
+def segment_mean(values, ptr, pos, device=None):
     """out[g] = mean of values[pos[ptr[g]:ptr[g+1]]] per column, in pandas' / numpy's summation order (same_segment_mean)."""
     values = np.ascontiguousarray(values, dtype=np.float64)
     if values.ndim == 1:
@@ -176,6 +190,7 @@ def segment_mean(values, ptr, pos, device: int = 0):
     if len(pos) != ptr[-1] or (len(pos) and (pos.min() < 0 or pos.max() >= len(values))):
         raise ValueError("member positions out of range")
     out = np.empty((G, values.shape[1]), dtype=np.float64)
+    device = default_device() if device is None else device
     L.check(L.load().same_segment_mean(device, values.shape[0], values.shape[1], L.ptr(values), G, L.ptr(ptr), L.ptr(pos), L.ptr(out)))
     return out
 

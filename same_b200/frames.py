@@ -23,7 +23,7 @@ def frame_arrays(df: pd.DataFrame, commonCT: Sequence[str]):
     return xy, prob, size
 
 
-def build_section(aligned_df: pd.DataFrame, ref_df: pd.DataFrame, commonCT: Sequence[str], device: int = 0, stream=None):
+def build_section(aligned_df: pd.DataFrame, ref_df: pd.DataFrame, commonCT: Sequence[str], device=None, stream=None):
     """Upload both frames (same_section_create)."""
     from .device import Section
     a_xy, a_prob, a_size = frame_arrays(aligned_df, commonCT)

@@ -15,7 +15,7 @@ import numpy as np
 def compute_mip_start_pairs(*, valid_pairs: Sequence[Tuple[int, int]], costs: Sequence[float], n_aligned: int, n_ref: int,
                             aligned_sizes: np.ndarray, no_match_penalty: float, max_matches: int, init_method: str,
                             init_big_m: float = 1e9, init_hungarian_max_n: int = 2000, verbose: bool = True,
-                            device: int = 0) -> Tuple[List[Tuple[int, int, int]], Set[int]]:
+                            device=None) -> Tuple[List[Tuple[int, int, int]], Set[int]]:
     """-> (chosen (aligned_i, ref_j, var_idx) in selection order, set of unmatched aligned indices)  (src/init_helpers.py:46-177)"""
     method = str(init_method).lower()
     if method not in {"greedy", "hungarian"}:

@@ -12,7 +12,7 @@ from . import _lib as L
 _PAIRS = ((0, 1), (0, 2), (1, 2))
 
 
-def postsolve_arrays(tri, a_xy, r_xy, match_j, device=0):
+def postsolve_arrays(tri, a_xy, r_xy, match_j, device=None):
     """Stateless GPU call (same_postsolve_arrays) -> mask, area_before, area_after, flipped."""
     tri = np.ascontiguousarray(tri, dtype=np.int32).reshape(-1, 3)
     a_xy = np.ascontiguousarray(a_xy, dtype=np.float64).reshape(-1, 2)
@@ -20,6 +20,8 @@ def postsolve_arrays(tri, a_xy, r_xy, match_j, device=0):
     mj = np.ascontiguousarray(match_j, dtype=np.int32)
     t = len(tri)
     mask, ab, aa, fl = np.zeros(t, np.int32), np.zeros(t), np.zeros(t), np.zeros(t, np.uint8)
+    from .device import default_device
+    device = default_device() if device is None else device
     L.check(L.load().same_postsolve_arrays(device, t, L.ptr(tri), len(a_xy), L.ptr(a_xy), len(r_xy), L.ptr(r_xy), L.ptr(mj),
                                            L.ptr(mask), L.ptr(ab), L.ptr(aa), L.ptr(fl)))
     return mask, ab, aa, fl.astype(bool)

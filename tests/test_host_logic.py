@@ -230,3 +230,17 @@ def test_metacell_filter_thresholds_follow_reference_expressions():
         want = np.array([_reference_valid(coords[a], coords[b], coords[c], r_max, ang) for a, b, c in tri])
         assert np.array_equal(got, want), (r_max, ang)
     assert _valid_triangles(coords, tri, 50.0, None)[0] and not _valid_triangles(coords, tri, 49.99999999999999, None)[0]
+
+
+def test_default_device_follows_local_rank(monkeypatch):
+    """One process per GPU: the device of a process is SAME_B200_DEVICE, else LOCAL_RANK (torchrun), else 0."""
+    from same_b200.device import default_device
+    monkeypatch.delenv("SAME_B200_DEVICE", raising=False)
+    monkeypatch.delenv("LOCAL_RANK", raising=False)
+    assert default_device() == 0
+    monkeypatch.setenv("LOCAL_RANK", "3")
+    assert default_device() == 3
+    monkeypatch.setenv("SAME_B200_DEVICE", "5")
+    assert default_device() == 5
+    monkeypatch.setenv("SAME_B200_DEVICE", "junk")
+    assert default_device() == 3
