@@ -335,3 +335,31 @@ def test_tongue_sections_vs_reference(fake_gurobi, tmp_path):
     assert int(g["n_models"]) >= 1
     _compare_models(fake_gurobi, g)
     _compare_matches(got, g)
+
+
+def test_highs_cut_loop_same_solution_on_both_pipelines():
+    """A real MIP solver in the loop (scipy/HiGHS: solve -> separate -> add cuts -> re-solve, capped at 24 cuts): `run_same` on the
+    GPU path and the same loop over the CPU oracle's arrays with the oracle's separation reach the same cuts and the same
+    solution vector — "final matches identical given identical candidates and costs" exercised with an actual solver."""
+    import same_b200
+    from oracle import oracle as O
+    from same_b200.solver import HighsCutLoopBackend
+    from tests.test_host_logic import _spec_from_oracle
+    from tests.test_oracle_golden import _pipeline
+    g = load_golden("simulated_st")
+    ref_df, al_df = golden_frame(g, "ref"), golden_frame(g, "aligned")
+    ct = [str(c) for c in g["commonCT"]]
+    optim = golden_params(g, "optim")
+    gurobi = {"time_limit": 120, "mip_gap": 0.0, "lazy_allowed_flip_fraction": 0.0, "lazy_max_cuts_per_incumbent": 12, "lazy_max_cuts": 24}
+    import contextlib, io
+    with contextlib.redirect_stdout(io.StringIO()):
+        got, var_out = same_b200.run_same(ref_df, al_df, ct, outprefix=None, optim_params=dict(optim), gurobi_params=dict(gurobi), solver="highs")
+    _, spec = _spec_from_oracle("simulated_st")
+    o, res = _pipeline(g)
+    r_xy = g["ref_xy"][res["keepR"]]
+    cpu = HighsCutLoopBackend().solve(spec, lambda x, n: O.lazy_cuts(x, res["pairs"], res["tri"], res["sign"], r_xy, len(res["keepA"]), 0.0, 12, 24, n),
+                                      dict(gurobi))
+    assert cpu.status == "optimal" and cpu.cuts_added == var_out["lazy_cuts_added"] == 24
+    assert np.array_equal(np.asarray(var_out["x"]) > 0.5, cpu.x > 0.5)
+    sel = np.flatnonzero(cpu.x > 0.5)
+    assert np.array_equal(got["aligned_idx"].to_numpy(), res["pairs"][sel, 0]) and np.array_equal(got["ref_idx"].to_numpy(), res["pairs"][sel, 1])
