@@ -396,3 +396,36 @@ def test_edge_cases():
             b.tri_finalize(True)
         with pytest.raises(L.SameError):
             b.candidates(1.0, 1000)
+
+
+def test_batched_windows_priority_vs_oracle():
+    """Cell-type priority KNN (src/knn_utils.py:31-65) for several overlapping windows in one batch: the claim of a reference cell
+    is per window (the same cell seen from two windows is claimed independently), pairs / costs / groups equal the oracle's."""
+    from same_b200 import _lib as L
+    from same_b200 import datagen
+    from same_b200.device import Section
+    ref, qry, ct = datagen.make_section_pair(n_tiles=9, n_types=3, seed=21)
+    a_xy, r_xy = qry[["X", "Y"]].to_numpy(), ref[["X", "Y"]].to_numpy()
+    a_prob, r_prob = qry[ct].to_numpy(), ref[ct].to_numpy()
+    lut = {c: i for i, c in enumerate(ct)}
+    tA, tR = qry["cell_type"].map(lut).to_numpy(np.int32), ref["cell_type"].map(lut).to_numpy(np.int32)
+    sA, sR = np.ones(len(qry)), np.ones(len(ref))
+    ext = max(a_xy.max(), r_xy.max()) + 1
+    step, ws = ext / 3 + 0.01, ext / 3 + 3.0
+    rects = np.array([[i * step, i * step + ws, j * step, j * step + ws] for i in range(3) for j in range(3)])
+    kw = dict(radius=1.3, knn=6, dist_ct_coeff=2.5, min_angle_deg=15, ignore_same_type_triangles=True, ignore_knn_if_matched=True, max_matches=1)
+    n_single = 0
+    with Section(a_xy, r_xy, a_prob, r_prob, tA, tR, sA, sR) as sec, sec.batch(rects) as b:
+        b.candidates(1.3, 6, True, 2.5)
+        b.groups(1, None)
+        po, ko, ro = b.offsets(L.PAIRS), b.offsets(L.KEEP_A), b.offsets(L.KEEP_R)
+        for w in range(len(rects)):
+            res = _oracle_window(a_xy, r_xy, a_prob, r_prob, tA, tR, sA, sR, rects[w], **kw)   # runs the priority rule (pipeline.py)
+            assert np.array_equal(b.get(L.KEEP_A, int(ko[w]), int(ko[w + 1])), res["rowsA"][res["keepA"]])
+            assert np.array_equal(b.get(L.KEEP_R, int(ro[w]), int(ro[w + 1])), res["rowsR"][res["keepR"]])
+            assert np.array_equal(b.get(L.PAIRS, int(po[w]), int(po[w + 1])), res["pairs"])
+            assert np.array_equal(b.get(L.COST, int(po[w]), int(po[w + 1])), res["cost"])
+            m = b.window_model(w)
+            assert np.array_equal(m["ref_group_node"], res["ref_group_node"]) and np.array_equal(m["ref_group_idx"], res["ref_group_idx"])
+            n_single += int((np.bincount(res["pairs"][:, 0]) == 1).sum())
+    assert n_single > 50, "the priority rule should have collapsed many rows to their single claimed pair"
