@@ -439,11 +439,15 @@ def main():
             gc.collect()
             gc.disable()                                         # a gen-2 collection inside the timed loop costs 10+ ms
             t0 = time.perf_counter()
+            its = []
             for _ in range(n_e2e):
+                t1 = time.perf_counter()
                 npairs, nbytes = fn()
+                its.append(round((time.perf_counter() - t1) * 1e3, 2))
             barrier()
             ms = (time.perf_counter() - t0) * 1e3 / n_e2e
             gc.enable()
+            sys.stderr.write(f"[bench] e2e {fn.__name__} iterations ms: {its}\n")
             return ms, npairs, nbytes
 
         c_ms, c_P, c_d2h = timed(cand_once)
