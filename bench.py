@@ -409,7 +409,7 @@ def main():
     e2e = None
     if not args.no_e2e:
         sec.close()
-        n_e2e = max(2, min(args.steps, 5))
+        n_e2e = max(2, min(args.steps, 10))
         x_pin = pinned(x_dev["t"].cpu().numpy())                 # the incumbent comes from the host solver in real use
         saved = x_dev["t"]
         import gc
