@@ -505,7 +505,7 @@ def main():
             "k_postsolve": 12 * s["T"] + 20 * s["nKA"] + 16 * s["nKR"] + 21 * s["T"],
             "k_tri_classify": 12 * s["Tin"] + 20 * s["nKA"] + 9 * s["Tin"],
             "k_tri_tables": 12 * s["T"] + 24 * s["nKA"] + (8 + 1 + 32 + 16) * s["T"],
-            "k_match_rows": 8 * s["P"] + 8 * s["P"] + 4 * s["nKA"] + 8 * s["nKA"],
+            "k_match_rows": 8 * s["P"] + 4 * s["nKA"] + 8 * s["nKA"] + 8 * s["nKA"],   # x streamed; row_ptr; ONE pair read per row; two outputs
         }
         traffic = {}
         try:
