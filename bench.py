@@ -89,7 +89,6 @@ def exchange_halo(W, rank, world, device):
 
 def window_rects(W, rank, world):
     """Window grid over the global section (same.py:481-488); this rank runs the window rows that START in its strip."""
-    from same_b200 import windows as WN
     x_min = min(W["a_xy"][:, 0].min(), W["r_xy"][:, 0].min())
     x_max = max(W["a_xy"][:, 0].max(), W["r_xy"][:, 0].max())
     y_lo, y_hi = W["strip_lo"], W["strip_lo"] + W["strip_h"]

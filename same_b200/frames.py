@@ -1,7 +1,7 @@
 """DataFrame contract -> flat arrays for the C-ABI (reference README.md:95-101, src/same.py:934-970)."""
 from __future__ import annotations
 
-from typing import List, Optional, Sequence
+from typing import Sequence
 
 import numpy as np
 import pandas as pd

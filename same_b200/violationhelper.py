@@ -3,7 +3,6 @@
 only folds the resulting bit masks into the reference's report dictionary."""
 from __future__ import annotations
 
-import ctypes as C
 
 import numpy as np
 

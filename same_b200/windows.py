@@ -8,7 +8,7 @@ contract.  `enumerate_windows` reproduces that walk but onl
 """
 from __future__ import annotations
 
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from typing import Callable, List, Optional, Sequence, Set, Tuple
 
 import numpy as np
