@@ -299,34 +299,42 @@ __global__ void __launch_bounds__(128) k_knn(const double2 *__restrict__ sa_xy, 
         knn_exact_one(q, g, cbx, cby, bin_start, sr_xy, sr_inst, r2, knn, out, cnt + inst, r_used);
         return;
     }
-    // exact d2 of the survivors; unused slots sort last
-    double bd[KCAP];
+    // Survivors in different buckets are already in exact order; only when two live slots share a bucket (rare off a lattice)
+    // are the exact d2 recomputed and the list put in (d2, instance) order by an odd-even transposition pass.
     i32 bj[KCAP];
     int found = 0;
+    bool shared_bucket = false;
 #pragma unroll
     for (int u = 0; u < KCAP; ++u) {
         const bool ok = (u >= head) & (bk[u] != KEY_NONE);
-        const double2 p = sr_xy[bs[u]];
-        const double ddx = __dsub_rn(p.x, q.x), ddy = __dsub_rn(p.y, q.y);
-        bd[u] = ok ? __dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy)) : ((u < head) ? -INFINITY : INFINITY);
         bj[u] = ok ? sr_inst[bs[u]] : ((u < head) ? (i32)0x80000000 : 0x7fffffff);
         found += ok;
+        if (u > 0) shared_bucket |= ok & (bk[u] == bk[u - 1]) & (u - 1 >= head);
     }
-    // the list is sorted by bucket; inside a bucket the exact (d2, instance) order is restored here
-    bool swapped = true;
-    while (swapped) {
-        swapped = false;
+    if (shared_bucket) {
+        double bd[KCAP];
 #pragma unroll
-        for (int par = 0; par < 2; ++par)
+        for (int u = 0; u < KCAP; ++u) {
+            const bool ok = (u >= head) & (bk[u] != KEY_NONE);
+            const double2 p = sr_xy[bs[u]];
+            const double ddx = __dsub_rn(p.x, q.x), ddy = __dsub_rn(p.y, q.y);
+            bd[u] = ok ? __dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy)) : ((u < head) ? -INFINITY : INFINITY);
+        }
+        bool swapped = true;
+        while (swapped) {
+            swapped = false;
 #pragma unroll
-            for (int u = par; u + 1 < KCAP; u += 2) {
-                const bool sw = cand_less(bd[u + 1], bj[u + 1], bd[u], bj[u]);
-                const double d0 = bd[u], d1 = bd[u + 1];
-                const i32 j0 = bj[u], j1 = bj[u + 1];
-                bd[u] = sw ? d1 : d0; bd[u + 1] = sw ? d0 : d1;
-                bj[u] = sw ? j1 : j0; bj[u + 1] = sw ? j0 : j1;
-                swapped |= sw;
-            }
+            for (int par = 0; par < 2; ++par)
+#pragma unroll
+                for (int u = par; u + 1 < KCAP; u += 2) {
+                    const bool sw = cand_less(bd[u + 1], bj[u + 1], bd[u], bj[u]);
+                    const double d0 = bd[u], d1 = bd[u + 1];
+                    const i32 j0 = bj[u], j1 = bj[u + 1];
+                    bd[u] = sw ? d1 : d0; bd[u + 1] = sw ? d0 : d1;
+                    bj[u] = sw ? j1 : j0; bj[u + 1] = sw ? j0 : j1;
+                    swapped |= sw;
+                }
+        }
     }
     cnt[inst] = found;
 #pragma unroll
