@@ -191,18 +191,24 @@ __global__ void __launch_bounds__(128) k_knn(const double2 *__restrict__ sa_xy, 
     bin_of(g, q, cbx, cby);
     const double px = q.x - g.x0, py = q.y - g.y0;
 
-    // Sorted keys in registers, right-aligned: slots [KCAP-knn, KCAP) hold the list (ascending), the slots before it
-    // are zero keys that never move (no key is < 0), so the k-th best is always the LAST slot (a static register
-    // index; a runtime index would push the arrays into local memory).
+    // Sorted keys in registers, right-aligned: slots [KCAP-knn, KCAP) hold the list (ascending), the slots before it hold
+    // zero keys that never move, so the k-th best is always the LAST slot (a static register index; a runtime index would push
+    // the array into local memory).  A key = distance bucket (high word of d2 without its SB lowest bits, + one bucket so that
+    // no real key is below the zero keys) | id of the POSITION SLOT that remembers where the candidate sits in the sorted
+    // array.  Keys are all distinct, so an insertion is two integer min/max per slot; the evicted key's slot id is the free
+    // position slot, written with one shared-memory store ([slot][thread], conflict-free).
+    constexpr int SB = KCAP <= 4 ? 2 : (KCAP <= 8 ? 3 : (KCAP <= 16 ? 4 : 5));
+    constexpr unsigned SLOT = (1u << SB) - 1u, ONE = 1u << SB, NONE_B = KEY_NONE + ONE;
+    __shared__ i32 spos[KCAP * 128];
     unsigned bk[KCAP];
-    i32 bs[KCAP];
     const int head = KCAP - knn;
 #pragma unroll
-    for (int s = 0; s < KCAP; ++s) { bk[s] = (s < head) ? 0u : KEY_NONE; bs[s] = 0; }
+    for (int s = 0; s < KCAP; ++s) bk[s] = ((s < head) ? 0u : NONE_B) | (unsigned)s;
 #define last_k bk[KCAP - 1]
     bool tie = false;
-    // Candidates with d2 > thr cannot enter: thr = min(r2, upper edge of the k-th key's bucket), kept as its two words
-    // (upper edge = high word last_k + 1, low word 0; it is below r2 exactly when last_k + 1 <= high word of r2).
+    // Candidates with d2 > thr cannot enter: thr = min(r2, upper edge of the k-th key's bucket), kept as its two words (the
+    // upper edge has the bucket field of last_k as its high word — the one-bucket offset cancels — and a zero low word; it is
+    // below r2 exactly when that high word is <= the high word of r2).
     const unsigned r2_hi = (unsigned)__double2hiint(r2), r2_lo = (unsigned)__double2loint(r2);
     double thr = r2;
     // Bin pruning runs in fp32 on lower bounds of the point-to-bin distance: fx, fy (position inside the own bin) and the
@@ -267,26 +273,22 @@ __global__ void __launch_bounds__(128) k_knn(const double2 *__restrict__ sa_xy, 
                     const double d2 = h ? dB : dA;
                     const i32 s = s0 + h;
                     if (d2 <= thr) {
-                        const unsigned key = (unsigned)__double2hiint(d2);
-                        if (key < last_k) {
-                            // branch-free sorted insertion: lt[u] = candidate sorts before slot u (computed on the old
-                            // values); slot u takes slot u-1 if lt[u-1], the candidate if lt[u] only, else keeps its value
-                            const unsigned old_last = last_k;
-                            bool lt[KCAP];
+                        const unsigned hb = ((unsigned)__double2hiint(d2) & ~SLOT) + ONE, lb = last_k & ~SLOT;
+                        if (hb < lb) {
+                            const unsigned free_slot = last_k & SLOT;           // the evicted entry's position slot
+                            const unsigned nk = hb | free_slot;
+                            spos[free_slot * 128 + threadIdx.x] = s;
+                            // sorted insertion of a key that differs from every key in the list (top down: each slot reads the
+                            // OLD value of its left neighbour): slot u keeps its key, takes the new one, or takes slot u-1's
 #pragma unroll
-                            for (int u = 0; u < KCAP; ++u) lt[u] = key < bk[u];
-#pragma unroll
-                            for (int u = KCAP - 1; u > 0; --u) {
-                                bk[u] = lt[u - 1] ? bk[u - 1] : (lt[u] ? key : bk[u]);
-                                bs[u] = lt[u - 1] ? bs[u - 1] : (lt[u] ? s : bs[u]);
-                            }
-                            bk[0] = lt[0] ? key : bk[0];
-                            bs[0] = lt[0] ? s : bs[0];
-                            tie = last_k == old_last;   // the dropped candidate shares the new k-th's bucket (or the list is not full yet)
-                            const bool below = last_k + 1u <= r2_hi;   // never for KEY_NONE: r2 is finite
-                            thr = __hiloint2double((int)(below ? last_k + 1u : r2_hi), (int)(below ? 0u : r2_lo));
+                            for (int u = KCAP - 1; u > 0; --u) bk[u] = min(bk[u], max(bk[u - 1], nk));
+                            bk[0] = min(bk[0], nk);
+                            const unsigned nb = last_k & ~SLOT;
+                            tie = nb == lb;   // the dropped candidate shares the new k-th's bucket (or the list is not full yet)
+                            const bool below = nb <= r2_hi;   // never for the empty-slot key: r2 is finite
+                            thr = __hiloint2double((int)(below ? nb : r2_hi), (int)(below ? 0u : r2_lo));
                             thrf = __double2float_ru(thr);
-                        } else if (key == last_k) {
+                        } else if (hb == lb) {
                             tie = true;
                         }
                     }
@@ -295,27 +297,28 @@ __global__ void __launch_bounds__(128) k_knn(const double2 *__restrict__ sa_xy, 
         }
     }
     i32 *out = cand + (i64)inst * knn;
-    if (tie && last_k != KEY_NONE) {
+    if (tie && (last_k & ~SLOT) != NONE_B) {
         knn_exact_one(q, g, cbx, cby, bin_start, sr_xy, sr_inst, r2, knn, out, cnt + inst, r_used);
         return;
     }
     // Survivors in different buckets are already in exact order; only when two live slots share a bucket (rare off a lattice)
     // are the exact d2 recomputed and the list put in (d2, instance) order by an odd-even transposition pass.
-    i32 bj[KCAP];
+    i32 bj[KCAP], bs[KCAP];
     int found = 0;
     bool shared_bucket = false;
 #pragma unroll
     for (int u = 0; u < KCAP; ++u) {
-        const bool ok = (u >= head) & (bk[u] != KEY_NONE);
+        const bool ok = (u >= head) & ((bk[u] & ~SLOT) != NONE_B);
+        bs[u] = ok ? spos[(bk[u] & SLOT) * 128 + threadIdx.x] : 0;
         bj[u] = ok ? sr_inst[bs[u]] : ((u < head) ? (i32)0x80000000 : 0x7fffffff);
         found += ok;
-        if (u > 0) shared_bucket |= ok & (bk[u] == bk[u - 1]) & (u - 1 >= head);
+        if (u > 0) shared_bucket |= ok & ((bk[u] & ~SLOT) == (bk[u - 1] & ~SLOT)) & (u - 1 >= head);
     }
     if (shared_bucket) {
         double bd[KCAP];
 #pragma unroll
         for (int u = 0; u < KCAP; ++u) {
-            const bool ok = (u >= head) & (bk[u] != KEY_NONE);
+            const bool ok = (u >= head) & ((bk[u] & ~SLOT) != NONE_B);
             const double2 p = sr_xy[bs[u]];
             const double ddx = __dsub_rn(p.x, q.x), ddy = __dsub_rn(p.y, q.y);
             bd[u] = ok ? __dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy)) : ((u < head) ? -INFINITY : INFINITY);
