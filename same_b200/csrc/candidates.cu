@@ -665,8 +665,8 @@ void batch_candidates(Batch *b, double radius, int knn, int priority, double dis
     LAUNCH(k_window_offsets, blocks_for(W + 1, 128), 128, 0, s, b->newA.p, newR.p, poff.p, b->d_a_off.p, b->d_r_off.p, (int)W, off3.p, b->d_ka_off.p,
            b->d_kr_off.p, b->d_p_off.p);
     // (measured and not kept: one thread per row with 8 gather chains in flight, 224 us vs 129 us; rows visited in bin order so
-    // that neighbouring warps gather the same reference rows, 128 us — the kernel moves 292 MB of scattered 32-byte sectors
-    // through DRAM at 2.3 TB/s either way; profiles/r1m)
+    // that neighbouring warps gather the same reference rows, 128 us; two slots per thread, 130 us — the kernel moves 292 MB of
+    // scattered 32-byte sectors through DRAM at 2.3 TB/s either way; profiles/r1m)
     if (nAi > 0)
         LAUNCH(k_emit_pairs, blocks_for(nAi * knn, 256), 256, 0, s, b->cand.p, eff, knn, nAi, b->newA.p, newR.p, poff.p, b->d_a_off.p, (int)W,
                b->d_ka_off.p, b->d_kr_off.p, b->a_src.p, b->r_src.p, sec->a_xy.p, sec->r_xy.p, sec->a_prob.p, sec->r_prob.p, sec->K,
