@@ -33,7 +33,9 @@ def launches(path, out):
     with open(out, "w") as f:
         f.write(f"# ncu launch list summary ({path})\n\n")
         f.write("`ncu --metrics gpu__time_duration.sum --clock-control none` — cold-cache, serialised: compare SHARES.\n\n")
-        f.write(f"{len(rows)} launches, {tot / 1e6:.3f} ms total\n\n| kernel | launches | total us | avg us | share |\n|---|---:|---:|---:|---:|\n")
+        f.write(f"{len(rows)} launches, {tot / 1e6:.3f} ms total\n\n")
+        f.write("Not part of a step: `k_fp64_fma` (FP64 peak micro-benchmark, after the timed region), `at::...FillFunctor` (the 512 MiB L2 "
+                "flush between steps), `k_resolve_*` / `k_bbox` (section set-up).\n\n| kernel | launches | total us | avg us | share |\n|---|---:|---:|---:|---:|\n")
         for k, (n, ns) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             f.write(f"| `{k}` | {n} | {ns / 1e3:.1f} | {ns / n / 1e3:.2f} | {ns / tot:.3f} |\n")
     print(open(out).read())
