@@ -29,15 +29,17 @@ def launches(path, out):
         a = agg[short(r[ki])]
         a[0] += 1
         a[1] += float(r[vi].replace(",", ""))
-    tot = sum(v[1] for v in agg.values())
+    NOT_STEP = ("k_fp64_fma", "FillFunctor", "k_resolve_", "k_bbox", "k_fill_f64", "k_iota")
+    off_step = lambda k: any(t in k for t in NOT_STEP)
+    tot = sum(v[1] for k, v in agg.items() if not off_step(k))
     with open(out, "w") as f:
         f.write(f"# ncu launch list summary ({path})\n\n")
         f.write("`ncu --metrics gpu__time_duration.sum --clock-control none` — cold-cache, serialised: compare SHARES.\n\n")
-        f.write(f"{len(rows)} launches, {tot / 1e6:.3f} ms total\n\n")
+        f.write(f"{len(rows)} launches, {tot / 1e6:.3f} ms in step kernels (shares are of this)\n\n")
         f.write("Not part of a step: `k_fp64_fma` (FP64 peak micro-benchmark, after the timed region), `at::...FillFunctor` (the 512 MiB L2 "
                 "flush between steps), `k_resolve_*` / `k_bbox` (section set-up).\n\n| kernel | launches | total us | avg us | share |\n|---|---:|---:|---:|---:|\n")
         for k, (n, ns) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
-            f.write(f"| `{k}` | {n} | {ns / 1e3:.1f} | {ns / n / 1e3:.2f} | {ns / tot:.3f} |\n")
+            f.write(f"| `{k}` | {n} | {ns / 1e3:.1f} | {ns / n / 1e3:.2f} | {'(not a step kernel)' if off_step(k) else f'{ns / tot:.3f}'} |\n")
     print(open(out).read())
 
 
