@@ -236,7 +236,7 @@ def run_reference(args, rank, world):
                          "sample": f"all {len(rects)} windows per step x {args.steps} steps, candidate stage (subset + KNN + cost); OpenMP C oracle; {tot_t:.1f} s"},
         "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_same_wall(tiles, seed=1):
@@ -277,8 +277,30 @@ def workload_config(args, world, grid, n_windows):
 
 
 # ----------------------------------------------------------------------------------------------
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """stdout carries exactly ONE JSON line: everything else any library writes to fd 1 (NCCL prints its version banner there when
+    NCCL_DEBUG is set in the environment) is sent to stderr; emit() writes the line to the real stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
     args = parse()
+    claim_stdout()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
@@ -592,7 +614,7 @@ def main():
                                     "sample": f"candidate stage of all {len(rects)} windows x {c['reps']} repetitions = {c['seconds']:.1f} s of CPU work; "
                                               f"OpenMP C oracle (the Python reference cannot travel to the GPU box)",
                                     "triangle_checks_per_s": c["tri"] / max(c["tri_seconds"], 1e-12)}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
