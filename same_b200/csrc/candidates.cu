@@ -738,26 +738,44 @@ __global__ void k_group_fill(const int2 *__restrict__ pairs, i64 P, const i32 *_
     const i32 g = ref_gid[kr_off[w] + pairs[p].y];
     g_idx[g_ptr[g] + atomicAdd(cursor + g, 1)] = (i32)p - p_off[w];
 }
-// ascending pair index inside every group (insertion sort; groups hold ~knn entries)
+// ascending pair index inside every group.  Groups hold ~knn entries: up to 16 they are sorted in registers by a bitonic
+// network of integer min/max (static indices, no divergence, no local memory); longer ones by insertion sort in place.
+template <int N>
+__device__ __forceinline__ void bitonic_sort_regs(i32 (&v)[N]) {
+#pragma unroll
+    for (int k = 2; k <= N; k <<= 1)
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1)
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                const int l = i ^ j;
+                if (l > i) {
+                    const bool up = (i & k) == 0;
+                    const i32 lo = min(v[i], v[l]), hi = max(v[i], v[l]);
+                    v[i] = up ? lo : hi;
+                    v[l] = up ? hi : lo;
+                }
+            }
+}
+template <int N>
+__device__ __forceinline__ void sort_group_regs(i32 *__restrict__ a, i32 n) {
+    i32 v[N];
+#pragma unroll
+    for (int k = 0; k < N; ++k) v[k] = k < n ? a[k] : 0x7fffffff;
+    bitonic_sort_regs<N>(v);
+#pragma unroll
+    for (int k = 0; k < N; ++k)
+        if (k < n) a[k] = v[k];
+}
 __global__ void k_group_sort(const i32 *__restrict__ g_ptr, const i32 *__restrict__ n_groups, i32 *__restrict__ g_idx) {
     i64 g = (i64)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= *n_groups) return;
     const i32 lo = g_ptr[g], n = g_ptr[g + 1] - lo;
     i32 *a = g_idx + lo;
-    if (n <= 32) {
-        i32 v[32];
-#pragma unroll
-        for (int k = 0; k < 32; ++k) v[k] = k < n ? a[k] : 0x7fffffff;
-        // odd-even transposition network would touch all 32 slots; groups are ~8 long, so a bounded insertion sort over the
-        // live prefix is cheaper.  Indexing is dynamic -> local memory, but it stays in L1.
-        for (int i = 1; i < n; ++i) {
-            const i32 x = v[i];
-            int j = i - 1;
-            while (j >= 0 && v[j] > x) { v[j + 1] = v[j]; --j; }
-            v[j + 1] = x;
-        }
-        for (int k = 0; k < n; ++k) a[k] = v[k];
-    } else {
+    if (n <= 1) return;
+    if (n <= 8) sort_group_regs<8>(a, n);
+    else if (n <= 16) sort_group_regs<16>(a, n);
+    else {
         for (int i = 1; i < n; ++i) {
             const i32 x = a[i];
             int j = i - 1;
