@@ -47,14 +47,24 @@ __device__ __forceinline__ void remap_hits(const i32 *__restrict__ tri_rows, i64
 
 __global__ void __launch_bounds__(REMAP_CT) k_remap_count(const i32 *__restrict__ tri_rows, i64 Tg, const i32 *__restrict__ row_pos,
                                                           const int2 *__restrict__ row_inst, const i32 *__restrict__ cnt, const i32 *__restrict__ newA,
-                                                          const i32 *__restrict__ ka_off, ScanCtx sc, i32 *__restrict__ pos) {
+                                                          const i32 *__restrict__ ka_off, ScanCtx sc, i32 *__restrict__ pos,
+                                                          int4 *__restrict__ first_hit) {
     __shared__ int smem[REMAP_CT / 32 + 1];
     const i64 base = ((i64)blockIdx.x * REMAP_CT + threadIdx.x) * REMAP_CI;
     int c[REMAP_CI], sum[1] = {0};
 #pragma unroll
     for (int k = 0; k < REMAP_CI; ++k) {
         c[k] = 0;
-        if (base + k < Tg) remap_hits(tri_rows, base + k, row_pos, row_inst, cnt, newA, ka_off, [&](i32, i32, i32, i32) { ++c[k]; });
+        // most triangles lie in exactly one window: their only hit is remembered so that the fill pass does not walk the
+        // row -> instance table a second time
+        if (base + k < Tg) {
+            int4 h = make_int4(0, 0, 0, 0);
+            remap_hits(tri_rows, base + k, row_pos, row_inst, cnt, newA, ka_off, [&](i32 w, i32 la, i32 lb, i32 lc) {
+                if (c[k] == 0) h = make_int4(w, la, lb, lc);
+                ++c[k];
+            });
+            if (c[k] == 1) first_hit[base + k] = h;
+        }
         sum[0] += c[k];
     }
     int excl[1], tot[1], pre[1];
@@ -70,12 +80,20 @@ __global__ void __launch_bounds__(REMAP_CT) k_remap_count(const i32 *__restrict_
 template <typename KeyT>
 __global__ void __launch_bounds__(256) k_remap_fill(const i32 *__restrict__ tri_rows, i64 Tg, const i32 *__restrict__ row_pos,
                                                     const int2 *__restrict__ row_inst, const i32 *__restrict__ cnt, const i32 *__restrict__ newA,
-                                                    const i32 *__restrict__ ka_off, const i32 *__restrict__ pos, int tbits, KeyT *__restrict__ keys,
-                                                    i32 *__restrict__ idx, int3 *__restrict__ recs) {
+                                                    const i32 *__restrict__ ka_off, const i32 *__restrict__ pos, const int4 *__restrict__ first_hit,
+                                                    int tbits, KeyT *__restrict__ keys, i32 *__restrict__ idx, int3 *__restrict__ recs) {
     const i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= Tg) return;
     i32 out = pos[t];
-    if (out == pos[t + 1]) return;
+    const i32 n = pos[t + 1] - out;
+    if (n == 0) return;
+    if (n == 1) {   // the single hit the counting pass remembered
+        const int4 h = first_hit[t];
+        keys[out] = (KeyT)(((unsigned long long)h.x << tbits) | (unsigned long long)t);
+        idx[out] = out;
+        recs[out] = make_int3(h.y, h.z, h.w);
+        return;
+    }
     remap_hits(tri_rows, t, row_pos, row_inst, cnt, newA, ka_off, [&](i32 w, i32 la, i32 lb, i32 lc) {
         keys[out] = (KeyT)(((unsigned long long)w << tbits) | (unsigned long long)t);
         idx[out] = out;
@@ -114,10 +132,12 @@ static void remap_t(Batch *b, int tbits, int wbits) {
     cudaStream_t s = b->stream;
     const i64 W = b->W, Tg = sec->Tg;
     DevBuf<i32> pos;
+    DevBuf<int4> first_hit;
     pos.alloc(Tg + 1, s);
+    first_hit.alloc(Tg, s);
     const unsigned tiles = blocks_for(Tg + 1, REMAP_CT * REMAP_CI);
     LAUNCH(k_remap_count, tiles, REMAP_CT, 0, s, sec->tri_rows.p, Tg, b->row_pos.p, b->row_inst.p, b->cnt.p, b->newA.p, b->d_ka_off.p,
-           scan_ctx(sec, tiles, 1, s), pos.p);
+           scan_ctx(sec, tiles, 1, s), pos.p, first_hit.p);
     CK(cudaMemcpyAsync(b->pin_misc(), pos.p + Tg, sizeof(i32), cudaMemcpyDeviceToHost, s));
     batch_sync(b);   // also brings in the candidate stage's window offsets
     b->Tin = (i64)b->pin_misc()[0];
@@ -132,7 +152,7 @@ static void remap_t(Batch *b, int tbits, int wbits) {
     const i32 *sorted_idx = idx.p;
     if (b->Tin > 0) {
         LAUNCH((k_remap_fill<KeyT>), blocks_for(Tg, 256), 256, 0, s, sec->tri_rows.p, Tg, b->row_pos.p, b->row_inst.p, b->cnt.p, b->newA.p, b->d_ka_off.p,
-               pos.p, tbits, keys.p, idx.p, recs.p);
+               pos.p, first_hit.p, tbits, keys.p, idx.p, recs.p);
         if (W > 1) {   // a single window is already in input order
             keys_out.alloc(b->Tin, s); idx_out.alloc(b->Tin, s);
             size_t bytes = 0;
