@@ -36,3 +36,26 @@ def test_reference_arm_under_torchrun_rank0_only():
     _check(r.stdout, 2)
     d = json.loads([l for l in r.stdout.splitlines() if l.strip()][0])
     assert d["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0))      # torchrun's OMP_NUM_THREADS=1 is overridden
+
+
+import pytest
+
+
+@pytest.mark.gpu
+def test_gpu_arm_line_has_every_contract_key():
+    """The GPU arm on a small section: one JSON line with the base keys, `clocks`, `e2e` (real byte counts), `gpu_launches` > 0,
+    `roofline` (bound / achieved / peak / frac / traffic) and `cpu_baseline`."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "3", "--warmup", "3", "--tiles", "100"],
+                       capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-3000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, r.stdout[:2000]
+    d = json.loads(lines[0])
+    base = (KEYS - {"impl"}) | {"clocks", "gpu_launches", "roofline"}
+    assert base <= set(d), base - set(d)
+    assert d["n_gpus"] == 1 and d["steps"] == 3 and d["warmup"] == 3 and d["value"] > 0 and d["higher_is_better"] is True and d["dtype"] == "f64"
+    assert d["gpu_launches"] > 0 and d["e2e"]["value"] > 0 and d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0
+    assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(d["roofline"]) and d["roofline"]["bound"] in ("hbm", "tensor")
+    assert abs(d["roofline"]["frac"] - d["roofline"]["achieved"] / d["roofline"]["peak"]) < 1e-9
+    assert {"value", "unit", "cores", "kind", "sample"} <= set(d["cpu_baseline"])
+    assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(d["clocks"])
