@@ -105,6 +105,7 @@ def precompute_triangle_info(aligned_df, aligned_delaunay, aligned_simplex_map, 
         pick = lambda m: tri[np.arange(len(tri)), m.argmax(1)]
         argv = np.stack([pick(px == bounds[:, 1:2]), pick(px == bounds[:, 0:1]), pick(py == bounds[:, 3:4]), pick(py == bounds[:, 2:3])], axis=1)
     info = {}
+    bounds, argv = np.asarray(bounds), np.asarray(argv)
     for ip in range(len(aligned_df)):
         for s in aligned_simplex_map[ip]:
             if s not in info:

@@ -235,9 +235,10 @@ def _solve_window(run: _Run, w: int, aligned_src: pd.DataFrame, ref_src: pd.Data
     flipped = np.flatnonzero(b.get_window(L.FLIPPED, w))
     match_j = b.get_window(L.MATCH_J, w)
     aligned_simplex_map = {i: set() for i in range(n_aligned)}                                     # same.py:1096-1099
-    for idx in range(T):
-        for v in tri[idx]:
-            aligned_simplex_map[int(v)].add(idx)
+    for idx, (va, vb, vc) in enumerate(tri.tolist()):       # same insertion order as the reference's nested loop, without numpy scalars
+        aligned_simplex_map[va].add(idx)
+        aligned_simplex_map[vb].add(idx)
+        aligned_simplex_map[vc].add(idx)
     aligned_delaunay = tri.astype(int)
     triangle_info = H.precompute_triangle_info(aligned_df, aligned_delaunay, aligned_simplex_map, bounds=m["bounds"], argv=m["argv"])
     a_xy = aligned_df[["X", "Y"]].to_numpy(dtype=np.float64)
