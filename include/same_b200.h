@@ -105,6 +105,11 @@ SAME_API int same_section_create(int device, void *stream, int64_t n_aligned, in
                         const double *a_xy, const double *r_xy, const double *a_prob, const double *r_prob,
                         const int32_t *a_type, const int32_t *r_type, const double *a_size, const double *r_size,
                         same_section_t **out);
+/* The coordinates are on the device when same_section_create returns; the other columns (probabilities, type codes, sizes) are
+ * uploaded on an auxiliary stream that overlaps the first stages of a batch.  PAGE-LOCKED host buffers are read asynchronously:
+ * keep them valid and unmodified until same_section_wait_uploads() (or the first same_batch_candidates on the section) has
+ * returned.  Pageable buffers are staged before same_section_create returns and may be released at once. */
+SAME_API int same_section_wait_uploads(same_section_t *sec);
 SAME_API int same_section_destroy(same_section_t *sec);
 /* bounding box of both frames: out[4] = x_min, x_max, y_min, y_max (src/same.py:481-482) */
 SAME_API int same_section_bbox(same_section_t *sec, double *out4);

@@ -49,7 +49,7 @@ SYMBOLS = [
     "same_batch_groups", "same_batch_separation", "same_batch_postsolve", "same_batch_offsets", "same_batch_length",
     "same_batch_get", "same_elem_size", "same_batch_sync", "same_batch_stream", "same_launch_count",
     "same_profile_enable", "same_profile_report", "same_batch_get_many", "same_pinned_alloc", "same_pinned_free",
-    "same_postsolve_arrays", "same_batch_mip_start", "same_greedy_select", "same_collapse_select", "same_segment_mean", "same_measure_fp64_peak",
+    "same_postsolve_arrays", "same_batch_mip_start", "same_greedy_select", "same_collapse_select", "same_segment_mean", "same_measure_fp64_peak", "same_section_wait_uploads",
 ]
 
 
@@ -78,6 +78,7 @@ def load():
     lib.same_device_count.argtypes = [C.POINTER(C.c_int)]
     lib.same_section_create.argtypes = [i32, vp, i64, i64, i32, vp, vp, vp, vp, vp, vp, vp, vp, C.POINTER(vp)]
     lib.same_section_destroy.argtypes = [vp]
+    lib.same_section_wait_uploads.argtypes = [vp]
     lib.same_section_bbox.argtypes = [vp, vp]
     lib.same_section_count_rects.argtypes = [vp, i64, vp, vp, vp]
     lib.same_section_set_triangles.argtypes = [vp, vp, vp, i64]

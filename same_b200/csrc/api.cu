@@ -160,6 +160,15 @@ int same_section_create(int device, void *stream, int64_t n_aligned, int64_t n_r
     });
 }
 
+int same_section_wait_uploads(same_section_t *h) {
+    return guarded([&] {
+        REQUIRE(h, SAME_E_ARG, "section is NULL");
+        Section *sec = (Section *)h;
+        CK(cudaSetDevice(sec->device));
+        if (sec->aux_ready) CK(cudaEventSynchronize(sec->aux_ready));
+    });
+}
+
 int same_section_destroy(same_section_t *h) {
     return guarded([&] {
         Section *sec = (Section *)h;

@@ -93,11 +93,15 @@ class Section:
         a_type, r_type = conv(a_type, np.int32, self.n_aligned), conv(r_type, np.int32, self.n_ref)
         a_size, r_size = conv(a_size, np.float64, self.n_aligned), conv(r_size, np.float64, self.n_ref)
         h = C.c_void_p()
+        a_prob, r_prob = np.ascontiguousarray(a_prob), np.ascontiguousarray(r_prob)
         L.check(lib.same_section_create(device, C.c_void_p(stream) if stream else None, self.n_aligned, self.n_ref, self.n_types,
-                                        L.ptr(a_xy), L.ptr(r_xy), L.ptr(np.ascontiguousarray(a_prob)), L.ptr(np.ascontiguousarray(r_prob)),
+                                        L.ptr(a_xy), L.ptr(r_xy), L.ptr(a_prob), L.ptr(r_prob),
                                         L.ptr(a_type), L.ptr(r_type), L.ptr(a_size), L.ptr(r_size), C.byref(h)))
         self._h = h
         self.device = device
+        # page-locked inputs are read asynchronously by the auxiliary upload stream (same_section_wait_uploads): the section
+        # keeps every array it handed to the library alive
+        self._keep = [a_xy, r_xy, a_prob, r_prob, a_type, r_type, a_size, r_size]
         self.h2d_bytes = a_xy.nbytes + r_xy.nbytes + a_prob.nbytes + r_prob.nbytes + sum(
             v.nbytes for v in (a_type, r_type, a_size, r_size) if v is not None)
 
@@ -128,6 +132,12 @@ class Section:
         if getattr(self, "_h", None):
             L.check(L.load().same_section_destroy(self._h))
             self._h = None
+            self._keep = []
+
+    def wait_uploads(self):
+        """Block until every column of both frames is on the device (same_section_wait_uploads)."""
+        L.check(L.load().same_section_wait_uploads(self._h))
+        self._keep = []
 
     def __del__(self):
         try:

@@ -429,3 +429,26 @@ def test_batched_windows_priority_vs_oracle():
             assert np.array_equal(m["ref_group_node"], res["ref_group_node"]) and np.array_equal(m["ref_group_idx"], res["ref_group_idx"])
             n_single += int((np.bincount(res["pairs"][:, 0]) == 1).sum())
     assert n_single > 50, "the priority rule should have collapsed many rows to their single claimed pair"
+
+
+def test_page_locked_inputs_may_be_reused_after_wait_uploads():
+    """same_section_create reads page-locked buffers asynchronously (auxiliary upload stream); after same_section_wait_uploads the
+    caller may overwrite them — the section's results must not change."""
+    from same_b200 import _lib as L
+    from same_b200 import datagen
+    from same_b200.device import Section, pinned_empty
+    ref, qry, ct = datagen.make_section_pair(n_tiles=9, n_types=3, seed=31)
+    src = dict(a_xy=qry[["X", "Y"]].to_numpy(), r_xy=ref[["X", "Y"]].to_numpy(), a_prob=qry[ct].to_numpy(), r_prob=ref[ct].to_numpy())
+    pins = {}
+    for k, v in src.items():
+        pins[k] = pinned_empty(v.shape, np.float64)
+        pins[k][...] = v
+    with Section(pins["a_xy"], pins["r_xy"], pins["a_prob"], pins["r_prob"]) as sec:
+        sec.wait_uploads()
+        for v in pins.values():
+            v[...] = -1.0e9                                  # scribble over the host buffers
+        with sec.batch() as b:
+            b.candidates(1.2, 6, False, 1.5)
+            keepA, keepR, pairs = O.find_knn_within_radius(src["a_xy"], src["r_xy"], 1.2, 6)
+            cost = O.pair_cost(pairs, src["a_xy"][keepA], src["r_xy"][keepR], src["a_prob"][keepA], src["r_prob"][keepR], 1.5)
+            assert np.array_equal(b.get(L.PAIRS), pairs) and np.array_equal(b.get(L.COST), cost)
