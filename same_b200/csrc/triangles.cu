@@ -201,6 +201,7 @@ void batch_triangles_set(Batch *b, const i32 *tri, const i64 *tri_off) {
     b->tin.alloc(b->Tin, s);
     if (b->Tin > 0) CK(cudaMemcpyAsync(b->tin.p, tri, sizeof(int3) * (size_t)b->Tin, cudaMemcpyDefault, s));
     upload_offsets(b->tin_off, b->d_tin_off, s);
+    CK(cudaStreamSynchronize(s));   // the caller's triangle array (possibly page-locked) was read asynchronously
     b->stage = 2;
 }
 
