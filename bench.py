@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--tiles", type=int, default=2500, help="tiles per GPU (2500 = the 1M-cell section)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work the cpu_baseline leg aims for")
     return ap.parse_args()
 
 
@@ -609,7 +610,7 @@ def main():
             O.build()
             os.sched_setaffinity(0, all_cpus)       # the CPU arm gets every host core back
             cores = O.set_threads(len(all_cpus))    # torchrun exports OMP_NUM_THREADS=1
-            c = cpu_arm(W, rects, target_s=12.0)
+            c = cpu_arm(W, rects, target_s=args.cpu_seconds)
             line["cpu_baseline"] = {"value": c["pairs"] / c["seconds"], "unit": "pairs/s", "cores": cores, "kind": "port",
                                     "sample": f"candidate stage of all {len(rects)} windows x {c['reps']} repetitions = {c['seconds']:.1f} s of CPU work; "
                                               f"OpenMP C oracle (the Python reference cannot travel to the GPU box)",

@@ -45,7 +45,7 @@ import pytest
 def test_gpu_arm_line_has_every_contract_key():
     """The GPU arm on a small section: one JSON line with the base keys, `clocks`, `e2e` (real byte counts), `gpu_launches` > 0,
     `roofline` (bound / achieved / peak / frac / traffic) and `cpu_baseline`."""
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "3", "--warmup", "3", "--tiles", "100"],
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "3", "--warmup", "3", "--tiles", "100", "--cpu-seconds", "1"],
                        capture_output=True, text=True, timeout=900, cwd=ROOT)
     assert r.returncode == 0, r.stderr[-3000:]
     lines = [l for l in r.stdout.splitlines() if l.strip()]
