@@ -34,10 +34,12 @@ __device__ __forceinline__ unsigned long long ts_load(const unsigned long long *
 }
 
 // Block-wide exclusive scan of NS independent int streams (one value per thread and stream).
-// `warp_tot` is shared memory, NS * (THREADS / 32) ints.  total[s] is returned to every thread.
-template <int NS, int THREADS>
-__device__ __forceinline__ void block_exclusive_scan(const int (&x)[NS], int (&excl)[NS], int (&total)[NS], int *warp_tot) {
+// `warp_tot` is shared memory, at least NS * (THREADS / 32) ints (checked at compile time: an undersized buffer would
+// silently scribble over the caller's other shared arrays).  total[s] is returned to every thread.
+template <int NS, int THREADS, int N>
+__device__ __forceinline__ void block_exclusive_scan(const int (&x)[NS], int (&excl)[NS], int (&total)[NS], int (&warp_tot)[N]) {
     constexpr int NW = THREADS / 32;
+    static_assert(N >= NS * NW, "block_exclusive_scan: shared buffer smaller than NS * (THREADS / 32) ints");
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int incl[NS];
 #pragma unroll
@@ -156,9 +158,10 @@ __device__ __forceinline__ int tile_segmented_carry(const ScanCtx &c, int tile, 
 
 // Convenience: per-thread value x[s] -> its device-wide exclusive prefix; `total_before_tile + block total` of the last
 // tile is the grand total.  smem: NS * (THREADS/32) + NS ints.
-template <int NS, int THREADS>
+template <int NS, int THREADS, int N>
 __device__ __forceinline__ void device_exclusive_scan(const ScanCtx &c, int tile, const int (&x)[NS], int (&excl)[NS], int (&tile_total)[NS],
-                                                      int (&tile_prefix)[NS], int *smem) {
+                                                      int (&tile_prefix)[NS], int (&smem)[N]) {
+    static_assert(N >= NS * (THREADS / 32) + NS, "device_exclusive_scan: shared buffer smaller than NS * (THREADS / 32) + NS ints");
     int local[NS];
     block_exclusive_scan<NS, THREADS>(x, local, tile_total, smem);
     tile_exclusive_prefix<NS>(c, tile, tile_total, tile_prefix, smem + NS * (THREADS / 32));

@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(SEP_THREADS) k_separation(const int3 *__restri
                                                             i32 *__restrict__ counts /* [2*nw] zeroed: n_viol, n_checked */, i32 *__restrict__ cuts) {
     __shared__ int E[SEP_TILE + 1];
     __shared__ __align__(8) unsigned char V[SEP_TILE];
-    __shared__ int smem[SEP_THREADS / 32 + 2];
+    __shared__ int smem[2 * (SEP_THREADS / 32) + 2];   // two scanned streams (violated, checked) + the carry word
     const i32 t0 = t_lo + (i32)blockIdx.x * SEP_TILE;
     const i32 tend = min(t0 + SEP_TILE, t_hi);
     const int wf = find_window(t_off, W, t0), wl = find_window(t_off, W, tend - 1);
