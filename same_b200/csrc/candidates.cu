@@ -10,18 +10,17 @@
 // are exact fp64 (d2 = dx*dx + dy*dy, no FMA; d2 <= r*r; order (d2, ref index)); only the
 // pruning uses conservative bounds.
 #include "common.cuh"
-#include "topk_net.cuh"
 
 namespace same {
 
-constexpr int MAX_RINGS = 8;
+constexpr int MAX_RINGS = 4;
 // reference cells per bin: the own bin plus ring 1 (nine bins) should hold the k nearest with room to spare, and no more —
 // smaller bins prune better (measured at knn = 8 on the 1 M-cell section with the bucketed top-k: 4/bin 194 us, 5/bin 182 us,
 // 6/bin 179 us, 8/bin 192 us, 10/bin 199 us)
 static double target_per_bin(int knn) {
     static const char *env = getenv("SAME_B200_BIN_TARGET");   // tuning knob for tools/dev_knn_sweep.sh (cells per bin = value * knn / 8)
-    const double scale = env && atof(env) > 0.0 ? atof(env) / 8.0 : 0.625;
-    return std::max(2.0, scale * knn);
+    const double scale = env ? atof(env) / 8.0 : 0.75;
+    return std::max(scale > 0.0 ? 2.0 : 4.0, (scale > 0.0 ? scale : 0.75) * knn);
 }
 constexpr int MAX_BINS_AXIS = 2048;
 
@@ -55,16 +54,15 @@ __global__ void k_bin_count(const i32 *__restrict__ a_src, const i32 *__restrict
 
 __global__ void k_bin_scatter(const i32 *__restrict__ a_src, const i32 *__restrict__ r_src, const double2 *__restrict__ a_xy,
                               const double2 *__restrict__ r_xy, i64 nAi, i64 nRi, i64 nb1, const i32 *__restrict__ bkey,
-                              const i32 *__restrict__ bstart, i32 *__restrict__ bcnt, double2 *__restrict__ sorted_xy, int2 *__restrict__ sorted_ir) {
+                              const i32 *__restrict__ bstart, i32 *__restrict__ bcnt, double2 *__restrict__ sorted_xy, i32 *__restrict__ sorted_inst) {
     const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nAi + nRi) return;
     const bool ref = i >= nAi;
     const i32 inst = (i32)(ref ? i - nAi : i);
     const i64 c = (ref ? nb1 : 0) + bkey[i];
     const i32 dst = bstart[c] + atomicSub(bcnt + c, 1) - 1;
-    const i32 row = ref ? r_src[inst] : a_src[inst];
-    sorted_xy[dst] = ref ? r_xy[row] : a_xy[row];
-    sorted_ir[dst] = make_int2(inst, row);   // (window instance, section row): the search reads the probability rows through the row
+    sorted_xy[dst] = ref ? r_xy[r_src[inst]] : a_xy[a_src[inst]];
+    sorted_inst[dst] = inst;
 }
 
 // out[i] = sum of in[0 .. i-1] for i in [0, n): one launch.  A thread owns 16 consecutive values (four 16-byte loads);
@@ -120,8 +118,8 @@ __device__ __forceinline__ void ring_slot(int ring, int slot, int &dx, int &dy) 
 // Exact search of ONE query with the (d2, ref instance) list in local memory: the path a query takes when the bucketed
 // search below cannot decide its k-th neighbour (two candidates in the same 2^-20-relative distance bucket at the
 // boundary — in practice only on exact lattices).  Writes the query's outputs itself.
-__device__ __noinline__ int knn_exact_one(double2 q, const GridParams &g, int cbx, int cby, const i32 *__restrict__ bin_start,
-                                           const double2 *__restrict__ sr_xy, const int2 *__restrict__ sr_ir, double r2, int knn,
+__device__ __noinline__ void knn_exact_one(double2 q, const GridParams &g, int cbx, int cby, const i32 *__restrict__ bin_start,
+                                           const double2 *__restrict__ sr_xy, const i32 *__restrict__ sr_inst, double r2, int knn,
                                            i32 *__restrict__ out, i32 *__restrict__ cnt_out, i32 *__restrict__ r_used) {
     double ld[32];
     i32 lj[32];
@@ -153,7 +151,7 @@ __device__ __noinline__ int knn_exact_one(double2 q, const GridParams &g, int cb
                 const double ddx = __dsub_rn(p.x, q.x), ddy = __dsub_rn(p.y, q.y);
                 const double d2 = __dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy));
                 if (d2 > r2) continue;
-                const i32 j = sr_ir[s].x;
+                const i32 j = sr_inst[s];
                 if (found == knn && !cand_less(d2, j, tau_d, tau_j)) continue;
                 int u = (found == knn) ? knn - 1 : found;
                 while (u > 0 && cand_less(d2, j, ld[u - 1], lj[u - 1])) { ld[u] = ld[u - 1]; lj[u] = lj[u - 1]; --u; }
@@ -168,7 +166,6 @@ __device__ __noinline__ int knn_exact_one(double2 q, const GridParams &g, int cb
         out[u] = (u < found) ? lj[u] : -1;
         if (u < found) r_used[lj[u]] = 1;
     }
-    return found;
 }
 
 // One thread per aligned instance.  The running top-k is kept on a 32-bit KEY — the high word of the fp64 d2, a monotone
@@ -180,14 +177,14 @@ __device__ __noinline__ int knn_exact_one(double2 q, const GridParams &g, int cb
 // (d2, ref instance) order by an odd-even transposition pass over an almost sorted list.
 constexpr unsigned KEY_NONE = 0x7ff00000u;   // high word of +inf: above the key of every finite d2
 template <int KCAP>
-__global__ void __launch_bounds__(128) k_knn(const double2 *__restrict__ sa_xy, const int2 *__restrict__ sa_ir, i64 nAi,
+__global__ void __launch_bounds__(128) k_knn(const double2 *__restrict__ sa_xy, const i32 *__restrict__ sa_inst, i64 nAi,
                                              const i32 *__restrict__ a_off, int W, const GridParams *__restrict__ grids,
                                              const i32 *__restrict__ bin_start, const double2 *__restrict__ sr_xy,
-                                             const int2 *__restrict__ sr_ir, double r2, int knn, i32 *__restrict__ cand,
+                                             const i32 *__restrict__ sr_inst, double r2, int knn, i32 *__restrict__ cand,
                                              i32 *__restrict__ cnt, i32 *__restrict__ r_used) {
     const i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nAi) return;
-    const i32 inst = sa_ir[t].x;
+    const i32 inst = sa_inst[t];
     const double2 q = sa_xy[t];
     const GridParams g = grids[find_window(a_off, W, inst)];
     int cbx, cby;
@@ -301,7 +298,7 @@ __global__ void __launch_bounds__(128) k_knn(const double2 *__restrict__ sa_xy, 
     }
     i32 *out = cand + (i64)inst * knn;
     if (tie && (last_k & ~SLOT) != NONE_B) {
-        knn_exact_one(q, g, cbx, cby, bin_start, sr_xy, sr_ir, r2, knn, out, cnt + inst, r_used);
+        knn_exact_one(q, g, cbx, cby, bin_start, sr_xy, sr_inst, r2, knn, out, cnt + inst, r_used);
         return;
     }
     // Survivors in different buckets are already in exact order; only when two live slots share a bucket (rare off a lattice)
@@ -313,7 +310,7 @@ __global__ void __launch_bounds__(128) k_knn(const double2 *__restrict__ sa_xy, 
     for (int u = 0; u < KCAP; ++u) {
         const bool ok = (u >= head) & ((bk[u] & ~SLOT) != NONE_B);
         bs[u] = ok ? spos[(bk[u] & SLOT) * 128 + threadIdx.x] : 0;
-        bj[u] = ok ? sr_ir[bs[u]].x : ((u < head) ? (i32)0x80000000 : 0x7fffffff);
+        bj[u] = ok ? sr_inst[bs[u]] : ((u < head) ? (i32)0x80000000 : 0x7fffffff);
         found += ok;
         if (u > 0) shared_bucket |= ok & ((bk[u] & ~SLOT) == (bk[u - 1] & ~SLOT)) & (u - 1 >= head);
     }
@@ -354,15 +351,15 @@ __global__ void __launch_bounds__(128) k_knn(const double2 *__restrict__ sa_xy, 
 }
 
 // generic path for knn > 32: top-k lives in global scratch ([slot][query] so threads coalesce)
-__global__ void __launch_bounds__(128) k_knn_big(const double2 *__restrict__ sa_xy, const int2 *__restrict__ sa_ir, i64 nAi,
+__global__ void __launch_bounds__(128) k_knn_big(const double2 *__restrict__ sa_xy, const i32 *__restrict__ sa_inst, i64 nAi,
                                                  const i32 *__restrict__ a_off, int W, const GridParams *__restrict__ grids,
                                                  const i32 *__restrict__ bin_start, const double2 *__restrict__ sr_xy,
-                                                 const int2 *__restrict__ sr_ir, double r2, int knn, double *__restrict__ gd,
+                                                 const i32 *__restrict__ sr_inst, double r2, int knn, double *__restrict__ gd,
                                                  i32 *__restrict__ gj, i32 *__restrict__ cand, i32 *__restrict__ cnt,
                                                  i32 *__restrict__ r_used) {
     const i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nAi) return;
-    const i32 inst = sa_ir[t].x;
+    const i32 inst = sa_inst[t];
     const double2 q = sa_xy[t];
     const GridParams g = grids[find_window(a_off, W, inst)];
     int cbx, cby;
@@ -399,7 +396,7 @@ __global__ void __launch_bounds__(128) k_knn_big(const double2 *__restrict__ sa_
                     const double ddx = __dsub_rn(p.x, q.x), ddy = __dsub_rn(p.y, q.y);
                     const double d2 = __dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy));
                     if (d2 > r2) continue;
-                    const i32 j = sr_ir[s].x;
+                    const i32 j = sr_inst[s];
                     if (found == knn && !cand_less(d2, j, tau_d, tau_j)) continue;
                     int u = (found == knn) ? knn - 1 : found;
                     while (u > 0 && cand_less(d2, j, GD(u - 1), GJ(u - 1))) { GD(u) = GD(u - 1); GJ(u) = GJ(u - 1); --u; }
@@ -417,315 +414,6 @@ __global__ void __launch_bounds__(128) k_knn_big(const double2 *__restrict__ sa_
     }
 #undef GD
 #undef GJ
-}
-
-// ---- tile search: a1 + a3 fused ---------------------------------------------------------------------------------
-// pair cost, one IEEE operation at a time and summed left to right (src/same.py:1183-1188)
-__device__ __forceinline__ double pair_cost(const double *__restrict__ pa, const double *__restrict__ pr, int K, double2 A, double2 R,
-                                            double ct_coeff, double dist_coeff) {
-    double s = 0.0;
-    for (int c = 0; c < K; ++c) s = __dadd_rn(s, fabs(__dsub_rn(pa[c], pr[c])));
-    const double dc = __dadd_rn(fabs(__dsub_rn(A.x, R.x)), fabs(__dsub_rn(A.y, R.y)));
-    return __dadd_rn(__dmul_rn(ct_coeff, s), __dmul_rn(dist_coeff, dc));
-}
-
-// Work unit = a CHUNK: up to 32 consecutive cells of the bin-sorted aligned frame that lie in ONE bin row of one window
-// (a block owns a bin row, its warps take the row's chunks round robin), one query per lane.  Both frames are sorted by
-// bin, so everything the chunk's queries can pair with inside ring 1 is three contiguous ranges of the sorted reference cells
-// (rows by, by-1, by+1, bins first-1 .. last+1): the warp stages them in its own slice of shared memory (coordinates and
-// the packed (instance, row)) — there is no block-wide barrier anywhere, warps never wait for each other.  Every lane then
-// walks its own three sub-ranges out of shared memory (own row first) in a loop whose trip count is warp-uniform per row (max
-// over lanes), with NO insertion inside the loop: a candidate within the radius whose distance bucket is not above the
-// current k-th best is appended to a small per-lane pending buffer ([slot][lane] in shared memory, a predicated store).  When
-// any lane's buffer is nearly full the whole warp folds its pending keys into the sorted best-k held in registers with a
-// fixed compare-exchange network (topk_net.cuh) — about 100 instructions at 32 of 32 lanes, four to five times per chunk,
-// instead of a divergent insertion per candidate.
-//
-// key = (high word of the fp64 d2 with its low TILE_IB bits cleared, + one bucket) | (row << 6 | position in the lane's range
-// of that row): a monotone 2^-12-relative bucket of the distance plus where to find the candidate again.  The k smallest keys
-// ARE the k nearest unless a rejected candidate shares the k-th's bucket (`rejb`, the smallest bucket ever dropped by a merge;
-// candidates that were never appended sit in strictly higher buckets).  Survivors in distinct buckets are in exact order;
-// equal buckets are put in (d2, reference instance) order from the exact d2.  A query leaves the fast path — it is appended to
-// a list that k_knn_exact_list searches exactly afterwards, about one query in a thousand — when (a) that tie cannot be
-// excluded, (b) ring 1 does not cover its k-th distance (or the radius, with fewer than k found) in a direction where more
-// bins exist, or (c) one of its ranges holds more than 64 cells.  A chunk whose ranges do not fit the slice (sparsely
-// populated rows) walks the sorted arrays in global memory instead, same code.
-//
-// Emission is transposed: the lanes publish their survivors' positions in shared memory, then lane = (query, slot) pair, so
-// that the probability-row gathers of 32 pairs are in flight together and the 8 results of a query leave as one contiguous
-// store.  The cost of every pair is computed here, where the reference rows of a tile are hot in L1, and written with the
-// candidate to a [instance][slot] table; k_emit_pairs then only streams that table into the compacted CSR.
-constexpr int TILE_THREADS = 128, TILE_WARPS = TILE_THREADS / 32, TILE_CAP = 320, TILE_IB = 8, TILE_RANGE_CAP = 64;
-
-__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
-
-template <int KCAP>
-__device__ __forceinline__ void tile_merge(unsigned (&bk)[KCAP], const unsigned *__restrict__ pend, int &cnt, unsigned &rejb, unsigned &thrb) {
-    constexpr unsigned MASK = (1u << TILE_IB) - 1u, ONE = 1u << TILE_IB, NONE_B = KEY_NONE + ONE;
-    unsigned pk[KCAP];
-#pragma unroll
-    for (int u = 0; u < KCAP; ++u) pk[u] = u < cnt ? pend[u * 32] : (NONE_B | (unsigned)u);
-    net_sort<KCAP>(pk);
-    const unsigned dropped = net_merge_smallest<KCAP>(bk, pk);
-    rejb = min(rejb, dropped & ~MASK);
-    thrb = (bk[KCAP - 1] & ~MASK) - ONE;   // a candidate is appended iff its (un-offset) bucket is <= the k-th best's
-    cnt = 0;
-}
-
-template <int KCAP>
-__global__ void __launch_bounds__(TILE_THREADS, KCAP <= 8 ? 6 : 3) k_knn_tile(
-    const double2 *__restrict__ sorted_xy, const int2 *__restrict__ sorted_ir, const i32 *__restrict__ row_base, int W,
-    const GridParams *__restrict__ grids, const i32 *__restrict__ a_bin_start, const i32 *__restrict__ r_bin_start, double r2, int knn,
-    const double *__restrict__ a_prob, const double *__restrict__ r_prob, int K, double ct_coeff, double dist_coeff, i32 *__restrict__ cand,
-    double *__restrict__ ctab, i32 *__restrict__ cnt_out, i32 *__restrict__ r_used, unsigned long long *__restrict__ stats,
-    i32 *__restrict__ fail_list, int dbg) {
-    constexpr unsigned MASK = (1u << TILE_IB) - 1u, ONE = 1u << TILE_IB, NONE_B = KEY_NONE + ONE;
-    // (+ TILE_RANGE_CAP + 2: the walk reads up to nmax + 1 entries from every lane's range start without clamping)
-    __shared__ double2 s_xy_all[TILE_WARPS * TILE_CAP + TILE_RANGE_CAP + 2];
-    __shared__ int2 s_ir_all[TILE_WARPS * TILE_CAP];
-    __shared__ unsigned s_pend[TILE_WARPS][KCAP * 32];   // pending keys [slot][lane]; then the survivors' positions [lane][slot]
-
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const i32 row = (i32)blockIdx.x;   // one block per bin row; its warps take the row's chunks round robin
-    const int w = find_window(row_base, W, row);
-    const GridParams g = grids[w];
-    const int by = row - row_base[w];
-    const i32 krow = g.base + by * g.nbx;
-    const i32 q_lo = a_bin_start[krow], q_hi = a_bin_start[krow + g.nbx];
-    double2 *s_xy = s_xy_all + warp * TILE_CAP;
-    int2 *s_ir = s_ir_all + warp * TILE_CAP;
-    unsigned *pend = &s_pend[warp][lane];
-    const int head = KCAP - knn;
-    for (i32 t0 = q_lo + warp * 32; t0 < q_hi; t0 += TILE_WARPS * 32) {
-        const i32 t = t0 + lane;
-        const bool active = t < q_hi;
-        if (t + TILE_WARPS * 32 < q_hi) { prefetch_l1(sorted_xy + t + TILE_WARPS * 32); prefetch_l1(sorted_ir + t + TILE_WARPS * 32); }
-
-        double2 q = make_double2(0.0, 0.0);
-        i32 inst = 0, arow = 0;
-        int cbx = 0;
-        if (active) {
-            q = sorted_xy[t];
-            const int2 ir = sorted_ir[t];
-            inst = ir.x; arow = ir.y;
-            int cby;
-            bin_of(g, q, cbx, cby);
-            prefetch_l1(a_prob + (i64)arow * K);
-            prefetch_l1(a_prob + (i64)arow * K + (K - 1));
-        }
-        // bins spanned by the chunk (the cells are sorted by bin: lane 0 holds the first, the last active lane the last)
-        const unsigned amask = __ballot_sync(0xffffffffu, active);
-        const int bxa = __shfl_sync(0xffffffffu, cbx, 0), bxb = __shfl_sync(0xffffffffu, cbx, 31 - __clz(amask));
-
-        // ranges of the sorted reference cells: slot r = bin row by, by-1, by+1 (own row first); lane ranges = bins cbx-1 .. cbx+1,
-        // the warp's staged ranges = bins bxa-1 .. bxb+1
-        i32 rs[3], off[4], g0[3] = {0, 0, 0}, n_r[3] = {0, 0, 0};
-        off[0] = 0;
-#pragma unroll
-        for (int r = 0; r < 3; ++r) {
-            const int yy = by + (r == 0 ? 0 : (r == 1 ? -1 : 1));
-            i32 len = 0;
-            rs[r] = 0;
-            if (yy >= 0 && yy < g.nby) {
-                const i32 kb = g.base + yy * g.nbx;
-                rs[r] = r_bin_start[kb + max(bxa - 1, 0)];
-                len = r_bin_start[kb + min(bxb + 2, g.nbx)] - rs[r];
-                if (active) {
-                    g0[r] = r_bin_start[kb + max(cbx - 1, 0)];
-                    n_r[r] = r_bin_start[kb + min(cbx + 2, g.nbx)] - g0[r];
-                }
-            }
-            off[r + 1] = off[r] + len;
-        }
-        const bool staged = off[3] <= TILE_CAP;
-        __syncwarp();   // the previous chunk's reads of the slice and of the survivor table are done
-        if (staged) {
-            // all loads of a batch are issued before its stores (TILE_CAP / 32 = 10 elements per lane, two batches of five)
-#pragma unroll
-            for (int bb = 0; bb < TILE_CAP / 32; bb += 5) {
-                double2 vx[5];
-                int2 vi[5];
-#pragma unroll
-                for (int k = 0; k < 5; ++k) {
-                    const i32 i = (bb + k) * 32 + lane;
-                    if (i < off[3]) {
-                        const int r = i < off[1] ? 0 : (i < off[2] ? 1 : 2);
-                        const i32 src = rs[r] + (i - off[r]);
-                        vx[k] = sorted_xy[src];
-                        vi[k] = sorted_ir[src];
-                    }
-                }
-#pragma unroll
-                for (int k = 0; k < 5; ++k) {
-                    const i32 i = (bb + k) * 32 + lane;
-                    if (i < off[3]) { s_xy[i] = vx[k]; s_ir[i] = vi[k]; }
-                }
-                if ((bb + 5) * 32 >= off[3]) break;
-            }
-        }
-        __syncwarp();
-        const double2 *c_xy = staged ? s_xy : sorted_xy;
-        const int2 *c_ir = staged ? s_ir : sorted_ir;
-        i32 a_r[3];
-#pragma unroll
-        for (int r = 0; r < 3; ++r) a_r[r] = n_r[r] == 0 ? 0 : (staged ? off[r] + (g0[r] - rs[r]) : g0[r]);   // (0: lanes without a range still read)
-        bool fail = false;
-        double cover2 = INFINITY;
-        if (active) {
-            if (max(n_r[0], max(n_r[1], n_r[2])) > TILE_RANGE_CAP) { fail = true; n_r[0] = n_r[1] = n_r[2] = 0; }
-            // distance from the query to the nearest side of its 3x3 block beyond which more bins exist (lower bound)
-            const double px = q.x - g.x0, py = q.y - g.y0;
-            const double fx = px - cbx * g.w, fy = py - by * g.w;
-            double cover = INFINITY;
-            if (cbx >= 2) cover = fmin(cover, fx + g.w);
-            if (cbx <= g.nbx - 3) cover = fmin(cover, 2.0 * g.w - fx);
-            if (by >= 2) cover = fmin(cover, fy + g.w);
-            if (by <= g.nby - 3) cover = fmin(cover, 2.0 * g.w - fy);
-            cover -= 1e-7 * g.w;
-            cover2 = cover > 0.0 ? cover * cover : 0.0;
-        }
-
-        // sorted best keys, right-aligned: slots [head, KCAP) hold the list, the slots before it zero keys that never move
-        unsigned bk[KCAP];
-#pragma unroll
-        for (int u = 0; u < KCAP; ++u) bk[u] = (u < head) ? 0u : (NONE_B | (unsigned)u);
-        unsigned rejb = 0xffffff00u, thrb = NONE_B - ONE;
-        int cnt = 0;
-#pragma unroll
-        for (int r = 0; r < 3; ++r) {
-            const int nmax = (dbg & 4) ? 0 : __reduce_max_sync(0xffffffffu, n_r[r]);
-            const double2 *sp = c_xy + a_r[r];
-            const unsigned key0 = ONE + ((unsigned)r << 6);   // + bucket = key of position 0 of this range
-            // two candidates per trip; the buffer is folded when a lane holds KCAP-1 or more, so two appends always fit
-            for (int i = 0; i < nmax; i += 2) {
-                const double2 pA = sp[i], pB = sp[i + 1];
-                const double ax = __dsub_rn(pA.x, q.x), ay = __dsub_rn(pA.y, q.y), bx = __dsub_rn(pB.x, q.x), byy = __dsub_rn(pB.y, q.y);
-                const double dA = __dadd_rn(__dmul_rn(ax, ax), __dmul_rn(ay, ay)), dB = __dadd_rn(__dmul_rn(bx, bx), __dmul_rn(byy, byy));
-                const unsigned hA = (unsigned)__double2hiint(dA) & ~MASK, hB = (unsigned)__double2hiint(dB) & ~MASK;
-                if (i < n_r[r] && dA <= r2 && hA <= thrb) {
-                    pend[cnt * 32] = hA + key0 + (unsigned)i;
-                    ++cnt;
-                }
-                if (i + 1 < n_r[r] && dB <= r2 && hB <= thrb) {
-                    pend[cnt * 32] = hB + key0 + (unsigned)(i + 1);
-                    ++cnt;
-                }
-                if (__any_sync(0xffffffffu, cnt >= KCAP - 1)) tile_merge<KCAP>(bk, pend, cnt, rejb, thrb);
-            }
-        }
-        if (__any_sync(0xffffffffu, cnt > 0)) tile_merge<KCAP>(bk, pend, cnt, rejb, thrb);
-
-        if (active && !fail) {
-            const unsigned lastb = bk[KCAP - 1] & ~MASK;
-            const bool full = lastb != NONE_B;
-            // what ring 1 must cover: the upper edge of the k-th best's bucket (its high word is lastb, the one-bucket
-            // offset cancels), or the whole radius when fewer than k were found
-            const double need2 = full ? fmin(r2, __hiloint2double((int)lastb, 0)) : r2;
-            fail = (full && rejb == lastb) || need2 > cover2;
-        }
-        if (active && fail) fail_list[atomicAdd(stats, 1ull)] = t;   // searched exactly by k_knn_exact_list
-
-        // ---- emission, phase 1 (lane = query): survivors' positions in c_xy / c_ir, exact order among equal buckets
-        int found = -1;   // -1: nothing to emit from this lane
-        __syncwarp();     // every lane is done with the pending buffer
-        unsigned *sur = &s_pend[warp][0];
-        if (active && !fail && !(dbg & 2)) {
-            i32 bs[KCAP];
-            found = 0;
-            bool shared_bucket = false;
-#pragma unroll
-            for (int u = 0; u < KCAP; ++u) {
-                const bool ok = (u >= head) & ((bk[u] & ~MASK) != NONE_B);
-                const unsigned idx = bk[u] & MASK;
-                const int r = (int)(idx >> 6);
-                bs[u] = ok ? (r == 0 ? a_r[0] : (r == 1 ? a_r[1] : a_r[2])) + (i32)(idx & 63u) : -1;
-                found += ok;
-                if (u > 0) shared_bucket |= ok & ((bk[u] & ~MASK) == (bk[u - 1] & ~MASK)) & (u - 1 >= head);
-            }
-            if (shared_bucket) {
-                double bd[KCAP];
-                i32 bj[KCAP];
-#pragma unroll
-                for (int u = 0; u < KCAP; ++u) {
-                    const bool ok = bs[u] >= 0;
-                    const double2 p = c_xy[ok ? bs[u] : 0];
-                    const double ddx = __dsub_rn(p.x, q.x), ddy = __dsub_rn(p.y, q.y);
-                    bd[u] = ok ? __dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy)) : ((u < head) ? -INFINITY : INFINITY);
-                    bj[u] = ok ? c_ir[bs[u]].x : ((u < head) ? (i32)0x80000000 : 0x7fffffff);
-                }
-                bool swapped = true;
-                while (swapped) {
-                    swapped = false;
-#pragma unroll
-                    for (int par = 0; par < 2; ++par)
-#pragma unroll
-                        for (int u = par; u + 1 < KCAP; u += 2) {
-                            const bool sw = cand_less(bd[u + 1], bj[u + 1], bd[u], bj[u]);
-                            const double d0 = bd[u], d1 = bd[u + 1];
-                            const i32 j0 = bj[u], j1 = bj[u + 1], s0 = bs[u], s1 = bs[u + 1];
-                            bd[u] = sw ? d1 : d0; bd[u + 1] = sw ? d0 : d1;
-                            bj[u] = sw ? j1 : j0; bj[u + 1] = sw ? j0 : j1;
-                            bs[u] = sw ? s1 : s0; bs[u + 1] = sw ? s0 : s1;
-                            swapped |= sw;
-                        }
-                }
-            }
-            cnt_out[inst] = found;
-#pragma unroll
-            for (int u = 0; u < KCAP; ++u) sur[lane * KCAP + u] = (unsigned)bs[u];
-        }
-        if (dbg && active && (fail || (dbg & 2))) cnt_out[inst] = 0;   // timing experiments: skipped queries emit nothing
-        __syncwarp();
-        // ---- phase 2 (lane = (query, slot) pair): gather, cost, contiguous stores
-#pragma unroll
-        for (int pass = 0; pass < KCAP; ++pass) {
-            const int idx = pass * 32 + lane, ql = idx / KCAP, u = idx % KCAP;
-            const int fq = __shfl_sync(0xffffffffu, found, ql);
-            const i32 qi = __shfl_sync(0xffffffffu, inst, ql), qr = __shfl_sync(0xffffffffu, arow, ql);
-            const double qx = __shfl_sync(0xffffffffu, q.x, ql), qy = __shfl_sync(0xffffffffu, q.y, ql);
-            if (u >= head && (u - head) < fq) {
-                const i32 pos = (i32)sur[idx];
-                const int2 ir = c_ir[pos];
-                const double2 R = c_xy[pos];
-                const double *pa = a_prob + (i64)qr * K, *pr = r_prob + (i64)ir.y * K;
-                double sum = 0.0;
-                for (int c = 0; c < K; ++c) sum = __dadd_rn(sum, fabs(__dsub_rn(pa[c], pr[c])));   // left to right
-                const double dc = __dadd_rn(fabs(__dsub_rn(qx, R.x)), fabs(__dsub_rn(qy, R.y)));
-                const i64 o = (i64)qi * knn + (u - head);
-                cand[o] = ir.x;
-                ctab[o] = __dadd_rn(__dmul_rn(ct_coeff, sum), __dmul_rn(dist_coeff, dc));
-                r_used[ir.x] = 1;
-            } else if (u >= head && fq >= 0) {
-                cand[(i64)qi * knn + (u - head)] = -1;
-            }
-        }
-    }   // chunks of this warp
-}
-
-// The queries the tile search handed over (fail_list[0 .. *n_fail) = positions in the sorted aligned frame): exact search
-// with the (d2, instance) list in local memory, one thread per query, then the costs of its pairs.
-__global__ void __launch_bounds__(128) k_knn_exact_list(const unsigned long long *__restrict__ n_fail, const i32 *__restrict__ fail_list,
-                                                        const double2 *__restrict__ sorted_xy, const int2 *__restrict__ sorted_ir,
-                                                        const i32 *__restrict__ a_off, int W, const GridParams *__restrict__ grids,
-                                                        const i32 *__restrict__ r_bin_start, double r2, int knn, const double *__restrict__ a_prob,
-                                                        const double *__restrict__ r_prob, int K, double ct_coeff, double dist_coeff,
-                                                        const i32 *__restrict__ r_src, const double2 *__restrict__ r_xy, i32 *__restrict__ cand,
-                                                        double *__restrict__ ctab, i32 *__restrict__ cnt_out, i32 *__restrict__ r_used) {
-    const i64 k = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= (i64)*n_fail) return;
-    const i32 t = fail_list[k];
-    const double2 q = sorted_xy[t];
-    const int2 ir = sorted_ir[t];
-    const GridParams g = grids[find_window(a_off, W, ir.x)];
-    int cbx, cby;
-    bin_of(g, q, cbx, cby);
-    i32 *oc = cand + (i64)ir.x * knn;
-    const int found = knn_exact_one(q, g, cbx, cby, r_bin_start, sorted_xy, sorted_ir, r2, knn, oc, cnt_out + ir.x, r_used);
-    const double *pa = a_prob + (i64)ir.y * K;
-    for (int u = 0; u < found; ++u) {   // knn_exact_one reports reference instances: row and coordinates through r_src
-        const i32 rrow = r_src[oc[u]];
-        ctab[(i64)ir.x * knn + u] = pair_cost(pa, r_prob + (i64)rrow * K, K, q, r_xy[rrow], ct_coeff, dist_coeff);
-    }
 }
 
 // ---- a2: cell-type priority ------------------------------------------------------------
@@ -834,34 +522,28 @@ __global__ void __launch_bounds__(COMPACT_THREADS, 2) k_compact_frames(
     }
 }
 
-// cost table of the searches that do not compute it themselves (knn > 16): one thread per (aligned instance, slot)
-__global__ void k_cost_table(const i32 *__restrict__ cand, const i32 *__restrict__ cnt, int knn, i64 nAi, const i32 *__restrict__ a_src,
+// one thread per (aligned instance, slot): pair indices + cost (src/same.py:1183-1188)
+__global__ void k_emit_pairs(const i32 *__restrict__ cand, const i32 *__restrict__ eff, int knn, i64 nAi, const i32 *__restrict__ newA,
+                             const i32 *__restrict__ newR, const i32 *__restrict__ poff, const i32 *__restrict__ a_off, int W,
+                             const i32 *__restrict__ ka_off, const i32 *__restrict__ kr_off, const i32 *__restrict__ a_src,
                              const i32 *__restrict__ r_src, const double2 *__restrict__ a_xy, const double2 *__restrict__ r_xy,
-                             const double *__restrict__ a_prob, const double *__restrict__ r_prob, int K, double ct_coeff, double dist_coeff,
-                             double *__restrict__ ctab) {
-    const i64 tid = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-    const i64 i = tid / knn;
-    const int slot = (int)(tid - i * knn);
-    if (i >= nAi || slot >= cnt[i]) return;
-    const i32 ar = a_src[i], rr = r_src[cand[tid]];
-    ctab[tid] = pair_cost(a_prob + (i64)ar * K, r_prob + (i64)rr * K, K, a_xy[ar], r_xy[rr], ct_coeff, dist_coeff);
-}
-
-// The [instance][slot] candidate/cost table -> compacted pairs + costs in the reference's order (src/utils.py:741,
-// src/same.py:1183-1188).  One thread per (aligned instance, slot): the table is read and the outputs are written in address
-// order; the only gather is the 4-byte kept index of the reference instance.
-__global__ void k_emit_pairs(const i32 *__restrict__ cand, const double *__restrict__ ctab, const i32 *__restrict__ eff, int knn, i64 nAi,
-                             const i32 *__restrict__ newA, const i32 *__restrict__ newR, const i32 *__restrict__ poff, const i32 *__restrict__ a_off,
-                             int W, const i32 *__restrict__ ka_off, const i32 *__restrict__ kr_off, int2 *__restrict__ pairs,
-                             double *__restrict__ cost) {
+                             const double *__restrict__ a_prob, const double *__restrict__ r_prob, int K, double ct_coeff,
+                             double dist_coeff, int2 *__restrict__ pairs, double *__restrict__ cost) {
     const i64 tid = (i64)blockIdx.x * blockDim.x + threadIdx.x;
     const i64 i = tid / knn;
     const int slot = (int)(tid - i * knn);
     if (i >= nAi || slot >= eff[i]) return;
     const int w = find_window(a_off, W, (i32)i);
+    const i32 jinst = cand[i * knn + slot];
     const i32 p = poff[i] + slot;
-    pairs[p] = make_int2(newA[i] - ka_off[w], newR[cand[tid]] - kr_off[w]);
-    cost[p] = ctab[tid];
+    pairs[p] = make_int2(newA[i] - ka_off[w], newR[jinst] - kr_off[w]);
+    const i32 ar = a_src[i], rr = r_src[jinst];
+    const double *pa = a_prob + (i64)ar * K, *pr = r_prob + (i64)rr * K;
+    double s = 0.0;
+    for (int c = 0; c < K; ++c) s = __dadd_rn(s, fabs(__dsub_rn(pa[c], pr[c])));  // left-to-right
+    const double2 A = a_xy[ar], R = r_xy[rr];
+    const double dc = __dadd_rn(fabs(__dsub_rn(A.x, R.x)), fabs(__dsub_rn(A.y, R.y)));
+    cost[p] = __dadd_rn(__dmul_rn(ct_coeff, s), __dmul_rn(dist_coeff, dc));
 }
 
 static int bits_for(i64 n) {
@@ -906,29 +588,15 @@ void batch_candidates(Batch *b, double radius, int knn, int priority, double dis
         nbins += (i64)g.nbx * g.nby;
         grids[w] = g;
     }
-    // tile search schedule: bin rows of all windows, numbered window-major (k_row_chunks numbers the chunks on the device)
-    const int kcap = knn <= 4 ? 4 : (knn <= 8 ? 8 : (knn <= 16 ? 16 : 0));
-    std::vector<i32> tile_base(W + 1, 0);   // first bin row of each window
-    for (i64 w = 0; w < W; ++w) {
-        const i64 nt = (i64)tile_base[w] + grids[w].nby;
-        REQUIRE(nt < (1ll << 30), SAME_E_LIMIT, "bin grid too large");
-        tile_base[w + 1] = (i32)nt;
-    }
-    const i32 n_rows = tile_base[W];
     DevBuf<GridParams> d_grids;
-    DevBuf<i32> d_tile_base;
     d_grids.alloc(W, s);
-    d_tile_base.alloc(W + 1, s);
     CK(cudaMemcpyAsync(d_grids.p, grids.data(), sizeof(GridParams) * W, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(d_tile_base.p, tile_base.data(), sizeof(i32) * (W + 1), cudaMemcpyHostToDevice, s));
 
     // counting sort of both frames' instances by bin
     const i64 nb1 = nbins + 1, nI = nAi + nRi;
-    DevBuf<i32> bkey, bcnt, bstart;
-    DevBuf<int2> sorted_ir;
+    DevBuf<i32> bkey, bcnt, bstart, sorted_inst;
     DevBuf<double2> sorted_xy;
-    bkey.alloc(nI, s); bcnt.alloc(2 * nb1, s); bstart.alloc(2 * nb1, s); sorted_ir.alloc(nI + 1, s);
-    sorted_xy.alloc(nI + TILE_RANGE_CAP + 2, s);   // the tile search reads a little past a lane's range without clamping
+    bkey.alloc(nI, s); bcnt.alloc(2 * nb1, s); bstart.alloc(2 * nb1, s); sorted_inst.alloc(nI, s); sorted_xy.alloc(nI, s);
     bcnt.zero(s);
     if (nI > 0)
         LAUNCH(k_bin_count, blocks_for(nI, 256), 256, 0, s, b->a_src.p, b->r_src.p, sec->a_xy.p, sec->r_xy.p, nAi, nRi, b->d_a_off.p, b->d_r_off.p, (int)W,
@@ -936,41 +604,22 @@ void batch_candidates(Batch *b, double radius, int knn, int priority, double dis
     scan_i32(sec, bcnt.p, bstart.p, 2 * nb1, s);
     if (nI > 0)
         LAUNCH(k_bin_scatter, blocks_for(nI, 256), 256, 0, s, b->a_src.p, b->r_src.p, sec->a_xy.p, sec->r_xy.p, nAi, nRi, nb1, bkey.p, bstart.p, bcnt.p,
-               sorted_xy.p, sorted_ir.p);
+               sorted_xy.p, sorted_inst.p);
 
-    // search (+ pair costs): aligned instances are sorted[0, nAi), reference instances sorted[nAi, nAi + nRi); the bin starts
-    // of the reference frame (second half of bstart) are positions in the whole sorted array
+    // top-k search: aligned instances are sorted[0, nAi), reference instances sorted[nAi, nAi + nRi); the bin starts of
+    // the reference frame (second half of bstart) are positions in the whole sorted array
     b->cand.alloc(nAi * knn, s);
-    b->ctab.alloc(nAi * knn, s);
     b->cnt.alloc(nAi + 1, s);
     b->r_used.alloc(nRi + 1, s);
     b->r_used.zero(s);
-    b->knn_stats.alloc(2, s);
-    b->knn_stats.zero(s);
     const double r2 = radius * radius;
-    const double dist_coeff = dist_ct_coeff * 0.001;   // src/same.py:1183
-    if (nAi > 0 && kcap != 0) {
-        // the probability rows go up on the auxiliary stream (section_build): first use is here
-        if (sec->aux_ready) CK(cudaStreamWaitEvent(s, sec->aux_ready, 0));
-        const unsigned grid = (unsigned)n_rows;   // one block per bin row
-        static const int tile_dbg = getenv("SAME_B200_TILE_DBG") ? atoi(getenv("SAME_B200_TILE_DBG")) : 0;   // timing experiments only
-        DevBuf<i32> fail_list;
-        fail_list.alloc(nAi, s);
-#define TILE_ARGS sorted_xy.p, sorted_ir.p, d_tile_base.p, (int)W, d_grids.p, bstart.p, bstart.p + nb1, r2, knn, sec->a_prob.p, sec->r_prob.p, sec->K, \
-                  dist_ct_coeff, dist_coeff, b->cand.p, b->ctab.p, b->cnt.p, b->r_used.p, b->knn_stats.p, fail_list.p, tile_dbg
-        if (kcap == 4) LAUNCH(k_knn_tile<4>, grid, TILE_THREADS, 0, s, TILE_ARGS);
-        else if (kcap == 8) LAUNCH(k_knn_tile<8>, grid, TILE_THREADS, 0, s, TILE_ARGS);
-        else LAUNCH(k_knn_tile<16>, grid, TILE_THREADS, 0, s, TILE_ARGS);
-        // the handed-over queries (count on the device: the grid covers the worst case, surplus blocks return at once)
-        if (!(tile_dbg & 1))
-            LAUNCH(k_knn_exact_list, blocks_for(nAi, 128), 128, 0, s, b->knn_stats.p, fail_list.p, sorted_xy.p, sorted_ir.p, b->d_a_off.p, (int)W, d_grids.p,
-                   bstart.p + nb1, r2, knn, sec->a_prob.p, sec->r_prob.p, sec->K, dist_ct_coeff, dist_coeff, b->r_src.p, sec->r_xy.p, b->cand.p, b->ctab.p,
-                   b->cnt.p, b->r_used.p);
-#undef TILE_ARGS
-    } else if (nAi > 0) {
+    if (nAi > 0) {
         const unsigned grid = blocks_for(nAi, 128);
-#define KNN_ARGS sorted_xy.p, sorted_ir.p, nAi, b->d_a_off.p, (int)W, d_grids.p, bstart.p + nb1, sorted_xy.p, sorted_ir.p, r2, knn
-        if (knn <= 32) LAUNCH(k_knn<32>, grid, 128, 0, s, KNN_ARGS, b->cand.p, b->cnt.p, b->r_used.p);
+#define KNN_ARGS sorted_xy.p, sorted_inst.p, nAi, b->d_a_off.p, (int)W, d_grids.p, bstart.p + nb1, sorted_xy.p, sorted_inst.p, r2, knn
+        if (knn <= 4) LAUNCH(k_knn<4>, grid, 128, 0, s, KNN_ARGS, b->cand.p, b->cnt.p, b->r_used.p);
+        else if (knn <= 8) LAUNCH(k_knn<8>, grid, 128, 0, s, KNN_ARGS, b->cand.p, b->cnt.p, b->r_used.p);
+        else if (knn <= 16) LAUNCH(k_knn<16>, grid, 128, 0, s, KNN_ARGS, b->cand.p, b->cnt.p, b->r_used.p);
+        else if (knn <= 32) LAUNCH(k_knn<32>, grid, 128, 0, s, KNN_ARGS, b->cand.p, b->cnt.p, b->r_used.p);
         else {
             DevBuf<double> gd;
             DevBuf<i32> gj;
@@ -978,9 +627,6 @@ void batch_candidates(Batch *b, double radius, int knn, int priority, double dis
             LAUNCH(k_knn_big, grid, 128, 0, s, KNN_ARGS, gd.p, gj.p, b->cand.p, b->cnt.p, b->r_used.p);
         }
 #undef KNN_ARGS
-        if (sec->aux_ready) CK(cudaStreamWaitEvent(s, sec->aux_ready, 0));
-        LAUNCH(k_cost_table, blocks_for(nAi * knn, 256), 256, 0, s, b->cand.p, b->cnt.p, knn, nAi, b->a_src.p, b->r_src.p, sec->a_xy.p, sec->r_xy.p,
-               sec->a_prob.p, sec->r_prob.p, sec->K, dist_ct_coeff, dist_coeff, b->ctab.p);
     }
 
     // first use of the columns that section_build uploads on the auxiliary stream (type codes, sizes, probabilities)
@@ -1018,18 +664,13 @@ void batch_candidates(Batch *b, double radius, int knn, int priority, double dis
     b->d_ka_off.alloc(W + 1, s); b->d_kr_off.alloc(W + 1, s); b->d_p_off.alloc(W + 1, s);
     LAUNCH(k_window_offsets, blocks_for(W + 1, 128), 128, 0, s, b->newA.p, newR.p, poff.p, b->d_a_off.p, b->d_r_off.p, (int)W, off3.p, b->d_ka_off.p,
            b->d_kr_off.p, b->d_p_off.p);
+    // (measured and not kept: one thread per row with 8 gather chains in flight, 224 us vs 129 us; rows visited in bin order so
+    // that neighbouring warps gather the same reference rows, 128 us; two slots per thread, 130 us — the kernel moves 292 MB of
+    // scattered 32-byte sectors through DRAM at 2.3 TB/s either way; profiles/r1m)
     if (nAi > 0)
-        LAUNCH(k_emit_pairs, blocks_for(nAi * knn, 256), 256, 0, s, b->cand.p, b->ctab.p, eff, knn, nAi, b->newA.p, newR.p, poff.p, b->d_a_off.p, (int)W,
-               b->d_ka_off.p, b->d_kr_off.p, b->pairs.p, b->cost.p);
-    {
-        static const bool show = getenv("SAME_B200_KNN_STATS") != nullptr;   // development aid: queries that took the exact path
-        if (show) {
-            unsigned long long h[2] = {0, 0};
-            CK(cudaMemcpyAsync(h, b->knn_stats.p, sizeof(h), cudaMemcpyDeviceToHost, s));
-            CK(cudaStreamSynchronize(s));
-            fprintf(stderr, "[same_b200] tile search: %llu of %lld queries took the exact path, %d bin rows\n", h[0], (long long)nAi, (int)n_rows);
-        }
-    }
+        LAUNCH(k_emit_pairs, blocks_for(nAi * knn, 256), 256, 0, s, b->cand.p, eff, knn, nAi, b->newA.p, newR.p, poff.p, b->d_a_off.p, (int)W,
+               b->d_ka_off.p, b->d_kr_off.p, b->a_src.p, b->r_src.p, sec->a_xy.p, sec->r_xy.p, sec->a_prob.p, sec->r_prob.p, sec->K,
+               dist_ct_coeff, dist_ct_coeff * 0.001, b->pairs.p, b->cost.p);
     // the window offsets come back asynchronously; whoever needs them on the host first waits for them (batch_settle)
     CK(cudaMemcpyAsync(b->pin_cand(), off3.p, sizeof(i32) * 3 * (W + 1), cudaMemcpyDeviceToHost, s));
     b->pend_cand = true;

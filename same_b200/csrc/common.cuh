@@ -154,7 +154,7 @@ void scan_reserve(Section *sec, i64 words, cudaStream_t s);
 ScanCtx scan_ctx_at(Section *sec, i64 word_offset, i64 tiles);
 void scan_i32(Section *sec, const i32 *in, i32 *out, i64 n, cudaStream_t s);   // out[i] = sum(in[0..i-1]), one launch
 
-struct GridParams {  // uniform bin grid of one window (both frames are binned on it)
+struct GridParams {  // uniform bin grid of one window (reference side)
     double x0, y0, inv_w, w;
     i32 nbx, nby, base, rings;
 };
@@ -211,8 +211,6 @@ struct Batch {
     int knn = 0;
     double radius = 0;
     DevBuf<i32> cand, cnt, eff;         // [nAi*knn] ref instance, [nAi], [nAi] pairs emitted (priority)
-    DevBuf<double> ctab;                // [nAi*knn] cost of each candidate (computed by the search, streamed out by k_emit_pairs)
-    DevBuf<unsigned long long> knn_stats;   // [1] queries that left the tile search for the exact per-query search
     DevBuf<i32> newA;                   // [nAi+1] batch-global kept index of each aligned instance (exclusive scan of cnt > 0)
     DevBuf<i32> r_used;                 // [nRi]
 
