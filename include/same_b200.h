@@ -86,7 +86,9 @@ enum {
     SAME_ARR_AREA_AFTER = 27,  /* [f64]   same on matched reference XY, NaN when a vertex is unmatched (src/same.py:1379-1395) */
     SAME_ARR_FLIPPED = 28,     /* [u8]    area_before*area_after < 0 (src/same.py:1398) */
     SAME_ARR_START_X = 29,     /* [u8]    greedy MIP start: 1 on the chosen pairs (src/init_helpers.py:124-130, x_vars[..].Start) */
-    SAME_ARR_START_UNMATCHED = 30 /* [u8] greedy MIP start: 1 on kept aligned rows left unmatched (src/init_helpers.py:132, no_match_vars[..].Start) */
+    SAME_ARR_START_UNMATCHED = 30,/* [u8] greedy MIP start: 1 on kept aligned rows left unmatched (src/init_helpers.py:132, no_match_vars[..].Start) */
+    SAME_ARR_PAIR_J = 31       /* [i32]   reference index of each pair = PAIRS[:, 1] on its own.  The aligned index PAIRS[:, 0] is implied by ROW_PTR
+                                  (pairs are sorted by aligned row, src/utils.py:720-731), so ROW_PTR + PAIR_J is valid_pairs in half the bytes over PCIe */
 };
 
 typedef struct same_section same_section_t;
@@ -211,6 +213,10 @@ SAME_API int same_batch_get(same_batch_t *b, int what, int64_t elem_lo, int64_t 
 /* n copies issued back to back on the batch's stream with ONE synchronisation at the end:
  * array what[k], elements [lo[k], hi[k]) -> dst[k] (host, ideally pinned, or device) */
 SAME_API int same_batch_get_many(same_batch_t *b, int64_t n, const int32_t *what, const int64_t *lo, const int64_t *hi, void *const *dst);
+/* The same copies WITHOUT the final synchronisation: the call returns once they are queued on the batch's stream, so the caller can
+ * start the next section on another stream while this one's results cross PCIe (full duplex with its uploads).  dst must be
+ * page-locked (or device) memory and stay valid until same_batch_sync(b) has returned; only then may it be read. */
+SAME_API int same_batch_get_many_async(same_batch_t *b, int64_t n, const int32_t *what, const int64_t *lo, const int64_t *hi, void *const *dst);
 /* page-locked host memory for inputs/outputs (cudaHostAlloc / cudaFreeHost) */
 SAME_API int same_pinned_alloc(int64_t bytes, void **out);
 SAME_API int same_pinned_free(void *p);
@@ -218,6 +224,13 @@ SAME_API int same_pinned_free(void *p);
 SAME_API int64_t same_elem_size(int what);
 /* block until everything queued on the batch's stream has finished */
 SAME_API int same_batch_sync(same_batch_t *b);
+/* A CUDA stream owned by the caller (cudaStreamCreateWithFlags(cudaStreamNonBlocking) / cudaStreamDestroy) for hosts without their
+ * own CUDA binding: pass it as `stream` to same_section_create.  Sections that alternate between a FIXED pair of such streams
+ * overlap one section's downloads with the next one's uploads and kernels, and the stream-ordered memory pool recycles their
+ * buffers without touching the driver (a new stream per section does not: its first allocations cannot reuse memory that
+ * was freed on other streams). */
+SAME_API int same_stream_create(int device, void **stream);
+SAME_API int same_stream_destroy(int device, void *stream);
 /* stream the batch runs on (cudaStream_t), for event timing by the caller */
 SAME_API void *same_batch_stream(same_batch_t *b);
 /* FP64 vector peak of the device in TFLOP/s, measured with an FMA micro-kernel (eight independent chains per thread, best of

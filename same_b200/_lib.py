@@ -23,6 +23,7 @@ TRI_IN, TRI_IN_SRC, TRI_CLASS, TRI_BAND, TRI, TRI_SRC = 12, 13, 14, 15, 16, 17
 TRI_WEIGHT, TRI_SIGN, TRI_BOUNDS, TRI_ARGV, UNCONSTRAINED = 18, 19, 20, 21, 22
 MATCH_J, MATCH_P, TRI_MASK, AREA_BEFORE, AREA_AFTER, FLIPPED = 23, 24, 25, 26, 27, 28
 START_X, START_UNMATCHED = 29, 30
+PAIR_J = 31
 
 #: numpy dtype and trailing shape of every retrievable array
 ARRAY_SPEC = {
@@ -35,7 +36,7 @@ ARRAY_SPEC = {
     TRI_BOUNDS: (np.float64, (4,)), TRI_ARGV: (np.int32, (4,)), UNCONSTRAINED: (np.int32, ()),
     MATCH_J: (np.int32, ()), MATCH_P: (np.int32, ()), TRI_MASK: (np.int32, ()),
     AREA_BEFORE: (np.float64, ()), AREA_AFTER: (np.float64, ()), FLIPPED: (np.uint8, ()),
-    START_X: (np.uint8, ()), START_UNMATCHED: (np.uint8, ()),
+    START_X: (np.uint8, ()), START_UNMATCHED: (np.uint8, ()), PAIR_J: (np.int32, ()),
 }
 
 TRI_DROP_RADIUS, TRI_DROP_ANGLE, TRI_SAME_TYPE, TRI_KEEP = 0, 1, 2, 3
@@ -48,8 +49,9 @@ SYMBOLS = [
     "same_batch_triangles_set", "same_batch_tri_classify", "same_batch_tri_override", "same_batch_tri_finalize",
     "same_batch_groups", "same_batch_separation", "same_batch_postsolve", "same_batch_offsets", "same_batch_length",
     "same_batch_get", "same_elem_size", "same_batch_sync", "same_batch_stream", "same_launch_count",
-    "same_profile_enable", "same_profile_report", "same_batch_get_many", "same_pinned_alloc", "same_pinned_free",
+    "same_profile_enable", "same_profile_report", "same_batch_get_many", "same_batch_get_many_async", "same_pinned_alloc", "same_pinned_free",
     "same_postsolve_arrays", "same_batch_mip_start", "same_greedy_select", "same_collapse_select", "same_segment_mean", "same_measure_fp64_peak", "same_section_wait_uploads",
+    "same_stream_create", "same_stream_destroy",
 ]
 
 
@@ -105,6 +107,7 @@ def load():
     lib.same_batch_stream.restype = vp
     lib.same_launch_count.restype = i64
     lib.same_batch_get_many.argtypes = [vp, i64, vp, vp, vp, vp]
+    lib.same_batch_get_many_async.argtypes = [vp, i64, vp, vp, vp, vp]
     lib.same_pinned_alloc.argtypes = [i64, C.POINTER(vp)]
     lib.same_pinned_free.argtypes = [vp]
     lib.same_postsolve_arrays.argtypes = [i32, i64, vp, i64, vp, i64, vp, vp, vp, vp, vp, vp]
@@ -114,6 +117,8 @@ def load():
     lib.same_segment_mean.argtypes = [i32, i64, i64, vp, i64, vp, vp, vp]
     lib.same_measure_fp64_peak.argtypes = [i32, C.POINTER(C.c_double)]
     lib.same_profile_enable.argtypes = [i32]
+    lib.same_stream_create.argtypes = [i32, C.POINTER(vp)]
+    lib.same_stream_destroy.argtypes = [i32, vp]
     lib.same_profile_report.argtypes = [C.c_char_p, i64]
     lib.same_profile_report.restype = i64
     assert lib.same_abi_version() == 1

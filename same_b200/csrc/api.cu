@@ -31,6 +31,7 @@ struct ArrayView {
 i64 elem_size(int what) {
     switch (what) {
         case SAME_ARR_PAIRS: return 8;
+        case SAME_ARR_PAIR_J: return 4;
         case SAME_ARR_COST: case SAME_ARR_TRI_WEIGHT: case SAME_ARR_AREA_BEFORE: case SAME_ARR_AREA_AFTER: return 8;
         case SAME_ARR_TRI_IN: case SAME_ARR_TRI: return 12;
         case SAME_ARR_TRI_CLASS: case SAME_ARR_TRI_SIGN: case SAME_ARR_FLIPPED: case SAME_ARR_START_X: case SAME_ARR_START_UNMATCHED: return 1;
@@ -52,6 +53,7 @@ ArrayView view(Batch *b, int what) {
         case SAME_ARR_KEEP_R: need(1, "candidates not run"); return {b->keepR.p, b->nKR, es, &b->kr_off};
         case SAME_ARR_PAIRS: need(1, "candidates not run"); return {b->pairs.p, b->P, es, &b->p_off};
         case SAME_ARR_COST: need(1, "candidates not run"); return {b->cost.p, b->P, es, &b->p_off};
+        case SAME_ARR_PAIR_J: need(1, "candidates not run"); batch_pair_j(b); return {b->pair_j.p, b->P, es, &b->p_off};
         case SAME_ARR_ROW_PTR: need(1, "candidates not run"); return {b->row_ptr.p, b->nKA + 1, es, nullptr};
         case SAME_ARR_REF_GROUP_NODE: REQUIRE(b->have_groups, SAME_E_STATE, "groups not built"); return {b->g_node.p, b->G, es, &b->g_off};
         case SAME_ARR_REF_GROUP_LIMIT: REQUIRE(b->have_groups, SAME_E_STATE, "groups not built"); return {b->g_limit.p, b->G, es, &b->g_off};
@@ -151,8 +153,9 @@ int same_section_create(int device, void *stream, int64_t n_aligned, int64_t n_r
         } catch (...) {
             cudaStream_t aux = sec->aux_stream;
             cudaEvent_t ev = sec->aux_ready;
+            if (aux) cudaStreamSynchronize(aux);   // before the buffers it writes are freed
             delete sec;
-            if (aux) { cudaStreamSynchronize(aux); cudaStreamDestroy(aux); }
+            if (aux) cudaStreamDestroy(aux);
             if (ev) cudaEventDestroy(ev);
             throw;
         }
@@ -177,7 +180,8 @@ int same_section_destroy(same_section_t *h) {
         cudaStream_t s = sec->stream, aux = sec->aux_stream;
         cudaEvent_t ev = sec->aux_ready;
         bool own = sec->own_stream;
-        CK(cudaStreamSynchronize(s));   // buffers allocated on the auxiliary stream are freed there: nothing on `s` may still read them
+        CK(cudaStreamSynchronize(s));
+        if (aux) CK(cudaStreamSynchronize(aux));   // the uploads write buffers that are freed (stream-ordered, on `s`) right below
         delete sec;
         CK(cudaStreamSynchronize(s));
         if (aux) { CK(cudaStreamSynchronize(aux)); CK(cudaStreamDestroy(aux)); }
@@ -242,6 +246,7 @@ int same_batch_destroy(same_batch_t *h) {
         if (!b) return;
         CK(cudaSetDevice(b->sec->device));
         cudaStream_t s = b->stream;
+        CK(cudaStreamSynchronize(s));   // nothing queued may still read the batch's page-locked staging blocks
         batch_pin_release(b);
         delete b;
         CK(cudaStreamSynchronize(s));
@@ -350,19 +355,27 @@ int same_batch_get(same_batch_t *h, int what, int64_t elem_lo, int64_t elem_hi, 
     });
 }
 
+// every entry is validated before the first copy is queued: an error must not leave copies into the caller's buffers in flight
+static void get_many(Batch *b, int64_t n, const int32_t *what, const int64_t *lo, const int64_t *hi, void *const *dst, bool sync) {
+    REQUIRE(n >= 0 && (n == 0 || (what && lo && hi && dst)), SAME_E_ARG, "NULL argument");
+    std::vector<ArrayView> views((size_t)n);
+    for (int64_t k = 0; k < n; ++k) {
+        views[k] = view(b, what[k]);
+        REQUIRE(lo[k] >= 0 && lo[k] <= hi[k] && hi[k] <= views[k].n, SAME_E_ARG, "element range out of bounds");
+        REQUIRE(hi[k] == lo[k] || dst[k], SAME_E_ARG, "dst is NULL");
+    }
+    for (int64_t k = 0; k < n; ++k)
+        if (hi[k] > lo[k])
+            CK(cudaMemcpyAsync(dst[k], (const char *)views[k].p + lo[k] * views[k].esize, (size_t)((hi[k] - lo[k]) * views[k].esize), cudaMemcpyDefault,
+                               b->stream));
+    if (sync) CK(cudaStreamSynchronize(b->stream));
+}
+
 int same_batch_get_many(same_batch_t *h, int64_t n, const int32_t *what, const int64_t *lo, const int64_t *hi, void *const *dst) {
-    BATCH_CALL(h, {
-        REQUIRE(n >= 0 && (n == 0 || (what && lo && hi && dst)), SAME_E_ARG, "NULL argument");
-        for (int64_t k = 0; k < n; ++k) {
-            ArrayView v = view(b, what[k]);
-            REQUIRE(lo[k] >= 0 && lo[k] <= hi[k] && hi[k] <= v.n, SAME_E_ARG, "element range out of bounds");
-            if (hi[k] > lo[k]) {
-                REQUIRE(dst[k], SAME_E_ARG, "dst is NULL");
-                CK(cudaMemcpyAsync(dst[k], (const char *)v.p + lo[k] * v.esize, (size_t)((hi[k] - lo[k]) * v.esize), cudaMemcpyDefault, b->stream));
-            }
-        }
-        CK(cudaStreamSynchronize(b->stream));
-    });
+    BATCH_CALL(h, get_many(b, n, what, lo, hi, dst, true));
+}
+int same_batch_get_many_async(same_batch_t *h, int64_t n, const int32_t *what, const int64_t *lo, const int64_t *hi, void *const *dst) {
+    BATCH_CALL(h, get_many(b, n, what, lo, hi, dst, false));
 }
 
 int same_pinned_alloc(int64_t bytes, void **out) {
@@ -376,5 +389,23 @@ int same_pinned_free(void *p) {
 }
 
 int same_batch_sync(same_batch_t *h) { BATCH_CALL(h, batch_sync(b)); }
+
+int same_stream_create(int device, void **stream) {
+    return guarded([&] {
+        REQUIRE(stream, SAME_E_ARG, "stream is NULL");
+        CK(cudaSetDevice(device));
+        cudaStream_t s;
+        CK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+        *stream = (void *)s;
+    });
+}
+int same_stream_destroy(int device, void *stream) {
+    return guarded([&] {
+        if (!stream) return;
+        CK(cudaSetDevice(device));
+        CK(cudaStreamSynchronize((cudaStream_t)stream));
+        CK(cudaStreamDestroy((cudaStream_t)stream));
+    });
+}
 
 }  // extern "C"

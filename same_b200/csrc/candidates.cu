@@ -546,6 +546,18 @@ __global__ void k_emit_pairs(const i32 *__restrict__ cand, const i32 *__restrict
     cost[p] = __dadd_rn(__dmul_rn(ct_coeff, s), __dmul_rn(dist_coeff, dc));
 }
 
+// SAME_ARR_PAIR_J: the reference index of every pair as its own array (half the bytes of PAIRS over PCIe)
+__global__ void k_pair_j(const int2 *__restrict__ pairs, i64 P, i32 *__restrict__ pj) {
+    const i64 p = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < P) pj[p] = pairs[p].y;
+}
+void batch_pair_j(Batch *b) {
+    if (b->have_pair_j) return;
+    b->pair_j.alloc(b->P, b->stream);
+    if (b->P > 0) LAUNCH(k_pair_j, blocks_for(b->P, 256), 256, 0, b->stream, b->pairs.p, b->P, b->pair_j.p);
+    b->have_pair_j = true;
+}
+
 static int bits_for(i64 n) {
     int b = 1;
     while ((1ll << b) < n) ++b;
@@ -590,7 +602,7 @@ void batch_candidates(Batch *b, double radius, int knn, int priority, double dis
     }
     DevBuf<GridParams> d_grids;
     d_grids.alloc(W, s);
-    CK(cudaMemcpyAsync(d_grids.p, grids.data(), sizeof(GridParams) * W, cudaMemcpyHostToDevice, s));
+    small_h2d(b->arena, d_grids.p, grids.data(), sizeof(GridParams) * W, s);
 
     // counting sort of both frames' instances by bin
     const i64 nb1 = nbins + 1, nI = nAi + nRi;
@@ -672,12 +684,13 @@ void batch_candidates(Batch *b, double radius, int knn, int priority, double dis
                b->d_ka_off.p, b->d_kr_off.p, b->a_src.p, b->r_src.p, sec->a_xy.p, sec->r_xy.p, sec->a_prob.p, sec->r_prob.p, sec->K,
                dist_ct_coeff, dist_ct_coeff * 0.001, b->pairs.p, b->cost.p);
     // the window offsets come back asynchronously; whoever needs them on the host first waits for them (batch_settle)
-    CK(cudaMemcpyAsync(b->pin_cand(), off3.p, sizeof(i32) * 3 * (W + 1), cudaMemcpyDeviceToHost, s));
+    small_d2h(b->pin_cand(), off3.p, sizeof(i32) * 3 * (W + 1), s);
     b->pend_cand = true;
     b->pend_renum = false;
     b->stage = 1;
     b->have_groups = false;
     b->have_start = false;
+    b->have_pair_j = false;
     b->Tin = b->T = 0;
 }
 
@@ -819,7 +832,7 @@ void batch_groups(Batch *b, int max_matches, int multiplier) {
     LAUNCH(k_group_heads, blocks_for(P + 1, 256), 256, 0, s, b->pairs.p, P, b->d_p_off.p, b->d_kr_off.p, (int)W, first.p, head.p);
     scan_i32(b->sec, head.p, gid_at.p, P + 1, s);
     LAUNCH(k_pick, blocks_for(W + 1, 128), 128, 0, s, gid_at.p, b->d_p_off.p, (int)(W + 1), goff.p);
-    CK(cudaMemcpyAsync(b->pin_groups(), goff.p, sizeof(i32) * (W + 1), cudaMemcpyDeviceToHost, s));
+    small_d2h(b->pin_groups(), goff.p, sizeof(i32) * (W + 1), s);
     b->pend_groups = true;
     LAUNCH(k_window_max_size, blocks_for(nKR, 256), 256, 0, s, b->kr_size.p, nKR, b->d_kr_off.p, (int)W, wmax.p);
     LAUNCH(k_group_setup, blocks_for(nKR, 256), 256, 0, s, nKR, b->d_kr_off.p, (int)W, first.p, cnt.p, gid_at.p, b->kr_size.p, wmax.p, max_matches,

@@ -4,6 +4,7 @@
 #include <cub/cub.cuh>
 
 #include <atomic>
+#include <mutex>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -119,6 +120,21 @@ struct Scratch {
 // exclusive prefix sum of n i32 -> out[n] (+ out[n] = total when with_total)
 void exclusive_scan_i32(const i32 *in, i32 *out, i64 n, Scratch &sc, cudaStream_t s);
 
+// Small host <-> device transfers (window offsets, counts, rectangle lists, grid parameters) do not go through the copy
+// engines: a large transfer of ANOTHER section queued on the same engine (CandidateStream overlaps one section's download with
+// the next one's upload and kernels) would hold a 32-byte read-back for milliseconds.  Instead a tiny kernel moves the words
+// between device memory and page-locked, device-mapped host memory, ordered on the stream like any other launch.
+struct PinArena {   // bump allocator over page-locked blocks of a process-wide pool (section.cu); blocks return to the pool on release
+    std::vector<std::pair<char *, size_t>> blocks;
+    size_t used = 0;
+    void *get(size_t bytes);
+    void release();
+    ~PinArena() { release(); }
+};
+constexpr size_t SMALL_COPY_LIMIT = 256 << 10;   // larger transfers use cudaMemcpyAsync
+void small_d2h(void *host_pinned, const void *dev, size_t bytes, cudaStream_t s);             // host_pinned: page-locked (cudaHostAlloc)
+void small_h2d(PinArena &arena, void *dev, const void *host, size_t bytes, cudaStream_t s);   // host: any memory, staged through the arena
+
 struct Section {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -137,14 +153,10 @@ struct Section {
     i64 Tg = -1;
     DevBuf<i32> tri_rows;  // [Tg*3]
     Scratch scratch;
+    PinArena arena;
     // tile states of the in-kernel prefix sums (scan.cuh): zeroed when (re)allocated, separated by epoch afterwards
     DevBuf<unsigned long long> scan_state;
     unsigned scan_epoch = 0;
-    // page-locked staging blocks handed to batches (small device results come back asynchronously, see Batch::pin)
-    std::vector<std::pair<i32 *, i64>> pin_pool;
-    ~Section() {
-        for (auto &b : pin_pool) cudaFreeHost(b.first);
-    }
 };
 
 // tile-state context for one launch of `tiles` blocks scanning `n_streams` sums; a launch that runs several independent
@@ -184,6 +196,7 @@ struct Batch {
     std::vector<i32> h_ri_ptr, h_ri_rects;
     RectIndexDev rindex{};
     Scratch scratch;
+    PinArena arena;
     int stage = 0;  // 0 created, 1 candidates, 2 triangles in, 3 classified, 4 finalized
 
     // Small per-window results (offsets, counts) are copied to this page-locked block asynchronously and parsed into the
@@ -223,6 +236,8 @@ struct Batch {
     DevBuf<i32> ka_type;
     DevBuf<double> ka_size, kr_size;
     DevBuf<int2> pairs;                 // window-local (i, j)
+    DevBuf<i32> pair_j;                 // pairs[].y on its own, built on first request (SAME_ARR_PAIR_J)
+    bool have_pair_j = false;
     DevBuf<double> cost;
     DevBuf<i32> row_ptr;                // [nKA+1] batch-global pair offset of each aligned row
 
@@ -287,6 +302,7 @@ void section_set_triangles(Section *sec, const i64 *a_vid, const i64 *tri_vid, i
 void batch_subset(Batch *b);
 void batch_candidates(Batch *b, double radius, int knn, int priority, double dist_ct_coeff);
 void batch_groups(Batch *b, int max_matches, int multiplier);
+void batch_pair_j(Batch *b);
 void batch_triangles_remap(Batch *b);
 void batch_triangles_set(Batch *b, const i32 *tri, const i64 *tri_off);
 void batch_tri_classify(Batch *b, double radius, int use_angle, double min_angle_deg, int ignore_same_type);

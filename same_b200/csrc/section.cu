@@ -27,20 +27,82 @@ void upload_offsets(const std::vector<i64> &h, DevBuf<i32> &d, cudaStream_t s) {
     CK(cudaStreamSynchronize(s));  // t goes out of scope
 }
 
+// ---- small transfers without the copy engines (see common.cuh) ----------------------------------------
+static std::mutex g_arena_mu;
+static std::vector<std::pair<char *, size_t>> g_arena_pool;
+constexpr size_t ARENA_BLOCK = 1 << 20;
+void *PinArena::get(size_t bytes) {
+    bytes = (bytes + 15) & ~(size_t)15;
+    if (blocks.empty() || used + bytes > blocks.back().second) {
+        const size_t want = std::max(bytes, ARENA_BLOCK);
+        std::pair<char *, size_t> blk{nullptr, 0};
+        {
+            std::lock_guard<std::mutex> lk(g_arena_mu);
+            for (size_t k = 0; k < g_arena_pool.size(); ++k)
+                if (g_arena_pool[k].second >= want) { blk = g_arena_pool[k]; g_arena_pool.erase(g_arena_pool.begin() + k); break; }
+        }
+        if (!blk.first) {
+            CK(cudaHostAlloc((void **)&blk.first, want, cudaHostAllocPortable | cudaHostAllocMapped));
+            blk.second = want;
+        }
+        blocks.push_back(blk);
+        used = 0;
+    }
+    void *p = blocks.back().first + used;
+    used += bytes;
+    return p;
+}
+void PinArena::release() {
+    if (blocks.empty()) return;
+    std::lock_guard<std::mutex> lk(g_arena_mu);
+    for (auto &b : blocks) g_arena_pool.push_back(b);   // kept for the life of the process: cudaFreeHost synchronises the device
+    blocks.clear();
+    used = 0;
+}
+__global__ void k_copy_words(unsigned *__restrict__ dst, const unsigned *__restrict__ src, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+static void copy_words(void *dst, const void *src, size_t bytes, cudaStream_t s) {
+    const size_t n = bytes / 4;
+    LAUNCH(k_copy_words, (unsigned)std::min<size_t>(64, (n + 255) / 256), 256, 0, s, (unsigned *)dst, (const unsigned *)src, n);
+}
+void small_d2h(void *host_pinned, const void *dev, size_t bytes, cudaStream_t s) {
+    if (bytes == 0) return;
+    if (bytes > SMALL_COPY_LIMIT || (bytes & 3)) { CK(cudaMemcpyAsync(host_pinned, dev, bytes, cudaMemcpyDeviceToHost, s)); return; }
+    copy_words(host_pinned, dev, bytes, s);
+}
+void small_h2d(PinArena &arena, void *dev, const void *host, size_t bytes, cudaStream_t s) {
+    if (bytes == 0) return;
+    if (bytes > SMALL_COPY_LIMIT || (bytes & 3)) { CK(cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, s)); return; }
+    void *stage = arena.get(bytes);
+    memcpy(stage, host, bytes);
+    copy_words(dev, stage, bytes, s);
+}
+
+// Page-locked staging blocks for the small per-window results live in a process-wide pool and are never handed back to the
+// driver while the library is loaded: cudaHostAlloc / cudaFreeHost synchronise the whole device, which would serialise
+// sections that are meant to overlap on different streams (CandidateStream).
+static std::mutex g_pin_mu;
+static std::vector<std::pair<i32 *, i64>> g_pin_pool;
 void batch_pin_acquire(Batch *b) {
     const i64 need = 10 * (b->W + 1) + 8;
-    auto &pool = b->sec->pin_pool;
-    for (size_t k = 0; k < pool.size(); ++k)
-        if (pool[k].second >= need) {
-            b->pin = pool[k].first; b->pin_n = pool[k].second;
-            pool.erase(pool.begin() + k);
-            return;
-        }
+    {
+        std::lock_guard<std::mutex> lk(g_pin_mu);
+        for (size_t k = 0; k < g_pin_pool.size(); ++k)
+            if (g_pin_pool[k].second >= need) {
+                b->pin = g_pin_pool[k].first; b->pin_n = g_pin_pool[k].second;
+                g_pin_pool.erase(g_pin_pool.begin() + k);
+                return;
+            }
+    }
     b->pin_n = std::max<i64>(need, 4096);
-    CK(cudaHostAlloc((void **)&b->pin, sizeof(i32) * (size_t)b->pin_n, cudaHostAllocDefault));
+    CK(cudaHostAlloc((void **)&b->pin, sizeof(i32) * (size_t)b->pin_n, cudaHostAllocPortable | cudaHostAllocMapped));
 }
 void batch_pin_release(Batch *b) {
-    if (b->pin) b->sec->pin_pool.emplace_back(b->pin, b->pin_n);
+    if (b->pin) {
+        std::lock_guard<std::mutex> lk(g_pin_mu);
+        g_pin_pool.emplace_back(b->pin, b->pin_n);
+    }
     b->pin = nullptr;
 }
 
@@ -129,28 +191,37 @@ void section_build(Section *sec, const double *a_xy, const double *r_xy, const d
     upload(sec->a_xy, a_xy, nA, s);
     upload(sec->r_xy, r_xy, nR, s);
     // everything else goes up on the auxiliary stream: the synchronisation below (bounding box) then waits for the
-    // coordinates only, and the first stages of a batch overlap the rest of the upload
+    // coordinates only, and the first stages of a batch overlap the rest of the upload.  The buffers themselves are allocated
+    // (and later freed) on the section's own stream, so that sections which reuse a stream recycle them through the
+    // stream-ordered pool; the auxiliary stream only waits for the allocations and copies.
+    sec->a_prob.alloc(nA * K, s); sec->r_prob.alloc(nR * K, s); sec->a_type.alloc(nA, s); sec->r_type.alloc(nR, s);
+    sec->a_size.alloc(nA, s); sec->r_size.alloc(nR, s);
     CK(cudaStreamCreateWithFlags(&sec->aux_stream, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&sec->aux_ready, cudaEventDisableTiming));
     cudaStream_t x = sec->aux_stream;
-    upload(sec->a_prob, a_prob, nA * K, x);
-    upload(sec->r_prob, r_prob, nR * K, x);
-    if (a_type) upload(sec->a_type, a_type, nA, x); else { sec->a_type.alloc(nA, x); sec->a_type.zero(x); }
-    if (r_type) upload(sec->r_type, r_type, nR, x); else { sec->r_type.alloc(nR, x); sec->r_type.zero(x); }
-    if (a_size) upload(sec->a_size, a_size, nA, x);
-    else { sec->a_size.alloc(nA, x); LAUNCH(k_fill_f64, blocks_for(nA, 256), 256, 0, x, sec->a_size.p, nA, 1.0); }
-    if (r_size) upload(sec->r_size, r_size, nR, x);
-    else { sec->r_size.alloc(nR, x); LAUNCH(k_fill_f64, blocks_for(nR, 256), 256, 0, x, sec->r_size.p, nR, 1.0); }
+    CK(cudaEventRecord(sec->aux_ready, s));            // (reused below for its real purpose)
+    CK(cudaStreamWaitEvent(x, sec->aux_ready, 0));
+    auto put = [&](void *dst, const void *src, size_t bytes) {
+        if (bytes > 0) CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, x));
+    };
+    put(sec->a_prob.p, a_prob, sizeof(double) * (size_t)(nA * K));
+    put(sec->r_prob.p, r_prob, sizeof(double) * (size_t)(nR * K));
+    if (a_type) put(sec->a_type.p, a_type, sizeof(i32) * (size_t)nA); else CK(cudaMemsetAsync(sec->a_type.p, 0, sizeof(i32) * (size_t)std::max<i64>(nA, 1), x));
+    if (r_type) put(sec->r_type.p, r_type, sizeof(i32) * (size_t)nR); else CK(cudaMemsetAsync(sec->r_type.p, 0, sizeof(i32) * (size_t)std::max<i64>(nR, 1), x));
+    if (a_size) put(sec->a_size.p, a_size, sizeof(double) * (size_t)nA);
+    else LAUNCH(k_fill_f64, blocks_for(nA, 256), 256, 0, x, sec->a_size.p, nA, 1.0);
+    if (r_size) put(sec->r_size.p, r_size, sizeof(double) * (size_t)nR);
+    else LAUNCH(k_fill_f64, blocks_for(nR, 256), 256, 0, x, sec->r_size.p, nR, 1.0);
     CK(cudaEventRecord(sec->aux_ready, x));
     // bounding box of both frames (src/same.py:481-482)
     DevBuf<unsigned long long> bb;
     bb.alloc(4, s);
     const unsigned long long init[4] = {~0ull, 0ull, ~0ull, 0ull};
-    CK(cudaMemcpyAsync(bb.p, init, sizeof(init), cudaMemcpyHostToDevice, s));
+    small_h2d(sec->arena, bb.p, init, sizeof(init), s);
     if (nA > 0) LAUNCH(k_bbox, std::min<unsigned>(blocks_for(nA, 256), 1184), 256, 0, s, sec->a_xy.p, nA, bb.p);
     if (nR > 0) LAUNCH(k_bbox, std::min<unsigned>(blocks_for(nR, 256), 1184), 256, 0, s, sec->r_xy.p, nR, bb.p);
-    unsigned long long h[4];
-    CK(cudaMemcpyAsync(h, bb.p, sizeof(h), cudaMemcpyDeviceToHost, s));
+    unsigned long long *h = (unsigned long long *)sec->arena.get(4 * sizeof(unsigned long long));
+    small_d2h(h, bb.p, 4 * sizeof(unsigned long long), s);
     CK(cudaStreamSynchronize(s));
     for (int i = 0; i < 4; ++i) sec->bbox[i] = (nA + nR > 0) ? dec_f64(h[i]) : 0.0;
 }
@@ -357,7 +428,7 @@ static void subset_frames_t(Batch *b, int rowbits, int wbits) {
     LAUNCH(k_subset_count, tiles, SUBSET_CT, W <= SUBSET_HIST_W ? sizeof(int) * 2 * (size_t)W : 0, s, sec->a_xy.p, nA, sec->r_xy.p, nR, b->d_rects.p, b->rindex, scan_ctx(sec, tiles, 1, s), W, b->row_pos.p,
            wcount.p);
     i32 *h = b->pin_misc();   // [2W] window sizes, [2] totals, then [2(W+1)] offsets built here for the upload
-    CK(cudaMemcpyAsync(h, wcount.p, sizeof(i32) * (2 * W + 2), cudaMemcpyDeviceToHost, s));
+    small_d2h(h, wcount.p, sizeof(i32) * (2 * W + 2), s);
     batch_sync(b);
     const i64 total = h[2 * W], totalA = h[2 * W + 1];
     REQUIRE(total >= 0 && totalA >= 0, SAME_E_LIMIT, "batch exceeds 2^31 window instances");
@@ -367,8 +438,8 @@ static void subset_frames_t(Batch *b, int rowbits, int wbits) {
     for (i64 w = 0; w < W; ++w) { b->a_off[w + 1] = b->a_off[w] + h[w]; b->r_off[w + 1] = b->r_off[w] + h[W + w]; }
     for (i64 w = 0; w <= W; ++w) { ho[w] = (i32)b->a_off[w]; ho[W + 1 + w] = (i32)b->r_off[w]; }
     b->d_a_off.alloc(W + 1, s); b->d_r_off.alloc(W + 1, s);
-    CK(cudaMemcpyAsync(b->d_a_off.p, ho, sizeof(i32) * (W + 1), cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(b->d_r_off.p, ho + W + 1, sizeof(i32) * (W + 1), cudaMemcpyHostToDevice, s));
+    small_h2d(b->arena, b->d_a_off.p, ho, sizeof(i32) * (W + 1), s);
+    small_h2d(b->arena, b->d_r_off.p, ho + W + 1, sizeof(i32) * (W + 1), s);
     b->a_src.alloc(b->nAi, s); b->r_src.alloc(b->nRi, s); b->row_inst.alloc(total, s);
     if (total == 0) return;
     DevBuf<KeyT> keys, keys_out;
@@ -444,8 +515,8 @@ static void build_rect_index(Batch *b) {
     }
     b->ri_ptr.alloc((i64)ptr.size(), s);
     b->ri_rects.alloc((i64)lst.size(), s);
-    CK(cudaMemcpyAsync(b->ri_ptr.p, ptr.data(), sizeof(i32) * ptr.size(), cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(b->ri_rects.p, lst.data(), sizeof(i32) * lst.size(), cudaMemcpyHostToDevice, s));
+    small_h2d(b->arena, b->ri_ptr.p, ptr.data(), sizeof(i32) * ptr.size(), s);
+    small_h2d(b->arena, b->ri_rects.p, lst.data(), sizeof(i32) * lst.size(), s);
     b->rindex = RectIndexDev{bx0, by0, inv, nx, ny, max_len, b->ri_ptr.p, b->ri_rects.p};
 }
 
@@ -454,7 +525,7 @@ void batch_subset(Batch *b) {
     cudaStream_t s = b->stream;
     batch_pin_acquire(b);
     b->d_rects.alloc(4 * b->W, s);
-    CK(cudaMemcpyAsync(b->d_rects.p, b->rects.data(), sizeof(double) * 4 * b->W, cudaMemcpyHostToDevice, s));
+    small_h2d(b->arena, b->d_rects.p, b->rects.data(), sizeof(double) * 4 * b->W, s);
     build_rect_index(b);
     subset_frames(b);
 }

@@ -169,7 +169,7 @@ void batch_separation(Batch *b, i64 w_lo, i64 w_hi, const double *x, i64 cap, i6
     // counts and cuts come back behind ONE synchronisation: the cut block is small (cap rows per window), so it is copied
     // whole instead of waiting for the counts to know how much of it was filled
     i32 *h_sep = b->pin_misc();   // page-locked (2 nw <= 4(W+1) + 8 ints): a pageable destination would stage and block
-    CK(cudaMemcpyAsync(h_sep, b->sep_counts.p, sizeof(i32) * 2 * nw, cudaMemcpyDeviceToHost, s));
+    small_d2h(h_sep, b->sep_counts.p, sizeof(i32) * 2 * nw, s);
     if (cuts && cap > 0 && nt > 0) CK(cudaMemcpyAsync(cuts, b->cuts.p, sizeof(i32) * 4 * (size_t)(nw * cap), cudaMemcpyDefault, s));
     batch_sync(b);
     for (i64 w = 0; w < nw; ++w) {

@@ -138,7 +138,7 @@ static void remap_t(Batch *b, int tbits, int wbits) {
     const unsigned tiles = blocks_for(Tg + 1, REMAP_CT * REMAP_CI);
     LAUNCH(k_remap_count, tiles, REMAP_CT, 0, s, sec->tri_rows.p, Tg, b->row_pos.p, b->row_inst.p, b->cnt.p, b->newA.p, b->d_ka_off.p,
            scan_ctx(sec, tiles, 1, s), pos.p, first_hit.p);
-    CK(cudaMemcpyAsync(b->pin_misc(), pos.p + Tg, sizeof(i32), cudaMemcpyDeviceToHost, s));
+    small_d2h(b->pin_misc(), pos.p + Tg, sizeof(i32), s);
     batch_sync(b);   // also brings in the candidate stage's window offsets
     b->Tin = (i64)b->pin_misc()[0];
     REQUIRE(b->Tin >= 0, SAME_E_LIMIT, "too many window triangles");
@@ -169,7 +169,7 @@ static void remap_t(Batch *b, int tbits, int wbits) {
     }
     LAUNCH((k_remap_gather<KeyT>), blocks_for(std::max<i64>(b->Tin, W + 1), 256), 256, 0, s, sorted_keys, sorted_idx, recs.p, b->Tin, tbits, W, b->tin.p,
            b->tin_src.p, b->d_tin_off.p);
-    CK(cudaMemcpyAsync(b->pin_tin(), b->d_tin_off.p, sizeof(i32) * (W + 1), cudaMemcpyDeviceToHost, s));
+    small_d2h(b->pin_tin(), b->d_tin_off.p, sizeof(i32) * (W + 1), s);
     b->pend_tin = true;
 }
 
@@ -265,7 +265,7 @@ void batch_tri_classify(Batch *b, double radius, int use_angle, double min_angle
     if (Tin > 0)
         LAUNCH(k_tri_classify, blocks_for(Tin, 256), 256, 0, s, b->tin.p, Tin, b->d_tin_off.p, b->d_ka_off.p, (int)b->W, b->ka_xy.p, b->ka_type.p,
                radius, use_angle, min_angle_deg, ignore_same_type, b->cls.p, b->score.p, b->band_idx.p, bc.p);
-    CK(cudaMemcpyAsync(b->pin_misc(), bc.p, sizeof(i32), cudaMemcpyDeviceToHost, s));
+    small_d2h(b->pin_misc(), bc.p, sizeof(i32), s);
     batch_sync(b);   // also brings in the remap's window offsets
     b->n_band = b->pin_misc()[0];
     b->stage = 3;
@@ -541,7 +541,7 @@ void batch_tri_finalize(Batch *b, int ignore_same_type, int ensure_min, int remo
     exclusive_scan_i32(node_valid.p, validpos.p, nKA + 1, b->scratch, s);  // node_valid[nKA] == 0 from the memset
     LAUNCH(k_tri_window_offsets, blocks_for(W + 1, 128), 128, 0, s, kpos.p, abpos.p, uncpos.p, validpos.p, b->d_tin_off.p, b->d_ka_off.p, (int)W, woff.p);
     const i32 *h = b->pin_misc();
-    CK(cudaMemcpyAsync(b->pin_misc(), woff.p, sizeof(i32) * 4 * (W + 1), cudaMemcpyDeviceToHost, s));
+    small_d2h(b->pin_misc(), woff.p, sizeof(i32) * 4 * (W + 1), s);
     batch_sync(b);   // the one host decision of this stage: sizes, and whether any node has to go
     b->t_off.assign(h, h + W + 1);
     b->unc_off.assign(h + 2 * (W + 1), h + 3 * (W + 1));
@@ -579,7 +579,7 @@ void batch_tri_finalize(Batch *b, int ignore_same_type, int ensure_min, int remo
                    b->row_ptr.p, nKA, scan_ctx(b->sec, tiles, 1, s), pairs2.p, cost2.p, row_ptr2.p, poff2.p);
         }
         // the new per-window pair offsets reach the host with the next synchronisation; the device copies are made in place
-        CK(cudaMemcpyAsync(b->pin_renum(), poff2.p, sizeof(i32) * (W + 1), cudaMemcpyDeviceToHost, s));
+        small_d2h(b->pin_renum(), poff2.p, sizeof(i32) * (W + 1), s);
         b->pend_renum = true;
         if (b->nAi > 0) LAUNCH(k_renumber_instances, blocks_for(b->nAi, 256), 256, 0, s, b->nAi, node_valid.p, validpos.p, b->cnt.p, b->newA.p);
         b->keepA.swap(keepA2); b->ka_xy.swap(xy2); b->ka_type.swap(type2); b->ka_size.swap(size2);
@@ -590,6 +590,7 @@ void batch_tri_finalize(Batch *b, int ignore_same_type, int ensure_min, int remo
         CK(cudaMemcpyAsync(b->d_p_off.p, poff2.p, sizeof(i32) * (W + 1), cudaMemcpyDeviceToDevice, s));
         b->have_groups = false;
         b->have_start = false;   // pairs and rows were renumbered
+        b->have_pair_j = false;
     }
 
     b->t_weight.alloc(b->T, s); b->t_sign.alloc(b->T, s); b->t_bounds.alloc(4 * b->T, s); b->t_argv.alloc(4 * b->T, s);

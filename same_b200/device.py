@@ -152,6 +152,112 @@ class Section:
         self.close()
 
 
+class CandidateStream:
+    """Candidate stage (window subsetting + KNN + pair costs, src/same.py:523-524, src/utils.py:709-742, src/same.py:1182-1189)
+    of a SEQUENCE of sections — serial tissue slices, or the strips of one large slice — with the transfers and kernels of
+    neighbouring sections overlapped.  Every section runs on one of `depth` CUDA streams (taken in turn) and is driven by its
+    own worker thread (the C-ABI calls release the GIL; distinct sections share no mutable state in the library), and its
+    results are copied back asynchronously: while section k's pairs and costs cross PCIe towards the host, section k+1's frames
+    cross it in the other direction and its kernels run.
+
+        cs = CandidateStream(radius, knn)
+        for frames, rects in sections:                # host arrays (ideally page-locked)
+            h = cs.submit(frames, rects)              # returns at once
+            if prev is not None: out = prev.result()  # {KEEP_A, KEEP_R, ROW_PTR, PAIR_J, COST} + "offsets"
+            prev = h
+
+    At most `depth` sections may be outstanding (submitted, `result()` not yet called).  `result()` gives valid_pairs in compact
+    form: the aligned index of pair p is the row r with ROW_PTR[r] <= p < ROW_PTR[r+1] (`pairs_from_rows`), the reference index
+    is PAIR_J[p]."""
+
+    ARRAYS = (L.KEEP_A, L.KEEP_R, L.ROW_PTR, L.PAIR_J, L.COST)
+
+    class Handle:
+        def __init__(self, owner, future):
+            self._owner, self._future = owner, future
+
+        def result(self):
+            """Wait for this section's downloads; release its device memory.  -> dict of numpy arrays (page-locked)."""
+            try:
+                sec, b, arrays = self._future.result()
+            finally:
+                self._owner._outstanding -= 1
+            try:
+                b.sync()
+                out = dict(arrays)
+                out["offsets"] = {w: b.offsets(w).copy() for w in (L.KEEP_A, L.KEEP_R, L.PAIRS)}
+            finally:
+                b.close()
+                sec.close()
+            return out
+
+    def __init__(self, radius, knn, priority=False, dist_ct_coeff=1.0, device=None, depth=2):
+        from concurrent.futures import ThreadPoolExecutor
+        self.radius, self.knn, self.priority, self.dist_ct_coeff = float(radius), int(knn), bool(priority), float(dist_ct_coeff)
+        self.device = default_device() if device is None else device
+        self._k = self._outstanding = 0
+        # a fixed set of streams, taken in turn: the stream-ordered memory pool then recycles a section's buffers for the
+        # section after next without a driver call (a new stream per section cannot reuse memory freed on other streams)
+        self._streams = []
+        for _ in range(max(1, int(depth))):
+            p = C.c_void_p()
+            L.check(L.load().same_stream_create(self.device, C.byref(p)))
+            self._streams.append(p.value)
+        self._pool = ThreadPoolExecutor(max_workers=len(self._streams), thread_name_prefix="same_b200-section")
+
+    def close(self):
+        if getattr(self, "_pool", None) is not None:
+            self._pool.shutdown(wait=True)
+            self._pool = None
+        for p in getattr(self, "_streams", []):
+            L.check(L.load().same_stream_destroy(self.device, C.c_void_p(p)))
+        self._streams = []
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _run(self, frames, rects, stream):
+        sec = Section(*frames, device=self.device, stream=stream)
+        try:
+            b = sec.batch(rects)
+            try:
+                b.candidates(self.radius, self.knn, self.priority, self.dist_ct_coeff)
+                return sec, b, b.get_many(self.ARRAYS, pinned=True, wait=False)
+            except BaseException:
+                b.close()
+                raise
+        except BaseException:
+            sec.close()
+            raise
+
+    def submit(self, frames, rects=None):
+        """frames = (a_xy, r_xy, a_prob, r_prob, a_type, r_type[, a_size, r_size]); sections take the streams in turn."""
+        if self._outstanding >= len(self._streams):
+            raise RuntimeError(f"CandidateStream: {self._outstanding} sections outstanding; call result() on the oldest first "
+                               f"(depth={len(self._streams)})")
+        stream = self._streams[self._k % len(self._streams)]
+        self._k += 1
+        self._outstanding += 1
+        return CandidateStream.Handle(self, self._pool.submit(self._run, frames, rects, stream))
+
+
+def pairs_from_rows(row_ptr, pair_j, row_base=0):
+    """valid_pairs [P, 2] (src/utils.py:741) from the compact form ROW_PTR + PAIR_J of one window: `row_ptr` = the window's
+    slice of ROW_PTR (nKA + 1 entries, any base), `pair_j` its slice of PAIR_J."""
+    rp = np.asarray(row_ptr, dtype=np.int64)
+    i = np.repeat(np.arange(len(rp) - 1, dtype=np.int32), np.diff(rp))
+    return np.column_stack([i, np.asarray(pair_j, dtype=np.int32)])
+
+
 def greedy_select(nodes, key, n_nodes, eligible=None, device=None, return_rounds=False):
     """Ordered greedy selection with disjoint endpoints (same_greedy_select): items visited in ascending (key, index) order,
     an item is taken iff it is eligible and none of its endpoints was taken before.  nodes [n, 1..3] int -> bool [n]."""
@@ -300,8 +406,12 @@ class WindowBatch:
         L.check(L.load().same_batch_get(self._h, what, lo, hi, L.ptr(out)))
         return out
 
-    def get_many(self, whats, pinned=True):
-        """Fetch several whole arrays with one stream synchronisation -> {what: ndarray}."""
+    def get_many(self, whats, pinned=True, wait=True):
+        """Fetch several whole arrays with one stream synchronisation -> {what: ndarray}.
+        `wait=False` (page-locked destinations only) queues the copies and returns at once: the arrays may be read after
+        `sync()`.  That is what lets the next section's upload and kernels overlap this one's download (`CandidateStream`)."""
+        if not wait and not pinned:
+            raise ValueError("asynchronous downloads need page-locked destinations")
         whats = list(whats)
         n = len(whats)
         outs, lo, hi = [], np.zeros(n, np.int64), np.zeros(n, np.int64)
@@ -311,7 +421,8 @@ class WindowBatch:
             outs.append(pinned_empty((int(hi[k]),) + tail, dt) if pinned else np.empty((int(hi[k]),) + tail, dt))
         dst = (C.c_void_p * n)(*[o.ctypes.data for o in outs])
         w = np.asarray(whats, dtype=np.int32)
-        L.check(L.load().same_batch_get_many(self._h, n, L.ptr(w), L.ptr(lo), L.ptr(hi), dst))
+        fn = L.load().same_batch_get_many if wait else L.load().same_batch_get_many_async
+        L.check(fn(self._h, n, L.ptr(w), L.ptr(lo), L.ptr(hi), dst))
         return dict(zip(whats, outs))
 
     def get_window(self, what, w):

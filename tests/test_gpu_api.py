@@ -363,3 +363,47 @@ def test_highs_cut_loop_same_solution_on_both_pipelines():
     assert np.array_equal(np.asarray(var_out["x"]) > 0.5, cpu.x > 0.5)
     sel = np.flatnonzero(cpu.x > 0.5)
     assert np.array_equal(got["aligned_idx"].to_numpy(), res["pairs"][sel, 0]) and np.array_equal(got["ref_idx"].to_numpy(), res["pairs"][sel, 1])
+
+
+@pytest.mark.gpu
+def test_pair_j_and_asynchronous_downloads_equal_the_blocking_path():
+    """SAME_ARR_PAIR_J is PAIRS[:, 1]; ROW_PTR + PAIR_J rebuild valid_pairs; same_batch_get_many_async + same_batch_sync deliver the
+    same bytes as the blocking call; CandidateStream (sections overlapped on several streams) returns what a plain batch returns."""
+    from same_b200 import _lib as L
+    from same_b200 import datagen
+    from same_b200.device import CandidateStream, Section, pairs_from_rows
+    ref, qry, ct = datagen.make_section_pair(n_tiles=9, n_types=3, seed=5)
+    lut = {c: i for i, c in enumerate(ct)}
+    D = dict(a_xy=qry[["X", "Y"]].to_numpy(), r_xy=ref[["X", "Y"]].to_numpy(), a_prob=qry[ct].to_numpy(), r_prob=ref[ct].to_numpy(),
+             a_type=qry["cell_type"].map(lut).to_numpy(np.int32), r_type=ref["cell_type"].map(lut).to_numpy(np.int32))
+    rects = np.array([[x, x + 20.0, y, y + 20.0] for x in (0.0, 17.5) for y in (0.0, 17.5)])
+    frames = (D["a_xy"], D["r_xy"], D["a_prob"], D["r_prob"], D["a_type"], D["r_type"])
+    with Section(*frames) as sec, sec.batch(rects) as b:
+        b.candidates(1.0, 8, False, 1.0)
+        want = b.get_many([L.KEEP_A, L.KEEP_R, L.ROW_PTR, L.PAIRS, L.COST, L.PAIR_J], pinned=False)
+        assert np.array_equal(want[L.PAIR_J], want[L.PAIRS][:, 1])
+        off_p, off_a = b.offsets(L.PAIRS), b.offsets(L.KEEP_A)
+        for w in range(len(rects)):
+            rp = want[L.ROW_PTR][off_a[w]:off_a[w + 1] + 1]
+            assert np.array_equal(pairs_from_rows(rp, want[L.PAIR_J][off_p[w]:off_p[w + 1]]), want[L.PAIRS][off_p[w]:off_p[w + 1]])
+        got = b.get_many([L.PAIR_J, L.COST, L.ROW_PTR], wait=False)
+        b.sync()
+        for k in got:
+            assert np.array_equal(got[k], want[k])
+        with pytest.raises(ValueError):
+            b.get_many([L.COST], pinned=False, wait=False)
+    with CandidateStream(1.0, 8, depth=2) as cs:
+        prev, n_done = None, 0
+        for _ in range(5):                                       # two sections in flight at any time
+            h = cs.submit(frames, rects)
+            if prev is not None:
+                out = prev.result()
+                n_done += 1
+                for k in (L.KEEP_A, L.KEEP_R, L.ROW_PTR, L.PAIR_J, L.COST):
+                    assert np.array_equal(out[k], want[k])
+                assert np.array_equal(out["offsets"][L.PAIRS], off_p)
+            prev = h
+        h2 = cs.submit(frames, rects)
+        with pytest.raises(RuntimeError):
+            cs.submit(frames, rects)                             # a third outstanding section is refused
+        assert len(prev.result()[L.COST]) == len(want[L.COST]) and len(h2.result()[L.PAIR_J]) == len(want[L.PAIR_J])
