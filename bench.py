@@ -61,31 +61,42 @@ def make_workload(tiles, rank, world):
     for df in (ref, qry):
         df["Y"] = df["Y"] + rank * strip_h
     lut = {c: i for i, c in enumerate(ct)}
+    t_prep = time.perf_counter()
     W = dict(
         a_xy=np.ascontiguousarray(qry[["X", "Y"]].to_numpy(np.float64)), r_xy=np.ascontiguousarray(ref[["X", "Y"]].to_numpy(np.float64)),
         a_prob=np.ascontiguousarray(qry[ct].to_numpy(np.float64)), r_prob=np.ascontiguousarray(ref[ct].to_numpy(np.float64)),
         a_type=qry["cell_type"].map(lut).to_numpy(np.int32), r_type=ref["cell_type"].map(lut).to_numpy(np.int32),
         strip_h=strip_h, strip_lo=rank * strip_h, ct=ct)
+    W["prep_ms"] = (time.perf_counter() - t_prep) * 1e3
     return W
 
 
 def exchange_halo(W, rank, world, device):
-    """The one collective of the path (same_b200.sharding.exchange_halo, NCCL all_gather): cells of the NEXT strip
-    within `WINDOW` of the strip border, so that windows starting in this strip see every cell of their rectangle."""
+    """The one collective of the path (same_b200.sharding.exchange_halo: a neighbour send/recv over NCCL): cells of the NEXT strip
+    within `WINDOW` of the strip border, so that windows starting in this strip see every cell of their rectangle.  Timed after
+    the communicator is warm (NCCL builds its channels on the first point-to-point call)."""
     import torch
+    import torch.distributed as dist
     from same_b200 import sharding as S
+    S.exchange_halo({"y": np.full((8, 1), -1.0)}, "y", 0.0, device=device)          # communicator warm-up: 8 rows each way
+    torch.cuda.synchronize(); dist.barrier()
     t0 = time.perf_counter()
     nbytes = rows = 0
+    out = {}
     for name in ("a", "r"):
         xy, prob, ty = W[f"{name}_xy"], W[f"{name}_prob"], W[f"{name}_type"]
-        halo, info = S.exchange_halo({"xy": xy, "prob": prob, "type": ty[:, None].astype(np.float64), "y": xy[:, 1:2]}, "y",
-                                     W["strip_lo"] + WINDOW, device=device)
-        W[f"{name}_xy"] = np.ascontiguousarray(np.concatenate([xy, halo["xy"]]))
-        W[f"{name}_prob"] = np.ascontiguousarray(np.concatenate([prob, halo["prob"]]))
-        W[f"{name}_type"] = np.concatenate([ty, halo["type"][:, 0].astype(np.int32)])
+        halo, info = S.exchange_halo({"xy": xy, "prob": prob, "type": ty}, ("xy", 1), W["strip_lo"] + WINDOW, device=device)
+        out[name] = halo
         nbytes += info["bytes"]; rows += info["rows"]
     torch.cuda.synchronize()
-    return dict(ms=(time.perf_counter() - t0) * 1e3, bytes=int(nbytes), halo_cells=int(rows))
+    ms = (time.perf_counter() - t0) * 1e3
+    for name in ("a", "r"):
+        halo = out[name]
+        W[f"{name}_xy"] = np.ascontiguousarray(np.concatenate([W[f"{name}_xy"], halo["xy"]]))
+        W[f"{name}_prob"] = np.ascontiguousarray(np.concatenate([W[f"{name}_prob"], halo["prob"]]))
+        W[f"{name}_type"] = np.concatenate([W[f"{name}_type"], halo["type"][:, 0].astype(np.int32)])
+    return dict(ms=ms, bytes=int(nbytes), halo_cells=int(rows), note="neighbour send/recv of packed rows (native dtypes), incl. packing on the "
+                "GPU, one upload of the band and one download of the received rows; communicator warmed up before")
 
 
 def window_rects(W, rank, world):
@@ -270,6 +281,115 @@ def run_same_wall(tiles, seed=1):
             "cuts": int(var_out["lazy_cuts_added"]), "matches": len(matches), "seconds": min(times), "seconds_first_call": times[0]}
 
 
+def strong_scaling_arm(args, rank, world, local_rank, stream):
+    """The product's own multi-GPU partition (sharding.distributed_sliding_window_matching, src/same.py:507-593 run per block):
+    EVERY rank holds the whole configs[3] section (replicated frames, identical seed) and runs one contiguous block of its window
+    list; strong scaling — the total work is fixed.  Device-timed candidate stage (max over ranks) and the same thing end to end
+    through CandidateStream (each rank uploads the whole section, downloads its block's results)."""
+    import gc
+    import torch
+    import torch.distributed as dist
+    from same_b200 import _lib as L
+    from same_b200.device import CandidateStream, Section
+    from same_b200.windows import shard_windows
+    W1 = make_workload(args.tiles, 0, 1)
+    rects_all, grid = window_rects(W1, 0, 1)
+    lo, hi = shard_windows(len(rects_all), world, rank)
+    mine = np.ascontiguousarray(rects_all[lo:hi])
+    frames = tuple(torch.from_numpy(W1[k]).pin_memory().numpy() for k in ("a_xy", "r_xy", "a_prob", "r_prob", "a_type", "r_type"))
+    device = torch.device("cuda", local_rank)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
+    sec = Section(*frames, device=local_rank, stream=stream)
+
+    def once(ev=None):
+        if ev is not None:
+            e0 = torch.cuda.Event(enable_timing=True); e0.record()
+        b = sec.batch(mine)
+        b.candidates(RADIUS, KNN, False, 1.0)
+        if ev is not None:
+            e1 = torch.cuda.Event(enable_timing=True); e1.record(); ev.append((e0, e1))
+        n = b.length(L.PAIRS)
+        b.close()
+        return n
+    for _ in range(3):
+        pairs = once()
+    torch.cuda.synchronize(); dist.barrier()
+    ms = 0.0
+    for _ in range(args.steps):
+        flush.fill_(1)
+        ev = []
+        pairs = once(ev)
+        torch.cuda.synchronize()
+        ms += ev[0][0].elapsed_time(ev[0][1])
+    ms /= args.steps
+    sec.close()
+    # end to end: the whole section goes up on every rank, the block's results come back
+    n_e2e = max(2, min(args.steps, 10))
+    with CandidateStream(RADIUS, KNN, False, 1.0, device=local_rank) as cs:
+        def stream_n(n):
+            prev = None
+            for _ in range(n):
+                h = cs.submit(frames, mine)
+                if prev is not None:
+                    out = prev.result()
+                prev = h
+            out = prev.result()
+            return sum(out[w].nbytes for w in CandidateStream.ARRAYS)
+        stream_n(3)
+        torch.cuda.synchronize(); dist.barrier()
+        gc.collect(); gc.disable()
+        t0 = time.perf_counter()
+        d2h = stream_n(n_e2e)
+        torch.cuda.synchronize(); dist.barrier()
+        e_ms = (time.perf_counter() - t0) * 1e3 / n_e2e
+        gc.enable()
+    t = torch.tensor([ms, e_ms, float(pairs)], dtype=torch.float64, device=device)
+    allr = [torch.zeros_like(t) for _ in range(world)]
+    dist.all_gather(allr, t)
+    allr = torch.stack(allr).cpu().numpy()
+    tot_pairs = float(allr[:, 2].sum())
+    return {"scaling": "strong", "value": tot_pairs / (allr[:, 0].max() * 1e-3), "unit": "pairs/s", "ms_per_step": float(allr[:, 0].max()),
+            "ms_per_step_per_rank": [float(v) for v in allr[:, 0]], "pairs_per_step": int(tot_pairs), "windows_total": int(len(rects_all)),
+            "windows_per_rank": [int(shard_windows(len(rects_all), world, r)[1] - shard_windows(len(rects_all), world, r)[0]) for r in range(world)],
+            "e2e": {"value": tot_pairs / (allr[:, 1].max() * 1e-3), "unit": "pairs/s", "ms_per_step": float(allr[:, 1].max()),
+                    "ms_per_step_per_rank": [float(v) for v in allr[:, 1]], "h2d_bytes_per_step": int(sum(f.nbytes for f in frames)),
+                    "d2h_bytes_per_step": int(d2h)},
+            "note": "ONE 2,500-tile section replicated on every rank, window list in contiguous blocks (same_b200.windows.shard_windows, the "
+                    "partition sharding.distributed_sliding_window_matching uses); no collective on the data path"}
+
+
+def luad_shape_arm(rank, world, window_size):
+    """BASELINE configs[4] (examples/luad/run_same.sh:92-108) at metacell scale: 40,000 reference / 37,600 query cells uniform over
+    13,000^2 units, K = 5 Dirichlet probabilities, sizes 1..3 as after greedy_triangle_collapse(max_metacell_size=3) (the collapse
+    itself: tools/time_collapse_luad.py), the script's optim parameters, through the PUBLIC sliding_window_matching with
+    window_shard=(rank, world) and IncumbentBackend in place of Gurobi.  Wall clock per rank."""
+    import contextlib, io
+    import same_b200
+    from same_b200 import datagen
+    from same_b200.solver import IncumbentBackend
+    ref, qry, ct = datagen.make_uniform_pair(40000, 37600, 13000.0, n_types=5, seed=4, id_col="metacell_id")
+    rng = np.random.default_rng(44)
+    ref["size"] = rng.integers(1, 4, len(ref)).astype(float)
+    qry["size"] = rng.integers(1, 4, len(qry)).astype(float)
+    optim = dict(window_size=window_size, overlap=250, min_cells_per_window=30, max_matches=1, radius=250, knn=8, no_match_penalty=10000,
+                 dist_ct_coeff=1, penalty_coeff=100, delaunay_penalty=10, cell_id_col="metacell_id", ref_metacell_match_multiplier=3)
+    gurobi = dict(mip_gap=0.05, lazy_allowed_flip_fraction=0.05)
+
+    def inc(spec):
+        rp = np.asarray(spec.row_ptr, dtype=np.int64)
+        rows = np.repeat(np.arange(len(rp) - 1), np.diff(rp))
+        return incumbent(np.column_stack([rows, rows]), seed=len(rows))
+    best, out = None, None
+    for _ in range(2):
+        t0 = time.perf_counter()
+        with contextlib.redirect_stdout(io.StringIO()):
+            out = same_b200.sliding_window_matching(ref, qry, commonCT=list(ct), optim_params=dict(optim), gurobi_params=dict(gurobi),
+                                                    solver=IncumbentBackend(inc), window_shard=(rank, world))
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return best, (0 if out is None else len(out)), (0 if out is None or not len(out) else int(out["window_id"].nunique()))
+
+
 def workload_config(args, world, grid, n_windows):
     return {"workload": f"BASELINE configs[3]: synthetic {args.tiles}-tile section per GPU (~{args.tiles * 411 / 1e6:.2f}M ref / ~{args.tiles * 372 / 1e6:.2f}M query cells, K={N_TYPES}), "
                         f"candidate+cost+triangle+separation kernels, sliding window {grid[0]}x{grid[1]} per GPU",
@@ -335,8 +455,16 @@ def main():
     # ---- workload (untimed setup) ----
     W = make_workload(args.tiles, rank, world)
     halo = exchange_halo(W, rank, world, device) if world > 1 else None
+    t_h = time.perf_counter()
     rects, grid = window_rects(W, rank, world)
+    host_ms = {"window_grid": (time.perf_counter() - t_h) * 1e3}
+    t_h = time.perf_counter()
     tri_vid = triangulate(W["a_xy"])            # global (per-strip) Delaunay, the "precomputed triangulation" of the examples
+    host_ms["qhull_delaunay_of_the_aligned_frame"] = (time.perf_counter() - t_h) * 1e3
+    host_ms["frames_to_arrays"] = W["prep_ms"]
+    host_ms["note"] = ("host work of the path that is NOT on the GPU and NOT inside any timed region above: scipy/Qhull Delaunay of the whole "
+                       "aligned frame (the precomputed triangulation every example hands to sliding_window_matching), the window grid, "
+                       "DataFrame -> contiguous arrays.  e2e.full_path excludes them; a section's wall clock does not")
     # one explicit stream for everything: the library launches on it and the stage events are recorded on it
     # (the default stream has handle 0, which the library reads as "create your own stream")
     tstream = torch.cuda.Stream(device=device)
@@ -519,6 +647,31 @@ def main():
     prof = L.profile_report()
     L.profile_enable(False)
 
+    # ---- the product's own partition (strong scaling of ONE section) and the LUAD-shape section through the public API ----
+    extra = {}
+    if world > 1 and not args.no_e2e:
+        sec.close()
+        extra["strong_scaling"] = strong_scaling_arm(args, rank, world, local_rank, stream)
+        sec = make_section()
+    if not args.no_e2e:
+        for ws in (13000, 4000):
+            secs, n_match, n_win = luad_shape_arm(rank, world, ws)
+            t = torch.tensor([secs, float(n_match), float(n_win)], dtype=torch.float64, device=device)
+            if world > 1:
+                allr = [torch.zeros_like(t) for _ in range(world)]
+                dist.all_gather(allr, t)
+                allr = torch.stack(allr).cpu().numpy()
+            else:
+                allr = t.cpu().numpy()[None]
+            extra.setdefault("configs4_luad_shape", {})[f"window_size_{ws}"] = {
+                "seconds": float(allr[:, 0].max()), "seconds_per_rank": [float(v) for v in allr[:, 0]], "matches": int(allr[:, 1].sum()),
+                "windows": int(allr[:, 2].sum()), "windows_per_rank": [int(v) for v in allr[:, 2]]}
+        extra["configs4_luad_shape"]["note"] = (
+            "BASELINE configs[4] at metacell scale (40,000 / 37,600 cells over 13,000^2, K=5, sizes 1..3, examples/luad/run_same.sh:92-104 "
+            "parameters) through the public sliding_window_matching(window_shard=(rank, world)) with IncumbentBackend (one seeded "
+            "incumbent + one separation call per window, no MIP); wall clock, max over ranks.  window_size_13000 is the script's "
+            "setting (one large window + border slivers: it cannot use more than a few GPUs); window_size_4000 cuts 4x4 windows")
+
     # ---- reduce over ranks ----
     def allmax(v):
         if world == 1:
@@ -535,6 +688,13 @@ def main():
         return t.cpu().numpy()
 
     stage_max = allmax(stage_ms)
+    if world > 1:
+        tt = torch.tensor(stage_ms, dtype=torch.float64, device=device)
+        allr = [torch.zeros_like(tt) for _ in range(world)]
+        dist.all_gather(allr, tt)
+        stage_per_rank = [[float(v) for v in r.cpu().numpy()] for r in allr]
+    else:
+        stage_per_rank = [[float(v) for v in stage_ms]]
     tot = allsum([stats["P"], stats["T"], stats["nAi"], stats["nRi"], stats["checked"], stats["viol"], e2e["P"] if e2e else 0,
                   e2e["full_P"] if e2e else 0])
     e2e_max, e2e_full_max, e2e_lat_max = allmax([e2e["ms"] if e2e else 0.0, e2e["full_ms"] if e2e else 0.0, e2e["latency_ms"] if e2e else 0.0])
@@ -606,9 +766,10 @@ def main():
             "triangle_checks": {"value": tot[1] / (sep_ms * 1e-3), "unit": "triangle checks/s", "ms_per_call": sep_ms,
                                 "triangles": int(tot[1]), "checked": int(tot[4]), "violated": int(tot[5])},
             "full_pass_ms": full_ms, "stage_ms": {k: float(v) for k, v in zip(STAGES, stage_max)},
+            "stage_ms_per_rank": {"stages": STAGES, "ms": stage_per_rank},
             "pairs_per_step": int(tot[0]), "cells_per_step": int(tot[2] + tot[3]), "wall_ms_per_step_incl_flush": wall_ms / args.steps,
             "gpu_launches": int(gpu_launches), "clocks": clocks,
-            "roofline": roofline, "roofline_kernels": kernels,
+            "roofline": roofline, "roofline_kernels": kernels, "host_ms": host_ms,
         }
         if e2e:
             line["e2e"] = {"value": tot[6] / (e2e_max * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": int(e2e["h2d"]),
@@ -625,6 +786,7 @@ def main():
                                          "h2d_bytes_per_step": int(e2e["full_h2d"]), "d2h_bytes_per_step": int(e2e["full_d2h"]),
                                          "note": "every stage of the hot path (candidates, triangles, groups, one separation call, post-solve) "
                                                  "from pinned host frames + triangulation + incumbent to everything the host model builder reads"}}
+        line.update(extra)
         if halo:
             line["halo_exchange"] = halo
         if world == 1 and not args.no_e2e:
@@ -643,7 +805,7 @@ def main():
                     "configs[1] (25 tiles, ~10k cells)": dict(run_same_wall(25), reference_seconds=ref_cpu[25])}
             except Exception as e:      # an extra, never the reason a bench line is missing
                 line["run_same_wall_clock"] = {"error": repr(e)}
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:   # (N > 1: the other ranks would spin in a barrier beside it; the reference arm is the CPU number there)
             from oracle import oracle as O
             O.build()
             os.sched_setaffinity(0, all_cpus)       # the CPU arm gets every host core back

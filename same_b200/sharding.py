@@ -4,7 +4,8 @@ Windows are independent units, so a section shards by contiguous blocks of its w
 collective.  Two small exchanges exist around it, both through `torch.distributed` (NCCL on GPUs, gloo in the CPU
 tests):
   * `exchange_halo` — when the *cells* are spatially partitioned across ranks (each rank loaded one strip of the
-    section), the cells of the next strip that a rank's last window row reaches into are all-gathered once;
+    section), the cells of the next strip that a rank's last window row reaches into are sent to it once, neighbour to
+    neighbour;
   * `gather_matches` — per-rank result frames are gathered in window order.
 """
 from __future__ import annotations
@@ -27,40 +28,65 @@ def rank_world(group=None):
     return 0, 1
 
 
-def exchange_halo(frames: Dict[str, np.ndarray], y_key: str, y_limit: float, device=None, group=None):
-    """All-gather the rows of every rank whose `frames[y_key]` (a column vector) is < that rank's `y_limit`, and return
-    for THIS rank the rows contributed by rank+1 (empty for the last rank) as a dict of arrays.
+def exchange_halo(frames: Dict[str, np.ndarray], y_key, y_limit: float, device=None, group=None):
+    """Neighbour exchange of border cells: every rank sends the rows with `frames[y_key] < y_limit` (the band of its strip that
+    the windows of the PREVIOUS strip reach into) to rank-1 and receives rank+1's band (empty for the last rank).  `y_key` is
+    the name of a single-column frame or `(name, column)` to select on one column of a wider frame (e.g. `("xy", 1)`).
 
-    `frames` maps names to [N, c] float64 arrays sharing N.  Padded to the largest contribution so a plain
-    `all_gather` works on both NCCL and gloo; total traffic is a few MB per rank (border strips only)."""
+    `frames` maps names to arrays sharing their first dimension, in their native dtypes (float64 coordinates and probabilities,
+    int32 type codes ...): the selected rows are packed column by column into one byte buffer, so nothing is widened or sent
+    twice.  Point-to-point (`batch_isend_irecv`: NCCL over NVLink between GPUs, gloo in the CPU tests): the traffic is the band
+    itself, once, whatever the number of ranks.  With `device` set the packing, the transfer and the unpacking run on that GPU
+    and the host sees one upload of the band and one download of the received rows.
+    -> ({name: received rows}, {"bytes": bytes received, "rows": rows received})"""
     import torch
     dist = _dist()
     rank, world = rank_world(group)
     names = list(frames)
-    cols = [np.asarray(frames[n], dtype=np.float64).reshape(len(frames[y_key]), -1) for n in names]
-    widths = [c.shape[1] for c in cols]
-    mask = np.asarray(frames[y_key]).reshape(-1) < y_limit
-    pack = np.concatenate([c[mask] for c in cols], axis=1) if cols else np.zeros((0, 0))
+    y_name, y_col = y_key if isinstance(y_key, tuple) else (y_key, 0)
+    n = len(np.asarray(frames[y_name]))
+    cols = [np.ascontiguousarray(np.asarray(frames[k]).reshape(n, -1)) for k in names]
+    shapes = [(c.shape[1], c.dtype) for c in cols]
+    empty = {k: np.zeros((0, w), dtype=dt) for k, (w, dt) in zip(names, shapes)}
     if world == 1:
-        return {n: np.zeros((0, w)) for n, w in zip(names, widths)}, dict(bytes=0, rows=0)
+        return empty, dict(bytes=0, rows=0)
     dev = device if device is not None else "cpu"
-    cnt = torch.tensor([len(pack)], dtype=torch.int64, device=dev)
-    cnts = [torch.zeros_like(cnt) for _ in range(world)]
-    dist.all_gather(cnts, cnt, group=group)
-    cnts = [int(c.item()) for c in cnts]
-    mx = max(max(cnts), 1)
-    buf = torch.zeros((mx, pack.shape[1]), dtype=torch.float64, device=dev)
-    if len(pack):
-        buf[: len(pack)] = torch.from_numpy(np.ascontiguousarray(pack)).to(dev)
-    outs = [torch.empty_like(buf) for _ in range(world)]
-    dist.all_gather(outs, buf, group=group)
-    nxt = rank + 1
-    got = outs[nxt][: cnts[nxt]].cpu().numpy() if nxt < world else np.zeros((0, pack.shape[1]))
-    res, c0 = {}, 0
-    for n, w in zip(names, widths):
-        res[n] = got[:, c0:c0 + w]
-        c0 += w
-    return res, dict(bytes=int(buf.numel() * 8 * world), rows=int(len(got)))
+    mask = np.asarray(frames[y_name]).reshape(n, -1)[:, y_col] < y_limit
+    row_bytes = [w * dt.itemsize for w, dt in shapes]
+    n_send = int(mask.sum())
+    # one byte buffer, column blocks back to back: [rows of column 0][rows of column 1] ...
+    send = torch.empty(max(n_send * sum(row_bytes), 1), dtype=torch.uint8, device=dev)
+    o = 0
+    for c, rb in zip(cols, row_bytes):
+        if n_send:
+            blk = torch.from_numpy(np.ascontiguousarray(c[mask]).view(np.uint8).reshape(-1))
+            send[o:o + n_send * rb].copy_(blk, non_blocking=True)
+        o += n_send * rb
+    # row counts travel first (8 bytes to the predecessor)
+    cnt_out = torch.tensor([n_send], dtype=torch.int64, device=dev)
+    cnt_in = torch.zeros(1, dtype=torch.int64, device=dev)
+    ops = []
+    if rank > 0:
+        ops.append(dist.P2POp(dist.isend, cnt_out, rank - 1, group))
+    if rank < world - 1:
+        ops.append(dist.P2POp(dist.irecv, cnt_in, rank + 1, group))
+    for r in (dist.batch_isend_irecv(ops) if ops else []):
+        r.wait()
+    n_recv = int(cnt_in.item()) if rank < world - 1 else 0
+    recv = torch.empty(max(n_recv * sum(row_bytes), 1), dtype=torch.uint8, device=dev)
+    ops = []
+    if rank > 0 and n_send:
+        ops.append(dist.P2POp(dist.isend, send, rank - 1, group))
+    if rank < world - 1 and n_recv:
+        ops.append(dist.P2POp(dist.irecv, recv, rank + 1, group))
+    for r in (dist.batch_isend_irecv(ops) if ops else []):
+        r.wait()
+    got = recv.cpu().numpy()
+    res, o = {}, 0
+    for k, (w, dt), rb in zip(names, shapes, row_bytes):
+        res[k] = got[o:o + n_recv * rb].view(dt).reshape(n_recv, w).copy() if n_recv else empty[k]
+        o += n_recv * rb
+    return res, dict(bytes=int(n_recv * sum(row_bytes)), rows=n_recv)
 
 
 def gather_matches(local: pd.DataFrame, group=None) -> Optional[pd.DataFrame]:

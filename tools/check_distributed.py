@@ -31,5 +31,27 @@ if rank == 0:
     b = full.sort_values(["window_id", "aligned_idx"]).reset_index(drop=True)[cols]
     assert len(a) == len(b) and all((a[c].to_numpy() == b[c].to_numpy()).all() for c in cols), "sharded result differs from the single-process result"
     print(f"distributed check ok: world={world}, {b['window_id'].nunique()} windows, {len(b)} matches identical")
+# neighbour exchange of border cells on the GPUs (NCCL send/recv): rank r receives exactly the band of rank r+1
+rng = np.random.default_rng(100 + rank)
+n = 4000 + 100 * rank
+xy = np.column_stack([rng.uniform(0, 50, n), rng.uniform(10.0 * rank, 10.0 * (rank + 1), n)])
+prob = rng.uniform(0, 100, (n, 3))
+ty = rng.integers(0, 3, n).astype(np.int32)
+halo, info = sharding.exchange_halo({"xy": xy, "prob": prob, "type": ty}, ("xy", 1), 10.0 * rank + 2.5, device=torch.device("cuda", local))
+nxt = np.random.default_rng(100 + rank + 1)
+n2 = 4000 + 100 * (rank + 1)
+xy2 = np.column_stack([nxt.uniform(0, 50, n2), nxt.uniform(10.0 * (rank + 1), 10.0 * (rank + 2), n2)])
+prob2 = nxt.uniform(0, 100, (n2, 3)); ty2 = nxt.integers(0, 3, n2).astype(np.int32)
+band = xy2[:, 1] < 10.0 * (rank + 1) + 2.5
+if rank < world - 1:
+    assert np.array_equal(halo["xy"], xy2[band]) and np.array_equal(halo["prob"], prob2[band]) and np.array_equal(halo["type"][:, 0], ty2[band])
+    assert halo["type"].dtype == np.int32 and info["rows"] == int(band.sum()) and info["bytes"] == int(band.sum()) * (16 + 24 + 4)
+else:
+    assert len(halo["xy"]) == 0 and info["rows"] == 0
+ok = torch.tensor([1], device=torch.device("cuda", local))
+dist.all_reduce(ok)
+if rank == 0:
+    assert int(ok.item()) == world
+    print("halo exchange ok")
 dist.barrier()
 dist.destroy_process_group()
