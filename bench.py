@@ -335,7 +335,7 @@ def strong_scaling_arm(args, rank, world, local_rank, stream):
                 prev = h
             out = prev.result()
             return sum(out[w].nbytes for w in CandidateStream.ARRAYS)
-        stream_n(3)
+        stream_n(8)
         torch.cuda.synchronize(); dist.barrier()
         gc.collect(); gc.disable()
         t0 = time.perf_counter()
@@ -585,14 +585,19 @@ def main():
             """n sections back to back through CandidateStream: section k+1 is submitted (upload + kernels on its own stream)
             before the downloads of section k are awaited, so the two PCIe directions and the kernels overlap.  Every section's
             inputs go up from page-locked host memory and every section's results come down inside the timed region."""
-            prev, npairs, nbytes = None, 0, 0
+            prev, npairs, nbytes, marks = None, 0, 0, [time.perf_counter()]
             for _ in range(n):
                 h = cstream.submit(frames_pinned, rects)
                 if prev is not None:
                     out = prev.result()
+                    marks.append(time.perf_counter())
                     npairs, nbytes = len(out[L.PAIR_J]), sum(out[w].nbytes for w in CAND_ARRAYS)
                 prev = h
             out = prev.result()
+            marks.append(time.perf_counter())
+            from same_b200 import device as DV
+            sys.stderr.write(f"[bench] e2e cand_stream results arrive after ms: {[round((b - a) * 1e3, 2) for a, b in zip(marks, marks[1:])]} "
+                             f"(page-locked blocks obtained so far {DV.PINNED_ALLOCS[0]}, device pool {L.mempool_stats(local_rank)[0] >> 20} MiB)\n")
             return len(out[L.PAIR_J]), sum(out[w].nbytes for w in CAND_ARRAYS)
 
         def full_once():
@@ -622,9 +627,9 @@ def main():
 
         c_ms, c_P, c_d2h = timed(cand_once)
         # throughput of a stream of sections (the headline e2e): n_e2e sections through CandidateStream, timed as a whole
-        cand_stream(3)
-        barrier()
         gc.collect(); gc.disable()
+        cand_stream(8)      # untimed: both streams' share of the memory pool and the page-locked result pool fill up
+        barrier()
         t0 = time.perf_counter()
         s_P, s_d2h = cand_stream(n_e2e)
         barrier()

@@ -163,6 +163,14 @@ SAME_API int same_batch_groups(same_batch_t *b, int max_matches, int ref_metacel
 SAME_API int same_batch_separation(same_batch_t *b, int64_t w_lo, int64_t w_hi, const double *x, int64_t cap,
                           int64_t *n_viol, int64_t *n_checked, int32_t *cuts);
 
+/* Exact-predicate diagnostic for the two orientation tests of the path, both evaluated in the reference's naive fp64 arithmetic
+ * and never changed by this call: which = 0 the source signs (aligned coordinates, src/same.py:1146), which = 1 the LAST
+ * same_batch_separation call (matched reference coordinates, src/same.py:658).  *n = number of triangles whose computed
+ * determinant lies inside Shewchuk's static error bound for that expression, i.e. whose naive sign MAY differ from the exact
+ * sign; the first min(*n, cap, 65536) batch-global TRI indices go to tri_idx (unordered).  The caller decides them exactly
+ * (same_b200/helpers.py::exact_orientation_sign) and reports the count of disagreements. */
+SAME_API int same_batch_uncertain(same_batch_t *b, int which, int64_t cap, int64_t *n, int32_t *tri_idx);
+
 /* a11 + a12: post-solve analysis of windows [w_lo, w_hi) (src/violationhelper.py:1-134,
  * src/same.py:1355-1408); results through same_batch_get(TRI_MASK / AREA_* / FLIPPED / MATCH_*). */
 SAME_API int same_batch_postsolve(same_batch_t *b, int64_t w_lo, int64_t w_hi, const double *x);
@@ -231,6 +239,8 @@ SAME_API int same_batch_sync(same_batch_t *b);
  * was freed on other streams). */
 SAME_API int same_stream_create(int device, void **stream);
 SAME_API int same_stream_destroy(int device, void *stream);
+/* Device memory the library's stream-ordered pool holds (reserved) and has handed out (used) right now, in bytes. */
+SAME_API int same_mempool_stats(int device, int64_t *reserved, int64_t *used);
 /* stream the batch runs on (cudaStream_t), for event timing by the caller */
 SAME_API void *same_batch_stream(same_batch_t *b);
 /* FP64 vector peak of the device in TFLOP/s, measured with an FMA micro-kernel (eight independent chains per thread, best of

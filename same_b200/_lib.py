@@ -51,7 +51,7 @@ SYMBOLS = [
     "same_batch_get", "same_elem_size", "same_batch_sync", "same_batch_stream", "same_launch_count",
     "same_profile_enable", "same_profile_report", "same_batch_get_many", "same_batch_get_many_async", "same_pinned_alloc", "same_pinned_free",
     "same_postsolve_arrays", "same_batch_mip_start", "same_greedy_select", "same_collapse_select", "same_segment_mean", "same_measure_fp64_peak", "same_section_wait_uploads",
-    "same_stream_create", "same_stream_destroy",
+    "same_stream_create", "same_stream_destroy", "same_mempool_stats", "same_batch_uncertain",
 ]
 
 
@@ -97,6 +97,7 @@ def load():
     lib.same_batch_groups.argtypes = [vp, i32, i32]
     lib.same_batch_separation.argtypes = [vp, i64, i64, vp, i64, vp, vp, vp]
     lib.same_batch_postsolve.argtypes = [vp, i64, i64, vp]
+    lib.same_batch_uncertain.argtypes = [vp, i32, i64, C.POINTER(i64), vp]
     lib.same_batch_offsets.argtypes = [vp, i32, vp]
     lib.same_batch_length.argtypes = [vp, i32, C.POINTER(i64)]
     lib.same_batch_get.argtypes = [vp, i32, i64, i64, vp]
@@ -119,6 +120,7 @@ def load():
     lib.same_profile_enable.argtypes = [i32]
     lib.same_stream_create.argtypes = [i32, C.POINTER(vp)]
     lib.same_stream_destroy.argtypes = [i32, vp]
+    lib.same_mempool_stats.argtypes = [i32, C.POINTER(i64), C.POINTER(i64)]
     lib.same_profile_report.argtypes = [C.c_char_p, i64]
     lib.same_profile_report.restype = i64
     assert lib.same_abi_version() == 1
@@ -148,6 +150,13 @@ def fp64_peak_tflops(device: int = 0) -> float:
 
 def launch_count() -> int:
     return int(load().same_launch_count())
+
+
+def mempool_stats(device=0):
+    """-> (reserved, used) bytes of the stream-ordered device memory pool the library allocates from."""
+    r, u = C.c_int64(0), C.c_int64(0)
+    check(load().same_mempool_stats(int(device), C.byref(r), C.byref(u)))
+    return r.value, u.value
 
 
 def profile_enable(on: bool):

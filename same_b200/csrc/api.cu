@@ -286,6 +286,7 @@ int same_batch_separation(same_batch_t *h, int64_t w_lo, int64_t w_hi, const dou
     BATCH_CALL(h, { REQUIRE(n_viol && n_checked, SAME_E_ARG, "NULL output"); batch_separation(b, w_lo, w_hi, x, cap, n_viol, n_checked, cuts); });
 }
 int same_batch_postsolve(same_batch_t *h, int64_t w_lo, int64_t w_hi, const double *x) { BATCH_CALL(h, batch_postsolve(b, w_lo, w_hi, x)); }
+int same_batch_uncertain(same_batch_t *h, int which, int64_t cap, int64_t *n, int32_t *tri_idx) { BATCH_CALL(h, batch_uncertain(b, which, cap, n, tri_idx)); }
 
 int same_batch_mip_start(same_batch_t *h, double no_match_penalty, int32_t *rounds) { BATCH_CALL(h, batch_mip_start(b, no_match_penalty, rounds)); }
 
@@ -390,6 +391,17 @@ int same_pinned_free(void *p) {
 
 int same_batch_sync(same_batch_t *h) { BATCH_CALL(h, batch_sync(b)); }
 
+int same_mempool_stats(int device, int64_t *reserved, int64_t *used) {
+    return guarded([&] {
+        cudaMemPool_t pool;
+        CK(cudaDeviceGetDefaultMemPool(&pool, device));
+        unsigned long long r = 0, u = 0;
+        CK(cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &r));
+        CK(cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &u));
+        if (reserved) *reserved = (int64_t)r;
+        if (used) *used = (int64_t)u;
+    });
+}
 int same_stream_create(int device, void **stream) {
     return guarded([&] {
         REQUIRE(stream, SAME_E_ARG, "stream is NULL");

@@ -277,7 +277,10 @@ struct Batch {
     // separation / postsolve
     DevBuf<double> x_dev;
     DevBuf<i32> match_j, match_p;       // [nKA]
+    DevBuf<double2> match_xy;           // [nKA] coordinates of the matched reference cell, NaN = unmatched
     DevBuf<i32> sep_counts, cuts;
+    i64 last_unc_sep = -1;
+    DevBuf<i32> unc_list[2], unc_count;   // [0] source signs (k_tri_tables), [1] last separation call: triangles the orientation filter could not decide
     DevBuf<i32> t_mask;
     DevBuf<double> area_before, area_after;
     DevBuf<unsigned char> flipped;
@@ -310,6 +313,7 @@ void batch_tri_override(Batch *b, i64 n, const i32 *idx, const unsigned char *cl
 void batch_tri_finalize(Batch *b, int ignore_same_type, int ensure_min, int remove_unconstrained);
 void batch_separation(Batch *b, i64 w_lo, i64 w_hi, const double *x, i64 cap, i64 *n_viol, i64 *n_checked, i32 *cuts);
 void batch_postsolve(Batch *b, i64 w_lo, i64 w_hi, const double *x);
+void batch_uncertain(Batch *b, int which, i64 cap, i64 *n, i32 *tri_idx);
 void postsolve_arrays(int device, i64 T, const i32 *tri, i64 nA, const double *a_xy, i64 nR, const double *r_xy, const i32 *match_j, i32 *mask,
                       double *area_before, double *area_after, unsigned char *flipped);
 
@@ -345,5 +349,18 @@ __device__ __forceinline__ double orient_naive(double ax, double ay, double bx, 
     return __dsub_rn(t1, t2);
 }
 __device__ __forceinline__ int sign_of(double v) { return (v > 0.0) - (v < 0.0); }
+
+// Exact-predicate DIAGNOSTIC (never changes a result): can the sign of the naive expression above differ from the sign of the
+// exact determinant?  Shewchuk's static filter for this very operation order: |computed - exact| <= (3 + 16 eps) eps (|t1| + |t2|),
+// eps = 2^-53.  Triangles inside the bound are listed for the host, which decides them with rational arithmetic
+// (same_b200/helpers.py::exact_orientation_sign) and counts the disagreements.
+__device__ __forceinline__ bool orient_uncertain(double ax, double ay, double bx, double by, double cx, double cy) {
+    const double t1 = __dmul_rn(__dsub_rn(bx, ax), __dsub_rn(cy, ay));
+    const double t2 = __dmul_rn(__dsub_rn(by, ay), __dsub_rn(cx, ax));
+    const double det = __dsub_rn(t1, t2);
+    const double bound = 3.3306690738754716e-16 * (fabs(t1) + fabs(t2));   // (3 + 16 eps) eps, rounded up
+    return !(fabs(det) > bound);   // (NaN coordinates count as uncertain)
+}
+constexpr int UNC_CAP = 1 << 16;   // listed triangles per call; the count is exact beyond it
 
 }  // namespace same

@@ -490,7 +490,8 @@ __global__ void k_fill_i32_tri(i32 *p, i64 n, i32 v) {
 // ---- a8 + a9 ------------------------------------------------------------------------------------------
 __global__ void k_tri_tables(const int3 *__restrict__ tri, i64 T, const i32 *__restrict__ t_off, const i32 *__restrict__ ka_off, int W,
                              const double2 *__restrict__ ka_xy, const double *__restrict__ ka_size, double *__restrict__ weight,
-                             signed char *__restrict__ sign, double *__restrict__ bounds, i32 *__restrict__ argv) {
+                             signed char *__restrict__ sign, double *__restrict__ bounds, i32 *__restrict__ argv, i32 *__restrict__ unc_list,
+                             i32 *__restrict__ unc_count) {
     const i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= T) return;
     const i32 nb = ka_off[find_window(t_off, W, (i32)t)];
@@ -499,6 +500,10 @@ __global__ void k_tri_tables(const int3 *__restrict__ tri, i64 T, const i32 *__r
     const double2 p[3] = {ka_xy[nb + v.x], ka_xy[nb + v.y], ka_xy[nb + v.z]};
     weight[t] = __dadd_rn(__dadd_rn(ka_size[nb + v.x], ka_size[nb + v.y]), ka_size[nb + v.z]);  // same.py:1131-1134
     sign[t] = (signed char)sign_of(orient_naive(p[0].x, p[0].y, p[1].x, p[1].y, p[2].x, p[2].y));  // same.py:1146
+    if (orient_uncertain(p[0].x, p[0].y, p[1].x, p[1].y, p[2].x, p[2].y)) {   // diagnostic only
+        const i32 at = atomicAdd(unc_count, 1);
+        if (at < UNC_CAP) unc_list[at] = (i32)t;
+    }
     const double mnx = fmin(p[0].x, fmin(p[1].x, p[2].x)), mxx = fmax(p[0].x, fmax(p[1].x, p[2].x));
     const double mny = fmin(p[0].y, fmin(p[1].y, p[2].y)), mxy = fmax(p[0].y, fmax(p[1].y, p[2].y));
     reinterpret_cast<double4 *>(bounds)[t] = make_double4(mnx, mxx, mny, mxy);
@@ -594,9 +599,12 @@ void batch_tri_finalize(Batch *b, int ignore_same_type, int ensure_min, int remo
     }
 
     b->t_weight.alloc(b->T, s); b->t_sign.alloc(b->T, s); b->t_bounds.alloc(4 * b->T, s); b->t_argv.alloc(4 * b->T, s);
+    b->unc_list[0].alloc(UNC_CAP, s); b->unc_list[1].alloc(UNC_CAP, s); b->unc_count.alloc(2, s);
+    b->unc_count.zero(s);
+    b->last_unc_sep = -1;
     if (b->T > 0)
         LAUNCH(k_tri_tables, blocks_for(b->T, 256), 256, 0, s, b->tri.p, b->T, b->d_t_off.p, b->d_ka_off.p, (int)W, b->ka_xy.p, b->ka_size.p, b->t_weight.p,
-               b->t_sign.p, b->t_bounds.p, b->t_argv.p);
+               b->t_sign.p, b->t_bounds.p, b->t_argv.p, b->unc_list[0].p, b->unc_count.p);
     b->stage = 4;
     b->have_post = false;
 }

@@ -17,6 +17,7 @@ def _f64(a, shape=None):
 
 
 _PINNED_POOL: dict = {}    # size class -> [host pointers ready for reuse]
+PINNED_ALLOCS = [0]        # page-locked blocks obtained from the driver so far (diagnostics)
 
 
 class _PinnedLease:
@@ -30,12 +31,15 @@ class _PinnedLease:
             p = C.c_void_p()
             L.check(L.load().same_pinned_alloc(nbytes, C.byref(p)))
             self.ptr = p.value
+            PINNED_ALLOCS[0] += 1
         self.nbytes = nbytes
 
     def __del__(self):
         try:
             pool = _PINNED_POOL.setdefault(self.nbytes, [])
-            if len(pool) < 8:
+            # generous: cudaFreeHost / cudaHostAlloc synchronise the device and cost milliseconds — a stream of sections keeps
+            # three result sets alive (two in flight, one being read), several arrays of which share a size class
+            if len(pool) < 32:
                 pool.append(self.ptr)
             else:
                 L.load().same_pinned_free(C.c_void_p(self.ptr))
@@ -379,6 +383,15 @@ class WindowBatch:
         if not isinstance(x, int):
             x = np.ascontiguousarray(x, dtype=np.float64)
         L.check(L.load().same_batch_postsolve(self._h, w_lo, w_hi, L.ptr(x)))
+
+    def uncertain(self, which, cap=65536):
+        """Triangles whose naive orientation sign the static error filter could not certify (same_batch_uncertain):
+        which = 0 source signs, 1 = the last separation call.  -> (count, batch-global TRI indices, ascending)."""
+        n = C.c_int64(0)
+        idx = np.zeros(max(int(cap), 1), np.int32)
+        L.check(L.load().same_batch_uncertain(self._h, int(which), int(cap), C.byref(n), L.ptr(idx)))
+        m = min(n.value, int(cap), 65536)
+        return n.value, np.sort(idx[:m])
 
     def mip_start(self, no_match_penalty):
         """Greedy MIP start of every window (init_helpers.py:110-132) -> parallel rounds used; results: START_X, START_UNMATCHED."""

@@ -24,6 +24,53 @@ def calculate_signed_area(p1, p2, p3):
 
 
 # ---------------------------------------------------------------------------------------------------------
+# exact-predicate diagnostic (north_star "with an exact-predicate fallback"; SURVEY.md §7 hard part 2: report only)
+# ---------------------------------------------------------------------------------------------------------
+def naive_orientation_sign(a, b, c):
+    """sign((bx-ax)*(cy-ay) - (by-ay)*(cx-ax)) one float64 operation at a time — the reference's arithmetic
+    (src/same.py:658, :1146) and what the kernels evaluate."""
+    ax, ay, bx, by, cx, cy = (np.float64(v) for v in (a[0], a[1], b[0], b[1], c[0], c[1]))
+    d = (bx - ax) * (cy - ay) - (by - ay) * (cx - ax)
+    return int(d > 0) - int(d < 0)
+
+
+def exact_orientation_sign(a, b, c):
+    """Sign of the same determinant in exact rational arithmetic (every float64 is a rational number)."""
+    from fractions import Fraction as F
+    ax, ay, bx, by, cx, cy = (F(float(v)) for v in (a[0], a[1], b[0], b[1], c[0], c[1]))
+    d = (bx - ax) * (cy - ay) - (by - ay) * (cx - ax)
+    return int(d > 0) - int(d < 0)
+
+
+def exact_predicate_check(batch, w, which, a_xy, r_xy, match_j=None):
+    """Window `w`: of the triangles whose naive orientation the device filter could not certify (`WindowBatch.uncertain`), how
+    many have a naive sign that differs from the exact one?  which = 0: source signs on the window's aligned coordinates `a_xy`
+    (kept rows); which = 1: the last separation call, on `r_xy[match_j]`.  The sets the path computes are NEVER changed by this:
+    bit-exact parity with the reference means reproducing its rounding.  -> dict(uncertain, listed, naive_differs_from_exact)"""
+    n, idx = batch.uncertain(which)
+    out = dict(uncertain=0, listed=0, naive_differs_from_exact=0, triangles=[])
+    if n == 0:
+        return out
+    t_off = batch.offsets(L.TRI)
+    mine = idx[(idx >= t_off[w]) & (idx < t_off[w + 1])]
+    out["uncertain"] = int(len(mine)) if n <= len(idx) else int(n)       # (beyond the device's list capacity only the total is known)
+    out["listed"] = int(len(mine))
+    for t in mine:
+        v = batch.get(L.TRI, int(t), int(t) + 1)[0]
+        if which == 0:
+            p = a_xy[v]
+        else:
+            j = np.asarray(match_j)[v]
+            if (j < 0).any():
+                continue
+            p = r_xy[j]
+        if naive_orientation_sign(p[0], p[1], p[2]) != exact_orientation_sign(p[0], p[1], p[2]):
+            out["naive_differs_from_exact"] += 1
+            out["triangles"].append(int(t - t_off[w]))
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------
 # guard band: the GPU decides every triangle whose side / angle is not within a few ulps of a threshold; the
 # (normally empty) in-band list is re-decided here with the very numpy expressions the reference evaluates
 # (BLAS dot / libm arccos are host-dependent at the last ulp; SURVEY.md §7 hard part 1, App. A.4)

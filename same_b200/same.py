@@ -189,12 +189,24 @@ def _solve_window(run: _Run, w: int, aligned_src: pd.DataFrame, ref_src: pd.Data
     per_inc = gurobi["lazy_max_cuts_per_incumbent"]
     lazy_max = gurobi["lazy_max_cuts"]
 
+    a_xy_kept = aligned_df[["X", "Y"]].to_numpy(dtype=np.float64)
+    r_xy_kept = ref_df[["X", "Y"]].to_numpy(dtype=np.float64)
+    # exact-predicate diagnostic: how often could the naive fp64 orientation the reference (and this path) evaluates differ in sign
+    # from the exact determinant?  Counted, never acted upon (helpers.exact_predicate_check).
+    epc = {"source_signs": H.exact_predicate_check(b, w, 0, a_xy_kept, r_xy_kept), "separation_calls": 0,
+           "separation_uncertain": 0, "separation_naive_differs_from_exact": 0}
+
     def separate(x_vals, cuts_so_far):
         """same.py:631-703 with the triangle loop on the GPU; returns the cuts to add, in order."""
         cap = T if per_inc is None else min(int(per_inc), T)
         if lazy_max is not None:
             cap = min(cap, max(0, int(lazy_max) - cuts_so_far))
         nv, nc, cuts = b.separation(x_vals, w, w + 1, cap=max(cap, 0))
+        epc["separation_calls"] += 1
+        if b.uncertain(1, cap=0)[0]:                 # the count came back with the call's own counters: no extra round trip
+            chk = H.exact_predicate_check(b, w, 1, a_xy_kept, r_xy_kept, b.get_window(L.MATCH_J, w))
+            epc["separation_uncertain"] += chk["uncertain"]
+            epc["separation_naive_differs_from_exact"] += chk["naive_differs_from_exact"]
         viol, checked = int(nv[0]), int(nc[0])
         if checked == 0 or viol == 0:
             return np.zeros((0, 4), np.int32)
@@ -262,6 +274,7 @@ def _solve_window(run: _Run, w: int, aligned_src: pd.DataFrame, ref_src: pd.Data
             "flipped_triangles": [int(t) for t in flipped],
             "matched_vertices": {t: [bool(matched_bits[t] & 1), bool(matched_bits[t] & 2), bool(matched_bits[t] & 4)] for t in range(T)}},
         "lazy_constraints": lazy, "lazy_cuts_added": res.cuts_added if lazy else 0,
+        "exact_predicate_check": epc,      # (extra key: diagnostic only, see helpers.exact_predicate_check)
     }
     if outprefix:                                                                                  # same.py:1455-1463
         os.makedirs(outprefix, exist_ok=True)

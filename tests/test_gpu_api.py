@@ -407,3 +407,46 @@ def test_pair_j_and_asynchronous_downloads_equal_the_blocking_path():
         with pytest.raises(RuntimeError):
             cs.submit(frames, rects)                             # a third outstanding section is refused
         assert len(prev.result()[L.COST]) == len(want[L.COST]) and len(h2.result()[L.PAIR_J]) == len(want[L.PAIR_J])
+
+
+@pytest.mark.gpu
+def test_exact_predicate_diagnostic_on_near_collinear_triangles():
+    """Triangles built to be almost degenerate (c = a + t (b - a), rounded): wherever the naive fp64 orientation sign (the
+    reference's arithmetic, which the kernels reproduce) differs from the exact sign, the device filter must have listed the
+    triangle, and the host's rational check must count exactly those — for the source signs and for a separation call.  The
+    computed signs themselves stay the naive ones."""
+    from same_b200 import _lib as L
+    from same_b200 import helpers as H
+    from same_b200.device import Section
+    rng = np.random.default_rng(7)
+    n_tri = 4000
+    a, b_ = rng.uniform(0, 100, (n_tri, 2)), rng.uniform(0, 100, (n_tri, 2))
+    c = a + rng.uniform(0.05, 0.95, (n_tri, 1)) * (b_ - a)
+    c[::7] += rng.uniform(-1, 1, (len(c[::7]), 2))          # some ordinary triangles in between
+    pts = np.concatenate([a, b_, c])
+    tri = np.column_stack([np.arange(n_tri), np.arange(n_tri) + n_tri, np.arange(n_tri) + 2 * n_tri]).astype(np.int32)
+    prob = np.full((len(pts), 2), 50.0)
+    naive = np.array([H.naive_orientation_sign(pts[t[0]], pts[t[1]], pts[t[2]]) for t in tri])
+    exact = np.array([H.exact_orientation_sign(pts[t[0]], pts[t[1]], pts[t[2]]) for t in tri])
+    differs = np.flatnonzero(naive != exact)
+    assert len(differs) > 20, "the construction should produce sign disagreements"
+    with Section(pts, pts, prob, prob) as sec, sec.batch() as b:
+        b.candidates(1e-6, 1, False, 1.0)                    # every cell pairs with its twin only
+        assert np.array_equal(b.get(L.KEEP_A), np.arange(len(pts))) and np.array_equal(b.get(L.PAIRS)[:, 1], np.arange(len(pts)))
+        b.triangles_set(tri, [0, n_tri])
+        b.tri_classify(1e9, None, False)
+        b.tri_finalize(False, True, False)
+        assert np.array_equal(b.get(L.TRI), tri)
+        assert np.array_equal(b.get(L.TRI_SIGN), naive)      # the path keeps the reference's naive signs
+        n0, listed0 = b.uncertain(0)
+        assert n0 == len(listed0) and set(differs.tolist()) <= set(listed0.tolist())
+        assert not (listed0 % 7 == 0).any()                  # the ordinary triangles pass the filter
+        chk0 = H.exact_predicate_check(b, 0, 0, pts, pts)
+        assert chk0["naive_differs_from_exact"] == len(differs) and chk0["triangles"] == differs.tolist()
+        x = np.ones(len(pts))
+        nv, nc, cuts = b.separation(x, cap=10)
+        assert nv[0] == 0 and nc[0] == int((naive != 0).sum())          # identity mapping: nothing flips
+        n1, listed1 = b.uncertain(1)
+        assert np.array_equal(listed1, listed0) and b.uncertain(1, cap=0)[0] == n1
+        chk1 = H.exact_predicate_check(b, 0, 1, pts, pts, b.get(L.MATCH_J))
+        assert chk1["naive_differs_from_exact"] == len(differs)

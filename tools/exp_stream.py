@@ -28,33 +28,15 @@ def once(stream=None):
 def finish(s2, b):
     t0 = time.perf_counter(); b.sync(); t1 = time.perf_counter(); b.close(); t15 = time.perf_counter(); s2.close(); t2 = time.perf_counter()
     return t1 - t0, t15 - t1, t2 - t15
-for mode in ("serial", "overlap"):
-    for rep in range(3):
-        torch.cuda.synchronize()
-        T0 = time.perf_counter()
-        prev = None; rows = []
-        for k in range(8):
-            s2, b, got, t = once()
-            row = [round((t[i + 1] - t[i]) * 1e3, 2) for i in range(4)]
-            if mode == "serial":
-                row += [round(v * 1e3, 2) for v in finish(s2, b)]
-            else:
-                if prev is not None:
-                    row += [round(v * 1e3, 2) for v in finish(*prev)]
-                prev = (s2, b)
-            rows.append(row)
-        if prev is not None:
-            finish(*prev)
-        torch.cuda.synchronize()
-        ms = (time.perf_counter() - T0) * 1e3 / 8
-    print(mode, "ms/section", round(ms, 2), "phases [create, batch, candidates, get_async, sync, batch close, section close]:", rows[-3:])
-
+from same_b200 import device as DV
 with CandidateStream(bench.RADIUS, bench.KNN, device=0) as cs:
     for rep in range(3):
-        torch.cuda.synchronize(); T0 = time.perf_counter(); prev = None
-        for k in range(10):
+        torch.cuda.synchronize(); T0 = time.perf_counter(); prev = None; rows = []
+        for k in range(16):
+            t0 = time.perf_counter()
             h = cs.submit(frames, rects)
             if prev is not None: prev.result()
             prev = h
+            rows.append((round((time.perf_counter() - t0) * 1e3, 1), DV.PINNED_ALLOCS[0], L.mempool_stats(0)[0] >> 20))
         prev.result(); torch.cuda.synchronize()
-        print("CandidateStream (threads) ms/section", round((time.perf_counter() - T0) * 1e3 / 10, 2))
+        print("CandidateStream ms/section", round((time.perf_counter() - T0) * 1e3 / 16, 2), "(ms, pinned allocs, pool MiB):", rows)
