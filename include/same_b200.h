@@ -87,6 +87,11 @@ enum {
     SAME_ARR_FLIPPED = 28,     /* [u8]    area_before*area_after < 0 (src/same.py:1398) */
     SAME_ARR_START_X = 29,     /* [u8]    greedy MIP start: 1 on the chosen pairs (src/init_helpers.py:124-130, x_vars[..].Start) */
     SAME_ARR_START_UNMATCHED = 30,/* [u8] greedy MIP start: 1 on kept aligned rows left unmatched (src/init_helpers.py:132, no_match_vars[..].Start) */
+    SAME_ARR_NODE_TRI_PTR = 32,/* [i32]   nKeepA_total+1 BATCH-GLOBAL offsets into NODE_TRI_IDX: the triangles of kept aligned node i start at ptr[i]
+                                  (aligned_simplex_map as CSR, src/same.py:1096-1099; a node fills NODE_TRI_LEN[i] slots, a triangle that names
+                                  a vertex twice counts once, as in the reference's sets) */
+    SAME_ARR_NODE_TRI_LEN = 33,/* [i32]   number of distinct triangles of each kept aligned node */
+    SAME_ARR_NODE_TRI_IDX = 34,/* [i32]   3*T_total slots, window-local TRI indices, ascending inside a node */
     SAME_ARR_PAIR_J = 31       /* [i32]   reference index of each pair = PAIRS[:, 1] on its own.  The aligned index PAIRS[:, 0] is implied by ROW_PTR
                                   (pairs are sorted by aligned row, src/utils.py:720-731), so ROW_PTR + PAIR_J is valid_pairs in half the bytes over PCIe */
 };

@@ -76,6 +76,9 @@ ArrayView view(Batch *b, int what) {
         case SAME_ARR_AREA_BEFORE: REQUIRE(b->have_post, SAME_E_STATE, "postsolve not run"); return {b->area_before.p, b->T, es, &b->t_off};
         case SAME_ARR_AREA_AFTER: REQUIRE(b->have_post, SAME_E_STATE, "postsolve not run"); return {b->area_after.p, b->T, es, &b->t_off};
         case SAME_ARR_FLIPPED: REQUIRE(b->have_post, SAME_E_STATE, "postsolve not run"); return {b->flipped.p, b->T, es, &b->t_off};
+        case SAME_ARR_NODE_TRI_PTR: need(4, "triangles not finalized"); batch_incidence(b); return {b->nt_ptr.p, b->nKA + 1, es, nullptr};
+        case SAME_ARR_NODE_TRI_LEN: need(4, "triangles not finalized"); batch_incidence(b); return {b->nt_len.p, b->nKA, es, &b->ka_off};
+        case SAME_ARR_NODE_TRI_IDX: need(4, "triangles not finalized"); batch_incidence(b); return {b->nt_idx.p, 3 * b->T, es, &b->nt_off};
         case SAME_ARR_START_X: REQUIRE(b->have_start, SAME_E_STATE, "mip start not computed"); return {b->start_x.p, b->P, es, &b->p_off};
         case SAME_ARR_START_UNMATCHED: REQUIRE(b->have_start, SAME_E_STATE, "mip start not computed"); return {b->start_unmatched.p, b->nKA, es, &b->ka_off};
         default: throw same::Error(SAME_E_ARG, "unknown array id");

@@ -270,6 +270,10 @@ struct Batch {
     DevBuf<signed char> t_sign;
     DevBuf<double> t_bounds;
     DevBuf<i32> t_argv;
+    // node -> triangle incidence (CSR, built on first request): slots [nt_ptr[i], nt_ptr[i] + nt_len[i]) of nt_idx, ascending
+    DevBuf<i32> nt_ptr, nt_idx, nt_len;
+    std::vector<i64> nt_off;
+    bool have_incidence = false;
     i64 nUnc = 0;
     std::vector<i64> unc_off;
     DevBuf<i32> unc;
@@ -306,6 +310,7 @@ void batch_subset(Batch *b);
 void batch_candidates(Batch *b, double radius, int knn, int priority, double dist_ct_coeff);
 void batch_groups(Batch *b, int max_matches, int multiplier);
 void batch_pair_j(Batch *b);
+void batch_incidence(Batch *b);
 void batch_triangles_remap(Batch *b);
 void batch_triangles_set(Batch *b, const i32 *tri, const i64 *tri_off);
 void batch_tri_classify(Batch *b, double radius, int use_angle, double min_angle_deg, int ignore_same_type);
@@ -355,6 +360,9 @@ __device__ __forceinline__ int sign_of(double v) { return (v > 0.0) - (v < 0.0);
 // eps = 2^-53.  Triangles inside the bound are listed for the host, which decides them with rational arithmetic
 // (same_b200/helpers.py::exact_orientation_sign) and counts the disagreements.
 __device__ __forceinline__ bool orient_uncertain(double ax, double ay, double bx, double by, double cx, double cy) {
+    // two coincident vertices (an incumbent that maps two cells to the same reference cell): the determinant is exactly zero and
+    // the naive expression evaluates to exactly zero as well (both products vanish, or are the same product)
+    if ((ax == bx && ay == by) || (ax == cx && ay == cy) || (bx == cx && by == cy)) return false;
     const double t1 = __dmul_rn(__dsub_rn(bx, ax), __dsub_rn(cy, ay));
     const double t2 = __dmul_rn(__dsub_rn(by, ay), __dsub_rn(cx, ax));
     const double det = __dsub_rn(t1, t2);

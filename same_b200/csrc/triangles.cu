@@ -518,6 +518,60 @@ __global__ void k_tri_tables(const int3 *__restrict__ tri, i64 T, const i32 *__r
     reinterpret_cast<int4 *>(argv)[t] = make_int4(vv[amx], vv[amn], vv[amy], vv[any_]);
 }
 
+// ---- a8: node -> triangle incidence as CSR (aligned_simplex_map, src/same.py:1096-1099) -----------------------------
+// count / scan / fill; the (few) triangles of a node are then put in ascending order by its own thread.
+__global__ void k_inc_count(const int3 *__restrict__ tri, i64 T, const i32 *__restrict__ t_off, const i32 *__restrict__ ka_off, int W,
+                            i32 *__restrict__ cnt) {
+    const i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    const i32 nb = ka_off[find_window(t_off, W, (i32)t)];
+    const int3 v = tri[t];
+    atomicAdd(cnt + nb + v.x, 1); atomicAdd(cnt + nb + v.y, 1); atomicAdd(cnt + nb + v.z, 1);
+}
+__global__ void k_inc_fill(const int3 *__restrict__ tri, i64 T, const i32 *__restrict__ t_off, const i32 *__restrict__ ka_off, int W,
+                           const i32 *__restrict__ ptr, i32 *__restrict__ cursor, i32 *__restrict__ idx) {
+    const i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    const int w = find_window(t_off, W, (i32)t);
+    const i32 nb = ka_off[w], tl = (i32)t - t_off[w];
+    const int3 v = tri[t];
+    const i32 node[3] = {nb + v.x, nb + v.y, nb + v.z};
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        if ((c == 1 && node[1] == node[0]) || (c == 2 && (node[2] == node[0] || node[2] == node[1]))) continue;   // a set: no duplicates
+        idx[ptr[node[c]] + atomicAdd(cursor + node[c], 1)] = tl;
+    }
+}
+__global__ void k_inc_sort(const i32 *__restrict__ ptr, const i32 *__restrict__ cursor, i64 nKA, i32 *__restrict__ idx, i32 *__restrict__ len) {
+    const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nKA) return;
+    i32 *a = idx + ptr[i];
+    const int n = cursor[i];
+    len[i] = n;
+    for (int k = 1; k < n; ++k) {
+        const i32 x = a[k];
+        int j = k - 1;
+        while (j >= 0 && a[j] > x) { a[j + 1] = a[j]; --j; }
+        a[j + 1] = x;
+    }
+}
+void batch_incidence(Batch *b) {
+    if (b->have_incidence) return;
+    cudaStream_t s = b->stream;
+    const i64 T = b->T, nKA = b->nKA, W = b->W;
+    DevBuf<i32> cnt, cursor;
+    cnt.alloc(nKA + 1, s); cursor.alloc(nKA + 1, s);
+    cnt.zero(s); cursor.zero(s);
+    b->nt_ptr.alloc(nKA + 1, s); b->nt_idx.alloc(3 * T, s); b->nt_len.alloc(nKA + 1, s);
+    if (T > 0) LAUNCH(k_inc_count, blocks_for(T, 256), 256, 0, s, b->tri.p, T, b->d_t_off.p, b->d_ka_off.p, (int)W, cnt.p);
+    scan_i32(b->sec, cnt.p, b->nt_ptr.p, nKA + 1, s);
+    if (T > 0) LAUNCH(k_inc_fill, blocks_for(T, 256), 256, 0, s, b->tri.p, T, b->d_t_off.p, b->d_ka_off.p, (int)W, b->nt_ptr.p, cursor.p, b->nt_idx.p);
+    if (nKA > 0) LAUNCH(k_inc_sort, blocks_for(nKA, 128), 128, 0, s, b->nt_ptr.p, cursor.p, nKA, b->nt_idx.p, b->nt_len.p);
+    b->nt_off.assign(W + 1, 0);
+    for (i64 w = 0; w <= W; ++w) b->nt_off[w] = 3 * b->t_off[w];
+    b->have_incidence = true;
+}
+
 void batch_tri_finalize(Batch *b, int ignore_same_type, int ensure_min, int remove_unconstrained) {
     cudaStream_t s = b->stream;
     REQUIRE(b->stage >= 3, SAME_E_STATE, "same_batch_tri_finalize before same_batch_tri_classify");
@@ -607,6 +661,7 @@ void batch_tri_finalize(Batch *b, int ignore_same_type, int ensure_min, int remo
                b->t_sign.p, b->t_bounds.p, b->t_argv.p, b->unc_list[0].p, b->unc_count.p);
     b->stage = 4;
     b->have_post = false;
+    b->have_incidence = false;
 }
 
 }  // namespace same

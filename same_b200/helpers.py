@@ -55,8 +55,9 @@ def exact_predicate_check(batch, w, which, a_xy, r_xy, match_j=None):
     mine = idx[(idx >= t_off[w]) & (idx < t_off[w + 1])]
     out["uncertain"] = int(len(mine)) if n <= len(idx) else int(n)       # (beyond the device's list capacity only the total is known)
     out["listed"] = int(len(mine))
+    tri_w = batch.get_window(L.TRI, w) if len(mine) > 4 else None
     for t in mine:
-        v = batch.get(L.TRI, int(t), int(t) + 1)[0]
+        v = tri_w[int(t - t_off[w])] if tri_w is not None else batch.get(L.TRI, int(t), int(t) + 1)[0]
         if which == 0:
             p = a_xy[v]
         else:

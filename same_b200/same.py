@@ -246,11 +246,15 @@ def _solve_window(run: _Run, w: int, aligned_src: pd.DataFrame, ref_src: pd.Data
     area_before, area_after = b.get_window(L.AREA_BEFORE, w), b.get_window(L.AREA_AFTER, w)
     flipped = np.flatnonzero(b.get_window(L.FLIPPED, w))
     match_j = b.get_window(L.MATCH_J, w)
-    aligned_simplex_map = {i: set() for i in range(n_aligned)}                                     # same.py:1096-1099
-    for idx, (va, vb, vc) in enumerate(tri.tolist()):       # same insertion order as the reference's nested loop, without numpy scalars
-        aligned_simplex_map[va].add(idx)
-        aligned_simplex_map[vb].add(idx)
-        aligned_simplex_map[vc].add(idx)
+    # node -> triangle incidence from the device CSR (same.py:1096-1099): a node's triangles arrive ascending, i.e. in the order the
+    # reference's triangle loop adds them to the node's set, so `set(list)` reproduces the reference's sets including their iteration order
+    ka0 = int(b.offsets(L.KEEP_A)[w])
+    nt_ptr = b.get(L.NODE_TRI_PTR, ka0, ka0 + n_aligned + 1).astype(np.int64)
+    nt_len = b.get_window(L.NODE_TRI_LEN, w).astype(np.int64)
+    nt_idx = b.get_window(L.NODE_TRI_IDX, w)
+    base = int(nt_ptr[0]) if n_aligned else 0
+    flat = nt_idx.tolist()
+    aligned_simplex_map = {i: set(flat[s0:s0 + ln]) for i, (s0, ln) in enumerate(zip((nt_ptr[:-1] - base).tolist(), nt_len.tolist()))}
     aligned_delaunay = tri.astype(int)
     triangle_info = H.precompute_triangle_info(aligned_df, aligned_delaunay, aligned_simplex_map, bounds=m["bounds"], argv=m["argv"])
     a_xy = aligned_df[["X", "Y"]].to_numpy(dtype=np.float64)
@@ -269,10 +273,10 @@ def _solve_window(run: _Run, w: int, aligned_src: pd.DataFrame, ref_src: pd.Data
                                          "points_only_penalties": list(penalty_points - violation_points)},
         "triangle_data": {
             "triangles": aligned_delaunay, "triangle_info": triangle_info, "aligned_simplex_map": aligned_simplex_map,
-            "areas_before": {t: area_before[t] for t in range(T)},
-            "areas_after": {t: (None if np.isnan(area_after[t]) else area_after[t]) for t in range(T)},
-            "flipped_triangles": [int(t) for t in flipped],
-            "matched_vertices": {t: [bool(matched_bits[t] & 1), bool(matched_bits[t] & 2), bool(matched_bits[t] & 4)] for t in range(T)}},
+            "areas_before": dict(zip(range(T), area_before)),
+            "areas_after": {t: (None if nan else a) for t, (a, nan) in enumerate(zip(area_after, np.isnan(area_after).tolist()))},
+            "flipped_triangles": flipped.tolist(),
+            "matched_vertices": dict(zip(range(T), (((matched_bits[:, None] >> np.arange(3)) & 1) != 0).tolist()))},
         "lazy_constraints": lazy, "lazy_cuts_added": res.cuts_added if lazy else 0,
         "exact_predicate_check": epc,      # (extra key: diagnostic only, see helpers.exact_predicate_check)
     }

@@ -30,35 +30,47 @@ def violations_from_mask(mask, tri, match_j, a_xy, r_xy, tri_order, n_triangle_i
     """Fold per-triangle masks (bits 0-2 x-order, 3-5 y-order violations of vertex pairs (0,1),(0,2),(1,2);
     bits 8-10 vertex matched) into the dictionary of src/violationhelper.py:24-134.  `tri_order` = iteration order
     of the reference's `triangle_info` dict."""
-    xv, yv = [], []
-    tri_set, pt_set = set(), set()
+    mask = np.asarray(mask)
+    tri = np.asarray(tri).reshape(-1, 3)
     matched = (mask >> 8) & 7
     n_matched = ((matched & 1) + ((matched >> 1) & 1) + ((matched >> 2) & 1))
-    total_comparisons = int(np.where(n_matched == 3, 3, np.where(n_matched == 2, 1, 0))[tri_order].sum()) if len(tri_order) else 0
-    total_violations = 0
-    violated = 0
-    hot = [int(t) for t in tri_order if mask[t] & 63]
-    for t in hot:
-        m = int(mask[t])
-        v = tri[t]
-        for q, (u, w) in enumerate(_PAIRS):
-            v1, v2 = int(v[u]), int(v[w])
-            if m & (1 << q):
-                j1, j2 = int(match_j[v1]), int(match_j[v2])
-                xv.append({"triangle_idx": t,
-                           "point1": {"aligned_idx": v1, "ref_idx": j1, "orig_x": a_xy[v1, 0], "matched_x": r_xy[j1, 0]},
-                           "point2": {"aligned_idx": v2, "ref_idx": j2, "orig_x": a_xy[v2, 0], "matched_x": r_xy[j2, 0]}})
-                pt_set.update([v1, v2])
-                total_violations += 1
-            if m & (1 << (3 + q)):
-                j1, j2 = int(match_j[v1]), int(match_j[v2])
-                yv.append({"triangle_idx": t,
-                           "point1": {"aligned_idx": v1, "ref_idx": j1, "orig_y": a_xy[v1, 1], "matched_y": r_xy[j1, 1]},
-                           "point2": {"aligned_idx": v2, "ref_idx": j2, "orig_y": a_xy[v2, 1], "matched_y": r_xy[j2, 1]}})
-                pt_set.update([v1, v2])
-                total_violations += 1
-        tri_set.add(t)
-        violated += 1
+    order = np.asarray(tri_order, dtype=np.int64)
+    total_comparisons = int(np.where(n_matched == 3, 3, np.where(n_matched == 2, 1, 0))[order].sum()) if len(order) else 0
+    hot = order[(mask[order] & 63) != 0] if len(order) else order
+    # one record per (violated triangle in `tri_order` order, vertex pair q, axis): the reference appends the x record of a pair,
+    # then its y record, pair by pair (src/violationhelper.py:62-121); the lists below keep that order per axis
+    bits = (mask[hot, None] >> np.arange(6)) & 1                 # [n_hot, 6]: x bits of pairs 0..2, then y bits
+    pu = np.array([0, 0, 1]); pw = np.array([1, 2, 2])
+    v1_all, v2_all = tri[hot][:, pu], tri[hot][:, pw]            # [n_hot, 3]
+    match_j = np.asarray(match_j)
+
+    def records(axis, name):
+        sel = bits[:, 3 * axis:3 * axis + 3] != 0
+        rows, q = np.nonzero(sel)                                # row-major: triangle order, then pair order
+        t = hot[rows]
+        v1, v2 = v1_all[rows, q], v2_all[rows, q]
+        j1, j2 = match_j[v1], match_j[v2]
+        o1, o2, m1, m2 = a_xy[v1, axis], a_xy[v2, axis], r_xy[j1, axis], r_xy[j2, axis]
+        ok, mk = f"orig_{name}", f"matched_{name}"
+        recs = [{"triangle_idx": tt, "point1": {"aligned_idx": a1, "ref_idx": b1, ok: c1, mk: d1},
+                 "point2": {"aligned_idx": a2, "ref_idx": b2, ok: c2, mk: d2}}
+                for tt, a1, b1, c1, d1, a2, b2, c2, d2 in zip(t.tolist(), v1.tolist(), j1.tolist(), o1, m1, v2.tolist(), j2.tolist(), o2, m2)]
+        return recs, v1, v2
+    xv, xa, xb = records(0, "x")
+    yv, ya, yb = records(1, "y")
+    total_violations = len(xv) + len(yv)
+    violated = int(len(hot))
+    # (the reference collects these in sets and returns list(set): iteration order of a set of small ints, reproduced by
+    # inserting in the same order — triangle by triangle, pair by pair, x before y)
+    tri_set = set(hot.tolist())
+    pt_set = set()
+    if total_violations:
+        sel_any = bits[:, :3] | bits[:, 3:]
+        rows, q = np.nonzero(sel_any)
+        seq = np.stack([v1_all[rows, q], v2_all[rows, q]], axis=1).reshape(-1)
+        pt_set = set()
+        for v in seq.tolist():
+            pt_set.add(v)
     summary = {"total_triangles": int(n_triangle_info), "violated_triangles": violated, "total_comparisons": total_comparisons,
                "total_violations": total_violations}
     summary["percent_triangles_violated"] = violated / summary["total_triangles"] * 100 if summary["total_triangles"] > 0 else 0

@@ -450,3 +450,41 @@ def test_exact_predicate_diagnostic_on_near_collinear_triangles():
         assert np.array_equal(listed1, listed0) and b.uncertain(1, cap=0)[0] == n1
         chk1 = H.exact_predicate_check(b, 0, 1, pts, pts, b.get(L.MATCH_J))
         assert chk1["naive_differs_from_exact"] == len(differs)
+
+
+@pytest.mark.gpu
+def test_incidence_csr_equals_aligned_simplex_map():
+    """SAME_ARR_NODE_TRI_PTR / LEN / IDX (a8): every kept aligned node's triangles, ascending — the reference's aligned_simplex_map
+    (src/same.py:1096-1099) as CSR, per window of a batch, also after the unconstrained-node removal renumbered the nodes."""
+    from scipy.spatial import Delaunay
+    from same_b200 import _lib as L
+    from same_b200 import datagen
+    from same_b200.device import Section
+    ref, qry, ct = datagen.make_section_pair(n_tiles=9, n_types=3, seed=11)
+    lut = {c: i for i, c in enumerate(ct)}
+    a_xy, r_xy = qry[["X", "Y"]].to_numpy(), ref[["X", "Y"]].to_numpy()
+    rects = np.array([[x, x + 22.0, y, y + 22.0] for x in (0.0, 16.0) for y in (0.0, 16.0)])
+    with Section(a_xy, r_xy, qry[ct].to_numpy(), ref[ct].to_numpy(), qry["cell_type"].map(lut).to_numpy(np.int32),
+                 ref["cell_type"].map(lut).to_numpy(np.int32)) as sec:
+        sec.set_triangles(Delaunay(a_xy).simplices.astype(np.int64), None)
+        with sec.batch(rects) as b:
+            b.candidates(1.0, 8, False, 1.0)
+            b.triangles_remap()
+            b.tri_classify(0.8, 25.0, True)
+            b.tri_finalize(True, True, True)
+            ptr, ln, idx = b.get(L.NODE_TRI_PTR), b.get(L.NODE_TRI_LEN), b.get(L.NODE_TRI_IDX)
+            ka, to = b.offsets(L.KEEP_A), b.offsets(L.TRI)
+            assert len(ptr) == ka[-1] + 1 and len(idx) == 3 * to[-1] and np.array_equal(b.offsets(L.NODE_TRI_IDX), 3 * to)
+            total = 0
+            for w in range(len(rects)):
+                tri = b.get_window(L.TRI, w)
+                n = int(ka[w + 1] - ka[w])
+                want = {i: set() for i in range(n)}
+                for t, simplex in enumerate(tri.tolist()):
+                    for v in simplex:
+                        want[v].add(t)
+                for i in range(n):
+                    got = idx[ptr[ka[w] + i]:ptr[ka[w] + i] + ln[ka[w] + i]]
+                    assert (np.diff(got) > 0).all() and set(got.tolist()) == want[i]
+                    total += len(got)
+            assert total == 3 * to[-1] == ptr[-1]
