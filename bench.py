@@ -390,6 +390,68 @@ def luad_shape_arm(rank, world, window_size):
     return best, (0 if out is None else len(out)), (0 if out is None or not len(out) else int(out["window_id"].nunique()))
 
 
+def separation_latency_arm(local_rank):
+    """Per-incumbent latency of the lazy separation at real window sizes: configs[0] (~2 k cells), configs[1]
+    (~10 k cells) and one configs[3] window (~30 k cells).  Gurobi hands the callback a HOST vector, so the call is H2D of x +
+    k_match_rows + k_separation + one synchronisation + D2H of counts and cuts; each part is also timed on its own."""
+    import torch
+    from scipy.spatial import Delaunay
+    from same_b200 import _lib as L
+    from same_b200 import datagen
+    from same_b200.device import Section, pinned_empty
+    out = {}
+    for label, tiles in (("configs[0] ~2k cells", 5), ("configs[1] ~10k cells", 25), ("one configs[3] window ~30k cells", 75)):
+        ref, qry, ct = datagen.make_section_pair(n_tiles=tiles, n_types=N_TYPES, seed=7, scale=SCALE)
+        lut = {c: i for i, c in enumerate(ct)}
+        a_xy, r_xy = qry[["X", "Y"]].to_numpy(), ref[["X", "Y"]].to_numpy()
+        with Section(a_xy, r_xy, qry[ct].to_numpy(), ref[ct].to_numpy(), qry["cell_type"].map(lut).to_numpy(np.int32),
+                     ref["cell_type"].map(lut).to_numpy(np.int32), device=local_rank) as sec, sec.batch() as b:
+            b.candidates(RADIUS, KNN, False, 1.0)
+            keepA = b.get(L.KEEP_A)
+            tri = Delaunay(a_xy[keepA]).simplices.astype(np.int32)
+            b.triangles_set(tri, [0, len(tri)])
+            b.tri_classify(RADIUS, MIN_ANGLE, True)
+            b.tri_finalize(True, True, False)
+            pairs = b.get(L.PAIRS)
+            x_host = pinned_empty(len(pairs), np.float64)
+            x_host[:] = incumbent(pairs, seed=tiles)
+            x_dev = torch.from_numpy(np.asarray(x_host)).to(torch.device("cuda", local_rank))
+            cap = 1000
+
+            def timed(fn, n=300):
+                for _ in range(20):
+                    fn()
+                torch.cuda.synchronize()
+                ts = []
+                for _ in range(n):
+                    t0 = time.perf_counter()
+                    fn()
+                    ts.append(time.perf_counter() - t0)
+                return float(np.median(ts) * 1e6), float(np.percentile(ts, 95) * 1e6)
+            host_med, host_p95 = timed(lambda: b.separation(x_host, cap=cap))
+            dev_med, dev_p95 = timed(lambda: b.separation(int(x_dev.data_ptr()), cap=cap))
+
+            def h2d_only():
+                x_dev.copy_(torch.from_numpy(np.asarray(x_host)), non_blocking=True)
+                torch.cuda.synchronize()
+            h2d_med, _ = timed(h2d_only)
+            L.profile_enable(True)
+            for _ in range(50):
+                b.separation(int(x_dev.data_ptr()), cap=cap)
+            prof = L.profile_report()
+            L.profile_enable(False)
+            kern = {k: v[1] / v[0] * 1e3 for k, v in prof.items() if k in ("k_match_rows", "k_separation", "k_copy_words")}
+            nv, nc, _ = b.separation(x_host, cap=cap)
+            out[label] = {"cells": [len(ref), len(qry)], "pairs": int(len(pairs)), "triangles": int(b.length(L.TRI)), "checked": int(nc[0]),
+                          "violated": int(nv[0]), "call_us_host_x": host_med, "call_us_host_x_p95": host_p95, "call_us_device_x": dev_med,
+                          "call_us_device_x_p95": dev_p95, "h2d_of_x_alone_us": h2d_med, "x_bytes": int(x_host.nbytes),
+                          "d2h_bytes": int(cap * 16 + 12), "kernel_us": kern}
+    out["note"] = ("median wall time of same_batch_separation per call (300 calls): with the solution vector in page-locked HOST memory "
+                   "(what the MIPSOL callback has), with a device-resident vector, the H2D of x alone (cudaMemcpyAsync + synchronise), "
+                   "and the device time of each kernel of the call (events, separate pass).  cap = 1000 cuts come back per call")
+    return out
+
+
 def workload_config(args, world, grid, n_windows):
     return {"workload": f"BASELINE configs[3]: synthetic {args.tiles}-tile section per GPU (~{args.tiles * 411 / 1e6:.2f}M ref / ~{args.tiles * 372 / 1e6:.2f}M query cells, K={N_TYPES}), "
                         f"candidate+cost+triangle+separation kernels, sliding window {grid[0]}x{grid[1]} per GPU",
@@ -513,7 +575,7 @@ def main():
         mark()
         b.postsolve(int(x_dev["t"].data_ptr()))
         mark()
-        stats = dict(P=b.length(L.PAIRS), T=b.length(L.TRI), Tin=b.length(L.TRI_IN), nKA=b.length(L.KEEP_A), nKR=b.length(L.KEEP_R),
+        stats = dict(evals=b.stat(L.STAT_KNN_EVALUATIONS), P=b.length(L.PAIRS), T=b.length(L.TRI), Tin=b.length(L.TRI_IN), nKA=b.length(L.KEEP_A), nKR=b.length(L.KEEP_R),
                      nAi=b.length(L.WIN_A), nRi=b.length(L.WIN_R), G=b.length(L.REF_GROUP_NODE), viol=int(nv.sum()), checked=int(nc.sum()))
         d2h = 0
         if fetch:   # everything the host model builder consumes, into pinned buffers, one synchronisation
@@ -648,7 +710,8 @@ def main():
     L.profile_enable(True)
     for _ in range(3):
         flush_buf.fill_(1)
-        one_pass(sec)
+        pstats, _ = one_pass(sec)
+    knn_evals = pstats["evals"]
     prof = L.profile_report()
     L.profile_enable(False)
 
@@ -658,6 +721,8 @@ def main():
         sec.close()
         extra["strong_scaling"] = strong_scaling_arm(args, rank, world, local_rank, stream)
         sec = make_section()
+    if not args.no_e2e and rank == 0:
+        extra["separation_callback_latency"] = separation_latency_arm(local_rank)
     if not args.no_e2e:
         for ws in (13000, 4000):
             secs, n_match, n_win = luad_shape_arm(rank, world, ws)
@@ -759,6 +824,19 @@ def main():
             roofline["fp64_peak_tflops_measured"] = L.fp64_peak_tflops(local_rank)
         except Exception as e:
             roofline["fp64_peak_tflops_measured"] = None
+        if "k_knn<8>" in kernels and knn_evals and knn_evals > 0 and roofline["fp64_peak_tflops_measured"]:
+            # compute side of the search kernel: every evaluated candidate costs 5 FP64 operations (2 subtractions, 2 products, 1 sum —
+            # unfused by contract, so the ceiling is the FP64 INSTRUCTION rate, half of the FMA-counted peak)
+            t_s = kernels["k_knn<8>"]["avg_ms"] * 1e-3
+            inst_peak = roofline["fp64_peak_tflops_measured"] * 1e12 / 2.0
+            kroof = {"distance_evaluations": int(knn_evals), "evaluations_per_query": knn_evals / max(s["nAi"], 1), "fp64_ops": int(5 * knn_evals),
+                     "achieved_gflops": 5 * knn_evals / t_s / 1e9, "fp64_instruction_peak_gflops": inst_peak / 1e9,
+                     "compute_frac": (5 * knn_evals / t_s) / inst_peak,
+                     "hbm_frac": kernels["k_knn<8>"]["frac_of_hbm_peak"],
+                     "bound": "neither: instruction issue under divergence (ncu: issue slots 70 % busy at 18 of 32 lanes)"}
+            roofline["k_knn_compute"] = kroof
+            if dom == "k_knn<8>":
+                roofline["compute_frac"] = kroof["compute_frac"]
         hb = max((n for n in kernels if n in alg and n != dom), key=lambda n: kernels[n]["avg_ms"] * kernels[n]["launches_per_step"])
         roofline["hbm_kernel"] = {"kernel": hb, "bound": "hbm", "achieved": kernels[hb]["achieved_gbs"], "peak": hbm_peak, "unit": "GB/s",
                                   "frac": kernels[hb]["frac_of_hbm_peak"], "traffic": traffic.get(hb), "avg_launch_ms": kernels[hb]["avg_ms"],

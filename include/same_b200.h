@@ -244,6 +244,10 @@ SAME_API int same_batch_sync(same_batch_t *b);
  * was freed on other streams). */
 SAME_API int same_stream_create(int device, void **stream);
 SAME_API int same_stream_destroy(int device, void *stream);
+/* Counters of a batch: SAME_STAT_KNN_EVALUATIONS = distance evaluations of the last same_batch_candidates (counted only while
+ * same_profile_enable(1) is in effect, -1 otherwise): bench.py's compute-side roofline = evaluations x 5 flops / kernel time. */
+enum { SAME_STAT_KNN_EVALUATIONS = 1 };
+SAME_API int same_batch_stat(same_batch_t *b, int what, int64_t *value);
 /* Device memory the library's stream-ordered pool holds (reserved) and has handed out (used) right now, in bytes. */
 SAME_API int same_mempool_stats(int device, int64_t *reserved, int64_t *used);
 /* stream the batch runs on (cudaStream_t), for event timing by the caller */

@@ -24,6 +24,7 @@ TRI_WEIGHT, TRI_SIGN, TRI_BOUNDS, TRI_ARGV, UNCONSTRAINED = 18, 19, 20, 21, 22
 MATCH_J, MATCH_P, TRI_MASK, AREA_BEFORE, AREA_AFTER, FLIPPED = 23, 24, 25, 26, 27, 28
 START_X, START_UNMATCHED = 29, 30
 PAIR_J = 31
+STAT_KNN_EVALUATIONS = 1
 NODE_TRI_PTR, NODE_TRI_LEN, NODE_TRI_IDX = 32, 33, 34
 
 #: numpy dtype and trailing shape of every retrievable array
@@ -52,7 +53,7 @@ SYMBOLS = [
     "same_batch_get", "same_elem_size", "same_batch_sync", "same_batch_stream", "same_launch_count",
     "same_profile_enable", "same_profile_report", "same_batch_get_many", "same_batch_get_many_async", "same_pinned_alloc", "same_pinned_free",
     "same_postsolve_arrays", "same_batch_mip_start", "same_greedy_select", "same_collapse_select", "same_segment_mean", "same_measure_fp64_peak", "same_section_wait_uploads",
-    "same_stream_create", "same_stream_destroy", "same_mempool_stats", "same_batch_uncertain",
+    "same_stream_create", "same_stream_destroy", "same_mempool_stats", "same_batch_uncertain", "same_batch_stat",
 ]
 
 
@@ -98,6 +99,7 @@ def load():
     lib.same_batch_groups.argtypes = [vp, i32, i32]
     lib.same_batch_separation.argtypes = [vp, i64, i64, vp, i64, vp, vp, vp]
     lib.same_batch_postsolve.argtypes = [vp, i64, i64, vp]
+    lib.same_batch_stat.argtypes = [vp, i32, C.POINTER(i64)]
     lib.same_batch_uncertain.argtypes = [vp, i32, i64, C.POINTER(i64), vp]
     lib.same_batch_offsets.argtypes = [vp, i32, vp]
     lib.same_batch_length.argtypes = [vp, i32, C.POINTER(i64)]

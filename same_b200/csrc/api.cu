@@ -394,6 +394,19 @@ int same_pinned_free(void *p) {
 
 int same_batch_sync(same_batch_t *h) { BATCH_CALL(h, batch_sync(b)); }
 
+int same_batch_stat(same_batch_t *h, int what, int64_t *value) {
+    BATCH_CALL(h, {
+        REQUIRE(value, SAME_E_ARG, "value is NULL");
+        REQUIRE(what == SAME_STAT_KNN_EVALUATIONS, SAME_E_ARG, "unknown counter");
+        *value = -1;
+        if (b->knn_evals.p) {
+            unsigned long long v = 0;
+            CK(cudaMemcpyAsync(&v, b->knn_evals.p, sizeof(v), cudaMemcpyDeviceToHost, b->stream));
+            CK(cudaStreamSynchronize(b->stream));
+            *value = (int64_t)v;
+        }
+    });
+}
 int same_mempool_stats(int device, int64_t *reserved, int64_t *used) {
     return guarded([&] {
         cudaMemPool_t pool;

@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(128) k_knn(const double2 *__restrict__ sa_xy, 
                                              const i32 *__restrict__ a_off, int W, const GridParams *__restrict__ grids,
                                              const i32 *__restrict__ bin_start, const double2 *__restrict__ sr_xy,
                                              const i32 *__restrict__ sr_inst, double r2, int knn, i32 *__restrict__ cand,
-                                             i32 *__restrict__ cnt, i32 *__restrict__ r_used) {
+                                             i32 *__restrict__ cnt, i32 *__restrict__ r_used, unsigned long long *__restrict__ evals) {
     const i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nAi) return;
     const i32 inst = sa_inst[t];
@@ -190,6 +190,7 @@ __global__ void __launch_bounds__(128) k_knn(const double2 *__restrict__ sa_xy, 
     int cbx, cby;
     bin_of(g, q, cbx, cby);
     const double px = q.x - g.x0, py = q.y - g.y0;
+    int nev = 0;   // distance evaluations of this query (only reported when profiling: the compute-side roofline of bench.py)
 
     // Sorted keys in registers, right-aligned: slots [KCAP-knn, KCAP) hold the list (ascending), the slots before it hold
     // zero keys that never move, so the k-th best is always the LAST slot (a static register index; a runtime index would push
@@ -264,6 +265,7 @@ __global__ void __launch_bounds__(128) k_knn(const double2 *__restrict__ sa_xy, 
                 // two candidates per trip: both loads are in flight before either is used (the second one re-reads the
                 // first when the bin ends on an odd count and is then skipped)
                 const bool two = s0 + 1 < s1;
+                nev += two ? 2 : 1;
                 const double2 pA = sr_xy[s0], pB = sr_xy[two ? s0 + 1 : s0];
                 const double ax = __dsub_rn(pA.x, q.x), ay = __dsub_rn(pA.y, q.y), bx2 = __dsub_rn(pB.x, q.x), by2 = __dsub_rn(pB.y, q.y);
                 const double dA = __dadd_rn(__dmul_rn(ax, ax), __dmul_rn(ay, ay));
@@ -295,6 +297,11 @@ __global__ void __launch_bounds__(128) k_knn(const double2 *__restrict__ sa_xy, 
                 }
             }
         }
+    }
+    if (evals) {   // one atomic per warp (the lanes have reconverged behind the walk)
+        const unsigned live = __activemask();
+        const unsigned tot = __reduce_add_sync(live, (unsigned)nev);
+        if ((threadIdx.x & 31) == (unsigned)(__ffs(live) - 1)) atomicAdd(evals, (unsigned long long)tot);
     }
     i32 *out = cand + (i64)inst * knn;
     if (tie && (last_k & ~SLOT) != NONE_B) {
@@ -628,10 +635,16 @@ void batch_candidates(Batch *b, double radius, int knn, int priority, double dis
     if (nAi > 0) {
         const unsigned grid = blocks_for(nAi, 128);
 #define KNN_ARGS sorted_xy.p, sorted_inst.p, nAi, b->d_a_off.p, (int)W, d_grids.p, bstart.p + nb1, sorted_xy.p, sorted_inst.p, r2, knn
-        if (knn <= 4) LAUNCH(k_knn<4>, grid, 128, 0, s, KNN_ARGS, b->cand.p, b->cnt.p, b->r_used.p);
-        else if (knn <= 8) LAUNCH(k_knn<8>, grid, 128, 0, s, KNN_ARGS, b->cand.p, b->cnt.p, b->r_used.p);
-        else if (knn <= 16) LAUNCH(k_knn<16>, grid, 128, 0, s, KNN_ARGS, b->cand.p, b->cnt.p, b->r_used.p);
-        else if (knn <= 32) LAUNCH(k_knn<32>, grid, 128, 0, s, KNN_ARGS, b->cand.p, b->cnt.p, b->r_used.p);
+        unsigned long long *evals = nullptr;
+        if (g_prof) {   // profiling pass only: count the distance evaluations
+            b->knn_evals.alloc(1, s);
+            b->knn_evals.zero(s);
+            evals = b->knn_evals.p;
+        }
+        if (knn <= 4) LAUNCH(k_knn<4>, grid, 128, 0, s, KNN_ARGS, b->cand.p, b->cnt.p, b->r_used.p, evals);
+        else if (knn <= 8) LAUNCH(k_knn<8>, grid, 128, 0, s, KNN_ARGS, b->cand.p, b->cnt.p, b->r_used.p, evals);
+        else if (knn <= 16) LAUNCH(k_knn<16>, grid, 128, 0, s, KNN_ARGS, b->cand.p, b->cnt.p, b->r_used.p, evals);
+        else if (knn <= 32) LAUNCH(k_knn<32>, grid, 128, 0, s, KNN_ARGS, b->cand.p, b->cnt.p, b->r_used.p, evals);
         else {
             DevBuf<double> gd;
             DevBuf<i32> gj;

@@ -226,6 +226,7 @@ struct Batch {
     DevBuf<i32> cand, cnt, eff;         // [nAi*knn] ref instance, [nAi], [nAi] pairs emitted (priority)
     DevBuf<i32> newA;                   // [nAi+1] batch-global kept index of each aligned instance (exclusive scan of cnt > 0)
     DevBuf<i32> r_used;                 // [nRi]
+    DevBuf<unsigned long long> knn_evals;   // [1] distance evaluations of the search (filled only while profiling is enabled)
 
     // kept nodes (post-KNN frames), batch-global "kept index" = window offset + local index
     i64 nKA = 0, nKR = 0, P = 0;
@@ -281,7 +282,6 @@ struct Batch {
     // separation / postsolve
     DevBuf<double> x_dev;
     DevBuf<i32> match_j, match_p;       // [nKA]
-    DevBuf<double2> match_xy;           // [nKA] coordinates of the matched reference cell, NaN = unmatched
     DevBuf<i32> sep_counts, cuts;
     i64 last_unc_sep = -1;
     DevBuf<i32> unc_list[2], unc_count;   // [0] source signs (k_tri_tables), [1] last separation call: triangles the orientation filter could not decide

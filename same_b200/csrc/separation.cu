@@ -8,16 +8,13 @@
 
 namespace same {
 
-// matching[i] = j of the LAST pair of row i with x > 0.5 (dict overwrite, src/same.py:636-639), plus ref_coords[j]
-// (src/same.py:654-656) of the match.  A block owns
+// matching[i] = j of the LAST pair of row i with x > 0.5 (dict overwrite, src/same.py:636-639).  A block owns
 // MATCH_ROWS consecutive rows; their pairs are one contiguous range of x, which the block reads coalesced and reduces
 // to one flag per pair in shared memory; every thread then scans the flags of its own row.
 constexpr int MATCH_ROWS = 256, MATCH_CHUNK = 2048;
 __global__ void __launch_bounds__(MATCH_ROWS) k_match_rows(const double *__restrict__ x, i32 x_base, const int2 *__restrict__ pairs,
                                                            const i32 *__restrict__ row_ptr, const i32 *__restrict__ ka_off, const i32 *__restrict__ p_off,
-                                                           int W, i32 k_lo, i32 k_hi, const i32 *__restrict__ kr_off,
-                                                           const double2 *__restrict__ kr_xy, i32 *__restrict__ match_j, i32 *__restrict__ match_p,
-                                                           double2 *__restrict__ match_xy) {
+                                                           int W, i32 k_lo, i32 k_hi, i32 *__restrict__ match_j, i32 *__restrict__ match_p) {
     __shared__ unsigned char flag[MATCH_CHUNK];
     __shared__ i32 range[2];
     const i32 k0 = k_lo + (i32)blockIdx.x * MATCH_ROWS;
@@ -38,18 +35,9 @@ __global__ void __launch_bounds__(MATCH_ROWS) k_match_rows(const double *__restr
     }
     if (k >= k_hi) return;
     i32 mj = -1;
-    // coordinates of the matched reference cell (NaN = unmatched): the triangle kernels then gather ONE level (triangle ->
-    // matched XY) instead of two (triangle -> match -> reference XY)
-    double2 mxy = make_double2(__longlong_as_double(0x7ff8000000000000ll), 0.0);
-    if (mp >= 0) {
-        const int w = find_window(ka_off, W, k);
-        mj = pairs[mp].y;
-        mp -= p_off[w];
-        mxy = kr_xy[kr_off[w] + mj];
-    }
+    if (mp >= 0) { mj = pairs[mp].y; mp -= p_off[find_window(ka_off, W, k)]; }
     match_j[k] = mj;
     match_p[k] = mp;
-    match_xy[k] = mxy;
 }
 
 // Separation of one incumbent in ONE launch: orientation test per triangle, ranks of the violated triangles inside
@@ -60,8 +48,8 @@ constexpr int SEP_THREADS = 256, SEP_ITEMS = 4, SEP_TILE = SEP_THREADS * SEP_ITE
 
 __global__ void __launch_bounds__(SEP_THREADS) k_separation(const int3 *__restrict__ tri, const signed char *__restrict__ src_sign, i32 t_lo, i32 t_hi,
                                                             const i32 *__restrict__ t_off, const i32 *__restrict__ ka_off, const i32 *__restrict__ kr_off,
-                                                            int W, int w_lo, const double2 *__restrict__ match_xy, const i32 *__restrict__ match_p,
-                                                            i64 cap, ScanCtx sc,
+                                                            int W, int w_lo, const i32 *__restrict__ match_j, const i32 *__restrict__ match_p,
+                                                            const double2 *__restrict__ kr_xy, i64 cap, ScanCtx sc,
                                                             i32 *__restrict__ counts /* [2*nw] zeroed: n_viol, n_checked */, i32 *__restrict__ cuts,
                                                             i32 *__restrict__ unc_list, i32 *__restrict__ unc_count) {
     __shared__ int E[SEP_TILE + 1];
@@ -80,10 +68,11 @@ __global__ void __launch_bounds__(SEP_THREADS) k_separation(const int3 *__restri
         unsigned char vi = 0;
         if (t < tend) {
             if (wf != wl) w = find_window(t_off, W, t);
-            const i32 nb = ka_off[w];
+            const i32 nb = ka_off[w], rb = kr_off[w];
             const int3 v = tri[t];
-            const double2 A = match_xy[nb + v.x], B = match_xy[nb + v.y], C = match_xy[nb + v.z];
-            if (A.x == A.x && B.x == B.x && C.x == C.x) {  // all three vertices matched (same.py:649-651); NaN = unmatched
+            const i32 ja = match_j[nb + v.x], jb = match_j[nb + v.y], jc = match_j[nb + v.z];
+            if (ja >= 0 && jb >= 0 && jc >= 0) {  // same.py:649-651
+                const double2 A = kr_xy[rb + ja], B = kr_xy[rb + jb], C = kr_xy[rb + jc];
                 const int rs = sign_of(orient_naive(A.x, A.y, B.x, B.y, C.x, C.y));  // same.py:658
                 if (orient_uncertain(A.x, A.y, B.x, B.y, C.x, C.y)) {   // diagnostic only: listed for the host's exact check
                     const i32 at = atomicAdd(unc_count, 1);
@@ -158,11 +147,10 @@ static void run_matching(Batch *b, i64 w_lo, i64 w_hi, const double *xd) {
     cudaStream_t s = b->stream;
     b->match_j.alloc(b->nKA, s);
     b->match_p.alloc(b->nKA, s);
-    b->match_xy.alloc(b->nKA, s);
     const i32 k_lo = (i32)b->ka_off[w_lo], k_hi = (i32)b->ka_off[w_hi];
     if (k_hi > k_lo)
         LAUNCH(k_match_rows, blocks_for(k_hi - k_lo, MATCH_ROWS), MATCH_ROWS, 0, s, xd, (i32)b->p_off[w_lo], b->pairs.p, b->row_ptr.p, b->d_ka_off.p,
-               b->d_p_off.p, (int)b->W, k_lo, k_hi, b->d_kr_off.p, b->kr_xy.p, b->match_j.p, b->match_p.p, b->match_xy.p);
+               b->d_p_off.p, (int)b->W, k_lo, k_hi, b->match_j.p, b->match_p.p);
 }
 
 void batch_separation(Batch *b, i64 w_lo, i64 w_hi, const double *x, i64 cap, i64 *n_viol, i64 *n_checked, i32 *cuts) {
@@ -175,20 +163,19 @@ void batch_separation(Batch *b, i64 w_lo, i64 w_hi, const double *x, i64 cap, i6
     run_matching(b, w_lo, w_hi, resolve_x(b, w_lo, w_hi, x));
     const i32 t_lo = (i32)b->t_off[w_lo], t_hi = (i32)b->t_off[w_hi];
     const i64 nt = t_hi - t_lo;
-    b->sep_counts.alloc(2 * nw, s);
+    b->sep_counts.alloc(2 * nw + 1, s);   // + the count of orientations the filter could not certify (diagnostic)
     b->cuts.alloc(std::max<i64>(1, nw * cap * 4), s);
-    CK(cudaMemsetAsync(b->sep_counts.p, 0, sizeof(i32) * 2 * nw, s));
-    CK(cudaMemsetAsync(b->unc_count.p + 1, 0, sizeof(i32), s));
+    CK(cudaMemsetAsync(b->sep_counts.p, 0, sizeof(i32) * (2 * nw + 1), s));
     if (nt > 0) {
         const unsigned tiles = blocks_for(nt, SEP_TILE);
         LAUNCH(k_separation, tiles, SEP_THREADS, 0, s, b->tri.p, b->t_sign.p, t_lo, t_hi, b->d_t_off.p, b->d_ka_off.p, b->d_kr_off.p, (int)b->W, (int)w_lo,
-               b->match_xy.p, b->match_p.p, cap, scan_ctx(b->sec, tiles, 1, s), b->sep_counts.p, b->cuts.p, b->unc_list[1].p, b->unc_count.p + 1);
+               b->match_j.p, b->match_p.p, b->kr_xy.p, cap, scan_ctx(b->sec, tiles, 1, s), b->sep_counts.p, b->cuts.p, b->unc_list[1].p,
+               b->sep_counts.p + 2 * nw);
     }
     // counts and cuts come back behind ONE synchronisation: the cut block is small (cap rows per window), so it is copied
     // whole instead of waiting for the counts to know how much of it was filled
     i32 *h_sep = b->pin_misc();   // page-locked (2 nw <= 4(W+1) + 8 ints): a pageable destination would stage and block
-    small_d2h(h_sep, b->sep_counts.p, sizeof(i32) * 2 * nw, s);
-    small_d2h(h_sep + 2 * nw, b->unc_count.p + 1, sizeof(i32), s);   // rides along: same_batch_uncertain(1, cap = 0) then needs no round trip
+    small_d2h(h_sep, b->sep_counts.p, sizeof(i32) * (2 * nw + 1), s);   // (the diagnostic count rides along: no extra round trip)
     if (cuts && cap > 0 && nt > 0) CK(cudaMemcpyAsync(cuts, b->cuts.p, sizeof(i32) * 4 * (size_t)(nw * cap), cudaMemcpyDefault, s));
     batch_sync(b);
     for (i64 w = 0; w < nw; ++w) {
@@ -206,8 +193,8 @@ void batch_uncertain(Batch *b, int which, i64 cap, i64 *n, i32 *tri_idx) {
     REQUIRE(which == 0 || which == 1, SAME_E_ARG, "which must be 0 or 1");
     REQUIRE(n && cap >= 0 && (cap == 0 || tri_idx), SAME_E_ARG, "bad output");
     batch_settle(b);
-    if (which == 1 && b->last_unc_sep >= 0) {
-        *n = b->last_unc_sep;       // came back with the counts of the separation call
+    if (which == 1) {
+        *n = std::max<i64>(b->last_unc_sep, 0);       // came back with the counts of the separation call (0 before the first one)
     } else {
         i32 *h = b->pin_misc();
         small_d2h(h, b->unc_count.p + which, sizeof(i32), s);
@@ -231,24 +218,23 @@ __device__ __forceinline__ double signed_area(double2 p1, double2 p2, double2 p3
 }
 
 __global__ void k_postsolve(const int3 *__restrict__ tri, i32 t_lo, i32 t_hi, const i32 *__restrict__ t_off, const i32 *__restrict__ ka_off,
-                            int W, const double2 *__restrict__ match_xy, const double2 *__restrict__ ka_xy,
-                            i32 *__restrict__ mask, double *__restrict__ area_before,
+                            const i32 *__restrict__ kr_off, int W, const i32 *__restrict__ match_j, const double2 *__restrict__ ka_xy,
+                            const double2 *__restrict__ kr_xy, i32 *__restrict__ mask, double *__restrict__ area_before,
                             double *__restrict__ area_after, unsigned char *__restrict__ flipped) {
     const i32 t = t_lo + blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= t_hi) return;
     const int w = find_window(t_off, W, t);
-    const i32 nb = ka_off[w];
+    const i32 nb = ka_off[w], rb = kr_off[w];
     const int3 v3 = tri[t];
     const i32 v[3] = {v3.x, v3.y, v3.z};
-    i32 j[3];   // >= 0: vertex matched
+    i32 j[3];
     double2 a[3], r[3];
     i32 m = 0;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
+        j[c] = match_j[nb + v[c]];
         a[c] = ka_xy[nb + v[c]];
-        r[c] = match_xy[nb + v[c]];
-        j[c] = (r[c].x == r[c].x) ? 0 : -1;
-        if (j[c] >= 0) m |= 1 << (8 + c); else r[c] = make_double2(0.0, 0.0);
+        if (j[c] >= 0) { m |= 1 << (8 + c); r[c] = kr_xy[rb + j[c]]; } else r[c] = make_double2(0.0, 0.0);
     }
     const int PU[3] = {0, 0, 1}, PW[3] = {1, 2, 2};
 #pragma unroll
@@ -284,17 +270,9 @@ void batch_postsolve(Batch *b, i64 w_lo, i64 w_hi, const double *x) {
     }
     const i32 t_lo = (i32)b->t_off[w_lo], t_hi = (i32)b->t_off[w_hi];
     if (t_hi > t_lo)
-        LAUNCH(k_postsolve, blocks_for(t_hi - t_lo, 256), 256, 0, s, b->tri.p, t_lo, t_hi, b->d_t_off.p, b->d_ka_off.p, (int)b->W,
-               b->match_xy.p, b->ka_xy.p, b->t_mask.p, b->area_before.p, b->area_after.p, b->flipped.p);
+        LAUNCH(k_postsolve, blocks_for(t_hi - t_lo, 256), 256, 0, s, b->tri.p, t_lo, t_hi, b->d_t_off.p, b->d_ka_off.p, b->d_kr_off.p, (int)b->W,
+               b->match_j.p, b->ka_xy.p, b->kr_xy.p, b->t_mask.p, b->area_before.p, b->area_after.p, b->flipped.p);
     if (xd != x) batch_sync(b);   // the caller's host vector was read asynchronously; a device-resident x needs no wait
-}
-
-// stateless path: matched reference coordinates from a match vector (NaN = unmatched)
-__global__ void k_match_xy(const i32 *__restrict__ match_j, const double2 *__restrict__ r_xy, i64 nA, i64 nR, double2 *__restrict__ match_xy) {
-    const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nA) return;
-    const i32 j = match_j[i];
-    match_xy[i] = (j >= 0 && j < nR) ? r_xy[j] : make_double2(__longlong_as_double(0x7ff8000000000000ll), 0.0);
 }
 
 void postsolve_arrays(int device, i64 T, const i32 *tri, i64 nA, const double *a_xy, i64 nR, const double *r_xy, const i32 *match_j, i32 *mask,
@@ -303,8 +281,8 @@ void postsolve_arrays(int device, i64 T, const i32 *tri, i64 nA, const double *a
     cudaStream_t s;
     CK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
     try {
-        DevBuf<int3> d_tri; DevBuf<double2> d_a, d_r, d_mxy; DevBuf<i32> d_m, d_off, d_mask; DevBuf<double> d_ab, d_aa; DevBuf<unsigned char> d_fl;
-        d_tri.alloc(T, s); d_a.alloc(nA, s); d_r.alloc(nR, s); d_m.alloc(nA, s); d_off.alloc(6, s); d_mxy.alloc(nA, s);
+        DevBuf<int3> d_tri; DevBuf<double2> d_a, d_r; DevBuf<i32> d_m, d_off, d_mask; DevBuf<double> d_ab, d_aa; DevBuf<unsigned char> d_fl;
+        d_tri.alloc(T, s); d_a.alloc(nA, s); d_r.alloc(nR, s); d_m.alloc(nA, s); d_off.alloc(6, s);
         d_mask.alloc(T, s); d_ab.alloc(T, s); d_aa.alloc(T, s); d_fl.alloc(T, s);
         if (T) CK(cudaMemcpyAsync(d_tri.p, tri, sizeof(int3) * T, cudaMemcpyDefault, s));
         if (nA) CK(cudaMemcpyAsync(d_a.p, a_xy, sizeof(double2) * nA, cudaMemcpyDefault, s));
@@ -312,10 +290,9 @@ void postsolve_arrays(int device, i64 T, const i32 *tri, i64 nA, const double *a
         if (nA) CK(cudaMemcpyAsync(d_m.p, match_j, sizeof(i32) * nA, cudaMemcpyDefault, s));
         const i32 off[6] = {0, (i32)T, 0, (i32)nA, 0, (i32)nR};
         CK(cudaMemcpyAsync(d_off.p, off, sizeof(off), cudaMemcpyHostToDevice, s));
-        if (nA > 0) LAUNCH(k_match_xy, blocks_for(nA, 256), 256, 0, s, d_m.p, d_r.p, nA, nR, d_mxy.p);
         if (T > 0)
-            LAUNCH(k_postsolve, blocks_for(T, 256), 256, 0, s, d_tri.p, 0, (i32)T, d_off.p, d_off.p + 2, 1, d_mxy.p, d_a.p, d_mask.p, d_ab.p, d_aa.p,
-                   d_fl.p);
+            LAUNCH(k_postsolve, blocks_for(T, 256), 256, 0, s, d_tri.p, 0, (i32)T, d_off.p, d_off.p + 2, d_off.p + 4, 1, d_m.p, d_a.p, d_r.p, d_mask.p,
+                   d_ab.p, d_aa.p, d_fl.p);
         if (T) {
             CK(cudaMemcpyAsync(mask, d_mask.p, sizeof(i32) * T, cudaMemcpyDefault, s));
             CK(cudaMemcpyAsync(area_before, d_ab.p, sizeof(double) * T, cudaMemcpyDefault, s));

@@ -438,6 +438,11 @@ class WindowBatch:
         L.check(fn(self._h, n, L.ptr(w), L.ptr(lo), L.ptr(hi), dst))
         return dict(zip(whats, outs))
 
+    def stat(self, what):
+        v = C.c_int64(0)
+        L.check(L.load().same_batch_stat(self._h, int(what), C.byref(v)))
+        return v.value
+
     def get_window(self, what, w):
         off = self.offsets(what)
         return self.get(what, int(off[w]), int(off[w + 1]))
