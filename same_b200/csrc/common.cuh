@@ -134,6 +134,8 @@ struct PinArena {   // bump allocator over page-locked blocks of a process-wide 
 constexpr size_t SMALL_COPY_LIMIT = 256 << 10;   // larger transfers use cudaMemcpyAsync
 void small_d2h(void *host_pinned, const void *dev, size_t bytes, cudaStream_t s);             // host_pinned: page-locked (cudaHostAlloc)
 void small_h2d(PinArena &arena, void *dev, const void *host, size_t bytes, cudaStream_t s);   // host: any memory, staged through the arena
+struct SmallCopy { void *dev; const void *host; size_t bytes; };
+void small_h2d_many(PinArena &arena, const SmallCopy *items, int n, cudaStream_t s);            // up to 4 uploads, ONE launch
 
 struct Section {
     int device = 0;

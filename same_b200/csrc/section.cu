@@ -71,6 +71,34 @@ void small_d2h(void *host_pinned, const void *dev, size_t bytes, cudaStream_t s)
     if (bytes > SMALL_COPY_LIMIT || (bytes & 3)) { CK(cudaMemcpyAsync(host_pinned, dev, bytes, cudaMemcpyDeviceToHost, s)); return; }
     copy_words(host_pinned, dev, bytes, s);
 }
+struct CopySegs { unsigned *dst[4]; unsigned long long src_word[4], n_word[4]; int n; };
+__global__ void k_copy_segments(CopySegs segs, const unsigned *__restrict__ stage) {
+    for (int k = 0; k < segs.n; ++k)
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < segs.n_word[k]; i += (size_t)gridDim.x * blockDim.x)
+            segs.dst[k][i] = stage[segs.src_word[k] + i];
+}
+void small_h2d_many(PinArena &arena, const SmallCopy *items, int n, cudaStream_t s) {
+    size_t total = 0;
+    bool ok = n <= 4;
+    for (int k = 0; k < n; ++k) { ok = ok && !(items[k].bytes & 3); total += (items[k].bytes + 15) & ~(size_t)15; }
+    if (!ok || total > SMALL_COPY_LIMIT) {
+        for (int k = 0; k < n; ++k) small_h2d(arena, items[k].dev, items[k].host, items[k].bytes, s);
+        return;
+    }
+    if (total == 0) return;
+    char *stage = (char *)arena.get(total);
+    CopySegs segs{};
+    size_t off = 0, most = 0;
+    for (int k = 0; k < n; ++k) {
+        if (items[k].bytes == 0) continue;
+        memcpy(stage + off, items[k].host, items[k].bytes);
+        segs.dst[segs.n] = (unsigned *)items[k].dev; segs.src_word[segs.n] = off / 4; segs.n_word[segs.n] = items[k].bytes / 4;
+        most = std::max(most, items[k].bytes / 4);
+        ++segs.n;
+        off += (items[k].bytes + 15) & ~(size_t)15;
+    }
+    LAUNCH(k_copy_segments, (unsigned)std::min<size_t>(64, (most + 255) / 256), 256, 0, s, segs, (const unsigned *)stage);
+}
 void small_h2d(PinArena &arena, void *dev, const void *host, size_t bytes, cudaStream_t s) {
     if (bytes == 0) return;
     if (bytes > SMALL_COPY_LIMIT || (bytes & 3)) { CK(cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, s)); return; }
@@ -438,8 +466,10 @@ static void subset_frames_t(Batch *b, int rowbits, int wbits) {
     for (i64 w = 0; w < W; ++w) { b->a_off[w + 1] = b->a_off[w] + h[w]; b->r_off[w + 1] = b->r_off[w] + h[W + w]; }
     for (i64 w = 0; w <= W; ++w) { ho[w] = (i32)b->a_off[w]; ho[W + 1 + w] = (i32)b->r_off[w]; }
     b->d_a_off.alloc(W + 1, s); b->d_r_off.alloc(W + 1, s);
-    small_h2d(b->arena, b->d_a_off.p, ho, sizeof(i32) * (W + 1), s);
-    small_h2d(b->arena, b->d_r_off.p, ho + W + 1, sizeof(i32) * (W + 1), s);
+    {
+        const SmallCopy up[2] = {{b->d_a_off.p, ho, sizeof(i32) * (size_t)(W + 1)}, {b->d_r_off.p, ho + W + 1, sizeof(i32) * (size_t)(W + 1)}};
+        small_h2d_many(b->arena, up, 2, s);
+    }
     b->a_src.alloc(b->nAi, s); b->r_src.alloc(b->nRi, s); b->row_inst.alloc(total, s);
     if (total == 0) return;
     DevBuf<KeyT> keys, keys_out;
@@ -515,8 +545,12 @@ static void build_rect_index(Batch *b) {
     }
     b->ri_ptr.alloc((i64)ptr.size(), s);
     b->ri_rects.alloc((i64)lst.size(), s);
-    small_h2d(b->arena, b->ri_ptr.p, ptr.data(), sizeof(i32) * ptr.size(), s);
-    small_h2d(b->arena, b->ri_rects.p, lst.data(), sizeof(i32) * lst.size(), s);
+    b->d_rects.alloc(4 * b->W, s);
+    {
+        const SmallCopy up[3] = {{b->ri_ptr.p, ptr.data(), sizeof(i32) * ptr.size()}, {b->ri_rects.p, lst.data(), sizeof(i32) * lst.size()},
+                                 {b->d_rects.p, b->rects.data(), sizeof(double) * 4 * (size_t)b->W}};
+        small_h2d_many(b->arena, up, 3, s);   // rectangle index and the rectangles themselves: one launch
+    }
     b->rindex = RectIndexDev{bx0, by0, inv, nx, ny, max_len, b->ri_ptr.p, b->ri_rects.p};
 }
 
@@ -524,9 +558,7 @@ void batch_subset(Batch *b) {
     Section *sec = b->sec;
     cudaStream_t s = b->stream;
     batch_pin_acquire(b);
-    b->d_rects.alloc(4 * b->W, s);
-    small_h2d(b->arena, b->d_rects.p, b->rects.data(), sizeof(double) * 4 * b->W, s);
-    build_rect_index(b);
+    build_rect_index(b);   // (also uploads the rectangles)
     subset_frames(b);
 }
 

@@ -109,6 +109,25 @@ class Section:
         self.h2d_bytes = a_xy.nbytes + r_xy.nbytes + a_prob.nbytes + r_prob.nbytes + sum(
             v.nbytes for v in (a_type, r_type, a_size, r_size) if v is not None)
 
+    @classmethod
+    def from_pointers(cls, n_aligned, n_ref, n_types, a_xy, r_xy, a_prob, r_prob, a_type=None, r_type=None, a_size=None, r_size=None,
+                      device=None, stream=None, keep=None):
+        """Section from raw addresses (host or device memory, `int`; layouts as in `same_section_create`).  `keep` = objects that
+        own the memory (kept alive until the uploads are done)."""
+        self = cls.__new__(cls)
+        if device is None:
+            device = default_device()
+        self.n_aligned, self.n_ref, self.n_types = int(n_aligned), int(n_ref), int(n_types)
+        h = C.c_void_p()
+        L.check(L.load().same_section_create(device, C.c_void_p(stream) if stream else None, self.n_aligned, self.n_ref, self.n_types,
+                                             L.ptr(a_xy), L.ptr(r_xy), L.ptr(a_prob), L.ptr(r_prob), L.ptr(a_type), L.ptr(r_type),
+                                             L.ptr(a_size), L.ptr(r_size), C.byref(h)))
+        self._h = h
+        self.device = device
+        self._keep = [keep]
+        self.h2d_bytes = 0
+        return self
+
     @property
     def bbox(self):
         out = np.zeros(4)
@@ -208,6 +227,13 @@ class CandidateStream:
             L.check(L.load().same_stream_create(self.device, C.byref(p)))
             self._streams.append(p.value)
         self._pool = ThreadPoolExecutor(max_workers=len(self._streams), thread_name_prefix="same_b200-section")
+
+    def reserve(self, nbytes=None):
+        """Give the device memory pool head-room for the overlap of `depth` sections (default: as much again as it holds now), so
+        that no section of the steady state has to wait for the driver to map new memory.  Call after the first results."""
+        if nbytes is None:
+            nbytes = L.mempool_stats(self.device)[0]
+        L.mempool_reserve(self.device, int(nbytes))
 
     def close(self):
         if getattr(self, "_pool", None) is not None:

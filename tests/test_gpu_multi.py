@@ -34,4 +34,4 @@ def test_distributed_sliding_window_matching_equals_single_process(world):
            "--master-port", str(_free_port()), os.path.join(ROOT, "tools", "check_distributed.py")]
     r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
-    assert "distributed check ok" in r.stdout and "halo exchange ok" in r.stdout
+    assert "distributed check ok" in r.stdout and "halo exchange ok" in r.stdout and "row-sharded section ok" in r.stdout

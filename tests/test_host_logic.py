@@ -135,6 +135,11 @@ def _worker(rank, world, port, q):
         xy = np.column_stack([rng.uniform(0, 100, n), rng.uniform(100 * rank, 100 * (rank + 1), n)])
         val = np.arange(n, dtype=np.float64)[:, None] + 1000 * rank
         halo, info = S.exchange_halo({"xy": xy, "val": val, "y": xy[:, 1:2]}, "y", 100 * rank + 30.0)
+        # row-sharded upload: every rank holds the same array, moves 1/world of it and gathers the rest
+        full = np.random.default_rng(99).uniform(0, 1, (101, 3))
+        codes = (np.arange(37) % 5).astype(np.int32)
+        got_full, got_codes = S.allgather_rows(full).numpy(), S.allgather_rows(codes).numpy()
+        assert np.array_equal(got_full, full) and np.array_equal(got_codes[:, 0], codes) and got_codes.dtype == np.int32
         lo, hi = shard_windows(7, world, rank)
         local = pd.DataFrame({"window_id": list(range(lo, hi)), "rank": rank})
         merged = S.gather_matches(local)

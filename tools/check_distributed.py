@@ -43,11 +43,29 @@ n2 = 4000 + 100 * (rank + 1)
 xy2 = np.column_stack([nxt.uniform(0, 50, n2), nxt.uniform(10.0 * (rank + 1), 10.0 * (rank + 2), n2)])
 prob2 = nxt.uniform(0, 100, (n2, 3)); ty2 = nxt.integers(0, 3, n2).astype(np.int32)
 band = xy2[:, 1] < 10.0 * (rank + 1) + 2.5
+dev = torch.device("cuda", local)      # the device-resident form: tensors in, tensors out, same rows
+halo_d, info_d = sharding.exchange_halo({"xy": torch.from_numpy(xy).to(dev), "prob": torch.from_numpy(prob).to(dev), "type": torch.from_numpy(ty).to(dev)},
+                                        ("xy", 1), 10.0 * rank + 2.5)
+assert info_d == info and all(np.array_equal(halo_d[k].cpu().numpy(), halo[k]) for k in halo) and halo_d["xy"].is_cuda
 if rank < world - 1:
     assert np.array_equal(halo["xy"], xy2[band]) and np.array_equal(halo["prob"], prob2[band]) and np.array_equal(halo["type"][:, 0], ty2[band])
     assert halo["type"].dtype == np.int32 and info["rows"] == int(band.sum()) and info["bytes"] == int(band.sum()) * (16 + 24 + 4)
 else:
     assert len(halo["xy"]) == 0 and info["rows"] == 0
+# row-sharded upload + NVLink all-gather builds the same section as a plain upload: candidates of a window block agree bit for bit
+from same_b200 import _lib as L
+from same_b200.device import Section
+lut = {c: i for i, c in enumerate(ct)}
+fr = (qry[["X", "Y"]].to_numpy(), ref[["X", "Y"]].to_numpy(), qry[list(ct)].to_numpy(), ref[list(ct)].to_numpy(),
+      qry["cell_type"].map(lut).to_numpy(np.int32), ref["cell_type"].map(lut).to_numpy(np.int32))
+rects = np.array([[x, x + 14.0, y, y + 14.0] for x in (0.0, 10.0, 20.0, 30.0) for y in (0.0, 10.0, 20.0, 30.0)])
+with sharding.section_from_row_shards(fr, device_index=local) as s1, Section(*fr, device=local) as s2:
+    with s1.batch(rects) as b1, s2.batch(rects) as b2:
+        b1.candidates(1.0, 6, False, 1.0); b2.candidates(1.0, 6, False, 1.0)
+        for w_ in (L.KEEP_A, L.KEEP_R, L.PAIRS, L.COST, L.ROW_PTR):
+            assert np.array_equal(b1.get(w_), b2.get(w_)), "row-sharded section differs from the plain upload"
+if rank == 0:
+    print("row-sharded section ok")
 ok = torch.tensor([1], device=torch.device("cuda", local))
 dist.all_reduce(ok)
 if rank == 0:
