@@ -150,7 +150,68 @@ class _Callback:
     MIPSOL = 4
 
 
+class MVar:
+    """Stand-in for gurobipy.MVar (1-D): what same_b200.solver.GurobiMatrixBackend uses of the matrix API."""
+
+    def __init__(self, vs):
+        self._vars = list(vs)
+
+    @staticmethod
+    def fromlist(vs):
+        return MVar(vs)
+
+    def tolist(self):
+        return list(self._vars)
+
+    def __len__(self):
+        return len(self._vars)
+
+    @property
+    def X(self):
+        import numpy as np
+        return np.array([v.x for v in self._vars], dtype=float)
+
+    def _set_start(self, values):
+        for v, val in zip(self._vars, values):
+            v.Start = float(val)
+
+    Start = property(lambda self: [v.Start for v in self._vars], _set_start)
+
+    def __rmatmul__(self, coeffs):          # ndarray @ MVar -> linear expression
+        e = LinExpr()
+        for c, v in zip(coeffs, self._vars):
+            e.terms[v.index] = e.terms.get(v.index, 0.0) + float(c)
+        return e
+
+    __array_ufunc__ = None                  # let `ndarray @ MVar` reach __rmatmul__
+
+
+class _Constr:
+    """Handle of one recorded constraint; setting ConstrName renames the record (gurobipy.Constr.ConstrName)."""
+
+    def __init__(self, model, pos):
+        self._model, self._pos = model, pos
+
+    def _get(self):
+        return self._model.constrs[self._pos][0]
+
+    def _set(self, name):
+        rec = self._model.constrs[self._pos]
+        self._model.constrs[self._pos] = (name,) + tuple(rec[1:])
+
+    ConstrName = property(_get, _set)
+
+
+class MConstr:
+    def __init__(self, cs):
+        self._cs = cs
+
+    def tolist(self):
+        return list(self._cs)
+
+
 class GRB:
+    LESS_EQUAL, EQUAL, GREATER_EQUAL = "<", "=", ">"
     BINARY, CONTINUOUS, INTEGER = "B", "C", "I"
     MINIMIZE, MAXIMIZE = 1, -1
     OPTIMAL, TIME_LIMIT, INFEASIBLE = 2, 9, 3
@@ -208,6 +269,24 @@ class Model:
     def addConstrs(self, gen, name=""):
         return [self.addConstr(tc, name) for tc in gen]
 
+    def addMVar(self, shape, lb=0.0, ub=GRB.INFINITY, obj=0.0, vtype=GRB.CONTINUOUS, name=""):
+        n = int(shape if not isinstance(shape, (tuple, list)) else shape[0])
+        return MVar([self.addVar(lb=lb, ub=ub, vtype=vtype, name=f"{name}[{k}]") for k in range(n)])
+
+    def addMConstr(self, A, x, sense, b, name=""):
+        """Rows of the sparse matrix A (scipy CSR) over the variables of `x` (None = all variables, in order)."""
+        vs = self.vars if x is None else x.tolist()
+        A = A.tocsr()
+        words = {"<": "<=", "=": "==", ">": ">="}
+        out = []
+        for r in range(A.shape[0]):
+            lo, hi = A.indptr[r], A.indptr[r + 1]
+            terms = {vs[int(c)].index: float(v) for c, v in zip(A.indices[lo:hi], A.data[lo:hi])}
+            sr = sense if isinstance(sense, str) else sense[r]
+            self.constrs.append((f"{name}[{r}]" if name else "", words[str(sr)], terms, float(b[r])))
+            out.append(_Constr(self, len(self.constrs) - 1))
+        return MConstr(out)
+
     def setObjective(self, expr, sense=GRB.MINIMIZE):
         self.objective = (LinExpr._lift(expr), sense)
 
@@ -258,7 +337,7 @@ def _any_callable(name):
 
 
 def install_stubs():
-    g = _stub("gurobipy", Model=Model, GRB=GRB, quicksum=quicksum, Env=Env, LinExpr=LinExpr, Var=Var)
+    g = _stub("gurobipy", Model=Model, GRB=GRB, quicksum=quicksum, Env=Env, LinExpr=LinExpr, Var=Var, MVar=MVar)
     g.tupledict = tupledict
     for name in ("scanpy", "alphashape"):
         if name not in sys.modules:

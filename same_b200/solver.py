@@ -204,10 +204,12 @@ def model_matrices(spec: ModelSpec):
 
 class GurobiMatrixBackend:
     """Same model, same variable / constraint / cut order and names as `GurobiBackend`, built through gurobipy's matrix API
-    (`addMVar` + one `addMConstr`) from `model_matrices` instead of one `quicksum` per row.  Selected with
-    `set_default_backend('gurobi_matrix')` or SAME_B200_SOLVER=gurobi_matrix.  Needs gurobipy >= 13 like the reference
-    (GRB.METHOD_PDHG, src/same.py:1169-1170); it cannot be exercised in a container without gurobipy — `model_matrices`
-    itself is pinned against the reference's recorded constraint list (tests/test_host_logic.py)."""
+    (`addMVar` + one `addMConstr`) from `model_matrices` instead of one `quicksum` per row.  The DEFAULT
+    back-end ('gurobi'); the per-row builder stays available as 'gurobi_rows' (SAME_B200_SOLVER / `set_default_backend`) and is
+    what this class falls back to when the installed gurobipy has no matrix API.  Needs gurobipy >= 13 like the reference
+    (GRB.METHOD_PDHG, src/same.py:1169-1170).  tests/test_gpu_api.py runs BOTH builders against the recording fake gurobipy
+    (oracle/ref_loader.py) and compares variables, objective, constraints (names, order, members, sense, rhs) and lazy cuts with the
+    reference's recorded models; with a real gurobipy installed, tests/test_gurobi_real.py solves the 144-cell fixtures."""
 
     name = "gurobi_matrix"
 
@@ -216,6 +218,10 @@ class GurobiMatrixBackend:
         from gurobipy import GRB
         from scipy.sparse import csr_matrix
 
+        if not (hasattr(gp.Model, "addMVar") and hasattr(gp.Model, "addMConstr") and hasattr(gp, "MVar") and hasattr(gp.MVar, "fromlist")):
+            import warnings
+            warnings.warn("this gurobipy has no matrix API (addMVar / addMConstr / MVar.fromlist): building the model row by row")
+            return GurobiBackend().solve(spec, separate, gurobi_params, outprefix=outprefix, env_options=env_options, start=start)
         log_dir = os.path.join(os.getcwd(), "gurobi_logs")
         os.makedirs(log_dir, exist_ok=True)
         options = {"OutputFlag": 1, "LogFile": os.path.join(log_dir, f"gurobi_{os.getpid()}.log")}
@@ -251,6 +257,7 @@ class GurobiMatrixBackend:
             if gurobi_params.get(key) is not None:
                 setattr(model.Params, attr, conv(gurobi_params[key]))
         xs, qs = x.tolist(), q.tolist()
+        model._x, model._q_tri, model._row_ptr = x, q, spec.row_ptr
         state = {"cuts": 0}
         lazy_max = gurobi_params.get("lazy_max_cuts")
 
@@ -352,12 +359,12 @@ class IncumbentBackend:
         return SolveResult("optimal", x, (~rows_matched).astype(np.float64), np.zeros(spec.n_ref), q, time.perf_counter() - t0, cuts)
 
 
-_BACKENDS = {"gurobi": GurobiBackend, "gurobi_matrix": GurobiMatrixBackend, "highs": HighsCutLoopBackend}
+_BACKENDS = {"gurobi": GurobiMatrixBackend, "gurobi_matrix": GurobiMatrixBackend, "gurobi_rows": GurobiBackend, "highs": HighsCutLoopBackend}
 _default_backend = None
 
 
 def set_default_backend(backend):
-    """`'gurobi'` (default), `'highs'`, or an object with a `.solve(spec, separate, gurobi_params, outprefix, env_options)` method."""
+    """`'gurobi'` (default: the matrix builder), `'gurobi_rows'` (one quicksum per row, as the reference writes it), `'highs'`, or an object with a `.solve(spec, separate, gurobi_params, outprefix, env_options)` method."""
     global _default_backend
     _default_backend = backend
 

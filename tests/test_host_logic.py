@@ -209,6 +209,51 @@ def test_model_matrices_equal_reference_model(case):
     assert np.array_equal(mm["obj"][P + nr + na:], g["w0_obj_q"])
 
 
+@pytest.mark.parametrize("case", ["fig2_direct", "simulated_st", "uniform_k8"])
+@pytest.mark.parametrize("backend", ["gurobi", "gurobi_rows"])
+def test_gurobi_builders_record_the_reference_model(case, backend, tmp_path, monkeypatch):
+    """Both Gurobi model builders — the default matrix builder (addMVar + addMConstr) and the row-by-row one — executed against the
+    recording fake gurobipy: variables, objective, every constraint (name, order, members, sense, right-hand side), the lazy cuts
+    of one callback and the MIP start land in the model exactly as the unmodified reference recorded them."""
+    import sys
+    from oracle import ref_loader
+    from same_b200.solver import get_backend
+    from tests.test_gpu_api import _record
+    saved = sys.modules.get("gurobipy")
+    ref_loader.install_stubs()
+    ref_loader.MODELS.clear()
+    monkeypatch.chdir(tmp_path)
+    try:
+        g, spec = _spec_from_oracle(case)
+        P = spec.n_pairs
+        ref_loader.INCUMBENT_FN = lambda model: (np.arange(P) % 3 == 0).astype(float)
+        cuts = np.array([[0, 1, 2, 0], [3, 4, 5, min(1, spec.n_tri - 1)]], dtype=np.int64)
+        seen = {}
+
+        def separate(x_vals, cuts_so_far):
+            seen["x"] = np.asarray(x_vals).copy()
+            return cuts
+        start = (np.r_[1.0, np.zeros(P - 1)], np.ones(spec.n_aligned))
+        res = get_backend(backend).solve(spec, separate, {"time_limit": 10, "mip_gap": 0.05}, start=start)
+        model = ref_loader.MODELS[-1]
+        rec = _record(model)
+        for k in ("cost", "obj_q", "obj_penalty", "obj_no_match", "con_name", "con_sense", "con_rhs", "con_ptr", "con_idx", "con_val"):
+            assert np.array_equal(rec[k], g[f"w0_{k}"]), (backend, k)
+        assert rec["n_vars"] == int(g["w0_n_vars"])
+        assert np.array_equal(rec["cuts"], cuts) and res.cuts_added == 2 and res.status == "optimal"
+        assert np.array_equal(seen["x"], (np.arange(P) % 3 == 0).astype(float)) and np.array_equal(res.x, seen["x"])
+        xs = [v for v in model.vars if v.VarName.startswith("x[")]
+        nm = [v for v in model.vars if v.VarName.startswith("no_match[")]
+        assert [v.Start for v in xs] == start[0].tolist() and [v.Start for v in nm] == start[1].tolist()
+        assert [v.VarName for v in model.vars[:2]] == ["x[0]", "x[1]"] and model.vars[-1].VarName == f"q_tri[{spec.n_tri - 1}]"
+    finally:
+        ref_loader.INCUMBENT_FN = None
+        if saved is not None:
+            sys.modules["gurobipy"] = saved
+        else:
+            sys.modules.pop("gurobipy", None)
+
+
 def test_highs_backend_solves_from_model_matrices():
     """The HiGHS stand-in consumes the same matrix; on the 144-cell known-answer fixture it returns a feasible one-to-one matching."""
     from same_b200.solver import HighsCutLoopBackend, model_matrices
