@@ -8,6 +8,7 @@ There is no CPU fallback: without the CUDA library / a CUDA device these functio
 from __future__ import annotations
 
 import os
+import time
 from typing import Any, Dict, List, Optional
 
 import numpy as np
@@ -97,17 +98,34 @@ class _Run:
     def __init__(self, aligned_df, ref_df, commonCT, optim, rects=None, aligned_delaunay=None, vertex_ids=None,
                  ignore_precomputed=False, section=None):
         self.aligned_df, self.ref_df, self.commonCT, self.optim = aligned_df, ref_df, list(commonCT), optim
+        o = optim
+        have_types = "cell_type" in aligned_df.columns and "cell_type" in ref_df.columns
+        if not have_types and (bool(o["ignore_same_type_triangles"]) or bool(o["ignore_knn_if_matched"])):
+            # the reference reads df['cell_type'] in both cases (src/helpers.py:329, src/knn_utils.py:37) and fails with KeyError;
+            # silently treating every cell as one type would drop every triangle / claim every nearest neighbour
+            raise KeyError("cell_type")
+        self.batch = None
+        self.window_errors = {}
         self.section = section if section is not None else build_section(aligned_df, ref_df, self.commonCT)
+        try:
+            self._build(aligned_df, ref_df, o, rects, aligned_delaunay, vertex_ids, ignore_precomputed, have_types)
+        except BaseException:
+            # nothing leaks when a stage fails (CUDA out of memory, no GPU, a bad triangle array ...)
+            if self.batch is not None:
+                self.batch.close()
+            self.section.close()
+            raise
+
+    def _build(self, aligned_df, ref_df, o, rects, aligned_delaunay, vertex_ids, ignore_precomputed, have_types):
         self.batch = self.section.batch(rects)
         self.W = self.batch.W
-        o = optim
         self.batch.candidates(o["radius"], o["knn"], bool(o["ignore_knn_if_matched"]), o["dist_ct_coeff"])
         p_off = self.batch.offsets(L.PAIRS)
         self.n_pairs = np.diff(p_off)
         self.using_precomputed = aligned_delaunay is not None and not ignore_precomputed
         self._a_xy = aligned_df[["X", "Y"]].to_numpy(dtype=np.float64)
         self._a_type = None
-        if "cell_type" in aligned_df.columns and "cell_type" in ref_df.columns:
+        if have_types:
             from .frames import joint_type_codes
             self._a_type, _ = joint_type_codes(aligned_df["cell_type"].to_numpy(), ref_df["cell_type"].to_numpy())
         if self.using_precomputed:
@@ -119,10 +137,12 @@ class _Run:
             tris, off = [], [0]
             for w in range(self.W):
                 rows = keepA[ka_off[w]:ka_off[w + 1]]
-                if self.n_pairs[w] == 0:
-                    t = np.zeros((0, 3), np.int32)
-                else:
-                    t = Delaunay(self._a_xy[rows]).simplices.astype(np.int32)         # same.py:1023 (Qhull stays on the host)
+                t = np.zeros((0, 3), np.int32)
+                if self.n_pairs[w] > 0:
+                    try:
+                        t = Delaunay(self._a_xy[rows]).simplices.astype(np.int32)     # same.py:1023 (Qhull stays on the host)
+                    except Exception as e:      # a degenerate window (QhullError): raised at that window's turn, like the reference's
+                        self.window_errors[w] = e          # per-window loop, so the windows before it still run and checkpoint
                 tris.append(t)
                 off.append(off[-1] + len(t))
             self.batch.triangles_set(np.concatenate(tris) if tris else np.zeros((0, 3), np.int32), off)
@@ -134,7 +154,8 @@ class _Run:
         self.batch.groups(o["max_matches"], o["ref_metacell_match_multiplier"])            # helpers.py:105-138
 
     def close(self):
-        self.batch.close()
+        if self.batch is not None:
+            self.batch.close()
         self.section.close()
 
 
@@ -142,7 +163,16 @@ def _solve_window(run: _Run, w: int, aligned_src: pd.DataFrame, ref_src: pd.Data
     """Model build + solve + post-analysis of window `w` (src/same.py:1112-1481).  `aligned_src` / `ref_src` are the
     frames whose `.iloc[section rows]` give the window's post-KNN frames."""
     b = run.batch
+    if w in run.window_errors:
+        raise run.window_errors[w]
+    t_stage = {"t0": time.perf_counter()}
+
+    def lap(name):
+        now = time.perf_counter()
+        t_stage[name] = now - t_stage.pop("t0")
+        t_stage["t0"] = now
     m = b.window_model(w)
+    lap("fetch_model_arrays_s")
     if len(m["pairs"]) == 0:
         raise ValueError("No valid_pairs after KNN filtering. Increase radius and/or knn.")       # same.py:1002-1003
     commonCT = run.commonCT
@@ -214,10 +244,12 @@ def _solve_window(run: _Run, w: int, aligned_src: pd.DataFrame, ref_src: pd.Data
             return np.zeros((0, 4), np.int32)
         return cuts[0, :min(viol, cap)].copy()
 
+    lap("prepare_model_s")
     if start is not None:
         res = backend.solve(spec, separate, gurobi, outprefix=outprefix, env_options=_env_options(), start=start)
     else:
         res = backend.solve(spec, separate, gurobi, outprefix=outprefix, env_options=_env_options())
+    lap("solve_s")
     time_limit_reached = res.status == "time_limit"
     if res.status not in ("optimal", "time_limit"):
         out_df, var_out = pd.DataFrame(), {}
@@ -280,11 +312,20 @@ def _solve_window(run: _Run, w: int, aligned_src: pd.DataFrame, ref_src: pd.Data
         "lazy_constraints": lazy, "lazy_cuts_added": res.cuts_added if lazy else 0,
         "exact_predicate_check": epc,      # (extra key: diagnostic only, see helpers.exact_predicate_check)
     }
+    lap("post_solve_analysis_s")
+    # machine-readable stage timers of this window (the reference only has prints and Gurobi's own Runtime)
+    timings = {k: float(v) for k, v in t_stage.items() if k != "t0"}
+    timings.update(solver_runtime_s=float(res.runtime), separation_calls=int(epc["separation_calls"]), lazy_cuts_added=int(res.cuts_added),
+                   n_pairs=int(P), n_triangles=int(T), n_aligned=int(n_aligned), n_ref=int(n_ref), solver=getattr(backend, "name", type(backend).__name__))
+    var_out["timings"] = timings
     if outprefix:                                                                                  # same.py:1455-1463
         os.makedirs(outprefix, exist_ok=True)
         np.save(os.path.join(outprefix, "var_out.npy"), var_out, allow_pickle=True)
         aligned_df.to_csv(os.path.join(outprefix, "aligned_df.csv"), index=False)
         ref_df.to_csv(os.path.join(outprefix, "ref_df.csv"), index=False)
+        import json
+        with open(os.path.join(outprefix, "timings.json"), "w") as f:
+            json.dump(timings, f, indent=1)
     flipped_nodes = set(int(v) for t in flipped for v in tri[t])                                   # same.py:1466-1472
     out_df["triangle_violation"] = out_df["aligned_idx"].isin(flipped_nodes)
     out_df["filtered_violation"] = out_df["aligned_idx"].isin(points_both)
@@ -448,7 +489,7 @@ def sliding_window_matching(ref, moving, commonCT=None, outprefix=None, moving_d
         section.close()
         return pd.concat(all_matches, ignore_index=True) if all_matches else pd.DataFrame()
 
-    vid = mov_p["__tri_vid"].to_numpy()
+    vid = mov_p["__tri_vid"].to_numpy()      # (_Run closes the section itself when one of its stages fails)
     run = _Run(mov_p, ref_p, commonCT, optim, rects=np.asarray([wd.rect for wd in runnable], dtype=np.float64),
                aligned_delaunay=moving_delaunay, vertex_ids=None if moving_delaunay is None else vid.astype(np.int64),
                ignore_precomputed=ignore_precomputed_triangulation, section=section)

@@ -488,3 +488,35 @@ def test_incidence_csr_equals_aligned_simplex_map():
                     assert (np.diff(got) > 0).all() and set(got.tolist()) == want[i]
                     total += len(got)
             assert total == 3 * to[-1] == ptr[-1]
+
+
+@pytest.mark.gpu
+def test_missing_cell_type_raises_like_the_reference_and_timings_are_recorded(tmp_path):
+    """Without a `cell_type` column the reference fails with KeyError whenever it has to read it (src/helpers.py:329,
+    src/knn_utils.py:37); nothing is silently treated as "one type".  A successful run leaves machine-readable stage timers
+    (var_out['timings'], window_<id>/timings.json)."""
+    import json
+    import same_b200
+    from same_b200 import datagen
+    from same_b200.solver import IncumbentBackend
+    ref, qry, ct = datagen.make_section_pair(n_tiles=1, n_types=3, seed=2)
+    optim = dict(radius=1.0, knn=6, max_matches=1, min_angle_deg=10, cell_id_col="Cell_Num_Old")
+
+    def inc(spec):
+        rp = np.asarray(spec.row_ptr, dtype=np.int64)
+        rows = np.repeat(np.arange(len(rp) - 1), np.diff(rp))
+        return incumbent_rule(np.column_stack([rows, rows]), 1)
+    no_type = qry.drop(columns=["cell_type"])
+    with pytest.raises(KeyError):
+        same_b200.run_same(ref, no_type, list(ct), optim_params=dict(optim, ignore_same_type_triangles=True), solver=IncumbentBackend(inc))
+    with pytest.raises(KeyError):
+        same_b200.run_same(ref, no_type, list(ct), optim_params=dict(optim, ignore_same_type_triangles=False, ignore_knn_if_matched=True),
+                           solver=IncumbentBackend(inc))
+    out, var_out = same_b200.run_same(ref, no_type, list(ct), outprefix=str(tmp_path / "w"),
+                                      optim_params=dict(optim, ignore_same_type_triangles=False), solver=IncumbentBackend(inc))
+    assert len(out) > 0
+    t = var_out["timings"]
+    assert {"fetch_model_arrays_s", "prepare_model_s", "solve_s", "post_solve_analysis_s", "n_pairs", "n_triangles", "separation_calls"} <= set(t)
+    assert json.load(open(tmp_path / "w" / "timings.json")) == t
+    epc = var_out["exact_predicate_check"]
+    assert epc["separation_calls"] == 1 and epc["source_signs"]["naive_differs_from_exact"] == 0

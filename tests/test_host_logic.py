@@ -112,6 +112,31 @@ def test_shard_windows_partitions():
             assert max(sizes) - min(sizes) <= 1
 
 
+def test_merge_window_matches_equals_reference_under_fixed_hash_seed():
+    """merge_window_matches_unique_ref (src/helpers.py:692-815) row for row against the unmodified reference.  The reference's own
+    result depends on PYTHONHASHSEED (networkx walks a set of string labels), so both the record
+    (tests/golden/next/gen_golden_merge.py) and this comparison run in a process with PYTHONHASHSEED=0."""
+    import subprocess
+    code = (
+        "import sys, numpy as np, importlib.util\n"
+        f"sys.path.insert(0, {ROOT!r})\n"
+        f"spec = importlib.util.spec_from_file_location('gm', {os.path.join(ROOT, 'tests', 'golden', 'next', 'gen_golden_merge.py')!r})\n"
+        "gm = importlib.util.module_from_spec(spec); spec.loader.exec_module(gm)\n"
+        "from same_b200.merge import merge_window_matches_unique_ref\n"
+        "out = merge_window_matches_unique_ref([f.copy() for f in gm.make_input()])\n"
+        f"g = np.load({os.path.join(ROOT, 'tests', 'golden', 'next', 'merge.npz')!r})\n"
+        "assert len(out) == len(g['out_aligned'])\n"
+        "assert np.array_equal(out['window_id'].to_numpy(), g['out_window'])\n"
+        "assert np.array_equal(out['Aligned_Cell_Num_Old'].to_numpy(), g['out_aligned'])\n"
+        "assert np.array_equal(out['Ref_Cell_Num_Old'].to_numpy(), g['out_ref'])\n"
+        "assert np.array_equal(out['X'].to_numpy(), g['out_x']) and np.array_equal(out['filtered_violation'].to_numpy(bool), g['out_fv'])\n"
+        "assert out['Aligned_Cell_Num_Old'].is_unique and out['Ref_Cell_Num_Old'].is_unique\n"
+        "print('merge parity ok', len(out))\n")
+    env = dict(os.environ, PYTHONHASHSEED="0")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "merge parity ok" in r.stdout, r.stdout + r.stderr
+
+
 # ---- gloo, world_size 2 ---------------------------------------------------------------------------------
 def _free_port():
     s = socket.socket()
