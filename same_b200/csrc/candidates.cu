@@ -462,13 +462,14 @@ __global__ void k_window_offsets(const i32 *__restrict__ newA, const i32 *__rest
 // Frame compaction in one launch (src/utils.py:734-741): blocks [0, tilesA) scan the aligned instances — kept flag
 // (cnt > 0) and emitted pairs (eff) together — and write the kept aligned rows; blocks [tilesA, ..) scan the used flag of
 // the reference instances and write the kept reference rows.  Item nAi / nRi is a sentinel that receives the totals.
+// Only the row lists are written here: the coordinate / type / size columns of the kept rows, which the triangle, grouping and
+// separation stages gather through, are materialised when the first of those stages runs (batch_kept_columns) — a caller
+// that only wants candidates and costs does not pay for them.
 constexpr int COMPACT_THREADS = 1024, COMPACT_ITEMS = 4;   // big tiles: one L2 round trip of look-back per 32 tiles
 __global__ void __launch_bounds__(COMPACT_THREADS, 2) k_compact_frames(
     const i32 *__restrict__ cnt, const i32 *__restrict__ eff, const i32 *__restrict__ r_used, i64 nAi, i64 nRi, unsigned tilesA, ScanCtx scA, ScanCtx scR,
-    const i32 *__restrict__ a_src, const i32 *__restrict__ r_src, const double2 *__restrict__ a_xy, const double2 *__restrict__ r_xy,
-    const i32 *__restrict__ a_type, const double *__restrict__ a_size, const double *__restrict__ r_size, i32 *__restrict__ newA,
-    i32 *__restrict__ newR, i32 *__restrict__ poff, i32 *__restrict__ keepA, double2 *__restrict__ ka_xy, i32 *__restrict__ ka_type,
-    double *__restrict__ ka_size, i32 *__restrict__ row_ptr, i32 *__restrict__ keepR, double2 *__restrict__ kr_xy, double *__restrict__ kr_size) {
+    const i32 *__restrict__ a_src, const i32 *__restrict__ r_src, i32 *__restrict__ newA, i32 *__restrict__ newR, i32 *__restrict__ poff,
+    i32 *__restrict__ keepA, i32 *__restrict__ row_ptr, i32 *__restrict__ keepR) {
     __shared__ int smem[2 * (COMPACT_THREADS / 32) + 2];
     int f[COMPACT_ITEMS], e[COMPACT_ITEMS], sum[2] = {0, 0}, excl[2], tot[2], pre[2];
     if (blockIdx.x < tilesA) {
@@ -491,11 +492,7 @@ __global__ void __launch_bounds__(COMPACT_THREADS, 2) k_compact_frames(
                 poff[i] = ppos;
                 if (i == nAi) row_ptr[kpos] = ppos;   // row_ptr[nKA] = P
                 if (f[k]) {
-                    const i32 row = a_src[i];
-                    keepA[kpos] = row;
-                    ka_xy[kpos] = a_xy[row];
-                    ka_type[kpos] = a_type[row];
-                    ka_size[kpos] = a_size[row];
+                    keepA[kpos] = a_src[i];
                     row_ptr[kpos] = ppos;
                 }
             }
@@ -517,12 +514,7 @@ __global__ void __launch_bounds__(COMPACT_THREADS, 2) k_compact_frames(
             const i64 i = base + k;
             if (i <= nRi) {
                 newR[i] = kpos;
-                if (f[k]) {
-                    const i32 row = r_src[i];
-                    keepR[kpos] = row;
-                    kr_xy[kpos] = r_xy[row];
-                    kr_size[kpos] = r_size[row];
-                }
+                if (f[k]) keepR[kpos] = r_src[i];
             }
             kpos += f[k];
         }
@@ -558,6 +550,37 @@ __global__ void k_pair_j(const int2 *__restrict__ pairs, i64 P, i32 *__restrict_
     const i64 p = (i64)blockIdx.x * blockDim.x + threadIdx.x;
     if (p < P) pj[p] = pairs[p].y;
 }
+// coordinate / type / size columns of the kept rows of both frames (gathered once, on first use by a later stage).  The kept
+// counts are read from device memory (last entry of the kept offsets), so the launch needs no host round trip.
+__global__ void k_kept_columns(const i32 *__restrict__ keepA, const i32 *__restrict__ keepR, const i32 *__restrict__ ka_off,
+                               const i32 *__restrict__ kr_off, int W, i64 nAi, const double2 *__restrict__ a_xy, const double2 *__restrict__ r_xy,
+                               const i32 *__restrict__ a_type, const double *__restrict__ a_size, const double *__restrict__ r_size,
+                               double2 *__restrict__ ka_xy, i32 *__restrict__ ka_type, double *__restrict__ ka_size, double2 *__restrict__ kr_xy,
+                               double *__restrict__ kr_size) {
+    const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nAi) {
+        if (i >= ka_off[W]) return;
+        const i32 row = keepA[i];
+        ka_xy[i] = a_xy[row]; ka_type[i] = a_type[row]; ka_size[i] = a_size[row];
+    } else {
+        const i64 k = i - nAi;
+        if (k >= kr_off[W]) return;
+        const i32 row = keepR[k];
+        kr_xy[k] = r_xy[row]; kr_size[k] = r_size[row];
+    }
+}
+void batch_kept_columns(Batch *b) {
+    if (b->have_kept_cols) return;
+    cudaStream_t s = b->stream;
+    Section *sec = b->sec;
+    const i64 nAi = b->nAi, nRi = b->nRi;   // upper bounds of the kept counts
+    b->ka_xy.alloc(nAi, s); b->ka_type.alloc(nAi, s); b->ka_size.alloc(nAi, s); b->kr_xy.alloc(nRi, s); b->kr_size.alloc(nRi, s);
+    if (nAi + nRi > 0)
+        LAUNCH(k_kept_columns, blocks_for(nAi + nRi, 256), 256, 0, s, b->keepA.p, b->keepR.p, b->d_ka_off.p, b->d_kr_off.p, (int)b->W, nAi, sec->a_xy.p,
+               sec->r_xy.p, sec->a_type.p, sec->a_size.p, sec->r_size.p, b->ka_xy.p, b->ka_type.p, b->ka_size.p, b->kr_xy.p, b->kr_size.p);
+    b->have_kept_cols = true;
+}
+
 void batch_pair_j(Batch *b) {
     if (b->have_pair_j) return;
     b->pair_j.alloc(b->P, b->stream);
@@ -674,17 +697,17 @@ void batch_candidates(Batch *b, double radius, int knn, int priority, double dis
     // pairs <= knn per aligned instance); the per-window offsets come back once, at the end
     DevBuf<i32> newR, poff, off3;
     b->newA.alloc(nAi + 1, s); newR.alloc(nRi + 1, s); poff.alloc(nAi + 1, s); off3.alloc(3 * (W + 1), s);
-    b->keepA.alloc(nAi, s); b->ka_xy.alloc(nAi, s); b->ka_type.alloc(nAi, s); b->ka_size.alloc(nAi, s);
+    b->keepA.alloc(nAi, s);
     b->row_ptr.alloc(nAi + 1, s);
-    b->keepR.alloc(nRi, s); b->kr_xy.alloc(nRi, s); b->kr_size.alloc(nRi, s);
+    b->keepR.alloc(nRi, s);
+    b->have_kept_cols = false;
     b->pairs.alloc(nAi * knn, s); b->cost.alloc(nAi * knn, s);
     const unsigned tilesA = blocks_for(nAi + 1, COMPACT_THREADS * COMPACT_ITEMS), tilesR = blocks_for(nRi + 1, COMPACT_THREADS * COMPACT_ITEMS);
     {
         scan_reserve(sec, 2 * ((i64)tilesA + tilesR), s);   // two independent scans in one launch: disjoint tile-state words
         const ScanCtx scA = scan_ctx_at(sec, 0, tilesA), scR = scan_ctx_at(sec, 2 * (i64)tilesA, tilesR);
         LAUNCH(k_compact_frames, tilesA + tilesR, COMPACT_THREADS, 0, s, b->cnt.p, eff, b->r_used.p, nAi, nRi, tilesA, scA, scR, b->a_src.p, b->r_src.p,
-               sec->a_xy.p, sec->r_xy.p, sec->a_type.p, sec->a_size.p, sec->r_size.p, b->newA.p, newR.p, poff.p, b->keepA.p, b->ka_xy.p, b->ka_type.p,
-               b->ka_size.p, b->row_ptr.p, b->keepR.p, b->kr_xy.p, b->kr_size.p);
+               b->newA.p, newR.p, poff.p, b->keepA.p, b->row_ptr.p, b->keepR.p);
     }
     b->d_ka_off.alloc(W + 1, s); b->d_kr_off.alloc(W + 1, s); b->d_p_off.alloc(W + 1, s);
     LAUNCH(k_window_offsets, blocks_for(W + 1, 128), 128, 0, s, b->newA.p, newR.p, poff.p, b->d_a_off.p, b->d_r_off.p, (int)W, off3.p, b->d_ka_off.p,
@@ -819,6 +842,7 @@ void batch_groups(Batch *b, int max_matches, int multiplier) {
     cudaStream_t s = b->stream;
     REQUIRE(b->stage >= 1, SAME_E_STATE, "same_batch_groups before same_batch_candidates");
     batch_settle(b);
+    batch_kept_columns(b);
     const i64 W = b->W, P = b->P, nKR = b->nKR;
     b->g_off.assign(W + 1, 0);
     b->G = 0;

@@ -238,6 +238,7 @@ struct Batch {
     DevBuf<double2> ka_xy, kr_xy;
     DevBuf<i32> ka_type;
     DevBuf<double> ka_size, kr_size;
+    bool have_kept_cols = false;        // the five columns above are gathered on first use (batch_kept_columns)
     DevBuf<int2> pairs;                 // window-local (i, j)
     DevBuf<i32> pair_j;                 // pairs[].y on its own, built on first request (SAME_ARR_PAIR_J)
     bool have_pair_j = false;
@@ -312,6 +313,7 @@ void batch_subset(Batch *b);
 void batch_candidates(Batch *b, double radius, int knn, int priority, double dist_ct_coeff);
 void batch_groups(Batch *b, int max_matches, int multiplier);
 void batch_pair_j(Batch *b);
+void batch_kept_columns(Batch *b);   // ka_xy / ka_type / ka_size / kr_xy / kr_size, gathered on first use
 void batch_incidence(Batch *b);
 void batch_triangles_remap(Batch *b);
 void batch_triangles_set(Batch *b, const i32 *tri, const i64 *tri_off);

@@ -333,6 +333,7 @@ void batch_mip_start(Batch *b, double no_match_penalty, i32 *rounds_out) {
     cudaStream_t s = b->stream;
     REQUIRE(b->stage >= 1, SAME_E_STATE, "same_batch_mip_start before same_batch_candidates");
     batch_settle(b);
+    batch_kept_columns(b);
     const i64 P = b->P, nKA = b->nKA, nKR = b->nKR;
     b->start_x.alloc(P, s);
     b->start_unmatched.alloc(nKA, s);

@@ -159,6 +159,7 @@ void batch_separation(Batch *b, i64 w_lo, i64 w_hi, const double *x, i64 cap, i6
     REQUIRE(w_lo >= 0 && w_hi <= b->W && w_lo < w_hi, SAME_E_ARG, "bad window range");
     REQUIRE(cap >= 0, SAME_E_ARG, "cap must be >= 0");
     batch_settle(b);
+    batch_kept_columns(b);
     const i64 nw = w_hi - w_lo;
     run_matching(b, w_lo, w_hi, resolve_x(b, w_lo, w_hi, x));
     const i32 t_lo = (i32)b->t_off[w_lo], t_hi = (i32)b->t_off[w_hi];
@@ -262,6 +263,7 @@ void batch_postsolve(Batch *b, i64 w_lo, i64 w_hi, const double *x) {
     REQUIRE(b->stage >= 4, SAME_E_STATE, "same_batch_postsolve before same_batch_tri_finalize");
     REQUIRE(w_lo >= 0 && w_hi <= b->W && w_lo < w_hi, SAME_E_ARG, "bad window range");
     batch_settle(b);
+    batch_kept_columns(b);
     const double *xd = resolve_x(b, w_lo, w_hi, x);
     run_matching(b, w_lo, w_hi, xd);
     if (!b->have_post) {

@@ -258,6 +258,7 @@ void batch_tri_classify(Batch *b, double radius, int use_angle, double min_angle
     cudaStream_t s = b->stream;
     REQUIRE(b->stage >= 2, SAME_E_STATE, "same_batch_tri_classify before triangles were provided");
     const i64 Tin = b->Tin;
+    batch_kept_columns(b);   // (no synchronisation: the kernel takes the kept counts from device memory)
     b->cls.alloc(Tin, s); b->score.alloc(Tin, s); b->band_idx.alloc(Tin + 1, s);
     DevBuf<i32> bc;
     bc.alloc(1, s);
@@ -576,6 +577,7 @@ void batch_tri_finalize(Batch *b, int ignore_same_type, int ensure_min, int remo
     cudaStream_t s = b->stream;
     REQUIRE(b->stage >= 3, SAME_E_STATE, "same_batch_tri_finalize before same_batch_tri_classify");
     batch_settle(b);
+    batch_kept_columns(b);
     const i64 W = b->W, Tin = b->Tin, nKA = b->nKA, P = b->P;
     const int addback = ignore_same_type && ensure_min;
     DevBuf<i32> node_valid, has_tri, best_tri, kept_flag, kpos, ab_flag, abpos, unc_flag, uncpos, validpos, woff;
