@@ -48,6 +48,7 @@ struct ProfRec { const char *name; cudaEvent_t a, b; };
 extern bool g_prof;
 extern bool g_debug;  // SAME_B200_DEBUG=1: synchronise + check after every launch
 extern std::vector<ProfRec> g_prof_recs;
+extern std::mutex g_prof_mu;   // sections may be driven from several host threads (CandidateStream)
 struct ProfScope {
     ProfRec r{nullptr, nullptr, nullptr};
     cudaStream_t s;
@@ -60,6 +61,7 @@ struct ProfScope {
     ~ProfScope() {
         if (!r.name) return;
         cudaEventRecord(r.b, s);
+        std::lock_guard<std::mutex> lk(g_prof_mu);
         g_prof_recs.push_back(r);
     }
 };

@@ -4,7 +4,9 @@
 // blocks by looking back at their published aggregates, and writes its output in place.
 //
 // Tile = one thread block (blockIdx.x order; blocks of a 1-D grid are dispatched in index order, so a block only ever
-// waits for blocks that are already resident or finished).  Per tile and per stream one 64-bit word
+// waits for blocks that are already resident or finished — the same assumption cub::DeviceScan's decoupled look-back makes).
+// One scan state per Section: calls on one section must come from one host thread at a time (include/same_b200.h); different
+// sections — one per worker thread and stream in CandidateStream — share nothing.  Per tile and per stream one 64-bit word
 //     [ epoch : 30 | status : 2 | value : 32 ]
 // written and read as ONE word, so no fence is needed between a value and its status.  status 1 = "aggregate of this
 // tile", 2 = "inclusive prefix up to this tile".  The epoch makes a word of an earlier launch look empty, so the state

@@ -9,6 +9,7 @@ std::atomic<long long> g_launches{0};
 bool g_prof = false;
 bool g_debug = getenv("SAME_B200_DEBUG") != nullptr && getenv("SAME_B200_DEBUG")[0] == '1';
 std::vector<ProfRec> g_prof_recs;
+std::mutex g_prof_mu;
 
 void exclusive_scan_i32(const i32 *in, i32 *out, i64 n, Scratch &sc, cudaStream_t s) {
     size_t bytes = 0;
