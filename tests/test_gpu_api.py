@@ -520,3 +520,30 @@ def test_missing_cell_type_raises_like_the_reference_and_timings_are_recorded(tm
     assert json.load(open(tmp_path / "w" / "timings.json")) == t
     epc = var_out["exact_predicate_check"]
     assert epc["separation_calls"] == 1 and epc["source_signs"]["naive_differs_from_exact"] == 0
+
+
+@pytest.mark.gpu
+def test_candidate_stream_errors_and_pool_accounting():
+    """A section that cannot be built surfaces its error in result() and frees its slot; the memory-pool calls behave."""
+    from same_b200 import _lib as L
+    from same_b200 import datagen
+    from same_b200.device import CandidateStream
+    ref, qry, ct = datagen.make_section_pair(n_tiles=1, n_types=3, seed=3)
+    lut = {c: i for i, c in enumerate(ct)}
+    good = (qry[["X", "Y"]].to_numpy(), ref[["X", "Y"]].to_numpy(), qry[ct].to_numpy(), ref[ct].to_numpy(),
+            qry["cell_type"].map(lut).to_numpy(np.int32), ref["cell_type"].map(lut).to_numpy(np.int32))
+    bad = (good[0], good[1], good[2], good[3][:, :2], good[4], good[5])          # probability blocks of different widths
+    with CandidateStream(1.0, 8, depth=2) as cs:
+        h_bad, h_good = cs.submit(bad), cs.submit(good)
+        with pytest.raises(ValueError):
+            h_bad.result()
+        out = h_good.result()
+        assert len(out[L.PAIR_J]) == len(out[L.COST]) > 0
+        h2 = cs.submit(good)                                                     # both slots are free again
+        assert np.array_equal(h2.result()[L.PAIR_J], out[L.PAIR_J])
+        r0, u0 = L.mempool_stats(0)
+        cs.reserve(8 << 20)
+        r1, u1 = L.mempool_stats(0)
+        assert r1 >= r0 and r1 >= 8 << 20 and u1 <= r1
+    with pytest.raises(L.SameError):
+        L.mempool_reserve(0, -1)
