@@ -385,7 +385,7 @@ int same_batch_get_many_async(same_batch_t *h, int64_t n, const int32_t *what, c
 int same_pinned_alloc(int64_t bytes, void **out) {
     return guarded([&] {
         REQUIRE(out && bytes >= 0, SAME_E_ARG, "bad argument");
-        CK(cudaHostAlloc(out, (size_t)std::max<int64_t>(bytes, 1), cudaHostAllocDefault));
+        CK(cudaHostAlloc(out, (size_t)std::max<int64_t>(bytes, 1), cudaHostAllocPortable | cudaHostAllocMapped));   // device-addressable: kernels may write results in place
     });
 }
 int same_pinned_free(void *p) {

@@ -165,19 +165,34 @@ void batch_separation(Batch *b, i64 w_lo, i64 w_hi, const double *x, i64 cap, i6
     const i32 t_lo = (i32)b->t_off[w_lo], t_hi = (i32)b->t_off[w_hi];
     const i64 nt = t_hi - t_lo;
     b->sep_counts.alloc(2 * nw + 1, s);   // + the count of orientations the filter could not certify (diagnostic)
-    b->cuts.alloc(std::max<i64>(1, nw * cap * 4), s);
     CK(cudaMemsetAsync(b->sep_counts.p, 0, sizeof(i32) * (2 * nw + 1), s));
+    // Where the cuts go: straight into the caller's block when the GPU can address it — page-locked host memory (the kernel's
+    // stores cross PCIe as posted writes, no copy-engine launch behind the kernel) or device memory — else into a device buffer
+    // that is copied afterwards.
+    i32 *cut_dst = nullptr;
+    bool direct = false;
+    if (cuts && cap > 0 && nt > 0) {
+        cudaPointerAttributes attr;   // asked on every call (about a microsecond): a recycled address may have changed its kind
+        if (cudaPointerGetAttributes(&attr, cuts) == cudaSuccess &&
+            ((attr.type == cudaMemoryTypeHost && attr.devicePointer) || (attr.type == cudaMemoryTypeDevice && attr.device == b->sec->device)))
+            cut_dst = (i32 *)attr.devicePointer;
+        cudaGetLastError();
+        direct = cut_dst != nullptr;
+    }
+    if (!direct) {
+        b->cuts.alloc(std::max<i64>(1, nw * cap * 4), s);
+        cut_dst = b->cuts.p;
+    }
     if (nt > 0) {
         const unsigned tiles = blocks_for(nt, SEP_TILE);
         LAUNCH(k_separation, tiles, SEP_THREADS, 0, s, b->tri.p, b->t_sign.p, t_lo, t_hi, b->d_t_off.p, b->d_ka_off.p, b->d_kr_off.p, (int)b->W, (int)w_lo,
-               b->match_j.p, b->match_p.p, b->kr_xy.p, cap, scan_ctx(b->sec, tiles, 1, s), b->sep_counts.p, b->cuts.p, b->unc_list[1].p,
+               b->match_j.p, b->match_p.p, b->kr_xy.p, cap, scan_ctx(b->sec, tiles, 1, s), b->sep_counts.p, cut_dst, b->unc_list[1].p,
                b->sep_counts.p + 2 * nw);
     }
-    // counts and cuts come back behind ONE synchronisation: the cut block is small (cap rows per window), so it is copied
-    // whole instead of waiting for the counts to know how much of it was filled
-    i32 *h_sep = b->pin_misc();   // page-locked (2 nw <= 4(W+1) + 8 ints): a pageable destination would stage and block
+    // counts (and the cut block, unless the kernel wrote it in place) come back behind ONE synchronisation
+    i32 *h_sep = b->pin_misc();   // page-locked (2 nw + 1 <= 4(W+1) + 8 ints)
     small_d2h(h_sep, b->sep_counts.p, sizeof(i32) * (2 * nw + 1), s);   // (the diagnostic count rides along: no extra round trip)
-    if (cuts && cap > 0 && nt > 0) CK(cudaMemcpyAsync(cuts, b->cuts.p, sizeof(i32) * 4 * (size_t)(nw * cap), cudaMemcpyDefault, s));
+    if (!direct && cuts && cap > 0 && nt > 0) CK(cudaMemcpyAsync(cuts, b->cuts.p, sizeof(i32) * 4 * (size_t)(nw * cap), cudaMemcpyDefault, s));
     batch_sync(b);
     for (i64 w = 0; w < nw; ++w) {
         n_viol[w] = h_sep[2 * w];
