@@ -330,6 +330,7 @@ def strong_scaling_arm(args, rank, world, local_rank, stream):
     sec.close()
     # end to end: the whole section goes up on every rank, the block's results come back
     n_e2e = max(2, min(args.steps, 10))
+    L.set_host_wait(world * 3 > len(os.sched_getaffinity(0)) // 2)
     with CandidateStream(RADIUS, KNN, False, 1.0, device=local_rank) as cs:
         def stream_n(n):
             prev = None
@@ -373,6 +374,7 @@ def strong_scaling_arm(args, rank, world, local_rank, stream):
     torch.cuda.synchronize(); dist.barrier()
     g_ms = (time.perf_counter() - t0) * 1e3 / n_e2e
     gc.enable()
+    L.set_host_wait(False)
     t = torch.tensor([ms, e_ms, float(pairs), g_ms], dtype=torch.float64, device=device)
     allr = [torch.zeros_like(t) for _ in range(world)]
     dist.all_gather(allr, t)
@@ -678,6 +680,9 @@ def main():
             return npairs, nbytes
 
         from same_b200.device import CandidateStream
+        # several ranks x (main thread + two section threads) on a host with few cores: waiting threads sleep instead of spinning
+        yield_wait = world * 3 > len(all_cpus) // 2
+        L.set_host_wait(yield_wait)
         cstream = CandidateStream(RADIUS, KNN, False, 1.0, device=local_rank)
 
         def cand_stream(n):
@@ -737,6 +742,7 @@ def main():
         gc.enable()
         sys.stderr.write(f"[bench] e2e cand_stream: {s_ms:.2f} ms per section over {n_e2e} sections\n")
         assert s_P == c_P
+        L.set_host_wait(False)
         f_ms, f_P, f_d2h = timed(full_once)
         x_dev["t"] = saved
         frames = sum(p[1].nbytes for p in pins.values())
@@ -897,6 +903,7 @@ def main():
                            "d2h_bytes_per_step": int(e2e["d2h"]), "ms_per_step": e2e_max,
                            "per_rank_gb_per_s": (e2e["h2d"] + e2e["d2h"]) / (e2e_max * 1e-3) / 1e9,
                            "single_section_latency_ms": e2e_lat_max,
+                           "host_wait": "yield (blocking-sync events)" if world * 3 > len(all_cpus) // 2 else "spin",
                            "note": "candidate stage (the scope of `value` and of --impl reference: subset + KNN + cost) through the public API "
                                    "(same_b200.device.CandidateStream over the C-ABI) on a stream of sections: every section's frames go up from "
                                    "page-locked host memory and its kept rows, row pointers, pair reference indices and costs come back, all inside "

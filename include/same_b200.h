@@ -244,6 +244,9 @@ SAME_API int same_batch_sync(same_batch_t *b);
  * was freed on other streams). */
 SAME_API int same_stream_create(int device, void **stream);
 SAME_API int same_stream_destroy(int device, void *stream);
+/* How host threads wait for the device: 0 (default) = spin (cudaStreamSynchronize: lowest latency), 1 = sleep on a blocking-sync
+ * event (yields the core: for hosts where many ranks / section threads share few cores).  Also SAME_B200_HOST_WAIT=yield. */
+SAME_API int same_set_host_wait(int yield);
 /* Counters of a batch: SAME_STAT_KNN_EVALUATIONS = distance evaluations of the last same_batch_candidates (counted only while
  * same_profile_enable(1) is in effect, -1 otherwise): bench.py's compute-side roofline = evaluations x 5 flops / kernel time. */
 enum { SAME_STAT_KNN_EVALUATIONS = 1 };

@@ -53,7 +53,7 @@ SYMBOLS = [
     "same_batch_get", "same_elem_size", "same_batch_sync", "same_batch_stream", "same_launch_count",
     "same_profile_enable", "same_profile_report", "same_batch_get_many", "same_batch_get_many_async", "same_pinned_alloc", "same_pinned_free",
     "same_postsolve_arrays", "same_batch_mip_start", "same_greedy_select", "same_collapse_select", "same_segment_mean", "same_measure_fp64_peak", "same_section_wait_uploads",
-    "same_stream_create", "same_stream_destroy", "same_mempool_stats", "same_mempool_reserve", "same_batch_uncertain", "same_batch_stat",
+    "same_stream_create", "same_stream_destroy", "same_mempool_stats", "same_mempool_reserve", "same_set_host_wait", "same_batch_uncertain", "same_batch_stat",
 ]
 
 
@@ -124,6 +124,7 @@ def load():
     lib.same_stream_create.argtypes = [i32, C.POINTER(vp)]
     lib.same_stream_destroy.argtypes = [i32, vp]
     lib.same_mempool_reserve.argtypes = [i32, i64]
+    lib.same_set_host_wait.argtypes = [i32]
     lib.same_mempool_stats.argtypes = [i32, C.POINTER(i64), C.POINTER(i64)]
     lib.same_profile_report.argtypes = [C.c_char_p, i64]
     lib.same_profile_report.restype = i64
@@ -161,6 +162,11 @@ def mempool_stats(device=0):
     r, u = C.c_int64(0), C.c_int64(0)
     check(load().same_mempool_stats(int(device), C.byref(r), C.byref(u)))
     return r.value, u.value
+
+
+def set_host_wait(yield_core: bool):
+    """How host threads wait for the GPU: spin (False, default, lowest latency) or sleep on a blocking event (True)."""
+    check(load().same_set_host_wait(int(bool(yield_core))))
 
 
 def mempool_reserve(device, nbytes):

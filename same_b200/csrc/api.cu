@@ -394,6 +394,10 @@ int same_pinned_free(void *p) {
 
 int same_batch_sync(same_batch_t *h) { BATCH_CALL(h, batch_sync(b)); }
 
+int same_set_host_wait(int yield) {
+    same::g_host_wait_yield.store(yield ? 1 : 0);
+    return SAME_OK;
+}
 int same_batch_stat(same_batch_t *h, int what, int64_t *value) {
     BATCH_CALL(h, {
         REQUIRE(value, SAME_E_ARG, "value is NULL");

@@ -82,6 +82,14 @@ struct ProfScope {
         if (same::g_debug) CK(cudaStreamSynchronize(stream));                                               \
     } while (0)
 
+// Host waits for a stream.  Default: cudaStreamSynchronize (the calling thread spins: lowest latency, what a solver callback
+// wants).  Yielding mode (same_set_host_wait(1) / SAME_B200_HOST_WAIT=yield): the thread sleeps on a blocking-sync event
+// instead — for hosts where several ranks with several section threads each share few cores and spinning waiters steal the
+// cores that the other ranks' launches need.
+extern std::atomic<int> g_host_wait_yield;
+cudaError_t stream_wait(cudaStream_t s);
+#define cudaStreamSynchronize(s) same::stream_wait(s)
+
 inline unsigned blocks_for(i64 n, int per_block) { return (unsigned)std::max<i64>(1, (n + per_block - 1) / per_block); }
 
 // stream-ordered device buffer

@@ -4,6 +4,26 @@
 
 namespace same {
 
+#undef cudaStreamSynchronize
+std::atomic<int> g_host_wait_yield{getenv("SAME_B200_HOST_WAIT") != nullptr && std::string(getenv("SAME_B200_HOST_WAIT")) == "yield" ? 1 : 0};
+cudaError_t stream_wait(cudaStream_t s) {
+    if (!g_host_wait_yield.load(std::memory_order_relaxed)) return cudaStreamSynchronize(s);
+    thread_local cudaEvent_t ev = nullptr;       // one blocking-sync event per host thread (per device: threads here stay on one device)
+    thread_local int ev_dev = -1;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (!ev || ev_dev != dev) {
+        if (ev) cudaEventDestroy(ev);
+        e = cudaEventCreateWithFlags(&ev, cudaEventBlockingSync | cudaEventDisableTiming);
+        if (e != cudaSuccess) { ev = nullptr; return e; }
+        ev_dev = dev;
+    }
+    e = cudaEventRecord(ev, s);
+    if (e != cudaSuccess) return e;
+    return cudaEventSynchronize(ev);
+}
+#define cudaStreamSynchronize(s) same::stream_wait(s)
 thread_local std::string g_err;
 std::atomic<long long> g_launches{0};
 bool g_prof = false;
