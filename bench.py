@@ -681,7 +681,7 @@ def main():
 
         from same_b200.device import CandidateStream
         # several ranks x (main thread + two section threads) on a host with few cores: waiting threads sleep instead of spinning
-        yield_wait = world * 3 > len(all_cpus) // 2
+        yield_wait = (os.environ.get("SAME_B200_HOST_WAIT") == "yield") if "SAME_B200_HOST_WAIT" in os.environ else world * 3 > len(all_cpus) // 2
         L.set_host_wait(yield_wait)
         cstream = CandidateStream(RADIUS, KNN, False, 1.0, device=local_rank)
 
@@ -903,7 +903,7 @@ def main():
                            "d2h_bytes_per_step": int(e2e["d2h"]), "ms_per_step": e2e_max,
                            "per_rank_gb_per_s": (e2e["h2d"] + e2e["d2h"]) / (e2e_max * 1e-3) / 1e9,
                            "single_section_latency_ms": e2e_lat_max,
-                           "host_wait": "yield (blocking-sync events)" if world * 3 > len(all_cpus) // 2 else "spin",
+                           "host_wait": "yield (blocking-sync events)" if yield_wait else "spin",
                            "note": "candidate stage (the scope of `value` and of --impl reference: subset + KNN + cost) through the public API "
                                    "(same_b200.device.CandidateStream over the C-ABI) on a stream of sections: every section's frames go up from "
                                    "page-locked host memory and its kept rows, row pointers, pair reference indices and costs come back, all inside "

@@ -253,7 +253,7 @@ enum { SAME_STAT_KNN_EVALUATIONS = 1 };
 SAME_API int same_batch_stat(same_batch_t *b, int what, int64_t *value);
 /* Device memory the library's stream-ordered pool holds (reserved) and has handed out (used) right now, in bytes. */
 SAME_API int same_mempool_stats(int device, int64_t *reserved, int64_t *used);
-/* Grow the pool by `bytes` of headroom now (one allocation that is freed again at once; the pool never returns memory to the driver):
+/* Make the pool hold at least `bytes` (one allocation that is freed again at once; the pool never returns memory to the driver):
  * a stream of overlapping sections then does not meet a cudaMalloc — tens of milliseconds when several processes share the host —
  * in the middle of its steady state.  Blocks until done. */
 SAME_API int same_mempool_reserve(int device, int64_t bytes);

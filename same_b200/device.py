@@ -229,10 +229,12 @@ class CandidateStream:
         self._pool = ThreadPoolExecutor(max_workers=len(self._streams), thread_name_prefix="same_b200-section")
 
     def reserve(self, nbytes=None):
-        """Give the device memory pool head-room for the overlap of `depth` sections (default: as much again as it holds now), so
-        that no section of the steady state has to wait for the driver to map new memory.  Call after the first results."""
+        """Give the device memory pool head-room for the overlap of `depth` sections (default: twice what it holds now), so that no
+        section of the steady state has to wait for the driver to map new memory — tens of milliseconds when several processes
+        share the host.  Call between sections (nothing outstanding), after the first results.  The request is ONE allocation that
+        is freed again at once, so the pool ends up holding max(what it held, nbytes)."""
         if nbytes is None:
-            nbytes = L.mempool_stats(self.device)[0]
+            nbytes = 2 * L.mempool_stats(self.device)[0]
         L.mempool_reserve(self.device, int(nbytes))
 
     def close(self):
