@@ -491,6 +491,42 @@ def separation_latency_arm(local_rank):
     return out
 
 
+def host_link_probe(device, world):
+    """The ceiling of any transfer-bound end-to-end number on THIS box: every rank copies 128 MiB host->device and 128 MiB
+    device->host at the same time (page-locked memory, two streams, plain cudaMemcpyAsync), all ranks together.
+    -> GB/s per rank (both directions summed, slowest rank) and the aggregate over ranks."""
+    import torch
+    import torch.distributed as dist
+    n = 128 << 20
+    h_up, h_dn = torch.empty(n, dtype=torch.uint8).pin_memory(), torch.empty(n, dtype=torch.uint8).pin_memory()
+    d_up, d_dn = torch.empty(n, dtype=torch.uint8, device=device), torch.zeros(n, dtype=torch.uint8, device=device)
+    s_up, s_dn = torch.cuda.Stream(device=device), torch.cuda.Stream(device=device)
+
+    def once():
+        with torch.cuda.stream(s_up):
+            d_up.copy_(h_up, non_blocking=True)
+        with torch.cuda.stream(s_dn):
+            h_dn.copy_(d_dn, non_blocking=True)
+    for _ in range(2):
+        once()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    reps = 8
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        once()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dt = float(t.item())
+    per_rank = 2 * n * reps / dt / 1e9
+    return {"per_rank_gb_per_s": per_rank, "aggregate_gb_per_s": per_rank * world,
+            "note": "128 MiB up + 128 MiB down per rank at once, page-locked memory, all ranks together, slowest rank's clock"}
+
+
 def workload_config(args, world, grid, n_windows):
     return {"workload": f"BASELINE configs[3]: synthetic {args.tiles}-tile section per GPU (~{args.tiles * 411 / 1e6:.2f}M ref / ~{args.tiles * 372 / 1e6:.2f}M query cells, K={N_TYPES}), "
                         f"candidate+cost+triangle+separation kernels, sliding window {grid[0]}x{grid[1]} per GPU",
@@ -765,6 +801,8 @@ def main():
         sec.close()
         extra["strong_scaling"] = strong_scaling_arm(args, rank, world, local_rank, stream)
         sec = make_section()
+    if not args.no_e2e:
+        extra["host_link_probe"] = host_link_probe(device, world)
     if not args.no_e2e and rank == 0:
         extra["separation_callback_latency"] = separation_latency_arm(local_rank)
     if not args.no_e2e:
@@ -902,6 +940,9 @@ def main():
             line["e2e"] = {"value": tot[6] / (e2e_max * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": int(e2e["h2d"]),
                            "d2h_bytes_per_step": int(e2e["d2h"]), "ms_per_step": e2e_max,
                            "per_rank_gb_per_s": (e2e["h2d"] + e2e["d2h"]) / (e2e_max * 1e-3) / 1e9,
+                           "aggregate_gb_per_s": world * (e2e["h2d"] + e2e["d2h"]) / (e2e_max * 1e-3) / 1e9,
+                           "frac_of_host_link_probe": ((e2e["h2d"] + e2e["d2h"]) / (e2e_max * 1e-3) / 1e9) / extra["host_link_probe"]["per_rank_gb_per_s"]
+                           if "host_link_probe" in extra else None,
                            "single_section_latency_ms": e2e_lat_max,
                            "host_wait": "yield (blocking-sync events)" if yield_wait else "spin",
                            "note": "candidate stage (the scope of `value` and of --impl reference: subset + KNN + cost) through the public API "
