@@ -147,8 +147,12 @@ def section_from_row_shards(frames, device_index=None, group=None):
             a_type, r_type, a_size, r_size]
     tens = [None if h is None else allgather_rows(h, dev, group) for h in host]
     ptrs = [None if t is None else int(t.data_ptr()) for t in tens]
-    return Section.from_pointers(len(host[0]), len(host[1]), host[2].shape[1], *ptrs, device=di,
-                                 stream=torch.cuda.current_stream(dev).cuda_stream, keep=tens)
+    cur = torch.cuda.current_stream(dev)
+    if not cur.cuda_stream:
+        # the legacy default stream cannot be handed over (handle 0 means "create a private stream" to the library): the gathers
+        # must have finished before that private stream reads their output
+        cur.synchronize()
+    return Section.from_pointers(len(host[0]), len(host[1]), host[2].shape[1], *ptrs, device=di, stream=cur.cuda_stream or None, keep=tens)
 
 
 def gather_matches(local: pd.DataFrame, group=None) -> Optional[pd.DataFrame]:
