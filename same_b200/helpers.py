@@ -7,6 +7,7 @@ Same names, argument meaning and return types as the reference so call sites and
 from __future__ import annotations
 
 import os
+from collections.abc import Mapping
 
 import numpy as np
 import pandas as pd
@@ -141,10 +142,53 @@ def filter_triangles_by_radius(points, triangles, radius, aligned_df=None, ignor
     return filtered
 
 
-def precompute_triangle_info(aligned_df, aligned_delaunay, aligned_simplex_map, bounds=None, argv=None):
+class LazyDict(Mapping):
+    """A read-only MAPPING whose items are produced by `build()` the first time anything but its length is asked for (same idea
+    as violationhelper.LazyRecords): equal to the plain dict, `dict(x)` gives it, and it pickles AS a plain dict."""
+
+    def __init__(self, n, build):
+        self._n, self._build, self._items = int(n), build, None
+
+    def _fill(self):
+        if self._items is None:
+            self._items = dict(self._build())
+            self._build = None
+        return self._items
+
+    def __len__(self):
+        return self._n
+
+    def __getitem__(self, k):
+        return self._fill()[k]
+
+    def __iter__(self):
+        return iter(self._fill())
+
+    def __repr__(self):
+        return repr(self._fill())
+
+    def __reduce__(self):
+        return (dict, (self._fill(),))
+
+
+def triangle_info_order(n_nodes, aligned_simplex_map):
+    """Key order of the reference's triangle_info dict (src/helpers.py:190-195): first appearance while walking nodes 0..n-1 and
+    each node's simplex SET in its iteration order."""
+    seen, order = set(), []
+    for ip in range(n_nodes):
+        for s in aligned_simplex_map[ip]:
+            if s not in seen:
+                seen.add(s)
+                order.append(s)
+    return order
+
+
+def precompute_triangle_info(aligned_df, aligned_delaunay, aligned_simplex_map, bounds=None, argv=None, order=None, lazy=False, n_entries=None):
     """dict[simplex] -> vertices, bounds, arg-min/max vertices (src/helpers.py:184-210).  Key order follows the
     reference: first appearance while walking nodes 0..n-1 and each node's simplex set.  `bounds`/`argv` are the
-    GPU tables (TRI_BOUNDS / TRI_ARGV); when omitted they are computed here with numpy."""
+    GPU tables (TRI_BOUNDS / TRI_ARGV); when omitted they are computed here with numpy.  `order` = a precomputed
+    `triangle_info_order` (or, with `lazy=True`, a callable returning it); `lazy=True` returns a mapping that builds its entries
+    on first access (`n_entries` = its length when the order is not known yet: every triangle has an entry)."""
     tri = np.asarray(aligned_delaunay).reshape(-1, 3)
     if bounds is None or argv is None:
         xy = aligned_df[["X", "Y"]].to_numpy(dtype=np.float64)
@@ -152,16 +196,21 @@ def precompute_triangle_info(aligned_df, aligned_delaunay, aligned_simplex_map, 
         bounds = np.stack([px.min(1), px.max(1), py.min(1), py.max(1)], axis=1)
         pick = lambda m: tri[np.arange(len(tri)), m.argmax(1)]
         argv = np.stack([pick(px == bounds[:, 1:2]), pick(px == bounds[:, 0:1]), pick(py == bounds[:, 3:4]), pick(py == bounds[:, 2:3])], axis=1)
-    info = {}
     bounds, argv = np.asarray(bounds), np.asarray(argv)
-    for ip in range(len(aligned_df)):
-        for s in aligned_simplex_map[ip]:
-            if s not in info:
-                b, a = bounds[s], argv[s]
-                info[s] = {"vertices": aligned_delaunay[s],
-                           "bounds": {"min_x": b[0], "max_x": b[1], "min_y": b[2], "max_y": b[3]},
-                           "max_x_vertex": a[0], "min_x_vertex": a[1], "max_y_vertex": a[2], "min_y_vertex": a[3]}
-    return info
+    if order is None:
+        order = triangle_info_order(len(aligned_df), aligned_simplex_map)
+
+    def build():
+        info = {}
+        for s in (order() if callable(order) else order):
+            b, a = bounds[s], argv[s]
+            info[s] = {"vertices": aligned_delaunay[s],
+                       "bounds": {"min_x": b[0], "max_x": b[1], "min_y": b[2], "max_y": b[3]},
+                       "max_x_vertex": a[0], "min_x_vertex": a[1], "max_y_vertex": a[2], "min_y_vertex": a[3]}
+        return info
+    if not lazy:
+        return build()
+    return LazyDict(n_entries if callable(order) else len(order), build)
 
 
 def get_unprocessed_windows(moving_df, output_name, x_windows, y_windows, window_size, overlap, cell_id_col="Cell_Num_Old",

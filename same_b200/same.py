@@ -21,7 +21,7 @@ from . import windows as WN
 from .frames import build_section
 from .params import init_gurobi_params, init_optim_params
 from .solver import ModelSpec, get_backend
-from .violationhelper import violations_from_mask
+from .violationhelper import eager_report, violations_from_mask
 
 
 # --------------------------------------------------------------------------------------------------------
@@ -125,9 +125,6 @@ class _Run:
         self.using_precomputed = aligned_delaunay is not None and not ignore_precomputed
         self._a_xy = aligned_df[["X", "Y"]].to_numpy(dtype=np.float64)
         self._a_type = None
-        if have_types:
-            from .frames import joint_type_codes
-            self._a_type, _ = joint_type_codes(aligned_df["cell_type"].to_numpy(), ref_df["cell_type"].to_numpy())
         if self.using_precomputed:
             tri = _as_triangle_array(aligned_delaunay)
             self.section.set_triangles(tri.astype(np.int64), vertex_ids)
@@ -149,6 +146,9 @@ class _Run:
         same = bool(o["ignore_same_type_triangles"])
         mad = o.get("min_angle_deg", 15)
         if self.batch.tri_classify(o["radius"], mad, same) > 0:
+            if have_types:      # (only the guard band needs the codes on the host)
+                from .frames import joint_type_codes
+                self._a_type, _ = joint_type_codes(aligned_df["cell_type"].to_numpy(), ref_df["cell_type"].to_numpy())
             H.redecide_band(self.batch, self._a_xy, self._a_type, o["radius"], mad, same)
         self.batch.tri_finalize(same, True, remove_unconstrained=self.using_precomputed)   # same.py:1034-1085
         self.batch.groups(o["max_matches"], o["ref_metacell_match_multiplier"])            # helpers.py:105-138
@@ -260,17 +260,18 @@ def _solve_window(run: _Run, w: int, aligned_src: pd.DataFrame, ref_src: pd.Data
 
     x = np.asarray(res.x, dtype=np.float64)
     sel = np.flatnonzero(x > 0.5)
-    out_df = pd.DataFrame({"aligned_idx": pairs[sel, 0].astype(np.int64), "ref_idx": pairs[sel, 1].astype(np.int64)})
-    ai, rj = out_df["aligned_idx"].to_numpy(), out_df["ref_idx"].to_numpy()
+    ai, rj = pairs[sel, 0].astype(np.int64), pairs[sel, 1].astype(np.int64)
+    cols = {"aligned_idx": ai, "ref_idx": rj}                                                      # same.py:1264-1278, one frame construction
     for ct in list(commonCT) + ["X", "Y"]:
-        out_df[ct] = aligned_df[ct].to_numpy()[ai]
+        cols[ct] = aligned_df[ct].to_numpy()[ai]
     for ct in ["X", "Y"]:
-        out_df[f"ref_{ct}"] = ref_df[ct].to_numpy()[rj]
-    out_df["size"] = aligned_df["size"].to_numpy()[ai]
-    out_df["ref_size"] = ref_df["size"].to_numpy()[rj]
-    out_df[f"Ref_{cell_id_col}"] = ref_df[cell_id_col].to_numpy()[rj]
-    out_df[f"Aligned_{cell_id_col}"] = aligned_df[cell_id_col].to_numpy()[ai]
-    out_df["time_limit_reached"] = time_limit_reached
+        cols[f"ref_{ct}"] = ref_df[ct].to_numpy()[rj]
+    cols["size"] = aligned_df["size"].to_numpy()[ai]
+    cols["ref_size"] = ref_df["size"].to_numpy()[rj]
+    cols[f"Ref_{cell_id_col}"] = ref_df[cell_id_col].to_numpy()[rj]
+    cols[f"Aligned_{cell_id_col}"] = aligned_df[cell_id_col].to_numpy()[ai]
+    cols["time_limit_reached"] = np.full(len(ai), time_limit_reached)
+    out_df = pd.DataFrame(cols)
 
     # ---- post-solve analysis on the GPU (violationhelper.py:1-134, same.py:1355-1408) ----
     b.postsolve(x, w, w + 1)
@@ -285,19 +286,32 @@ def _solve_window(run: _Run, w: int, aligned_src: pd.DataFrame, ref_src: pd.Data
     nt_len = b.get_window(L.NODE_TRI_LEN, w).astype(np.int64)
     nt_idx = b.get_window(L.NODE_TRI_IDX, w)
     base = int(nt_ptr[0]) if n_aligned else 0
-    flat = nt_idx.tolist()
-    aligned_simplex_map = {i: set(flat[s0:s0 + ln]) for i, (s0, ln) in enumerate(zip((nt_ptr[:-1] - base).tolist(), nt_len.tolist()))}
+
+    def build_simplex_map():
+        flat = nt_idx.tolist()
+        return {i: set(flat[s0:s0 + ln]) for i, (s0, ln) in enumerate(zip((nt_ptr[:-1] - base).tolist(), nt_len.tolist()))}
+    aligned_simplex_map = build_simplex_map() if eager_report() else H.LazyDict(n_aligned, build_simplex_map)
     aligned_delaunay = tri.astype(int)
-    triangle_info = H.precompute_triangle_info(aligned_df, aligned_delaunay, aligned_simplex_map, bounds=m["bounds"], argv=m["argv"])
+    order_cache = []
+
+    def tri_order():      # key order of the reference's triangle_info (walks every node's set): computed when something first needs it
+        if not order_cache:
+            order_cache.append(H.triangle_info_order(n_aligned, aligned_simplex_map))
+        return order_cache[0]
+    eager = eager_report()
+    triangle_info = H.precompute_triangle_info(aligned_df, aligned_delaunay, aligned_simplex_map, bounds=m["bounds"], argv=m["argv"],
+                                               order=tri_order() if eager else tri_order, lazy=not eager, n_entries=T)
     a_xy = aligned_df[["X", "Y"]].to_numpy(dtype=np.float64)
     r_xy = ref_df[["X", "Y"]].to_numpy(dtype=np.float64)
-    violations = violations_from_mask(mask, tri, match_j, a_xy, r_xy, list(triangle_info.keys()), len(triangle_info))
-    violation_points = set(violations["points_with_violations"])
+    violations = violations_from_mask(mask, tri, match_j, a_xy, r_xy, tri_order() if eager else tri_order, T)
+    pts = violations["points_with_violations"]
+    violation_points = set(pts.unordered.tolist()) if getattr(pts, "unordered", None) is not None else set(pts)
     penalty_points = set()
     for t in np.flatnonzero(np.asarray(res.q) > 1e-6):                                             # same.py:1325-1346
         penalty_points.update(int(v) for v in tri[t])
     points_both = violation_points & penalty_points
     matched_bits = (mask >> 8) & 7
+    per_triangle = (lambda build: build()) if eager else (lambda build: H.LazyDict(T, build))   # dict[t] -> value, built when read
     var_out = {
         "x": x.tolist(), "no_match_vars": np.asarray(res.no_match).tolist(), "penalty_vars": np.asarray(res.penalty).tolist(),
         "area_penalty_vars": np.asarray(res.q).tolist(), "violations": violations,
@@ -305,10 +319,10 @@ def _solve_window(run: _Run, w: int, aligned_src: pd.DataFrame, ref_src: pd.Data
                                          "points_only_penalties": list(penalty_points - violation_points)},
         "triangle_data": {
             "triangles": aligned_delaunay, "triangle_info": triangle_info, "aligned_simplex_map": aligned_simplex_map,
-            "areas_before": dict(zip(range(T), area_before)),
-            "areas_after": {t: (None if nan else a) for t, (a, nan) in enumerate(zip(area_after, np.isnan(area_after).tolist()))},
+            "areas_before": per_triangle(lambda: dict(zip(range(T), area_before))),
+            "areas_after": per_triangle(lambda: {t: (None if nan else a) for t, (a, nan) in enumerate(zip(area_after, np.isnan(area_after).tolist()))}),
             "flipped_triangles": flipped.tolist(),
-            "matched_vertices": dict(zip(range(T), (((matched_bits[:, None] >> np.arange(3)) & 1) != 0).tolist()))},
+            "matched_vertices": per_triangle(lambda: dict(zip(range(T), (((matched_bits[:, None] >> np.arange(3)) & 1) != 0).tolist())))},
         "lazy_constraints": lazy, "lazy_cuts_added": res.cuts_added if lazy else 0,
         "exact_predicate_check": epc,      # (extra key: diagnostic only, see helpers.exact_predicate_check)
     }
@@ -326,9 +340,9 @@ def _solve_window(run: _Run, w: int, aligned_src: pd.DataFrame, ref_src: pd.Data
         import json
         with open(os.path.join(outprefix, "timings.json"), "w") as f:
             json.dump(timings, f, indent=1)
-    flipped_nodes = set(int(v) for t in flipped for v in tri[t])                                   # same.py:1466-1472
-    out_df["triangle_violation"] = out_df["aligned_idx"].isin(flipped_nodes)
-    out_df["filtered_violation"] = out_df["aligned_idx"].isin(points_both)
+    flipped_nodes = np.unique(tri[flipped].reshape(-1)) if len(flipped) else np.zeros(0, np.int64)  # same.py:1466-1472
+    out_df["triangle_violation"] = np.isin(ai, flipped_nodes)
+    out_df["filtered_violation"] = np.isin(ai, np.fromiter(points_both, dtype=np.int64, count=len(points_both)))
     out_df["run_time"] = res.runtime
     if outprefix:
         out_df.to_csv(os.path.join(outprefix, "matches_df.csv"), index=False)
