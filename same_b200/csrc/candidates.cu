@@ -220,81 +220,81 @@ __global__ void __launch_bounds__(128) k_knn(const double2 *__restrict__ sa_xy, 
     float thrf = __double2float_ru(thr);
     // The own bin and ring 1 — where nearly all the work is — are nine bins whose squared gaps are sums of four numbers: the
     // gap to the NEAR neighbour column / row (the one on the query's side of its bin) and to the FAR one.  They are walked
-    // nearest first (own, near column, near row, far column, far row, then the corners) from a packed 2-bit code table, so
+    // nearest first (own, near column, near row, far column, far row, then the corners), so
     // the k-th best tightens early and the far bins are pruned without an evaluation.  Rings >= 2 use the general walker.
     const int sx = (fxf + fxf < wf) ? -1 : 1, sy = (fyf + fyf < wf) ? -1 : 1;
     const float nxg = fmaxf(0.f, fminf(fxf, wf - fxf) - epsf), fxg = fmaxf(0.f, fmaxf(fxf, wf - fxf) - epsf);
     const float nyg = fmaxf(0.f, fminf(fyf, wf - fyf) - epsf), fyg = fmaxf(0.f, fmaxf(fyf, wf - fyf) - epsf);
     const float nx2 = nxg * nxg, fx2 = fxg * fxg, ny2 = nyg * nyg, fy2 = fyg * fyg;
     const float edge = fminf(nxg, nyg);                     // distance to the nearest side of the own bin (lower bound)
-    // codes 0 = own column/row, 1 = near, 2 = far; slot order: own, (N,0), (0,N), (F,0), (0,F), (N,N), (N,F), (F,N), (F,F)
-    constexpr unsigned XC = 0u | 1u << 2 | 0u << 4 | 2u << 6 | 0u << 8 | 1u << 10 | 1u << 12 | 2u << 14 | 2u << 16;
-    constexpr unsigned YC = 0u | 0u << 2 | 1u << 4 | 0u << 6 | 2u << 8 | 1u << 10 | 2u << 12 | 1u << 14 | 2u << 16;
-    int ring = 1, slot = 8;                                 // general walker state; the first general step moves to ring 2
-    for (int it = 0;; ++it) {
-        int dx, dy;
-        float g2;
-        if (it < 9) {
-            const unsigned cx = (XC >> (2 * it)) & 3u, cy = (YC >> (2 * it)) & 3u;
-            dx = cx == 0u ? 0 : (cx == 1u ? sx : -sx);
-            dy = cy == 0u ? 0 : (cy == 1u ? sy : -sy);
-            g2 = (cx == 0u ? 0.f : (cx == 1u ? nx2 : fx2)) + (cy == 0u ? 0.f : (cy == 1u ? ny2 : fy2));
-            if (it == 1 && edge * edge > thrf) break;       // nothing outside the own bin can enter any more
-        } else {
-            if (slot >= 8 * ring) { ++ring; slot = 0; }
-            if (ring > g.rings) break;
-            if (slot == 0) {
-                // nearest possible point of this ring (Chebyshev distance `ring` bins from the centre bin)
-                const float gap = (float)(ring - 1) * wf + edge;
-                if (gap * gap > thrf) break;
-            }
-            ring_slot(ring, slot, dx, dy);
-            ++slot;
-            // gap along one axis to a bin d bins away: d > 0: d*w - f;  d < 0: f + (-d - 1)*w;  own row/column: 0
-            const float gx = dx == 0 ? 0.f : fmaxf(0.f, (dx > 0 ? (float)dx * wf - fxf : fxf - (float)(dx + 1) * wf) - epsf);
-            const float gy = dy == 0 ? 0.f : fmaxf(0.f, (dy > 0 ? (float)dy * wf - fyf : fyf - (float)(dy + 1) * wf) - epsf);
-            g2 = gx * gx + gy * gy;
-        }
-        const int bx = cbx + dx, by = cby + dy;
-        if (bx < 0 || bx >= g.nbx || by < 0 || by >= g.nby) continue;
-        if (g2 > thrf) continue;
-        {
-            const i32 b = g.base + by * g.nbx + bx;
-            const i32 s1 = bin_start[b + 1];
-            for (i32 s0 = bin_start[b]; s0 < s1; s0 += 2) {
-                // two candidates per trip: both loads are in flight before either is used (the second one re-reads the
-                // first when the bin ends on an odd count and is then skipped)
-                const bool two = s0 + 1 < s1;
-                nev += two ? 2 : 1;
-                const double2 pA = sr_xy[s0], pB = sr_xy[two ? s0 + 1 : s0];
-                const double ax = __dsub_rn(pA.x, q.x), ay = __dsub_rn(pA.y, q.y), bx2 = __dsub_rn(pB.x, q.x), by2 = __dsub_rn(pB.y, q.y);
-                const double dA = __dadd_rn(__dmul_rn(ax, ax), __dmul_rn(ay, ay));
-                const double dB = two ? __dadd_rn(__dmul_rn(bx2, bx2), __dmul_rn(by2, by2)) : INFINITY;
+    // One bin: two candidates per trip — both loads are in flight before either is used (the second one re-reads the first
+    // when the bin ends on an odd count and is then skipped).
+    auto visit = [&](i32 b) {
+        const i32 s1 = bin_start[b + 1];
+        for (i32 s0 = bin_start[b]; s0 < s1; s0 += 2) {
+            const bool two = s0 + 1 < s1;
+            nev += two ? 2 : 1;
+            const double2 pA = sr_xy[s0], pB = sr_xy[two ? s0 + 1 : s0];
+            const double ax = __dsub_rn(pA.x, q.x), ay = __dsub_rn(pA.y, q.y), bx2 = __dsub_rn(pB.x, q.x), by2 = __dsub_rn(pB.y, q.y);
+            const double dA = __dadd_rn(__dmul_rn(ax, ax), __dmul_rn(ay, ay));
+            const double dB = two ? __dadd_rn(__dmul_rn(bx2, bx2), __dmul_rn(by2, by2)) : INFINITY;
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const double d2 = h ? dB : dA;
-                    const i32 s = s0 + h;
-                    if (d2 <= thr) {
-                        const unsigned hb = ((unsigned)__double2hiint(d2) & ~SLOT) + ONE, lb = last_k & ~SLOT;
-                        if (hb < lb) {
-                            const unsigned free_slot = last_k & SLOT;           // the evicted entry's position slot
-                            const unsigned nk = hb | free_slot;
-                            spos[free_slot * 128 + threadIdx.x] = s;
-                            // sorted insertion of a key that differs from every key in the list (top down: each slot reads the
-                            // OLD value of its left neighbour): slot u keeps its key, takes the new one, or takes slot u-1's
+            for (int h = 0; h < 2; ++h) {
+                const double d2 = h ? dB : dA;
+                const i32 s = s0 + h;
+                if (d2 <= thr) {
+                    const unsigned hb = ((unsigned)__double2hiint(d2) & ~SLOT) + ONE, lb = last_k & ~SLOT;
+                    if (hb < lb) {
+                        const unsigned free_slot = last_k & SLOT;           // the evicted entry's position slot
+                        const unsigned nk = hb | free_slot;
+                        spos[free_slot * 128 + threadIdx.x] = s;
+                        // sorted insertion of a key that differs from every key in the list (top down: each slot reads the
+                        // OLD value of its left neighbour): slot u keeps its key, takes the new one, or takes slot u-1's
 #pragma unroll
-                            for (int u = KCAP - 1; u > 0; --u) bk[u] = min(bk[u], max(bk[u - 1], nk));
-                            bk[0] = min(bk[0], nk);
-                            const unsigned nb = last_k & ~SLOT;
-                            tie = nb == lb;   // the dropped candidate shares the new k-th's bucket (or the list is not full yet)
-                            const bool below = nb <= r2_hi;   // never for the empty-slot key: r2 is finite
-                            thr = __hiloint2double((int)(below ? nb : r2_hi), (int)(below ? 0u : r2_lo));
-                            thrf = __double2float_ru(thr);
-                        } else if (hb == lb) {
-                            tie = true;
-                        }
+                        for (int u = KCAP - 1; u > 0; --u) bk[u] = min(bk[u], max(bk[u - 1], nk));
+                        bk[0] = min(bk[0], nk);
+                        const unsigned nb = last_k & ~SLOT;
+                        tie = nb == lb;   // the dropped candidate shares the new k-th's bucket (or the list is not full yet)
+                        const bool below = nb <= r2_hi;   // never for the empty-slot key: r2 is finite
+                        thr = __hiloint2double((int)(below ? nb : r2_hi), (int)(below ? 0u : r2_lo));
+                        thrf = __double2float_ru(thr);
+                    } else if (hb == lb) {
+                        tie = true;
                     }
                 }
+            }
+        }
+    };
+    // own bin, then ring 1 nearest first — (N,0), (0,N), (F,0), (0,F), (N,N), (N,F), (F,N), (F,F) with N / F the near / far
+    // neighbour column or row — written out so that the bin offsets, the bounds tests and the gaps are a few registers
+    // computed once (a table-driven loop spent ~50 instructions per bin on decoding)
+    const i32 b0 = g.base + cby * g.nbx + cbx, dyn = sy * g.nbx;
+    const bool xn = (unsigned)(cbx + sx) < (unsigned)g.nbx, xf = (unsigned)(cbx - sx) < (unsigned)g.nbx;
+    const bool yn = (unsigned)(cby + sy) < (unsigned)g.nby, yf = (unsigned)(cby - sy) < (unsigned)g.nby;
+    visit(b0);
+    if (!(edge * edge > thrf)) {                             // else nothing outside the own bin can enter any more
+        if (xn && !(nx2 > thrf)) visit(b0 + sx);
+        if (yn && !(ny2 > thrf)) visit(b0 + dyn);
+        if (xf && !(fx2 > thrf)) visit(b0 - sx);
+        if (yf && !(fy2 > thrf)) visit(b0 - dyn);
+        if (xn && yn && !(nx2 + ny2 > thrf)) visit(b0 + sx + dyn);
+        if (xn && yf && !(nx2 + fy2 > thrf)) visit(b0 + sx - dyn);
+        if (xf && yn && !(fx2 + ny2 > thrf)) visit(b0 - sx + dyn);
+        if (xf && yf && !(fx2 + fy2 > thrf)) visit(b0 - sx - dyn);
+        for (int ring = 2; ring <= g.rings; ++ring) {        // general walker
+            // nearest possible point of this ring (Chebyshev distance `ring` bins from the centre bin)
+            const float gap = (float)(ring - 1) * wf + edge;
+            if (gap * gap > thrf) break;
+            for (int slot = 0; slot < 8 * ring; ++slot) {
+                int dx, dy;
+                ring_slot(ring, slot, dx, dy);
+                // gap along one axis to a bin d bins away: d > 0: d*w - f;  d < 0: f + (-d - 1)*w;  own row/column: 0
+                const float gx = dx == 0 ? 0.f : fmaxf(0.f, (dx > 0 ? (float)dx * wf - fxf : fxf - (float)(dx + 1) * wf) - epsf);
+                const float gy = dy == 0 ? 0.f : fmaxf(0.f, (dy > 0 ? (float)dy * wf - fyf : fyf - (float)(dy + 1) * wf) - epsf);
+                const int bx = cbx + dx, by = cby + dy;
+                if (bx < 0 || bx >= g.nbx || by < 0 || by >= g.nby) continue;
+                if (gx * gx + gy * gy > thrf) continue;
+                visit(g.base + by * g.nbx + bx);
             }
         }
     }
@@ -449,12 +449,12 @@ __global__ void k_fill_i32(i32 *p, i64 n, i32 v) {
 }
 // off3[0..W] / [W+1..2W+1] / [2W+2..3W+2]: kept-aligned, kept-ref and pair offsets of each window
 // (also written to the three device-side offset arrays the later kernels read, instead of three device-to-device copies)
-__global__ void k_window_offsets(const i32 *__restrict__ newA, const i32 *__restrict__ newR, const i32 *__restrict__ poff,
+__global__ void k_window_offsets(const i32 *__restrict__ newA, const int2 *__restrict__ rmap, const i32 *__restrict__ poff,
                                  const i32 *__restrict__ a_off, const i32 *__restrict__ r_off, int W, i32 *__restrict__ off3,
                                  i32 *__restrict__ ka_off, i32 *__restrict__ kr_off, i32 *__restrict__ p_off) {
     int w = blockIdx.x * blockDim.x + threadIdx.x;
     if (w > W) return;
-    const i32 ka = newA[a_off[w]], kr = newR[r_off[w]], po = poff[a_off[w]];
+    const i32 ka = newA[a_off[w]], kr = rmap[r_off[w]].x, po = poff[a_off[w]];
     off3[w] = ka; off3[W + 1 + w] = kr; off3[2 * (W + 1) + w] = po;
     ka_off[w] = ka; kr_off[w] = kr; p_off[w] = po;
 }
@@ -468,7 +468,7 @@ __global__ void k_window_offsets(const i32 *__restrict__ newA, const i32 *__rest
 constexpr int COMPACT_THREADS = 1024, COMPACT_ITEMS = 4;   // big tiles: one L2 round trip of look-back per 32 tiles
 __global__ void __launch_bounds__(COMPACT_THREADS, 2) k_compact_frames(
     const i32 *__restrict__ cnt, const i32 *__restrict__ eff, const i32 *__restrict__ r_used, i64 nAi, i64 nRi, unsigned tilesA, ScanCtx scA, ScanCtx scR,
-    const i32 *__restrict__ a_src, const i32 *__restrict__ r_src, i32 *__restrict__ newA, i32 *__restrict__ newR, i32 *__restrict__ poff,
+    const i32 *__restrict__ a_src, const i32 *__restrict__ r_src, i32 *__restrict__ newA, int2 *__restrict__ rmap, i32 *__restrict__ poff,
     i32 *__restrict__ keepA, i32 *__restrict__ row_ptr, i32 *__restrict__ keepR) {
     __shared__ int smem[2 * (COMPACT_THREADS / 32) + 2];
     int f[COMPACT_ITEMS], e[COMPACT_ITEMS], sum[2] = {0, 0}, excl[2], tot[2], pre[2];
@@ -513,34 +513,79 @@ __global__ void __launch_bounds__(COMPACT_THREADS, 2) k_compact_frames(
         for (int k = 0; k < COMPACT_ITEMS; ++k) {
             const i64 i = base + k;
             if (i <= nRi) {
-                newR[i] = kpos;
-                if (f[k]) keepR[kpos] = r_src[i];
+                const i32 row = i < nRi ? r_src[i] : 0;
+                rmap[i] = make_int2(kpos, row);   // kept index (batch-wide) and section row of every reference instance
+                if (f[k]) keepR[kpos] = row;
             }
             kpos += f[k];
         }
     }
 }
 
-// one thread per (aligned instance, slot): pair indices + cost (src/same.py:1183-1188)
-__global__ void k_emit_pairs(const i32 *__restrict__ cand, const i32 *__restrict__ eff, int knn, i64 nAi, const i32 *__restrict__ newA,
-                             const i32 *__restrict__ newR, const i32 *__restrict__ poff, const i32 *__restrict__ a_off, int W,
-                             const i32 *__restrict__ ka_off, const i32 *__restrict__ kr_off, const i32 *__restrict__ a_src,
-                             const i32 *__restrict__ r_src, const double2 *__restrict__ a_xy, const double2 *__restrict__ r_xy,
-                             const double *__restrict__ a_prob, const double *__restrict__ r_prob, int K, double ct_coeff,
-                             double dist_coeff, int2 *__restrict__ pairs, double *__restrict__ cost) {
-    const i64 tid = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-    const i64 i = tid / knn;
-    const int slot = (int)(tid - i * knn);
+// Packed row records for the pair-cost kernel: [x, y, p_0 .. p_{K-1}, zero padding] per row, RS = 2 + K rounded up to even.
+__global__ void k_pack_records(const double2 *__restrict__ xy, const double *__restrict__ prob, i64 n, int K, int RS, double *__restrict__ rec) {
+    const i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n * RS) return;
+    const i64 row = idx / RS;
+    const int e = (int)(idx - row * RS);
+    double v = 0.0;
+    if (e == 0) v = xy[row].x;
+    else if (e == 1) v = xy[row].y;
+    else if (e - 2 < K) v = prob[row * K + (e - 2)];
+    rec[idx] = v;
+}
+static void section_records(Section *sec, cudaStream_t s) {
+    if (sec->have_rec) return;
+    const int K = sec->K, RS = (2 + K + 1) & ~1;
+    sec->rec_stride = RS;
+    sec->a_rec.alloc(sec->nA * RS, s); sec->r_rec.alloc(sec->nR * RS, s);
+    if (sec->nA > 0) LAUNCH(k_pack_records, blocks_for(sec->nA * RS, 256), 256, 0, s, sec->a_xy.p, sec->a_prob.p, sec->nA, K, RS, sec->a_rec.p);
+    if (sec->nR > 0) LAUNCH(k_pack_records, blocks_for(sec->nR * RS, 256), 256, 0, s, sec->r_xy.p, sec->r_prob.p, sec->nR, K, RS, sec->r_rec.p);
+    sec->have_rec = true;
+}
+
+// one thread per (aligned instance, slot): pair indices + cost (src/same.py:1183-1188).  Per pair the reference side costs one
+// 8-byte gather (rmap: kept index + section row of the candidate instance, written by k_compact_frames) and one run of
+// adjacent sectors (the row's packed record); the window of a warp's first row is found once and the other lanes step
+// forward from it.  The L1 sum runs over the zero padding too: s + |0 - 0| == s exactly.
+template <int NP>   // NP = double2 words per record (1 + ceil(K / 2)); 0 = any
+__global__ void __launch_bounds__(256, 8) k_emit_pairs(const i32 *__restrict__ cand, const i32 *__restrict__ eff, int knn, int knn_shift, i64 nAi,
+                                                    const i32 *__restrict__ newA, const int2 *__restrict__ rmap, const i32 *__restrict__ poff,
+                                                    const i32 *__restrict__ a_off, int W, const i32 *__restrict__ ka_off,
+                                                    const i32 *__restrict__ kr_off, const i32 *__restrict__ a_src, const double *__restrict__ a_rec,
+                                                    const double *__restrict__ r_rec, int RS, double ct_coeff, double dist_coeff,
+                                                    int2 *__restrict__ pairs, double *__restrict__ cost) {
+    const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x;     // nAi * knn < 2^31 (batch_candidates)
+    const unsigned i = knn_shift >= 0 ? tid >> knn_shift : tid / (unsigned)knn;
+    const int slot = (int)(tid - i * (unsigned)knn);
+    const unsigned i0 = min(__shfl_sync(0xffffffffu, i, 0), (unsigned)(nAi > 0 ? nAi - 1 : 0));
+    int w = 0;
+    if ((threadIdx.x & 31) == 0) w = find_window(a_off, W, (i32)i0);
+    w = __shfl_sync(0xffffffffu, w, 0);
     if (i >= nAi || slot >= eff[i]) return;
-    const int w = find_window(a_off, W, (i32)i);
-    const i32 jinst = cand[i * knn + slot];
+    while (w + 1 < W && a_off[w + 1] <= (i32)i) ++w;
+    const i32 jinst = cand[tid];
+    const int2 m = rmap[jinst];
     const i32 p = poff[i] + slot;
-    pairs[p] = make_int2(newA[i] - ka_off[w], newR[jinst] - kr_off[w]);
-    const i32 ar = a_src[i], rr = r_src[jinst];
-    const double *pa = a_prob + (i64)ar * K, *pr = r_prob + (i64)rr * K;
+    const double2 *__restrict__ ra = (const double2 *)(a_rec + (size_t)a_src[i] * RS), *__restrict__ rr = (const double2 *)(r_rec + (size_t)m.y * RS);
+    const double2 A = ra[0], R = rr[0];
     double s = 0.0;
-    for (int c = 0; c < K; ++c) s = __dadd_rn(s, fabs(__dsub_rn(pa[c], pr[c])));  // left-to-right
-    const double2 A = a_xy[ar], R = r_xy[rr];
+    if (NP > 0) {
+#pragma unroll
+        for (int c = 1; c < NP; ++c) {   // left-to-right
+            const double2 u = ra[c], v = rr[c];
+            s = __dadd_rn(s, fabs(__dsub_rn(u.x, v.x)));
+            s = __dadd_rn(s, fabs(__dsub_rn(u.y, v.y)));
+        }
+    } else {
+#pragma unroll 1
+        for (int c = 1; 2 * c < RS; ++c) {
+            const double2 u = ra[c], v = rr[c];
+            s = __dadd_rn(s, fabs(__dsub_rn(u.x, v.x)));
+            s = __dadd_rn(s, fabs(__dsub_rn(u.y, v.y)));
+        }
+    }
+    pairs[p] = make_int2(newA[i] - ka_off[w], m.x - kr_off[w]);
     const double dc = __dadd_rn(fabs(__dsub_rn(A.x, R.x)), fabs(__dsub_rn(A.y, R.y)));
     cost[p] = __dadd_rn(__dmul_rn(ct_coeff, s), __dmul_rn(dist_coeff, dc));
 }
@@ -695,8 +740,9 @@ void batch_candidates(Batch *b, double radius, int knn, int priority, double dis
 
     // compaction + emission without a host round trip: outputs are sized by their upper bounds (kept rows <= instances,
     // pairs <= knn per aligned instance); the per-window offsets come back once, at the end
-    DevBuf<i32> newR, poff, off3;
-    b->newA.alloc(nAi + 1, s); newR.alloc(nRi + 1, s); poff.alloc(nAi + 1, s); off3.alloc(3 * (W + 1), s);
+    DevBuf<i32> poff, off3;
+    DevBuf<int2> rmap;
+    b->newA.alloc(nAi + 1, s); rmap.alloc(nRi + 1, s); poff.alloc(nAi + 1, s); off3.alloc(3 * (W + 1), s);
     b->keepA.alloc(nAi, s);
     b->row_ptr.alloc(nAi + 1, s);
     b->keepR.alloc(nRi, s);
@@ -707,18 +753,30 @@ void batch_candidates(Batch *b, double radius, int knn, int priority, double dis
         scan_reserve(sec, 2 * ((i64)tilesA + tilesR), s);   // two independent scans in one launch: disjoint tile-state words
         const ScanCtx scA = scan_ctx_at(sec, 0, tilesA), scR = scan_ctx_at(sec, 2 * (i64)tilesA, tilesR);
         LAUNCH(k_compact_frames, tilesA + tilesR, COMPACT_THREADS, 0, s, b->cnt.p, eff, b->r_used.p, nAi, nRi, tilesA, scA, scR, b->a_src.p, b->r_src.p,
-               b->newA.p, newR.p, poff.p, b->keepA.p, b->row_ptr.p, b->keepR.p);
+               b->newA.p, rmap.p, poff.p, b->keepA.p, b->row_ptr.p, b->keepR.p);
     }
     b->d_ka_off.alloc(W + 1, s); b->d_kr_off.alloc(W + 1, s); b->d_p_off.alloc(W + 1, s);
-    LAUNCH(k_window_offsets, blocks_for(W + 1, 128), 128, 0, s, b->newA.p, newR.p, poff.p, b->d_a_off.p, b->d_r_off.p, (int)W, off3.p, b->d_ka_off.p,
+    LAUNCH(k_window_offsets, blocks_for(W + 1, 128), 128, 0, s, b->newA.p, rmap.p, poff.p, b->d_a_off.p, b->d_r_off.p, (int)W, off3.p, b->d_ka_off.p,
            b->d_kr_off.p, b->d_p_off.p);
     // (measured and not kept: one thread per row with 8 gather chains in flight, 224 us vs 129 us; rows visited in bin order so
     // that neighbouring warps gather the same reference rows, 128 us; two slots per thread, 130 us — the kernel moves 292 MB of
     // scattered 32-byte sectors through DRAM at 2.3 TB/s either way; profiles/r1m)
-    if (nAi > 0)
-        LAUNCH(k_emit_pairs, blocks_for(nAi * knn, 256), 256, 0, s, b->cand.p, eff, knn, nAi, b->newA.p, newR.p, poff.p, b->d_a_off.p, (int)W,
-               b->d_ka_off.p, b->d_kr_off.p, b->a_src.p, b->r_src.p, sec->a_xy.p, sec->r_xy.p, sec->a_prob.p, sec->r_prob.p, sec->K,
-               dist_ct_coeff, dist_ct_coeff * 0.001, b->pairs.p, b->cost.p);
+    if (nAi > 0) {
+        section_records(sec, s);
+        int knn_shift = -1;
+        for (int sh = 0; sh < 7; ++sh) if ((1 << sh) == knn) knn_shift = sh;
+#define EMIT(NP) LAUNCH(k_emit_pairs<NP>, blocks_for(nAi * knn, 256), 256, 0, s, b->cand.p, eff, knn, knn_shift, nAi, b->newA.p, rmap.p, poff.p,      \
+                        b->d_a_off.p, (int)W, b->d_ka_off.p, b->d_kr_off.p, b->a_src.p, sec->a_rec.p, sec->r_rec.p, sec->rec_stride, dist_ct_coeff,      \
+                        dist_ct_coeff * 0.001, b->pairs.p, b->cost.p)
+        switch (sec->rec_stride / 2) {
+        case 1: EMIT(1); break;
+        case 2: EMIT(2); break;
+        case 3: EMIT(3); break;
+        case 4: EMIT(4); break;
+        default: EMIT(0); break;
+        }
+#undef EMIT
+    }
     // the window offsets come back asynchronously; whoever needs them on the host first waits for them (batch_settle)
     small_d2h(b->pin_cand(), off3.p, sizeof(i32) * 3 * (W + 1), s);
     b->pend_cand = true;

@@ -160,6 +160,12 @@ struct Section {
     DevBuf<double2> a_xy, r_xy;
     DevBuf<double> a_prob, r_prob, a_size, r_size;
     DevBuf<i32> a_type, r_type;
+    // one packed record per row, [x, y, p_0 .. p_{K-1}, 0-padding to an even count] (rec_stride doubles): the pair-cost kernel
+    // gathers a row's coordinates and probabilities from ONE run of adjacent sectors instead of two arrays (built on the
+    // device the first time a batch of this section computes costs, section_records)
+    DevBuf<double> a_rec, r_rec;
+    int rec_stride = 0;
+    bool have_rec = false;
     double bbox[4] = {0, 0, 0, 0};  // x_min, x_max, y_min, y_max over both frames
     // precomputed triangulation (vertex ids resolved to section rows; -1 = id not present)
     i64 Tg = -1;

@@ -24,12 +24,39 @@ __device__ __forceinline__ i32 inst_in_window(const int2 *__restrict__ row_inst,
 
 constexpr int REMAP_CT = 1024, REMAP_CI = 2;   // counting pass: big tiles for the look-back chain
 
+// Row table: the (window, window-local kept index or -1) entries of every aligned row, at most ROW_TAB of them, in ONE 32-byte
+// sector per row — a triangle then costs three sector gathers instead of walking row_pos -> row_inst -> cnt / newA for each
+// vertex (five dependent gathers per vertex).  Unused entries hold window TAB_END (above every window, the entries ascend); a
+// row that lies in more than ROW_TAB windows (overlap above one half) is marked TAB_MANY and its triangles take the general walk.
+constexpr int ROW_TAB = 4;
+constexpr i32 TAB_END = 0x7fffffff, TAB_MANY = -2;
+__global__ void k_row_table(i64 nA, const i32 *__restrict__ row_pos, const int2 *__restrict__ row_inst, const i32 *__restrict__ cnt,
+                            const i32 *__restrict__ newA, const i32 *__restrict__ ka_off, int4 *__restrict__ tab) {
+    const i64 r = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nA) return;
+    const i32 e0 = row_pos[r], n = row_pos[r + 1] - e0;
+    i32 w[ROW_TAB], l[ROW_TAB];
+#pragma unroll
+    for (int k = 0; k < ROW_TAB; ++k) {
+        w[k] = TAB_END; l[k] = -1;
+        if (k < n) {
+            const int2 v = row_inst[e0 + k];
+            w[k] = v.x;
+            l[k] = cnt[v.y] > 0 ? newA[v.y] - ka_off[v.x] : -1;
+        }
+    }
+    if (n > ROW_TAB) w[0] = TAB_MANY;
+    tab[2 * r] = make_int4(w[0], l[0], w[1], l[1]);
+    tab[2 * r + 1] = make_int4(w[2], l[2], w[3], l[3]);
+}
+__device__ __forceinline__ i32 tab_find(const int4 &p, const int4 &q, i32 w) {   // local index of the row in window w, -1 if none
+    return p.x == w ? p.y : (p.z == w ? p.w : (q.x == w ? q.y : (q.z == w ? q.w : -1)));
+}
+
 // visits the hits of triangle t in ascending window order: f(window, local a, local b, local c)
 template <typename F>
-__device__ __forceinline__ void remap_hits(const i32 *__restrict__ tri_rows, i64 t, const i32 *__restrict__ row_pos, const int2 *__restrict__ row_inst,
-                                           const i32 *__restrict__ cnt, const i32 *__restrict__ newA, const i32 *__restrict__ ka_off, F &&f) {
-    const i32 ra = tri_rows[3 * t], rb = tri_rows[3 * t + 1], rc = tri_rows[3 * t + 2];
-    if (ra < 0 || rb < 0 || rc < 0) return;
+__device__ __forceinline__ void remap_hits_walk(i32 ra, i32 rb, i32 rc, const i32 *__restrict__ row_pos, const int2 *__restrict__ row_inst,
+                                                const i32 *__restrict__ cnt, const i32 *__restrict__ newA, const i32 *__restrict__ ka_off, F &&f) {
     const i32 a0 = row_pos[ra], a1 = row_pos[ra + 1];
     if (a0 == a1) return;
     const i32 b0 = row_pos[rb], b1 = row_pos[rb + 1], c0 = row_pos[rc], c1 = row_pos[rc + 1];
@@ -44,9 +71,31 @@ __device__ __forceinline__ void remap_hits(const i32 *__restrict__ tri_rows, i64
         f(va.x, newA[va.y] - kb, newA[ib] - kb, newA[ic] - kb);
     }
 }
+template <typename F>
+__device__ __forceinline__ void remap_hits(const i32 *__restrict__ tri_rows, i64 t, const int4 *__restrict__ tab, const i32 *__restrict__ row_pos,
+                                           const int2 *__restrict__ row_inst, const i32 *__restrict__ cnt, const i32 *__restrict__ newA,
+                                           const i32 *__restrict__ ka_off, F &&f) {
+    const i32 ra = tri_rows[3 * t], rb = tri_rows[3 * t + 1], rc = tri_rows[3 * t + 2];
+    if (ra < 0 || rb < 0 || rc < 0) return;
+    const int4 a0 = tab[2 * ra], a1 = tab[2 * ra + 1], b0 = tab[2 * rb], b1 = tab[2 * rb + 1], c0 = tab[2 * rc], c1 = tab[2 * rc + 1];
+    if (a0.x == TAB_MANY || b0.x == TAB_MANY || c0.x == TAB_MANY) {
+        remap_hits_walk(ra, rb, rc, row_pos, row_inst, cnt, newA, ka_off, f);
+        return;
+    }
+    const i32 wa[ROW_TAB] = {a0.x, a0.z, a1.x, a1.z}, la[ROW_TAB] = {a0.y, a0.w, a1.y, a1.w};
+#pragma unroll
+    for (int k = 0; k < ROW_TAB; ++k) {
+        if (wa[k] == TAB_END || la[k] < 0) continue;     // (an END entry has local -1 as well)
+        const i32 lb = tab_find(b0, b1, wa[k]);
+        if (lb < 0) continue;
+        const i32 lc = tab_find(c0, c1, wa[k]);
+        if (lc < 0) continue;
+        f(wa[k], la[k], lb, lc);
+    }
+}
 
-__global__ void __launch_bounds__(REMAP_CT) k_remap_count(const i32 *__restrict__ tri_rows, i64 Tg, const i32 *__restrict__ row_pos,
-                                                          const int2 *__restrict__ row_inst, const i32 *__restrict__ cnt, const i32 *__restrict__ newA,
+__global__ void __launch_bounds__(REMAP_CT) k_remap_count(const i32 *__restrict__ tri_rows, i64 Tg, const int4 *__restrict__ tab,
+                                                          const i32 *__restrict__ row_pos, const int2 *__restrict__ row_inst, const i32 *__restrict__ cnt, const i32 *__restrict__ newA,
                                                           const i32 *__restrict__ ka_off, ScanCtx sc, i32 *__restrict__ pos,
                                                           int4 *__restrict__ first_hit) {
     __shared__ int smem[REMAP_CT / 32 + 1];
@@ -59,7 +108,7 @@ __global__ void __launch_bounds__(REMAP_CT) k_remap_count(const i32 *__restrict_
         // row -> instance table a second time
         if (base + k < Tg) {
             int4 h = make_int4(0, 0, 0, 0);
-            remap_hits(tri_rows, base + k, row_pos, row_inst, cnt, newA, ka_off, [&](i32 w, i32 la, i32 lb, i32 lc) {
+            remap_hits(tri_rows, base + k, tab, row_pos, row_inst, cnt, newA, ka_off, [&](i32 w, i32 la, i32 lb, i32 lc) {
                 if (c[k] == 0) h = make_int4(w, la, lb, lc);
                 ++c[k];
             });
@@ -78,8 +127,8 @@ __global__ void __launch_bounds__(REMAP_CT) k_remap_count(const i32 *__restrict_
 }
 
 template <typename KeyT>
-__global__ void __launch_bounds__(256) k_remap_fill(const i32 *__restrict__ tri_rows, i64 Tg, const i32 *__restrict__ row_pos,
-                                                    const int2 *__restrict__ row_inst, const i32 *__restrict__ cnt, const i32 *__restrict__ newA,
+__global__ void __launch_bounds__(256) k_remap_fill(const i32 *__restrict__ tri_rows, i64 Tg, const int4 *__restrict__ tab,
+                                                    const i32 *__restrict__ row_pos, const int2 *__restrict__ row_inst, const i32 *__restrict__ cnt, const i32 *__restrict__ newA,
                                                     const i32 *__restrict__ ka_off, const i32 *__restrict__ pos, const int4 *__restrict__ first_hit,
                                                     int tbits, KeyT *__restrict__ keys, i32 *__restrict__ idx, int3 *__restrict__ recs) {
     const i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x;
@@ -94,7 +143,7 @@ __global__ void __launch_bounds__(256) k_remap_fill(const i32 *__restrict__ tri_
         recs[out] = make_int3(h.y, h.z, h.w);
         return;
     }
-    remap_hits(tri_rows, t, row_pos, row_inst, cnt, newA, ka_off, [&](i32 w, i32 la, i32 lb, i32 lc) {
+    remap_hits(tri_rows, t, tab, row_pos, row_inst, cnt, newA, ka_off, [&](i32 w, i32 la, i32 lb, i32 lc) {
         keys[out] = (KeyT)(((unsigned long long)w << tbits) | (unsigned long long)t);
         idx[out] = out;
         recs[out] = make_int3(la, lb, lc);
@@ -133,10 +182,13 @@ static void remap_t(Batch *b, int tbits, int wbits) {
     const i64 W = b->W, Tg = sec->Tg;
     DevBuf<i32> pos;
     DevBuf<int4> first_hit;
+    DevBuf<int4> tab;
     pos.alloc(Tg + 1, s);
     first_hit.alloc(Tg, s);
+    tab.alloc(2 * sec->nA, s);
+    if (sec->nA > 0) LAUNCH(k_row_table, blocks_for(sec->nA, 256), 256, 0, s, sec->nA, b->row_pos.p, b->row_inst.p, b->cnt.p, b->newA.p, b->d_ka_off.p, tab.p);
     const unsigned tiles = blocks_for(Tg + 1, REMAP_CT * REMAP_CI);
-    LAUNCH(k_remap_count, tiles, REMAP_CT, 0, s, sec->tri_rows.p, Tg, b->row_pos.p, b->row_inst.p, b->cnt.p, b->newA.p, b->d_ka_off.p,
+    LAUNCH(k_remap_count, tiles, REMAP_CT, 0, s, sec->tri_rows.p, Tg, tab.p, b->row_pos.p, b->row_inst.p, b->cnt.p, b->newA.p, b->d_ka_off.p,
            scan_ctx(sec, tiles, 1, s), pos.p, first_hit.p);
     small_d2h(b->pin_misc(), pos.p + Tg, sizeof(i32), s);
     batch_sync(b);   // also brings in the candidate stage's window offsets
@@ -151,7 +203,7 @@ static void remap_t(Batch *b, int tbits, int wbits) {
     const KeyT *sorted_keys = keys.p;
     const i32 *sorted_idx = idx.p;
     if (b->Tin > 0) {
-        LAUNCH((k_remap_fill<KeyT>), blocks_for(Tg, 256), 256, 0, s, sec->tri_rows.p, Tg, b->row_pos.p, b->row_inst.p, b->cnt.p, b->newA.p, b->d_ka_off.p,
+        LAUNCH((k_remap_fill<KeyT>), blocks_for(Tg, 256), 256, 0, s, sec->tri_rows.p, Tg, tab.p, b->row_pos.p, b->row_inst.p, b->cnt.p, b->newA.p, b->d_ka_off.p,
                pos.p, first_hit.p, tbits, keys.p, idx.p, recs.p);
         if (W > 1) {   // a single window is already in input order
             keys_out.alloc(b->Tin, s); idx_out.alloc(b->Tin, s);

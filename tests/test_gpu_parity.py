@@ -264,8 +264,10 @@ def test_batched_windows_vs_oracle(n_tiles, knn, k_types, seed):
             assert nv1[0] == nv[w] and nc1[0] == nc[w] and np.array_equal(cuts1[0, :k], cuts[w, :k])
 
 
-def test_precomputed_triangulation_batched_vs_oracle():
-    """Global triangulation in id space remapped into overlapping windows + unconstrained-node removal."""
+@pytest.mark.parametrize("step", [11.0, 5.0])
+def test_precomputed_triangulation_batched_vs_oracle(step):
+    """Global triangulation in id space remapped into overlapping windows + unconstrained-node removal.  step 11: a row lies in at
+    most four windows (the remap's one-sector row table); step 5: in up to nine (the general walk over the row's window list)."""
     from same_b200 import _lib as L
     from same_b200 import datagen
     from same_b200.device import Section
@@ -285,7 +287,7 @@ def test_precomputed_triangulation_batched_vs_oracle():
     tri_g = tri_g[side < 0.9]
     tri_vid = vid[tri_g]
     ext = max(a_xy.max(), r_xy.max()) + 1
-    rects = np.array([[x0, x0 + 14.0, y0, y0 + 14.0] for x0 in np.arange(0, ext, 11.0) for y0 in np.arange(0, ext, 11.0)])
+    rects = np.array([[x0, x0 + 14.0, y0, y0 + 14.0] for x0 in np.arange(0, ext, step) for y0 in np.arange(0, ext, step)])
     radius, knn = 1.0, 6
     kw = dict(radius=radius, knn=knn, dist_ct_coeff=1.0, min_angle_deg=12, ignore_same_type_triangles=True, max_matches=1)
     with Section(a_xy, r_xy, a_prob, r_prob, tA, tR, sA, sR) as sec, sec.batch(rects) as b:
@@ -452,3 +454,24 @@ def test_page_locked_inputs_may_be_reused_after_wait_uploads():
             keepA, keepR, pairs = O.find_knn_within_radius(src["a_xy"], src["r_xy"], 1.2, 6)
             cost = O.pair_cost(pairs, src["a_xy"][keepA], src["r_xy"][keepR], src["a_prob"][keepA], src["r_prob"][keepR], 1.5)
             assert np.array_equal(b.get(L.PAIRS), pairs) and np.array_equal(b.get(L.COST), cost)
+
+
+@pytest.mark.parametrize("n_types,knn", [(0, 4), (1, 3), (2, 8), (3, 5), (4, 8), (6, 7), (7, 8), (13, 6)])
+def test_pair_cost_over_type_counts(n_types, knn):
+    """The pair-cost kernel gathers packed row records [x, y, p_0..p_{K-1}, padding]: every record width (specialised 1-4
+    double2 words, general above) and both power-of-two and other knn against the oracle, bit-exact (src/same.py:1183-1188)."""
+    from same_b200 import _lib as L
+    from same_b200.device import Section
+    rng = np.random.default_rng(100 + n_types)
+    a, r = rng.uniform(0, 30, size=(2500, 2)), rng.uniform(0, 30, size=(2700, 2))
+    pa = rng.dirichlet(np.ones(max(n_types, 1)), size=2500)[:, :n_types]
+    pr = rng.dirichlet(np.ones(max(n_types, 1)), size=2700)[:, :n_types]
+    rects = np.array([[0, 17.0, 0, 31.0], [13.0, 31.0, 0, 31.0], [100.0, 101.0, 0, 1.0]])   # two overlapping windows and an empty one
+    with Section(a, r, pa, pr) as sec, sec.batch(rects) as b:
+        b.candidates(2.0, knn, False, 0.7)
+        for w in range(2):
+            ra, rr = O.subset(a, *rects[w]), O.subset(r, *rects[w])
+            keepA, keepR, pairs = O.find_knn_within_radius(a[ra], r[rr], 2.0, knn)
+            cost = O.pair_cost(pairs, a[ra][keepA], r[rr][keepR], pa[ra][keepA], pr[rr][keepR], 0.7)
+            assert np.array_equal(b.get_window(L.PAIRS, w), pairs)
+            assert np.array_equal(b.get_window(L.COST, w), cost)
