@@ -883,7 +883,9 @@ def main():
         s = stats
         alg = {   # algorithmic bytes per launch, this rank's batch
             "k_knn<8>": 20 * s["nAi"] + 20 * s["nRi"] + (4 * KNN + 4) * s["nAi"],
-            "k_emit_pairs": (4 * KNN + 4) * s["nAi"] + (16 + 8 * K) * (s["nKA"] + s["nKR"]) + 16 * s["P"],
+            # candidate table in; one packed record (x, y, K probabilities padded to an even count) per kept row of both frames and
+            # one (kept index, row) word per kept reference instance gathered; pair + cost out
+            "k_emit_pairs": (4 * KNN + 4) * s["nAi"] + 8 * ((2 + K + 1) // 2 * 2) * (s["nKA"] + s["nKR"]) + 8 * s["nKR"] + 16 * s["P"],
             "k_separation": 13 * s["T"] + 4 * s["nKA"] + 16 * s["nKR"] + 16 * min(s["viol"], 1000 * len(rects)),
             "k_postsolve": 12 * s["T"] + 20 * s["nKA"] + 16 * s["nKR"] + 21 * s["T"],
             "k_tri_classify": 12 * s["Tin"] + 20 * s["nKA"] + 9 * s["Tin"],
@@ -902,6 +904,8 @@ def main():
             pass
         kernels = {}
         for name, (cnt, ms) in sorted(prof.items(), key=lambda kv: -kv[1][1]):
+            if name.startswith("k_emit_pairs<"):
+                name = "k_emit_pairs"            # (instantiated per record width)
             per = ms / cnt
             ent = {"launches_per_step": cnt / 3.0, "avg_ms": per, "share_of_step": None}
             if name in alg:
