@@ -156,7 +156,7 @@ int same_section_create(int device, void *stream, int64_t n_aligned, int64_t n_r
         } catch (...) {
             cudaStream_t aux = sec->aux_stream;
             cudaEvent_t ev = sec->aux_ready;
-            if (aux) cudaStreamSynchronize(aux);   // before the buffers it writes are freed
+            if (aux) stream_wait(aux);   // before the buffers it writes are freed
             delete sec;
             if (aux) cudaStreamDestroy(aux);
             if (ev) cudaEventDestroy(ev);
@@ -183,11 +183,11 @@ int same_section_destroy(same_section_t *h) {
         cudaStream_t s = sec->stream, aux = sec->aux_stream;
         cudaEvent_t ev = sec->aux_ready;
         bool own = sec->own_stream;
-        CK(cudaStreamSynchronize(s));
-        if (aux) CK(cudaStreamSynchronize(aux));   // the uploads write buffers that are freed (stream-ordered, on `s`) right below
+        CK(stream_wait(s));
+        if (aux) CK(stream_wait(aux));   // the uploads write buffers that are freed (stream-ordered, on `s`) right below
         delete sec;
-        CK(cudaStreamSynchronize(s));
-        if (aux) { CK(cudaStreamSynchronize(aux)); CK(cudaStreamDestroy(aux)); }
+        CK(stream_wait(s));
+        if (aux) { CK(stream_wait(aux)); CK(cudaStreamDestroy(aux)); }
         if (ev) CK(cudaEventDestroy(ev));
         if (own) CK(cudaStreamDestroy(s));
     });
@@ -249,10 +249,10 @@ int same_batch_destroy(same_batch_t *h) {
         if (!b) return;
         CK(cudaSetDevice(b->sec->device));
         cudaStream_t s = b->stream;
-        CK(cudaStreamSynchronize(s));   // nothing queued may still read the batch's page-locked staging blocks
+        CK(stream_wait(s));   // nothing queued may still read the batch's page-locked staging blocks
         batch_pin_release(b);
         delete b;
-        CK(cudaStreamSynchronize(s));
+        CK(stream_wait(s));
     });
 }
 
@@ -354,7 +354,7 @@ int same_batch_get(same_batch_t *h, int what, int64_t elem_lo, int64_t elem_hi, 
         if (elem_hi > elem_lo) {
             REQUIRE(dst, SAME_E_ARG, "dst is NULL");
             CK(cudaMemcpyAsync(dst, (const char *)v.p + elem_lo * v.esize, (size_t)((elem_hi - elem_lo) * v.esize), cudaMemcpyDefault, b->stream));
-            CK(cudaStreamSynchronize(b->stream));
+            CK(stream_wait(b->stream));
         }
     });
 }
@@ -372,7 +372,7 @@ static void get_many(Batch *b, int64_t n, const int32_t *what, const int64_t *lo
         if (hi[k] > lo[k])
             CK(cudaMemcpyAsync(dst[k], (const char *)views[k].p + lo[k] * views[k].esize, (size_t)((hi[k] - lo[k]) * views[k].esize), cudaMemcpyDefault,
                                b->stream));
-    if (sync) CK(cudaStreamSynchronize(b->stream));
+    if (sync) CK(stream_wait(b->stream));
 }
 
 int same_batch_get_many(same_batch_t *h, int64_t n, const int32_t *what, const int64_t *lo, const int64_t *hi, void *const *dst) {
@@ -406,7 +406,7 @@ int same_batch_stat(same_batch_t *h, int what, int64_t *value) {
         if (b->knn_evals.p) {
             unsigned long long v = 0;
             CK(cudaMemcpyAsync(&v, b->knn_evals.p, sizeof(v), cudaMemcpyDeviceToHost, b->stream));
-            CK(cudaStreamSynchronize(b->stream));
+            CK(stream_wait(b->stream));
             *value = (int64_t)v;
         }
     });
@@ -434,7 +434,7 @@ int same_mempool_reserve(int device, int64_t bytes) {
         void *p = nullptr;
         CK(cudaMallocAsync(&p, (size_t)bytes, (cudaStream_t)0));
         CK(cudaFreeAsync(p, (cudaStream_t)0));
-        CK(cudaStreamSynchronize((cudaStream_t)0));
+        CK(stream_wait((cudaStream_t)0));
     });
 }
 int same_stream_create(int device, void **stream) {
@@ -450,7 +450,7 @@ int same_stream_destroy(int device, void *stream) {
     return guarded([&] {
         if (!stream) return;
         CK(cudaSetDevice(device));
-        CK(cudaStreamSynchronize((cudaStream_t)stream));
+        CK(stream_wait((cudaStream_t)stream));
         CK(cudaStreamDestroy((cudaStream_t)stream));
     });
 }

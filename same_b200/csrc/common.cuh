@@ -79,7 +79,7 @@ struct ProfScope {
         kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);                                         \
         same::g_launches.fetch_add(1, std::memory_order_relaxed);                                           \
         CK(cudaGetLastError());                                                                             \
-        if (same::g_debug) CK(cudaStreamSynchronize(stream));                                               \
+        if (same::g_debug) CK(same::stream_wait(stream));                                                   \
     } while (0)
 
 // Host waits for a stream.  Default: cudaStreamSynchronize (the calling thread spins: lowest latency, what a solver callback
@@ -87,8 +87,7 @@ struct ProfScope {
 // instead — for hosts where several ranks with several section threads each share few cores and spinning waiters steal the
 // cores that the other ranks' launches need.
 extern std::atomic<int> g_host_wait_yield;
-cudaError_t stream_wait(cudaStream_t s);
-#define cudaStreamSynchronize(s) same::stream_wait(s)
+cudaError_t stream_wait(cudaStream_t s);   // every host wait in this library goes through it
 
 inline unsigned blocks_for(i64 n, int per_block) { return (unsigned)std::max<i64>(1, (n + per_block - 1) / per_block); }
 

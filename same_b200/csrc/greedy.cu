@@ -126,7 +126,7 @@ static int greedy_select_dev(const i32 *nodes, const double *key, const unsigned
         for (;;) {
             LAUNCH(k_greedy_propose<D>, blocks, 256, 0, s, nodes, rank.p, n, (unsigned)rounds, used, alive.p, best.p, d_alive.p + rounds);
             CK(cudaMemcpyAsync(h_alive, d_alive.p + rounds, sizeof(i32), cudaMemcpyDeviceToHost, s));
-            CK(cudaStreamSynchronize(s));
+            CK(stream_wait(s));
             if (*h_alive == 0) break;
             if (rounds == GREEDY_MAX_ROUNDS) {
                 LAUNCH(k_greedy_tail<D>, 1, 32, 0, s, nodes, idx2.p, n, used, alive.p, selected);
@@ -173,14 +173,14 @@ void greedy_select_arrays(int device, i64 n, int degree, const i32 *nodes, const
         const int rounds = greedy_select_any(degree, d_nodes.p, d_key.p, eligible ? d_el.p : nullptr, n, n_nodes, d_sel.p, d_used.p, s);
         if (n && selected) CK(cudaMemcpyAsync(selected, d_sel.p, (size_t)n, cudaMemcpyDefault, s));
         if (n_nodes && used_out) CK(cudaMemcpyAsync(used_out, d_used.p, (size_t)n_nodes, cudaMemcpyDefault, s));
-        CK(cudaStreamSynchronize(s));
+        CK(stream_wait(s));
         if (rounds_out) *rounds_out = rounds;
     } catch (...) {
-        cudaStreamSynchronize(s);
+        stream_wait(s);
         cudaStreamDestroy(s);
         throw;
     }
-    CK(cudaStreamSynchronize(s));
+    CK(stream_wait(s));
     CK(cudaStreamDestroy(s));
 }
 
@@ -227,14 +227,14 @@ void collapse_select_arrays(int device, i64 n, const double *xy, const i32 *type
             CK(cudaMemcpyAsync(selected, d_sel.p, (size_t)T, cudaMemcpyDefault, s));
             if (perim_out) CK(cudaMemcpyAsync(perim_out, d_perim.p, sizeof(double) * (size_t)T, cudaMemcpyDefault, s));
         }
-        CK(cudaStreamSynchronize(s));
+        CK(stream_wait(s));
         if (rounds_out) *rounds_out = rounds;
     } catch (...) {
-        cudaStreamSynchronize(s);
+        stream_wait(s);
         cudaStreamDestroy(s);
         throw;
     }
-    CK(cudaStreamSynchronize(s));
+    CK(stream_wait(s));
     CK(cudaStreamDestroy(s));
 }
 
@@ -291,13 +291,13 @@ void segment_mean_arrays(int device, i64 n_rows, i64 C, const double *values, i6
             LAUNCH(k_member_mean, blocks_for(G * C, 128), 128, 0, s, d_v.p, C, d_pos.p, d_ptr.p, G, d_out.p);
             CK(cudaMemcpyAsync(out, d_out.p, sizeof(double) * (size_t)(G * C), cudaMemcpyDefault, s));
         }
-        CK(cudaStreamSynchronize(s));
+        CK(stream_wait(s));
     } catch (...) {
-        cudaStreamSynchronize(s);
+        stream_wait(s);
         cudaStreamDestroy(s);
         throw;
     }
-    CK(cudaStreamSynchronize(s));
+    CK(stream_wait(s));
     CK(cudaStreamDestroy(s));
 }
 

@@ -4,7 +4,6 @@
 
 namespace same {
 
-#undef cudaStreamSynchronize
 std::atomic<int> g_host_wait_yield{getenv("SAME_B200_HOST_WAIT") != nullptr && std::string(getenv("SAME_B200_HOST_WAIT")) == "yield" ? 1 : 0};
 cudaError_t stream_wait(cudaStream_t s) {
     if (!g_host_wait_yield.load(std::memory_order_relaxed)) return cudaStreamSynchronize(s);
@@ -23,7 +22,6 @@ cudaError_t stream_wait(cudaStream_t s) {
     if (e != cudaSuccess) return e;
     return cudaEventSynchronize(ev);
 }
-#define cudaStreamSynchronize(s) same::stream_wait(s)
 thread_local std::string g_err;
 std::atomic<long long> g_launches{0};
 bool g_prof = false;
@@ -45,7 +43,7 @@ void upload_offsets(const std::vector<i64> &h, DevBuf<i32> &d, cudaStream_t s) {
     for (size_t i = 0; i < h.size(); ++i) t[i] = (i32)h[i];
     d.alloc((i64)t.size(), s);
     CK(cudaMemcpyAsync(d.p, t.data(), sizeof(i32) * t.size(), cudaMemcpyHostToDevice, s));
-    CK(cudaStreamSynchronize(s));  // t goes out of scope
+    CK(stream_wait(s));  // t goes out of scope
 }
 
 // ---- small transfers without the copy engines (see common.cuh) ----------------------------------------
@@ -156,7 +154,7 @@ void batch_pin_release(Batch *b) {
 }
 
 void batch_sync(Batch *b) {
-    CK(cudaStreamSynchronize(b->stream));
+    CK(stream_wait(b->stream));
     const i64 W = b->W;
     if (b->pend_cand) {
         const i32 *h = b->pin_cand();
@@ -271,7 +269,7 @@ void section_build(Section *sec, const double *a_xy, const double *r_xy, const d
     if (nR > 0) LAUNCH(k_bbox, std::min<unsigned>(blocks_for(nR, 256), 1184), 256, 0, s, sec->r_xy.p, nR, bb.p);
     unsigned long long *h = (unsigned long long *)sec->arena.get(4 * sizeof(unsigned long long));
     small_d2h(h, bb.p, 4 * sizeof(unsigned long long), s);
-    CK(cudaStreamSynchronize(s));
+    CK(stream_wait(s));
     for (int i = 0; i < 4; ++i) sec->bbox[i] = (nA + nR > 0) ? dec_f64(h[i]) : 0.0;
 }
 
@@ -335,7 +333,7 @@ void section_count_rects(Section *sec, i64 m, const double *rects, i64 *cntA, i6
     if (sec->nR > 0) LAUNCH(k_rect_count, dim3(blocks_for(sec->nR, SUB_CHUNK), (unsigned)m), SUB_THREADS, 0, s, sec->r_xy.p, sec->nR, d_r.p, (i32 *)nullptr, tot.p + m);
     std::vector<unsigned long long> h(2 * m);
     CK(cudaMemcpyAsync(h.data(), tot.p, sizeof(unsigned long long) * 2 * m, cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
+    CK(stream_wait(s));
     for (i64 i = 0; i < m; ++i) { cntA[i] = (i64)h[i]; cntR[i] = (i64)h[m + i]; }
 }
 
@@ -655,7 +653,7 @@ void section_set_triangles(Section *sec, const i64 *a_vid, const i64 *tri_vid, i
     upload(d_tri, tri_vid, m, s);
     sec->tri_rows.alloc(m, s);
     sec->Tg = n_tri;
-    if (m == 0) { CK(cudaStreamSynchronize(s)); return; }
+    if (m == 0) { CK(stream_wait(s)); return; }
     if (!a_vid) {
         LAUNCH(k_resolve_identity, blocks_for(m, 256), 256, 0, s, d_tri.p, m, n, sec->tri_rows.p);
     } else {
@@ -674,7 +672,7 @@ void section_set_triangles(Section *sec, const i64 *a_vid, const i64 *tri_vid, i
         g_launches.fetch_add(1, std::memory_order_relaxed);
         LAUNCH(k_resolve_vids, blocks_for(m, 256), 256, 0, s, vid_out.p, row_out.p, n, d_tri.p, m, sec->tri_rows.p);
     }
-    CK(cudaStreamSynchronize(s));
+    CK(stream_wait(s));
 }
 
 }  // namespace same

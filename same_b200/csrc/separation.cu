@@ -214,13 +214,13 @@ void batch_uncertain(Batch *b, int which, i64 cap, i64 *n, i32 *tri_idx) {
     } else {
         i32 *h = b->pin_misc();
         small_d2h(h, b->unc_count.p + which, sizeof(i32), s);
-        CK(cudaStreamSynchronize(s));
+        CK(stream_wait(s));
         *n = h[0];
     }
     const i64 m = std::min<i64>(std::min<i64>(*n, UNC_CAP), cap);
     if (m > 0) {
         CK(cudaMemcpyAsync(tri_idx, b->unc_list[which].p, sizeof(i32) * (size_t)m, cudaMemcpyDefault, s));
-        CK(cudaStreamSynchronize(s));
+        CK(stream_wait(s));
     }
 }
 
@@ -316,13 +316,13 @@ void postsolve_arrays(int device, i64 T, const i32 *tri, i64 nA, const double *a
             CK(cudaMemcpyAsync(area_after, d_aa.p, sizeof(double) * T, cudaMemcpyDefault, s));
             CK(cudaMemcpyAsync(flipped, d_fl.p, T, cudaMemcpyDefault, s));
         }
-        CK(cudaStreamSynchronize(s));
+        CK(stream_wait(s));
     } catch (...) {
-        cudaStreamSynchronize(s);
+        stream_wait(s);
         cudaStreamDestroy(s);
         throw;
     }
-    CK(cudaStreamSynchronize(s));
+    CK(stream_wait(s));
     CK(cudaStreamDestroy(s));
 }
 

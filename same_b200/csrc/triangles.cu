@@ -253,7 +253,7 @@ void batch_triangles_set(Batch *b, const i32 *tri, const i64 *tri_off) {
     b->tin.alloc(b->Tin, s);
     if (b->Tin > 0) CK(cudaMemcpyAsync(b->tin.p, tri, sizeof(int3) * (size_t)b->Tin, cudaMemcpyDefault, s));
     upload_offsets(b->tin_off, b->d_tin_off, s);
-    CK(cudaStreamSynchronize(s));   // the caller's triangle array (possibly page-locked) was read asynchronously
+    CK(stream_wait(s));   // the caller's triangle array (possibly page-locked) was read asynchronously
     b->stage = 2;
 }
 
@@ -339,7 +339,7 @@ void batch_tri_override(Batch *b, i64 n, const i32 *idx, const unsigned char *cl
     CK(cudaMemcpyAsync(d_i.p, idx, sizeof(i32) * n, cudaMemcpyDefault, s));
     CK(cudaMemcpyAsync(d_c.p, cls, n, cudaMemcpyDefault, s));
     LAUNCH(k_tri_override, blocks_for(n, 256), 256, 0, s, n, d_i.p, d_c.p, b->Tin, b->cls.p);
-    CK(cudaStreamSynchronize(s));
+    CK(stream_wait(s));
 }
 
 // ---- a6 step 2 -----------------------------------------------------------------------------------
