@@ -21,6 +21,7 @@ from __future__ import annotations
 import argparse
 import json
 import os
+import re
 import subprocess
 import sys
 import threading
@@ -479,7 +480,7 @@ def separation_latency_arm(local_rank):
                 b.separation(int(x_dev.data_ptr()), cap=cap)
             prof = L.profile_report()
             L.profile_enable(False)
-            kern = {k: v[1] / v[0] * 1e3 for k, v in prof.items() if k in ("k_match_rows", "k_separation", "k_copy_words")}
+            kern = {k: v[1] / v[0] * 1e3 for k, v in prof.items() if k in ("k_match_rows", "k_copy_words") or k.startswith("k_separation")}
             nv, nc, _ = b.separation(x_host, cap=cap)
             out[label] = {"cells": [len(ref), len(qry)], "pairs": int(len(pairs)), "triangles": int(b.length(L.TRI)), "checked": int(nc[0]),
                           "violated": int(nv[0]), "call_us_host_x": host_med, "call_us_host_x_p95": host_p95, "call_us_device_x": dev_med,
@@ -904,8 +905,9 @@ def main():
             pass
         kernels = {}
         for name, (cnt, ms) in sorted(prof.items(), key=lambda kv: -kv[1][1]):
-            if name.startswith("k_emit_pairs<"):
-                name = "k_emit_pairs"            # (instantiated per record width)
+            name = re.sub(r"^(k_emit_pairs|k_separation|k_remap_count|k_subset_count)<\d+>$", r"\1", name)   # (instantiated per record width / tile size)
+            if name in kernels:
+                continue                         # (a second instantiation of the same kernel: the larger share is already listed)
             per = ms / cnt
             ent = {"launches_per_step": cnt / 3.0, "avg_ms": per, "share_of_step": None}
             if name in alg:
