@@ -3,7 +3,7 @@
 import collections, os, re, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OBJ = os.path.join(ROOT, "same_b200", "csrc", "_obj")
-TOP = ["k_knn<8>", "k_emit_pairs", "k_compact_frames", "k_bin_scatter", "k_subset_count", "k_separation", "k_match_rows", "k_tri_classify",
+TOP = ["k_knn<8>", "k_emit_pairs<3>", "k_row_table", "k_pack_records", "k_compact_frames", "k_bin_scatter", "k_subset_count", "k_separation", "k_match_rows", "k_tri_classify",
        "k_remap_count", "k_compact_pairs", "k_group_fill", "k_postsolve", "k_tri_tables"]
 out = ["# ptxas resources and SASS instruction mix of the hot kernels (round 2)\n",
        "`nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -Xptxas -v`; SASS from `cuobjdump -sass` of the objects in",
