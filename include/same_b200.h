@@ -247,6 +247,13 @@ SAME_API int same_stream_destroy(int device, void *stream);
 /* How host threads wait for the device: 0 (default) = spin (cudaStreamSynchronize: lowest latency), 1 = sleep on a blocking-sync
  * event (yields the core: for hosts where many ranks / section threads share few cores).  Also SAME_B200_HOST_WAIT=yield. */
 SAME_API int same_set_host_wait(int yield);
+/* The library's own memory checker (for hosts where compute-sanitizer cannot run): enable = 1 / 0 switches guard mode for buffers
+ * allocated from now on (-1 = leave as is; 2 = self-test: overrun a guarded probe buffer by one word on purpose, the corrupted count
+ * must rise by one; SAME_B200_GUARD=1 sets the mode at load time).  In guard mode every device buffer has a
+ * 256-byte canary zone on both sides, verified when the buffer is released, and its body is filled with 0xCD on every
+ * (re)allocation, so that reads of memory the library did not write change the results.  Waits for the device, then returns the
+ * number of buffers whose zones were found corrupted and the number of buffers checked since the library was loaded. */
+SAME_API int same_debug_guard(int enable, int64_t *corrupted, int64_t *checked);
 /* Counters of a batch: SAME_STAT_KNN_EVALUATIONS = distance evaluations of the last same_batch_candidates (counted only while
  * same_profile_enable(1) is in effect, -1 otherwise): bench.py's compute-side roofline = evaluations x 5 flops / kernel time. */
 enum { SAME_STAT_KNN_EVALUATIONS = 1 };

@@ -53,7 +53,7 @@ SYMBOLS = [
     "same_batch_get", "same_elem_size", "same_batch_sync", "same_batch_stream", "same_launch_count",
     "same_profile_enable", "same_profile_report", "same_batch_get_many", "same_batch_get_many_async", "same_pinned_alloc", "same_pinned_free",
     "same_postsolve_arrays", "same_batch_mip_start", "same_greedy_select", "same_collapse_select", "same_segment_mean", "same_measure_fp64_peak", "same_section_wait_uploads",
-    "same_stream_create", "same_stream_destroy", "same_mempool_stats", "same_mempool_reserve", "same_set_host_wait", "same_batch_uncertain", "same_batch_stat",
+    "same_stream_create", "same_stream_destroy", "same_mempool_stats", "same_mempool_reserve", "same_set_host_wait", "same_batch_uncertain", "same_batch_stat", "same_debug_guard",
 ]
 
 
@@ -125,6 +125,7 @@ def load():
     lib.same_stream_destroy.argtypes = [i32, vp]
     lib.same_mempool_reserve.argtypes = [i32, i64]
     lib.same_set_host_wait.argtypes = [i32]
+    lib.same_debug_guard.argtypes = [i32, C.POINTER(i64), C.POINTER(i64)]
     lib.same_mempool_stats.argtypes = [i32, C.POINTER(i64), C.POINTER(i64)]
     lib.same_profile_report.argtypes = [C.c_char_p, i64]
     lib.same_profile_report.restype = i64
@@ -167,6 +168,15 @@ def mempool_stats(device=0):
 def set_host_wait(yield_core: bool):
     """How host threads wait for the GPU: spin (False, default, lowest latency) or sleep on a blocking event (True)."""
     check(load().same_set_host_wait(int(bool(yield_core))))
+
+
+def debug_guard(enable=None):
+    """The library's own memory checker (same_debug_guard): enable True / False switches guard mode for buffers allocated from now
+    on, None leaves it, "selftest" overruns a guarded probe buffer on purpose (the first count must rise by one);
+    -> (buffers found with a corrupted canary zone, buffers checked) since the library was loaded."""
+    c, k = C.c_int64(0), C.c_int64(0)
+    check(load().same_debug_guard(-1 if enable is None else (2 if enable == "selftest" else int(bool(enable))), C.byref(c), C.byref(k)))
+    return int(c.value), int(k.value)
 
 
 def mempool_reserve(device, nbytes):

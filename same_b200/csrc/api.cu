@@ -398,6 +398,14 @@ int same_set_host_wait(int yield) {
     same::g_host_wait_yield.store(yield ? 1 : 0);
     return SAME_OK;
 }
+int same_debug_guard(int enable, int64_t *corrupted, int64_t *checked) {
+    return guarded([&] {
+        i64 c = 0, k = 0;
+        same::guard_report(enable, &c, &k);
+        if (corrupted) *corrupted = c;
+        if (checked) *checked = k;
+    });
+}
 int same_batch_stat(same_batch_t *h, int what, int64_t *value) {
     BATCH_CALL(h, {
         REQUIRE(value, SAME_E_ARG, "value is NULL");

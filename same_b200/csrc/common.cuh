@@ -91,31 +91,65 @@ cudaError_t stream_wait(cudaStream_t s);   // every host wait in this library go
 
 inline unsigned blocks_for(i64 n, int per_block) { return (unsigned)std::max<i64>(1, (n + per_block - 1) / per_block); }
 
+// Guard mode (SAME_B200_GUARD=1 / same_debug_guard): the library's own memory checker for boxes where compute-sanitizer is not
+// available.  Every device buffer is allocated with a GUARD_BYTES zone of 0xA5 in front of and behind it and its body is filled
+// with 0xCD on EVERY alloc() call (contents are never preserved across alloc), so a kernel that reads memory it did not write sees
+// poison — NaN-like doubles, huge negative ints — and changes a parity result, and a kernel that writes outside its buffer
+// breaks a zone: the zones are verified on the device when the buffer is released (guard_check counts corrupted zones,
+// same_debug_guard reports them).
+constexpr size_t GUARD_BYTES = 256;
+extern bool g_guard;
+void guard_fill(void *raw, size_t body_bytes, cudaStream_t s);     // zones + poison
+void guard_check(void *raw, size_t body_bytes, cudaStream_t s);    // zones still intact?
+void guard_report(int enable, i64 *corrupted, i64 *checked);
+
 // stream-ordered device buffer
 template <typename T>
 struct DevBuf {
     T *p = nullptr;
     i64 n = 0;
     cudaStream_t s = nullptr;
+    bool guarded = false;
     DevBuf() {}
     DevBuf(const DevBuf &) = delete;
     DevBuf &operator=(const DevBuf &) = delete;
     ~DevBuf() { release(); }
     void release() {
-        if (p) cudaFreeAsync(p, s);
+        if (p) {
+            if (guarded) {
+                void *raw = (char *)p - GUARD_BYTES;
+                guard_check(raw, sizeof(T) * (size_t)n, s);
+                cudaFreeAsync(raw, s);
+            } else {
+                cudaFreeAsync(p, s);
+            }
+        }
         p = nullptr;
         n = 0;
+        guarded = false;
     }
     // contents are NOT preserved
     void alloc(i64 count, cudaStream_t stream) {
-        if (count <= n && p) { s = stream; return; }
+        if (count <= n && p) {
+            s = stream;
+            if (guarded) guard_fill((char *)p - GUARD_BYTES, sizeof(T) * (size_t)n, stream);
+            return;
+        }
         release();
         s = stream;
         n = std::max<i64>(count, 1);
-        CK(cudaMallocAsync((void **)&p, sizeof(T) * (size_t)n, stream));
+        if (g_guard) {
+            void *raw = nullptr;
+            CK(cudaMallocAsync(&raw, sizeof(T) * (size_t)n + 2 * GUARD_BYTES, stream));
+            p = (T *)((char *)raw + GUARD_BYTES);
+            guarded = true;
+            guard_fill(raw, sizeof(T) * (size_t)n, stream);
+        } else {
+            CK(cudaMallocAsync((void **)&p, sizeof(T) * (size_t)n, stream));
+        }
     }
     void zero(cudaStream_t stream) { CK(cudaMemsetAsync(p, 0, sizeof(T) * (size_t)n, stream)); }
-    void swap(DevBuf &o) { std::swap(p, o.p); std::swap(n, o.n); std::swap(s, o.s); }
+    void swap(DevBuf &o) { std::swap(p, o.p); std::swap(n, o.n); std::swap(s, o.s); std::swap(guarded, o.guarded); }
 };
 
 struct Scratch {

@@ -22,6 +22,54 @@ cudaError_t stream_wait(cudaStream_t s) {
     if (e != cudaSuccess) return e;
     return cudaEventSynchronize(ev);
 }
+bool g_guard = getenv("SAME_B200_GUARD") != nullptr && getenv("SAME_B200_GUARD")[0] == '1';
+static int *g_guard_bad = nullptr;   // page-locked, device-mapped: [0] corrupted zones seen, [1] buffers checked
+static std::mutex g_guard_mu;
+__global__ void k_guard_check(const unsigned char *__restrict__ raw, size_t body, int *__restrict__ bad) {
+    const size_t i = threadIdx.x;   // one block of GUARD_BYTES threads: front zone, then back zone
+    const bool broken = raw[i] != 0xA5 || raw[GUARD_BYTES + body + i] != 0xA5;
+    if (__syncthreads_or(broken) && threadIdx.x == 0) atomicAdd_system(bad, 1);
+    if (threadIdx.x == 0) atomicAdd_system(bad + 1, 1);
+}
+static int *guard_counters() {
+    std::lock_guard<std::mutex> lk(g_guard_mu);
+    if (!g_guard_bad) {
+        CK(cudaHostAlloc((void **)&g_guard_bad, 2 * sizeof(int), cudaHostAllocMapped | cudaHostAllocPortable));
+        g_guard_bad[0] = g_guard_bad[1] = 0;
+    }
+    return g_guard_bad;
+}
+void guard_fill(void *raw, size_t body, cudaStream_t s) {
+    CK(cudaMemsetAsync(raw, 0xA5, GUARD_BYTES, s));
+    CK(cudaMemsetAsync((char *)raw + GUARD_BYTES, 0xCD, body, s));
+    CK(cudaMemsetAsync((char *)raw + GUARD_BYTES + body, 0xA5, GUARD_BYTES, s));
+}
+void guard_check(void *raw, size_t body, cudaStream_t s) {   // (called from destructors: no throw)
+    int *bad = nullptr;
+    try { bad = guard_counters(); } catch (...) { return; }
+    int *dbad = nullptr;
+    if (cudaHostGetDevicePointer((void **)&dbad, bad, 0) != cudaSuccess) return;
+    k_guard_check<<<1, (unsigned)GUARD_BYTES, 0, s>>>((const unsigned char *)raw, body, dbad);
+}
+__global__ void k_guard_selftest(int *p, int n) { p[n] = 1; }   // one word past the end: lands in the back zone
+void guard_report(int enable, i64 *corrupted, i64 *checked) {
+    if (enable == 2) {   // self-test of the checker: a deliberate overrun of a guarded buffer must be counted
+        const bool was = g_guard;
+        g_guard = true;
+        {
+            DevBuf<int> probe;
+            probe.alloc(100, nullptr);
+            k_guard_selftest<<<1, 1>>>(probe.p, 100);
+        }
+        g_guard = was;
+    } else if (enable >= 0) {
+        g_guard = enable != 0;
+    }
+    CK(cudaDeviceSynchronize());
+    int *bad = guard_counters();
+    if (corrupted) *corrupted = bad[0];
+    if (checked) *checked = bad[1];
+}
 thread_local std::string g_err;
 std::atomic<long long> g_launches{0};
 bool g_prof = false;

@@ -24,3 +24,24 @@ def pytest_collection_modifyitems(config, items):
     for it in items:
         if "gpu" in it.keywords:
             it.add_marker(skip)
+
+
+def pytest_sessionfinish(session, exitstatus):
+    """SAME_B200_GUARD=1 python -m pytest tests -m gpu: the whole suite on canary-guarded, poisoned device buffers (the library's own
+    memory checker, include/same_b200.h same_debug_guard).  Report the counters and fail the session if any zone was overwritten."""
+    if os.environ.get("SAME_B200_GUARD", "0")[:1] != "1":
+        return
+    try:
+        import torch
+        if not torch.cuda.is_available():
+            return
+        from same_b200 import _lib as L
+        bad, checked = L.debug_guard()
+    except Exception as e:   # the library never loaded in this session
+        print(f"\n[guard] no counters: {e}")
+        return
+    expected = int(os.environ.get("SAME_B200_GUARD_EXPECTED", "0"))   # deliberate overruns of the checker's own self-test
+    print(f"\n[guard] device buffers checked on release: {checked}; canary zones found overwritten: {bad} "
+          f"(of which {expected} on purpose, tests/test_gpu_guard.py)")
+    if bad != expected:
+        session.exitstatus = 1
