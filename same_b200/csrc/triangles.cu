@@ -260,15 +260,11 @@ void batch_triangles_set(Batch *b, const i32 *tri, const i64 *tri_off) {
 // ---- a6 step 1: classification ---------------------------------------------------------------
 // 1-D np.linalg.norm / np.dot go through BLAS ddot == fma(y1,y2,x1*x2)
 __device__ __forceinline__ double norm2_blas(double x, double y) { return __dsqrt_rn(__fma_rn(y, y, __dmul_rn(x, x))); }
-// compute_angle(p1, p2, p3): angle at p2 in degrees (src/helpers.py:278-288)
-__device__ __forceinline__ double angle_at(double2 p1, double2 p2, double2 p3) {
-    const double v1x = __dsub_rn(p1.x, p2.x), v1y = __dsub_rn(p1.y, p2.y);
-    const double v2x = __dsub_rn(p3.x, p2.x), v2y = __dsub_rn(p3.y, p2.y);
-    const double n1 = norm2_blas(v1x, v1y), n2 = norm2_blas(v2x, v2y);
-    if (n1 == 0.0 || n2 == 0.0) return 0.0;
-    double c = __ddiv_rn(__fma_rn(v1y, v2y, __dmul_rn(v1x, v2x)), __dmul_rn(n1, n2));
-    c = fmin(fmax(c, -1.0), 1.0);
-    return __dmul_rn(acos(c), 57.29577951308232);  // np.degrees: x * (180/pi)
+// Clipped cosine of the angle between v1 and v2 as compute_angle forms it (src/helpers.py:278-288: dot / (|v1| |v2|), np.clip),
+// from the dot product and the two norms; a zero-length side gives angle 0 there, i.e. cosine 1 here.
+__device__ __forceinline__ double angle_cos(double dot, double n1, double n2) {
+    if (n1 == 0.0 || n2 == 0.0) return 1.0;
+    return fmin(fmax(__ddiv_rn(dot, __dmul_rn(n1, n2)), -1.0), 1.0);
 }
 
 __global__ void __launch_bounds__(256, 4) k_tri_classify(const int3 *__restrict__ tin, i64 Tin, const i32 *__restrict__ tin_off, const i32 *__restrict__ ka_off, int W,
@@ -292,8 +288,17 @@ __global__ void __launch_bounds__(256, 4) k_tri_classify(const int3 *__restrict_
     else {
         k = SAME_TRI_KEEP;
         if (use_angle) {  // helpers.py:315-321
-            const double a1 = angle_at(p2, p1, p3), a2 = angle_at(p1, p2, p3), a3 = angle_at(p1, p3, p2);
-            const double mn = fmin(a1, fmin(a2, a3));
+            // The three angles share the three edge vectors e1 = p2 - p1, e2 = p3 - p2, e3 = p1 - p3 whose norms are the sides
+            // above: compute_angle's vectors at a vertex are one edge and the NEGATED other one, negation is exact in every
+            // operation involved (x*x, fma, division), so dot_at_vertex = -fma(ey, e'y, ex * e'x) bit for bit.  Only the smallest
+            // angle is compared: min_i acos(c_i) = acos(max_i c_i) (acos decreases; a last-place wobble of the device acos
+            // falls inside the guard band below, which the host re-decides with numpy).  One acos, three square roots.
+            const double e1x = __dsub_rn(p2.x, p1.x), e1y = __dsub_rn(p2.y, p1.y), e2x = __dsub_rn(p3.x, p2.x), e2y = __dsub_rn(p3.y, p2.y);
+            const double e3x = __dsub_rn(p1.x, p3.x), e3y = __dsub_rn(p1.y, p3.y);
+            const double c1 = angle_cos(-__fma_rn(e1y, e3y, __dmul_rn(e1x, e3x)), s1, s3);   // at p1: v1 = e1, v2 = -e3
+            const double c2 = angle_cos(-__fma_rn(e1y, e2y, __dmul_rn(e1x, e2x)), s1, s2);   // at p2: v1 = -e1, v2 = e2
+            const double c3 = angle_cos(-__fma_rn(e3y, e2y, __dmul_rn(e3x, e2x)), s3, s2);   // at p3: v1 = e3, v2 = -e2
+            const double mn = __dmul_rn(acos(fmax(c1, fmax(c2, c3))), 57.29577951308232);  // np.degrees: x * (180/pi)
             if (fabs(mn - min_angle) <= 1e-9) band = true;
             if (mn < min_angle) k = SAME_TRI_DROP_ANGLE;
         }
