@@ -599,6 +599,19 @@ def main():
     t_h = time.perf_counter()
     tri_vid = triangulate(W["a_xy"])            # global (per-strip) Delaunay, the "precomputed triangulation" of the examples
     host_ms["qhull_delaunay_of_the_aligned_frame"] = (time.perf_counter() - t_h) * 1e3
+    if rank == 0:
+        # the other route of the product (no precomputed triangulation): one Delaunay per window, which run_same spreads over the
+        # host's cores (Qhull runs outside the GIL) — here on the cells of each window rectangle
+        from concurrent.futures import ThreadPoolExecutor
+        from scipy.spatial import Delaunay
+        from same_b200.same import host_threads
+        a = W["a_xy"]
+        t_h = time.perf_counter()
+        sel = [a[(a[:, 0] >= r[0]) & (a[:, 0] < r[1]) & (a[:, 1] >= r[2]) & (a[:, 1] < r[3])] for r in rects]
+        with ThreadPoolExecutor(max_workers=host_threads()) as ex:
+            n_tri = sum(ex.map(lambda p: len(Delaunay(p).simplices) if len(p) >= 3 else 0, sel))
+        host_ms["qhull_delaunay_per_window_on_host_threads"] = {"ms": (time.perf_counter() - t_h) * 1e3, "threads": host_threads(),
+                                                                "windows": len(rects), "triangles": int(n_tri)}
     host_ms["frames_to_arrays"] = W["prep_ms"]
     host_ms["note"] = ("host work of the path that is NOT on the GPU and NOT inside any timed region above: scipy/Qhull Delaunay of the whole "
                        "aligned frame (the precomputed triangulation every example hands to sliding_window_matching), the window grid, "

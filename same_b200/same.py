@@ -91,6 +91,18 @@ def _env_options():
 
 
 # --------------------------------------------------------------------------------------------------------
+def host_threads():
+    """Host threads for work that runs outside the GIL (per-window Qhull): SAME_B200_HOST_THREADS, else the cores this process
+    may run on."""
+    env = os.environ.get("SAME_B200_HOST_THREADS")
+    if env:
+        return max(1, int(env))
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 class _Run:
     """A section + one batch of windows on the GPU, driven stage by stage; shared by run_same (one unbounded
     window) and sliding_window_matching (all runnable windows at once)."""
@@ -131,17 +143,26 @@ class _Run:
             self.batch.triangles_remap()                                              # same.py:1028-1031
         else:
             ka_off, keepA = self.batch.offsets(L.KEEP_A), self.batch.get(L.KEEP_A)
-            tris, off = [], [0]
-            for w in range(self.W):
-                rows = keepA[ka_off[w]:ka_off[w + 1]]
-                t = np.zeros((0, 3), np.int32)
-                if self.n_pairs[w] > 0:
-                    try:
-                        t = Delaunay(self._a_xy[rows]).simplices.astype(np.int32)     # same.py:1023 (Qhull stays on the host)
-                    except Exception as e:      # a degenerate window (QhullError): raised at that window's turn, like the reference's
-                        self.window_errors[w] = e          # per-window loop, so the windows before it still run and checkpoint
-                tris.append(t)
-                off.append(off[-1] + len(t))
+
+            def triangulate(w):
+                if self.n_pairs[w] <= 0:
+                    return np.zeros((0, 3), np.int32)
+                try:
+                    return Delaunay(self._a_xy[keepA[ka_off[w]:ka_off[w + 1]]]).simplices.astype(np.int32)   # same.py:1023 (Qhull stays on the host)
+                except Exception as e:          # a degenerate window (QhullError): raised at that window's turn, like the reference's
+                    self.window_errors[w] = e   # per-window loop, so the windows before it still run and checkpoint
+                    return np.zeros((0, 3), np.int32)
+
+            # Qhull runs outside the GIL (scipy wraps qh_new_qhull in `with nogil`): the windows are triangulated on the host's
+            # cores at once — 8 windows of 30 k cells: 1.72 s one after the other, 0.42 s on 8 threads, identical simplices
+            n_thr = min(self.W, host_threads())
+            if n_thr > 1:
+                from concurrent.futures import ThreadPoolExecutor
+                with ThreadPoolExecutor(max_workers=n_thr, thread_name_prefix="same_b200-qhull") as ex:
+                    tris = list(ex.map(triangulate, range(self.W)))
+            else:
+                tris = [triangulate(w) for w in range(self.W)]
+            off = np.concatenate([[0], np.cumsum([len(t) for t in tris])]).astype(np.int64).tolist()
             self.batch.triangles_set(np.concatenate(tris) if tris else np.zeros((0, 3), np.int32), off)
         same = bool(o["ignore_same_type_triangles"])
         mad = o.get("min_angle_deg", 15)
