@@ -381,31 +381,54 @@ __global__ void k_tri_best(const int3 *__restrict__ tin, i64 Tin, const i32 *__r
     if (best_score[nb + v.z] == k) atomicMin(best_tri + nb + v.z, (i32)t);
 }
 // node v re-adds its best same-type triangle unless a smaller uncovered node already did (helpers.py:365-383)
-__global__ void k_addback(i64 nKA, const i32 *__restrict__ ka_off, int W, const i32 *__restrict__ node_valid, const i32 *__restrict__ has_tri,
-                          const i32 *__restrict__ best_tri, const int3 *__restrict__ tin, int enabled, i32 *__restrict__ ab_flag,
-                          i32 *__restrict__ unc_flag) {
-    const i64 v = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (v == nKA) { ab_flag[v] = 0; unc_flag[v] = 0; }
-    if (v >= nKA) return;
-    unc_flag[v] = node_valid[v] == 0;
-    int f = 0;
-    if (enabled && !has_tri[v] && node_valid[v] && best_tri[v] != 0x7fffffff) {
-        const i32 t = best_tri[v];
-        const i32 nb = ka_off[find_window(ka_off, W, (i32)v)];
-        const int3 tv = tin[t];
-        f = 1;
-        const i32 u3[3] = {nb + tv.x, nb + tv.y, nb + tv.z};
+// Add-back decision per node fused with the three node-indexed prefix sums of the stage (add-back triangles, unconstrained
+// nodes, surviving nodes) — one launch with a three-stream in-kernel scan (scan.cuh) instead of a flag kernel and three
+// device-wide scans.  A thread owns AB_ITEMS consecutive nodes; item nKA is the sentinel that receives the totals.
+constexpr int AB_THREADS = 256, AB_ITEMS = 4;
+__global__ void __launch_bounds__(AB_THREADS) k_addback_scan(i64 nKA, const i32 *__restrict__ ka_off, int W, const i32 *__restrict__ node_valid,
+                                                             const i32 *__restrict__ has_tri, const i32 *__restrict__ best_tri,
+                                                             const int3 *__restrict__ tin, int enabled, ScanCtx sc, i32 *__restrict__ ab_flag,
+                                                             i32 *__restrict__ unc_flag, i32 *__restrict__ abpos, i32 *__restrict__ uncpos,
+                                                             i32 *__restrict__ validpos) {
+    __shared__ int smem[3 * (AB_THREADS / 32) + 3];
+    const i64 base = ((i64)blockIdx.x * AB_THREADS + threadIdx.x) * AB_ITEMS;
+    int fa[AB_ITEMS], fu[AB_ITEMS], fv[AB_ITEMS], sum[3] = {0, 0, 0};
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            const i32 u = u3[c];
-            if (u < (i32)v && !has_tri[u] && best_tri[u] == t) f = 0;
+    for (int k = 0; k < AB_ITEMS; ++k) {
+        const i64 v = base + k;
+        fa[k] = fu[k] = fv[k] = 0;
+        if (v < nKA) {
+            fv[k] = node_valid[v] != 0;
+            fu[k] = !fv[k];
+            if (enabled && fv[k] && !has_tri[v] && best_tri[v] != 0x7fffffff) {
+                const i32 t = best_tri[v];
+                const i32 nb = ka_off[find_window(ka_off, W, (i32)v)];
+                const int3 tv = tin[t];
+                int f = 1;
+                const i32 u3[3] = {nb + tv.x, nb + tv.y, nb + tv.z};
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const i32 u = u3[c];
+                    if (u < (i32)v && !has_tri[u] && best_tri[u] == t) f = 0;
+                }
+                fa[k] = f;
+            }
         }
+        sum[0] += fa[k]; sum[1] += fu[k]; sum[2] += fv[k];
     }
-    ab_flag[v] = f;
+    int excl[3], tot[3], pre[3];
+    device_exclusive_scan<3, AB_THREADS>(sc, (int)blockIdx.x, sum, excl, tot, pre, smem);
+    int ra = excl[0], ru = excl[1], rv = excl[2];
+#pragma unroll
+    for (int k = 0; k < AB_ITEMS; ++k) {
+        const i64 v = base + k;
+        if (v <= nKA) {
+            ab_flag[v] = fa[k]; unc_flag[v] = fu[k];
+            abpos[v] = ra; uncpos[v] = ru; validpos[v] = rv;
+        }
+        ra += fa[k]; ru += fu[k]; rv += fv[k];
+    }
 }
-
-// per-window output offsets: the triangles of window w start after every kept triangle and every add-back of the earlier
-// windows, i.e. at kpos[first input triangle of w] + abpos[first node of w]
 __global__ void k_tri_window_offsets(const i32 *__restrict__ kpos, const i32 *__restrict__ abpos, const i32 *__restrict__ uncpos,
                                      const i32 *__restrict__ validpos, const i32 *__restrict__ tin_off, const i32 *__restrict__ ka_off, int W,
                                      i32 *__restrict__ out /* 4*(W+1): t_off, nkept(per window), unc_off, new ka_off */) {
@@ -651,12 +674,12 @@ void batch_tri_finalize(Batch *b, int ignore_same_type, int ensure_min, int remo
     if (addback && Tin > 0)
         LAUNCH(k_tri_best, blocks_for(Tin, 256), 256, 0, s, b->tin.p, Tin, b->d_tin_off.p, b->d_ka_off.p, (int)W, b->cls.p, b->score.p, best_score.p,
                best_tri.p);
-    LAUNCH(k_addback, blocks_for(nKA + 1, 256), 256, 0, s, nKA, b->d_ka_off.p, (int)W, node_valid.p, has_tri.p, best_tri.p, b->tin.p, addback, ab_flag.p,
-           unc_flag.p);
+    {
+        const unsigned tiles = blocks_for(nKA + 1, AB_THREADS * AB_ITEMS);
+        LAUNCH(k_addback_scan, tiles, AB_THREADS, 0, s, nKA, b->d_ka_off.p, (int)W, node_valid.p, has_tri.p, best_tri.p, b->tin.p, addback,
+               scan_ctx(b->sec, tiles, 3, s), ab_flag.p, unc_flag.p, abpos.p, uncpos.p, validpos.p);
+    }
     exclusive_scan_i32(kept_flag.p, kpos.p, Tin + 1, b->scratch, s);
-    exclusive_scan_i32(ab_flag.p, abpos.p, nKA + 1, b->scratch, s);
-    exclusive_scan_i32(unc_flag.p, uncpos.p, nKA + 1, b->scratch, s);
-    exclusive_scan_i32(node_valid.p, validpos.p, nKA + 1, b->scratch, s);  // node_valid[nKA] == 0 from the memset
     LAUNCH(k_tri_window_offsets, blocks_for(W + 1, 128), 128, 0, s, kpos.p, abpos.p, uncpos.p, validpos.p, b->d_tin_off.p, b->d_ka_off.p, (int)W, woff.p);
     const i32 *h = b->pin_misc();
     small_d2h(b->pin_misc(), woff.p, sizeof(i32) * 4 * (W + 1), s);
