@@ -332,7 +332,7 @@ def strong_scaling_arm(args, rank, world, local_rank, stream):
     # end to end: the whole section goes up on every rank, the block's results come back
     n_e2e = max(2, min(args.steps, 10))
     L.set_host_wait(world * 3 > len(os.sched_getaffinity(0)) // 2)
-    with CandidateStream(RADIUS, KNN, False, 1.0, device=local_rank) as cs:
+    with CandidateStream(RADIUS, KNN, False, 1.0, device=local_rank, j16=True) as cs:
         def stream_n(n):
             prev = None
             for _ in range(n):
@@ -715,7 +715,9 @@ def main():
         saved = x_dev["t"]
         import gc
 
-        CAND_ARRAYS = [L.KEEP_A, L.KEEP_R, L.ROW_PTR, L.PAIR_J, L.COST]     # valid_pairs in compact form: i is implied by ROW_PTR
+        # valid_pairs in compact form: i is implied by ROW_PTR, j is window-local and fits 16 bits (every window keeps < 65,536 rows)
+        CAND_ARRAYS = [L.KEEP_A, L.KEEP_R, L.ROW_PTR, L.PAIR_J, L.COST]
+        CAND_ARRAYS_ONCE = [L.KEEP_A, L.KEEP_R, L.ROW_PTR, L.PAIR_J16, L.COST]
         frames_pinned = (pins["a_xy"][1], pins["r_xy"][1], pins["a_prob"][1], pins["r_prob"][1], pins["a_type"][1], pins["r_type"][1])
 
         def cand_once():
@@ -723,7 +725,7 @@ def main():
             s2 = Section(*frames_pinned, device=local_rank, stream=stream)
             b = s2.batch(rects)
             b.candidates(RADIUS, KNN, False, 1.0)
-            got = b.get_many(CAND_ARRAYS)
+            got = b.get_many(CAND_ARRAYS_ONCE)
             npairs, nbytes = b.length(L.PAIRS), sum(v.nbytes for v in got.values())
             b.close()
             s2.close()
@@ -733,7 +735,7 @@ def main():
         # several ranks x (main thread + two section threads) on a host with few cores: waiting threads sleep instead of spinning
         yield_wait = (os.environ.get("SAME_B200_HOST_WAIT") == "yield") if "SAME_B200_HOST_WAIT" in os.environ else world * 3 > len(all_cpus) // 2
         L.set_host_wait(yield_wait)
-        cstream = CandidateStream(RADIUS, KNN, False, 1.0, device=local_rank)
+        cstream = CandidateStream(RADIUS, KNN, False, 1.0, device=local_rank, j16=True)
 
         def cand_stream(n):
             """n sections back to back through CandidateStream: section k+1 is submitted (upload + kernels on its own stream)
@@ -983,7 +985,7 @@ def main():
                            "host_wait": "yield (blocking-sync events)" if yield_wait else "spin",
                            "note": "candidate stage (the scope of `value` and of --impl reference: subset + KNN + cost) through the public API "
                                    "(same_b200.device.CandidateStream over the C-ABI) on a stream of sections: every section's frames go up from "
-                                   "page-locked host memory and its kept rows, row pointers, pair reference indices and costs come back, all inside "
+                                   "page-locked host memory and its kept rows, row pointers, pair reference indices (16-bit, window-local: SAME_ARR_PAIR_J16) and costs come back, all inside "
                                    "the timed region; section k+1 is submitted before section k's download is awaited, so both PCIe directions and "
                                    "the kernels overlap.  wall clock over all sections / sections, per rank, max over ranks.  "
                                    "single_section_latency_ms = one section alone, nothing overlapped",

@@ -92,8 +92,10 @@ enum {
                                   a vertex twice counts once, as in the reference's sets) */
     SAME_ARR_NODE_TRI_LEN = 33,/* [i32]   number of distinct triangles of each kept aligned node */
     SAME_ARR_NODE_TRI_IDX = 34,/* [i32]   3*T_total slots, window-local TRI indices, ascending inside a node */
-    SAME_ARR_PAIR_J = 31       /* [i32]   reference index of each pair = PAIRS[:, 1] on its own.  The aligned index PAIRS[:, 0] is implied by ROW_PTR
+    SAME_ARR_PAIR_J = 31,      /* [i32]   reference index of each pair = PAIRS[:, 1] on its own.  The aligned index PAIRS[:, 0] is implied by ROW_PTR
                                   (pairs are sorted by aligned row, src/utils.py:720-731), so ROW_PTR + PAIR_J is valid_pairs in half the bytes over PCIe */
+    SAME_ARR_PAIR_J16 = 35     /* [u16]   PAIR_J in two bytes per pair — a quarter of PAIRS over PCIe.  Only when every window keeps at most 65,536
+                                  reference rows (the index is window-local); SAME_E_LIMIT otherwise: fall back to PAIR_J */
 };
 
 typedef struct same_section same_section_t;

@@ -24,6 +24,7 @@ TRI_WEIGHT, TRI_SIGN, TRI_BOUNDS, TRI_ARGV, UNCONSTRAINED = 18, 19, 20, 21, 22
 MATCH_J, MATCH_P, TRI_MASK, AREA_BEFORE, AREA_AFTER, FLIPPED = 23, 24, 25, 26, 27, 28
 START_X, START_UNMATCHED = 29, 30
 PAIR_J = 31
+PAIR_J16 = 35
 STAT_KNN_EVALUATIONS = 1
 NODE_TRI_PTR, NODE_TRI_LEN, NODE_TRI_IDX = 32, 33, 34
 
@@ -38,7 +39,7 @@ ARRAY_SPEC = {
     TRI_BOUNDS: (np.float64, (4,)), TRI_ARGV: (np.int32, (4,)), UNCONSTRAINED: (np.int32, ()),
     MATCH_J: (np.int32, ()), MATCH_P: (np.int32, ()), TRI_MASK: (np.int32, ()),
     AREA_BEFORE: (np.float64, ()), AREA_AFTER: (np.float64, ()), FLIPPED: (np.uint8, ()),
-    START_X: (np.uint8, ()), START_UNMATCHED: (np.uint8, ()), PAIR_J: (np.int32, ()), NODE_TRI_PTR: (np.int32, ()), NODE_TRI_LEN: (np.int32, ()), NODE_TRI_IDX: (np.int32, ()),
+    START_X: (np.uint8, ()), START_UNMATCHED: (np.uint8, ()), PAIR_J: (np.int32, ()), PAIR_J16: (np.uint16, ()), NODE_TRI_PTR: (np.int32, ()), NODE_TRI_LEN: (np.int32, ()), NODE_TRI_IDX: (np.int32, ()),
 }
 
 TRI_DROP_RADIUS, TRI_DROP_ANGLE, TRI_SAME_TYPE, TRI_KEEP = 0, 1, 2, 3

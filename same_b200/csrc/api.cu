@@ -32,6 +32,7 @@ i64 elem_size(int what) {
     switch (what) {
         case SAME_ARR_PAIRS: return 8;
         case SAME_ARR_PAIR_J: return 4;
+        case SAME_ARR_PAIR_J16: return 2;
         case SAME_ARR_COST: case SAME_ARR_TRI_WEIGHT: case SAME_ARR_AREA_BEFORE: case SAME_ARR_AREA_AFTER: return 8;
         case SAME_ARR_TRI_IN: case SAME_ARR_TRI: return 12;
         case SAME_ARR_TRI_CLASS: case SAME_ARR_TRI_SIGN: case SAME_ARR_FLIPPED: case SAME_ARR_START_X: case SAME_ARR_START_UNMATCHED: return 1;
@@ -54,6 +55,7 @@ ArrayView view(Batch *b, int what) {
         case SAME_ARR_PAIRS: need(1, "candidates not run"); return {b->pairs.p, b->P, es, &b->p_off};
         case SAME_ARR_COST: need(1, "candidates not run"); return {b->cost.p, b->P, es, &b->p_off};
         case SAME_ARR_PAIR_J: need(1, "candidates not run"); batch_pair_j(b); return {b->pair_j.p, b->P, es, &b->p_off};
+        case SAME_ARR_PAIR_J16: need(1, "candidates not run"); batch_pair_j16(b); return {b->pair_j16.p, b->P, es, &b->p_off};
         case SAME_ARR_ROW_PTR: need(1, "candidates not run"); return {b->row_ptr.p, b->nKA + 1, es, nullptr};
         case SAME_ARR_REF_GROUP_NODE: REQUIRE(b->have_groups, SAME_E_STATE, "groups not built"); return {b->g_node.p, b->G, es, &b->g_off};
         case SAME_ARR_REF_GROUP_LIMIT: REQUIRE(b->have_groups, SAME_E_STATE, "groups not built"); return {b->g_limit.p, b->G, es, &b->g_off};

@@ -626,6 +626,18 @@ void batch_kept_columns(Batch *b) {
     b->have_kept_cols = true;
 }
 
+__global__ void k_pair_j16(const int2 *__restrict__ pairs, i64 P, unsigned short *__restrict__ pj) {
+    const i64 p = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < P) pj[p] = (unsigned short)pairs[p].y;
+}
+void batch_pair_j16(Batch *b) {
+    if (b->have_pair_j16) return;
+    for (i64 w = 0; w < b->W; ++w)   // (the caller settled the batch: the kept offsets are on the host)
+        REQUIRE(b->kr_off[w + 1] - b->kr_off[w] <= 65536, SAME_E_LIMIT, "a window keeps more than 65,536 reference rows: PAIR_J16 cannot hold its indices");
+    b->pair_j16.alloc(b->P, b->stream);
+    if (b->P > 0) LAUNCH(k_pair_j16, blocks_for(b->P, 256), 256, 0, b->stream, b->pairs.p, b->P, b->pair_j16.p);
+    b->have_pair_j16 = true;
+}
 void batch_pair_j(Batch *b) {
     if (b->have_pair_j) return;
     b->pair_j.alloc(b->P, b->stream);
@@ -785,6 +797,7 @@ void batch_candidates(Batch *b, double radius, int knn, int priority, double dis
     b->have_groups = false;
     b->have_start = false;
     b->have_pair_j = false;
+    b->have_pair_j16 = false;
     b->Tin = b->T = 0;
 }
 

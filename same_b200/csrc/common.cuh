@@ -291,6 +291,8 @@ struct Batch {
     DevBuf<int2> pairs;                 // window-local (i, j)
     DevBuf<i32> pair_j;                 // pairs[].y on its own, built on first request (SAME_ARR_PAIR_J)
     bool have_pair_j = false;
+    DevBuf<unsigned short> pair_j16;    // the same in 16 bits (SAME_ARR_PAIR_J16), when every window keeps <= 65,536 reference rows
+    bool have_pair_j16 = false;
     DevBuf<double> cost;
     DevBuf<i32> row_ptr;                // [nKA+1] batch-global pair offset of each aligned row
 
@@ -362,6 +364,7 @@ void batch_subset(Batch *b);
 void batch_candidates(Batch *b, double radius, int knn, int priority, double dist_ct_coeff);
 void batch_groups(Batch *b, int max_matches, int multiplier);
 void batch_pair_j(Batch *b);
+void batch_pair_j16(Batch *b);
 void batch_kept_columns(Batch *b);   // ka_xy / ka_type / ka_size / kr_xy / kr_size, gathered on first use
 void batch_incidence(Batch *b);
 void batch_triangles_remap(Batch *b);

@@ -732,6 +732,7 @@ void batch_tri_finalize(Batch *b, int ignore_same_type, int ensure_min, int remo
         b->have_groups = false;
         b->have_start = false;   // pairs and rows were renumbered
         b->have_pair_j = false;
+        b->have_pair_j16 = false;
     }
 
     b->t_weight.alloc(b->T, s); b->t_sign.alloc(b->T, s); b->t_bounds.alloc(4 * b->T, s); b->t_argv.alloc(4 * b->T, s);

@@ -191,7 +191,9 @@ class CandidateStream:
 
     At most `depth` sections may be outstanding (submitted, `result()` not yet called).  `result()` gives valid_pairs in compact
     form: the aligned index of pair p is the row r with ROW_PTR[r] <= p < ROW_PTR[r+1] (`pairs_from_rows`), the reference index
-    is PAIR_J[p]."""
+    is PAIR_J[p].  With `j16=True` PAIR_J comes back as uint16 (two bytes per pair over PCIe instead of four; the index is
+    window-local) whenever every window keeps at most 65,536 reference rows, and as int32 otherwise — the key is L.PAIR_J either
+    way."""
 
     ARRAYS = (L.KEEP_A, L.KEEP_R, L.ROW_PTR, L.PAIR_J, L.COST)
 
@@ -214,9 +216,10 @@ class CandidateStream:
                 sec.close()
             return out
 
-    def __init__(self, radius, knn, priority=False, dist_ct_coeff=1.0, device=None, depth=2):
+    def __init__(self, radius, knn, priority=False, dist_ct_coeff=1.0, device=None, depth=2, j16=False):
         from concurrent.futures import ThreadPoolExecutor
         self.radius, self.knn, self.priority, self.dist_ct_coeff = float(radius), int(knn), bool(priority), float(dist_ct_coeff)
+        self.j16 = bool(j16)
         self.device = default_device() if device is None else device
         self._k = self._outstanding = 0
         # a fixed set of streams, taken in turn: the stream-ordered memory pool then recycles a section's buffers for the
@@ -263,6 +266,10 @@ class CandidateStream:
             b = sec.batch(rects)
             try:
                 b.candidates(self.radius, self.knn, self.priority, self.dist_ct_coeff)
+                if self.j16 and int(np.diff(b.offsets(L.KEEP_R)).max(initial=0)) <= 65536:
+                    got = b.get_many(tuple(L.PAIR_J16 if w == L.PAIR_J else w for w in self.ARRAYS), pinned=True, wait=False)
+                    got[L.PAIR_J] = got.pop(L.PAIR_J16)
+                    return sec, b, got
                 return sec, b, b.get_many(self.ARRAYS, pinned=True, wait=False)
             except BaseException:
                 b.close()

@@ -392,6 +392,12 @@ def test_pair_j_and_asynchronous_downloads_equal_the_blocking_path():
             assert np.array_equal(got[k], want[k])
         with pytest.raises(ValueError):
             b.get_many([L.COST], pinned=False, wait=False)
+        j16 = b.get(L.PAIR_J16)                                  # two bytes per pair: the index is window-local
+        assert j16.dtype == np.uint16 and np.array_equal(j16.astype(np.int32), want[L.PAIR_J])
+    with CandidateStream(1.0, 8, depth=2, j16=True) as cs:
+        out = cs.submit(frames, rects).result()
+        assert out[L.PAIR_J].dtype == np.uint16 and np.array_equal(out[L.PAIR_J].astype(np.int32), want[L.PAIR_J])
+        assert np.array_equal(out[L.COST], want[L.COST]) and np.array_equal(out[L.ROW_PTR], want[L.ROW_PTR])
     with CandidateStream(1.0, 8, depth=2) as cs:
         prev, n_done = None, 0
         for _ in range(5):                                       # two sections in flight at any time

@@ -161,6 +161,10 @@ def test_luad_shape_single_window_vs_oracle():
     with Section(a_xy, r_xy, a_prob, r_prob, tA, tR, sA, sR) as sec, sec.batch() as b:
         b.candidates(radius, knn, False, 1.0)
         keepA = b.get(L.KEEP_A)
+        assert b.length(L.KEEP_R) > 65536
+        with pytest.raises(L.SameError) as limit:       # a window with more than 65,536 kept reference rows has no 16-bit form
+            b.get(L.PAIR_J16)
+        assert limit.value.code == L.E_LIMIT
         tri = Delaunay(a_xy[keepA]).simplices.astype(np.int32)
         b.triangles_set(tri, [0, len(tri)])
         nb = b.tri_classify(50.0, 15.0, True)
