@@ -391,7 +391,8 @@ def strong_scaling_arm(args, rank, world, local_rank, stream):
                     "how": "row-sharded upload (1/world of every frame per rank over its own PCIe link) + all_gather over NVLink "
                            "(sharding.section_from_row_shards), kernels on the rank's window block, download of the block's results"},
             "e2e_replicated_upload": {"value": tot_pairs / (allr[:, 1].max() * 1e-3), "unit": "pairs/s", "ms_per_step": float(allr[:, 1].max()),
-                                      "ms_per_step_per_rank": [float(v) for v in allr[:, 1]], "h2d_bytes_per_step": h2d_all,
+                                      "ms_per_step_per_rank": [float(v) for v in allr[:, 1]],
+                                      "h2d_bytes_per_step": int(sum(f.nbytes for f in frames[:4])),    # (CandidateStream leaves the type codes on the host)
                                       "d2h_bytes_per_step": int(d2h),
                                       "how": "every rank uploads the whole section (CandidateStream), no collective"},
             "note": "ONE 2,500-tile section held by every rank, window list in contiguous blocks (same_b200.windows.shard_windows, the "
@@ -798,7 +799,8 @@ def main():
         f_ms, f_P, f_d2h = timed(full_once)
         x_dev["t"] = saved
         frames = sum(p[1].nbytes for p in pins.values())
-        e2e = dict(ms=s_ms, latency_ms=c_ms, h2d=frames, d2h=s_d2h, P=s_P, full_ms=f_ms, full_h2d=frames + tri_pin[1].nbytes + x_pin[1].nbytes,
+        cand_h2d = sum(p[1].nbytes for k, p in pins.items() if k not in ("a_type", "r_type"))   # CandidateStream leaves the type codes on the host
+        e2e = dict(ms=s_ms, latency_ms=c_ms, h2d=cand_h2d, d2h=s_d2h, P=s_P, full_ms=f_ms, full_h2d=frames + tri_pin[1].nbytes + x_pin[1].nbytes,
                    full_d2h=f_d2h, full_P=f_P)
         sec = make_section()
 

@@ -261,6 +261,8 @@ class CandidateStream:
         self.close()
 
     def _run(self, frames, rects, stream):
+        if not self.priority:       # type codes (and sizes) are read by the priority filter / later stages only: they stay on the host
+            frames = tuple(frames[:4]) + (None,) * (len(frames) - 4)
         sec = Section(*frames, device=self.device, stream=stream)
         try:
             b = sec.batch(rects)
@@ -279,7 +281,8 @@ class CandidateStream:
             raise
 
     def submit(self, frames, rects=None):
-        """frames = (a_xy, r_xy, a_prob, r_prob, a_type, r_type[, a_size, r_size]); sections take the streams in turn."""
+        """frames = (a_xy, r_xy, a_prob, r_prob, a_type, r_type[, a_size, r_size]); sections take the streams in turn.  The type
+        codes are uploaded only when the stream was created with priority=True (nothing else in this stage reads them)."""
         if self._outstanding >= len(self._streams):
             raise RuntimeError(f"CandidateStream: {self._outstanding} sections outstanding; call result() on the oldest first "
                                f"(depth={len(self._streams)})")
