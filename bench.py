@@ -711,7 +711,7 @@ def main():
     e2e = None
     if not args.no_e2e:
         sec.close()
-        n_e2e = max(2, min(args.steps, 10))
+        n_e2e = max(2, min(2 * args.steps, 20))     # sections in the stream (the first result pays the whole latency: pipeline fill)
         x_pin = pinned(x_dev["t"].cpu().numpy())                 # the incumbent comes from the host solver in real use
         saved = x_dev["t"]
         import gc
@@ -736,22 +736,23 @@ def main():
         # several ranks x (main thread + two section threads) on a host with few cores: waiting threads sleep instead of spinning
         yield_wait = (os.environ.get("SAME_B200_HOST_WAIT") == "yield") if "SAME_B200_HOST_WAIT" in os.environ else world * 3 > len(all_cpus) // 2
         L.set_host_wait(yield_wait)
-        cstream = CandidateStream(RADIUS, KNN, False, 1.0, device=local_rank, j16=True)
+        E2E_DEPTH = int(os.environ.get("SAME_BENCH_E2E_DEPTH", "3"))   # measured: 2 -> 2.41, 3 -> 2.23, 4 -> no better (ms per section)
+        cstream = CandidateStream(RADIUS, KNN, False, 1.0, device=local_rank, j16=True, depth=E2E_DEPTH)
 
         def cand_stream(n):
             """n sections back to back through CandidateStream: section k+1 is submitted (upload + kernels on its own stream)
             before the downloads of section k are awaited, so the two PCIe directions and the kernels overlap.  Every section's
             inputs go up from page-locked host memory and every section's results come down inside the timed region."""
-            prev, npairs, nbytes, marks = None, 0, 0, [time.perf_counter()]
+            from collections import deque
+            queue, npairs, nbytes, marks = deque(), 0, 0, [time.perf_counter()]
             for _ in range(n):
-                h = cstream.submit(frames_pinned, rects)
-                if prev is not None:
-                    out = prev.result()
+                if len(queue) == E2E_DEPTH:                     # at most `depth` sections outstanding: take the oldest result first
+                    out = queue.popleft().result()
                     marks.append(time.perf_counter())
-                    npairs, nbytes = len(out[L.PAIR_J]), sum(out[w].nbytes for w in CAND_ARRAYS)
-                prev = h
-            out = prev.result()
-            marks.append(time.perf_counter())
+                queue.append(cstream.submit(frames_pinned, rects))
+            while queue:
+                out = queue.popleft().result()
+                marks.append(time.perf_counter())
             from same_b200 import device as DV
             sys.stderr.write(f"[bench] e2e cand_stream results arrive after ms: {[round((b - a) * 1e3, 2) for a, b in zip(marks, marks[1:])]} "
                              f"(page-locked blocks obtained so far {DV.PINNED_ALLOCS[0]}, device pool {L.mempool_stats(local_rank)[0] >> 20} MiB)\n")

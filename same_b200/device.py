@@ -216,7 +216,7 @@ class CandidateStream:
                 sec.close()
             return out
 
-    def __init__(self, radius, knn, priority=False, dist_ct_coeff=1.0, device=None, depth=2, j16=False):
+    def __init__(self, radius, knn, priority=False, dist_ct_coeff=1.0, device=None, depth=3, j16=False):
         from concurrent.futures import ThreadPoolExecutor
         self.radius, self.knn, self.priority, self.dist_ct_coeff = float(radius), int(knn), bool(priority), float(dist_ct_coeff)
         self.j16 = bool(j16)
