@@ -319,3 +319,14 @@ def test_default_device_follows_local_rank(monkeypatch):
     assert default_device() == 5
     monkeypatch.setenv("SAME_B200_DEVICE", "junk")
     assert default_device() == 3
+
+
+def test_host_threads_follow_the_environment(monkeypatch):
+    """run_same triangulates the windows on `host_threads()` threads: SAME_B200_HOST_THREADS, else the cores of the process."""
+    from same_b200.same import host_threads
+    monkeypatch.setenv("SAME_B200_HOST_THREADS", "3")
+    assert host_threads() == 3
+    monkeypatch.setenv("SAME_B200_HOST_THREADS", "0")
+    assert host_threads() == 1
+    monkeypatch.delenv("SAME_B200_HOST_THREADS")
+    assert 1 <= host_threads() <= (os.cpu_count() or 1)
