@@ -711,7 +711,7 @@ def main():
     e2e = None
     if not args.no_e2e:
         sec.close()
-        n_e2e = max(2, min(2 * args.steps, 20))     # sections in the stream (the first result pays the whole latency: pipeline fill)
+        n_e2e = max(10, min(2 * args.steps, 20))    # sections in the stream (the first result pays the whole latency: pipeline fill)
         x_pin = pinned(x_dev["t"].cpu().numpy())                 # the incumbent comes from the host solver in real use
         saved = x_dev["t"]
         import gc
