@@ -240,7 +240,7 @@ SAME_API int64_t same_elem_size(int what);
 /* block until everything queued on the batch's stream has finished */
 SAME_API int same_batch_sync(same_batch_t *b);
 /* A CUDA stream owned by the caller (cudaStreamCreateWithFlags(cudaStreamNonBlocking) / cudaStreamDestroy) for hosts without their
- * own CUDA binding: pass it as `stream` to same_section_create.  Sections that alternate between a FIXED pair of such streams
+ * own CUDA binding: pass it as `stream` to same_section_create.  Sections that rotate through a FIXED set of such streams
  * overlap one section's downloads with the next one's uploads and kernels, and the stream-ordered memory pool recycles their
  * buffers without touching the driver (a new stream per section does not: its first allocations cannot reuse memory that
  * was freed on other streams). */
